@@ -1,0 +1,242 @@
+/* quokka_b200.h -- C ABI of libquokka_b200.so: the B200-native (sm_100a) implementation of Quokka's
+ * per-patch hydro update hot path (PPM -> shock flattening -> HLLC -> RK2 update with dual energy)
+ * and, in the same style, the two-moment radiation transport sweep.
+ *
+ * Quokka has no FFI: its seam is the static-function surface of HydroSystem<problem_t> /
+ * HyperbolicSystem<problem_t> / RadSystem<problem_t> as called from QuokkaSimulation<problem_t>
+ * (reference: src/QuokkaSimulation.hpp:1096-1278 hydro, :1806-1848 radiation).  Every entry point
+ * below names the reference operator (file:line) it replaces.  The compile-time traits of the
+ * reference (EOS_Traits<>, HydroSystem_Traits<>, Physics_Traits<>) become the run-time
+ * qk_hydro_params; amrex::Array4<double> becomes the layout-identical POD qk_array4, so a
+ * maintainer can pass `reinterpret_cast<qk_array4 const*>(&mf.arrays()[i])`-style views without
+ * copying.
+ *
+ * Conventions
+ *  - all pointers inside qk_array4 are DEVICE pointers; descriptor arrays themselves are HOST arrays
+ *  - a "MultiFab" is `nboxes` descriptors + `nboxes` valid boxes (cell-centred, inclusive bounds)
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except where a
+ *    scalar is returned to the host (qk_*_reduce_*, ncells_bad), which synchronise that stream
+ *  - return value: 0 = ok, >0 = cudaError_t, <0 = QK_ERR_*; kernels never abort: bad cells are
+ *    reported through redoFlag / ncells_bad exactly as the reference does
+ *    (src/QuokkaSimulation.hpp:1146,1234)
+ *  - there is NO CPU fallback: without a CUDA device every compute entry returns QK_ERR_NO_DEVICE
+ */
+#ifndef QUOKKA_B200_H_
+#define QUOKKA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_ABI_VERSION 1
+#define QK_MAX_SCALARS 8
+
+enum { QK_OK = 0, QK_ERR_NO_DEVICE = -1, QK_ERR_BAD_ARG = -2, QK_ERR_UNSUPPORTED = -3, QK_ERR_NOMEM = -4 };
+
+/* flux direction: FluxDir::{X1,X2,X3}, src/util/ArrayView_3d.hpp:18 */
+enum { QK_X1 = 0, QK_X2 = 1, QK_X3 = 2 };
+/* RiemannSolver::{HLLC,LLF}, src/hydro/hydro_system.hpp:43 (HLLD/MHD is out of scope) */
+enum { QK_HLLC = 0, QK_LLF = 1 };
+/* reconstruction order as QuokkaSimulation::reconstructionOrder_ (src/QuokkaSimulation.hpp:1498-1506):
+ * 1 donor cell, 2 PLM, 3 PPM.  SlopeLimiter::{minmod,MC}, src/hyperbolic_system.hpp:38 */
+enum { QK_MINMOD = 0, QK_MC = 1 };
+/* amrex::BCType values used by the path (extern/amrex/Src/Base/AMReX_BC_TYPES.H) */
+enum { QK_BC_INT_DIR = 0, QK_BC_REFLECT_ODD = -1, QK_BC_REFLECT_EVEN = 1, QK_BC_FOEXTRAP = 2, QK_BC_EXT_DIR = 3 };
+/* arithmetic mode: EXACT reproduces the reference's IEEE operation order with FMA contraction off
+ * (the reference builds with --fmad=false, CMakeLists.txt:31) and is bit-identical to it;
+ * FAST allows contraction and algebraically-equivalent EOS shortcuts (drift is reported) */
+enum { QK_ARITH_EXACT = 0, QK_ARITH_FAST = 1 };
+
+/* == amrex::Array4<double> (extern/amrex/Src/Base/AMReX_Array4.H:59-68): Fortran order, x fastest,
+ * component-major: p[(i-begin[0]) + (j-begin[1])*jstride + (k-begin[2])*kstride + n*nstride];
+ * `end` is one past the last index, as in AMReX. */
+typedef struct qk_array4 {
+	double *p;
+	int64_t jstride, kstride, nstride;
+	int32_t begin[3];
+	int32_t end[3];
+	int32_t ncomp;
+} qk_array4;
+
+/* == amrex::Array4<int> (redoFlag, src/hyperbolic_system.hpp:34) */
+typedef struct qk_iarray4 {
+	int32_t *p;
+	int64_t jstride, kstride, nstride;
+	int32_t begin[3];
+	int32_t end[3];
+	int32_t ncomp;
+} qk_iarray4;
+
+/* == amrex::Box (cell-centred), inclusive bounds */
+typedef struct qk_box {
+	int32_t lo[3];
+	int32_t hi[3];
+} qk_box;
+
+/* run-time image of EOS_Traits<problem_t> (src/hydro/EOS.hpp:32-37), HydroSystem_Traits<problem_t>
+ * (src/hydro/hydro_system.hpp:38-41), Physics_Traits<problem_t> and the hydro.* / top-level
+ * parameters the path reads (src/QuokkaSimulation.hpp:107-131, src/simulation.hpp:172-173) */
+typedef struct qk_hydro_params {
+	double gamma;		      /* EOS_Traits::gamma -> eos_rp::eos_gamma (QuokkaSimulation.hpp:160) */
+	double mean_molecular_weight; /* EOS_Traits::mean_molecular_weight [g] */
+	double boltzmann_constant;    /* EOS_Traits::boltzmann_constant */
+	double small_temp;	      /* eos_init small_temp = 1e-10 (QuokkaSimulation.hpp:165) */
+	double small_dens;	      /* eos_init small_dens = 1e-100 (QuokkaSimulation.hpp:166) */
+	double density_floor;	      /* densityFloor_ (simulation.hpp:172) */
+	double temp_floor;	      /* tempFloor_ (simulation.hpp:173) */
+	double K_visc;		      /* artificialViscosityK_ (QuokkaSimulation.hpp:120); only 0 is supported by the fused path */
+	double small_x;		      /* network_rp::small_x, mass-scalar floor (hydro_system.hpp:730) */
+	int32_t reconstruct_eint;     /* HydroSystem_Traits::reconstruct_eint */
+	int32_t nscalars;	      /* Physics_Traits::numPassiveScalars (includes mass scalars) */
+	int32_t nmscalars;	      /* Physics_Traits::numMassScalars */
+	int32_t reconstruction_order; /* reconstructionOrder_: 1|2|3 */
+	int32_t use_dual_energy;      /* useDualEnergy_ */
+	int32_t integrator_order;     /* integratorOrder_: 1|2 */
+	int32_t abort_on_fofc_failure; /* abortOnFofcFailure_ */
+	int32_t arith;		      /* QK_ARITH_* */
+} qk_hydro_params;
+
+/* ---- library / device --------------------------------------------------------------------- */
+int qk_abi_version(void);
+/* number of CUDA devices visible (0 => every compute entry returns QK_ERR_NO_DEVICE) */
+int qk_device_count(void);
+const char *qk_error_string(int code);
+/* total kernels launched by this library since load (for bench.py "gpu_launches") */
+int64_t qk_launch_count(void);
+
+/* ---- per-operator entry points (one per reference operator; parity harness + drop-in) ------ */
+
+/* HydroSystem::ConservedToPrimitive(cons_mf, primVar_mf, nghost)  src/hydro/hydro_system.hpp:138-196 */
+int qk_hydro_conserved_to_primitive(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, const qk_array4 *prim,
+				    int nghost, void *stream);
+
+/* HydroSystem::ComputeFlatteningCoefficients<DIR>(primVar_mf, x1Chi_mf, nghost)  hydro_system.hpp:531-626 */
+int qk_hydro_flattening_coefficients(const qk_hydro_params *prm, int dir, int nboxes, const qk_box *valid, const qk_array4 *prim,
+				     const qk_array4 *chi, int nghost, void *stream);
+
+/* HyperbolicSystem::ReconstructStates{Constant,PLM<limiter>,PPM}<DIR>(q, left, right, nghost, nvars)
+ * src/hyperbolic_system.hpp:129-181,183-247,295-433.  left/right are nodal in `dir`. */
+int qk_reconstruct_states(int order, int limiter, int dir, int nboxes, const qk_box *valid, const qk_array4 *q, const qk_array4 *left,
+			  const qk_array4 *right, int nghost, int nvars, void *stream);
+
+/* HydroSystem::FlattenShocks<DIR>(q, chi1, chi2, chi3, left, right, nghost, nvars)  hydro_system.hpp:628-694 */
+int qk_hydro_flatten_shocks(int dir, int nboxes, const qk_box *valid, const qk_array4 *q, const qk_array4 *chi1, const qk_array4 *chi2,
+			    const qk_array4 *chi3, const qk_array4 *left, const qk_array4 *right, int nghost, int nvars, void *stream);
+
+/* HydroSystem::ComputeFluxes<RIEMANN,DIR>(flux, faceVel, left, right, primVar, K_visc)  hydro_system.hpp:852-1112
+ * (+ Riemann::HLLC src/hydro/HLLC.hpp:21-153, Riemann::LLF src/hydro/LLF.hpp:15-43).
+ * Computes on the faces of `valid` (nodal in dir: hi[dir]+1 included). */
+int qk_hydro_compute_fluxes(const qk_hydro_params *prm, int solver, int dir, int nboxes, const qk_box *valid, const qk_array4 *flux,
+			    const qk_array4 *facevel, const qk_array4 *left, const qk_array4 *right, const qk_array4 *prim, void *stream);
+
+/* hydroFluxFunction<DIR> fused (Reconstruct + FlattenShocks + ComputeFluxes<HLLC>)  QuokkaSimulation.hpp:1492-1517,
+ * and hydroFOFluxFunction<DIR> (donor cell + LLF) :1559-1568 when fo != 0.
+ * chi1..3 may be NULL when fo != 0.  No left/right states are materialised. */
+int qk_hydro_flux_function(const qk_hydro_params *prm, int fo, int dir, int nboxes, const qk_box *valid, const qk_array4 *prim,
+			   const qk_array4 *chi1, const qk_array4 *chi2, const qk_array4 *chi3, const qk_array4 *flux, const qk_array4 *facevel,
+			   void *stream);
+
+/* MultiFab::Saxpy(dst, a, src, 0, 0, ncomp, 0) on the valid faces/cells  QuokkaSimulation.hpp:1105-1108 */
+int qk_saxpy(int nboxes, const qk_box *region, const qk_array4 *dst, double a, const qk_array4 *src, int ncomp, void *stream);
+
+/* HydroSystem::ComputeRhsFromFluxes(rhs, fluxArray, dx, nvars)  hydro_system.hpp:448-473 */
+int qk_hydro_rhs_from_fluxes(int nboxes, const qk_box *valid, const qk_array4 *rhs, const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz,
+			     const double dx[3], int nvars, void *stream);
+
+/* HydroSystem::AddInternalEnergyPdV(rhs, consVar, dx, faceVelArray, redoFlag)  hydro_system.hpp:775-814 */
+int qk_hydro_add_internal_energy_pdv(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *rhs, const qk_array4 *cons,
+				     const double dx[3], const qk_array4 *vx, const qk_array4 *vy, const qk_array4 *vz, const qk_iarray4 *redo,
+				     void *stream);
+
+/* HydroSystem::PredictStep(consVarOld, consVarNew, rhs, dt, nvars, redoFlag)  hydro_system.hpp:475-497;
+ * *ncells_bad = redoFlag.sum(0) (QuokkaSimulation.hpp:1146) if ncells_bad != NULL (synchronises) */
+int qk_hydro_predict_step(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons_old, const qk_array4 *cons_new,
+			  const qk_array4 *rhs, double dt, int nvars, const qk_iarray4 *redo, int64_t *ncells_bad, void *stream);
+
+/* HydroSystem::EnforceLimits(densityFloor, tempFloor, state)  hydro_system.hpp:698-773 */
+int qk_hydro_enforce_limits(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *state, void *stream);
+
+/* HydroSystem::SyncDualEnergy(consVar)  hydro_system.hpp:816-850.  Cells with rho<=0 (where the
+ * reference calls amrex::Abort) are counted into *nabort instead (may be NULL). */
+int qk_hydro_sync_dual_energy(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *state, int64_t *nabort, void *stream);
+
+/* QuokkaSimulation::replaceFluxes(fluxes, FOfluxes, redoFlag) for one direction  QuokkaSimulation.hpp:1324-1368 */
+int qk_hydro_replace_fluxes(int dir, int nboxes, const qk_box *valid, const qk_array4 *flux, const qk_array4 *fo_flux, const qk_iarray4 *redo,
+			    int ncomp, void *stream);
+
+/* HydroSystem::ComputeMaxSignalSpeed + MultiFab::norminf (hydro_system.hpp:223-252, simulation.hpp:709-710)
+ * == HydroSystem::maxSignalSpeedLocal up to the |v| formula: which=0 uses the ComputeMaxSignalSpeed
+ * expression, which=1 the maxSignalSpeedLocal one (hydro_system.hpp:198-221).  Synchronises. */
+int qk_hydro_max_signal_speed(const qk_hydro_params *prm, int which, int nboxes, const qk_box *valid, const qk_array4 *cons, double *max_out,
+			      void *stream);
+
+/* ---- level object: fused path + ghost fill -------------------------------------------------- */
+
+/* Description of the boxes of ONE AMR level owned by this rank (a MultiFab's local part) and of
+ * the whole level (for box<->box ghost copies): the run-time image of BoxArray +
+ * DistributionMapping + Geometry + BCRec as used by fillBoundaryConditions (simulation.hpp:1704-1785). */
+typedef struct qk_level_desc {
+	qk_box domain;	     /* geom.Domain() */
+	int32_t periodic[3]; /* geom.isPeriodic(d) */
+	double dx[3];	     /* geom.CellSizeArray() */
+	int32_t nghost;	     /* nghost_cc_ = 4 */
+	int32_t ncomp;	     /* components of the state MultiFab */
+	int32_t nboxes_global;
+	const qk_box *boxes_global; /* BoxArray */
+	const int32_t *owner;	    /* DistributionMapping: rank of each global box */
+	int32_t my_rank;
+	/* BCRec per component: bc_lo[n*3+d], bc_hi[n*3+d] = QK_BC_* */
+	const int32_t *bc_lo;
+	const int32_t *bc_hi;
+} qk_level_desc;
+
+typedef struct qk_level qk_level; /* opaque */
+
+/* one remote copy the caller must transport (pack on src rank -> send -> unpack on dst rank) */
+typedef struct qk_copy_tag {
+	int32_t src_box, dst_box; /* global box ids */
+	int32_t src_rank, dst_rank;
+	qk_box src_region; /* cells to read in the source box's index space */
+	int32_t shift[3];  /* dst index = src index + shift (periodic wrap) */
+	int64_t offset;	   /* offset in doubles of this tag inside the (src_rank -> dst_rank) message, per component */
+	int64_t ncells;
+} qk_copy_tag;
+
+int qk_level_create(const qk_level_desc *desc, qk_level **out);
+void qk_level_destroy(qk_level *lev);
+int qk_level_nlocal(const qk_level *lev);
+/* global ids of the local boxes, in local order (== MFIter order) */
+int qk_level_local_ids(const qk_level *lev, int32_t *ids);
+/* copy tags whose src or dst is this rank and src_rank != dst_rank; returns count (tags may be NULL) */
+int qk_level_remote_tags(const qk_level *lev, qk_copy_tag *tags, int max_tags);
+
+/* FabArray::FillBoundary, same-rank part (FB_local_copy_gpu, extern/amrex/Src/Base/AMReX_FBI.H:272) */
+int qk_fill_boundary_local(qk_level *lev, const qk_array4 *state, int scomp, int ncomp, void *stream);
+/* pack_send_buffer_gpu / unpack_recv_buffer_gpu (AMReX_FBI.H:730,790) for the message to/from `peer`:
+ * buffer layout = for each tag (in qk_level_remote_tags order restricted to that peer): ncomp x ncells doubles */
+int qk_pack_ghosts(qk_level *lev, int peer, const qk_array4 *state, int scomp, int ncomp, double *buf, int64_t *ndoubles, void *stream);
+int qk_unpack_ghosts(qk_level *lev, int peer, const qk_array4 *state, int scomp, int ncomp, const double *buf, void *stream);
+/* PhysBCFunct<GpuBndryFuncFab<..>> with amrex::FilccCell (simulation.hpp:1760-1765;
+ * extern/amrex/Src/Base/AMReX_FilCC_3D_C.H): reflect_even/odd, foextrap; ext_dir cells are left for the caller */
+int qk_fill_physical_bc(qk_level *lev, const qk_array4 *state, int scomp, int ncomp, void *stream);
+
+/* One RK stage of QuokkaSimulation::advanceHydroAtLevel (src/QuokkaSimulation.hpp:1099-1198 stage 1,
+ * :1202-1285 stage 2) for all local boxes: computeHydroFluxes (K1-K5) -> RK2 flux average ->
+ * ComputeRhsFromFluxes -> AddInternalEnergyPdV -> PredictStep -> [FOFC: computeFOHydroFluxes,
+ * replaceFluxes, redo] -> EnforceLimits -> SyncDualEnergy.
+ *   stage 1: Uout = U0 + dt L(U0)                       (Ustage == U0, ghost-filled)
+ *   stage 2: Uout = U0 + dt L(0.5 F(U0) + 0.5 F(Ustage)) (Ustage = stage-1 result, ghost-filled)
+ * The level keeps 0.5*F(U0) and 0.5*faceVel(U0) between the two calls.  *ncells_bad receives the
+ * redoFlag.sum() that survived FOFC (0 => success).  Synchronises `stream` once (for ncells_bad). */
+int qk_hydro_advance_stage(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
+			   const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
+
+/* bytes of device scratch currently held by the level */
+int64_t qk_level_scratch_bytes(const qk_level *lev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUOKKA_B200_H_ */

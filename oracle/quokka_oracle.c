@@ -1,0 +1,1262 @@
+/* oracle/quokka_oracle.c -- CPU restatement (plain C) of Quokka's hydro hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see quokka_oracle.h).  Parity status: PINNED against the reference's own
+ * code compiled here (oracle/_ref), see tests/test_oracle_vs_ref.py and tests/golden/.
+ *
+ * Each function cites the reference file:line it follows.  Paths are relative to /root/reference.
+ * Compile with -O2 -ffp-contract=off (no FMA contraction; matches the reference's --fmad=false).
+ */
+#include "quokka_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define A4(a, i, j, k, n)                                                                                                                            \
+	((a)->p[((int64_t)(i) - (a)->begin[0]) + ((int64_t)(j) - (a)->begin[1]) * (a)->jstride + ((int64_t)(k) - (a)->begin[2]) * (a)->kstride +      \
+		(int64_t)(n) * (a)->nstride])
+
+/* std::min / std::max semantics (first argument returned on ties / unordered) */
+static inline double dmin(double a, double b) { return (b < a) ? b : a; }
+static inline double dmax(double a, double b) { return (a < b) ? b : a; }
+/* src/math/math_impl.hpp:17,20 */
+static inline double clampd(double v, double lo, double hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
+static inline int sgnd(double v) { return (0.0 < v) - (v < 0.0); }
+
+/* extern/Microphysics/constants/fundamental_constants.H:22,55 */
+static const double C_k_B = 1.3806488e-16;
+static const double C_m_u = 1.6605390666e-24;
+
+enum { RHO = 0, MX = 1, MY = 2, MZ = 3, EN = 4, EI = 5, SC0 = 6 }; /* src/hydro/hydro_system.hpp:54-72 */
+#define MAXV (6 + QK_MAX_SCALARS)
+
+/* ------------------------------------------------------------------------------------------------
+ * gamma-law EOS through Microphysics: extern/Microphysics/interfaces/eos.H:395-435 (eos),
+ * :141-205 (reset_inputs), :69-79 (eos_reset); EOS/gamma_law/actual_eos.H:47-294; chem_eos_t
+ * interfaces/eos_type.H:144-164.  Limits from eos_init (eos.H:16-49) with small_temp/small_dens
+ * from src/QuokkaSimulation.hpp:165-167.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	double rho, T, p, e, dpdT, dpdr, dpde, dpdr_e, dedT, dedr, G, mu, cs, cv, cp, gam1;
+} eos_state;
+enum { EOS_RT, EOS_RP, EOS_RE };
+
+static void actual_eos(const qk_hydro_params *prm, int input, eos_state *s)
+{
+	const double gam = prm->gamma;
+	const double m_nucleon = C_m_u;
+	switch (input) {
+	case EOS_RT:
+		break;
+	case EOS_RP: /* actual_eos.H:115 */
+		s->T = s->p * s->mu * m_nucleon / (C_k_B * s->rho);
+		break;
+	case EOS_RE: /* actual_eos.H:128 */
+		s->T = s->e * s->mu * m_nucleon * (gam - 1.0) / C_k_B;
+		break;
+	}
+	/* actual_eos.H:194-206 */
+	const double Tinv = 1.0 / s->T;
+	const double rhoinv = 1.0 / s->rho;
+	const double pressure = s->rho * s->T * C_k_B / (s->mu * m_nucleon);
+	const double energy = pressure / (gam - 1.0) * rhoinv;
+	s->p = pressure;
+	s->e = energy;
+	/* :225-231 */
+	s->dpdT = s->p * Tinv;
+	s->dpdr = s->p * rhoinv;
+	s->dedT = s->e * Tinv;
+	s->dedr = 0.0;
+	/* :252-269 */
+	s->cv = s->dedT;
+	s->cp = gam * s->cv;
+	s->gam1 = gam;
+	s->dpdr_e = s->dpdr - s->dpdT * s->dedr * (1.0 / s->dedT);
+	s->dpde = s->dpdT * (1.0 / s->dedT);
+	s->cs = sqrt(gam * s->p * rhoinv);
+	s->G = 0.5 * (1.0 + gam);
+}
+
+static void eos_call(const qk_hydro_params *prm, int input, eos_state *s)
+{
+	/* eos_init: mintemp = max(1e-200, small_temp), mindens = max(1e-200, small_dens) */
+	const double mintemp = dmax(1.e-200, prm->small_temp), maxtemp = 1.e200;
+	const double mindens = dmax(1.e-200, prm->small_dens), maxdens = 1.e200;
+	const double mine = 1.e-200, maxe = 1.e200, minp = 1.e-200, maxp = 1.e200;
+	int has_been_reset = 0;
+	/* reset_inputs, eos.H:141-205 */
+	if (input == EOS_RT) {
+		s->rho = dmin(maxdens, dmax(mindens, s->rho));
+		s->T = dmin(maxtemp, dmax(mintemp, s->T));
+	} else {
+		s->rho = dmin(maxdens, dmax(mindens, s->rho));
+		int bad = (input == EOS_RE) ? (s->e < mine || s->e > maxe) : (s->p < minp || s->p > maxp);
+		if (bad) { /* eos_reset, eos.H:69-79 */
+			s->T = dmin(maxtemp, dmax(mintemp, s->T));
+			s->rho = dmin(maxdens, dmax(mindens, s->rho));
+			actual_eos(prm, EOS_RT, s);
+			has_been_reset = 1;
+		}
+	}
+	if (!has_been_reset) {
+		actual_eos(prm, input, s);
+	}
+}
+
+static inline eos_state eos_new(const qk_hydro_params *prm)
+{
+	eos_state s;
+	memset(&s, 0, sizeof(s));
+	s.mu = prm->mean_molecular_weight / C_m_u; /* src/hydro/EOS.hpp:104,336 */
+	return s;
+}
+
+/* src/hydro/EOS.hpp:299-340 */
+static double eos_pressure(const qk_hydro_params *prm, double rho, double Eint)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.e = (rho == 0.0) ? 0.0 : Eint / rho;
+	eos_call(prm, EOS_RE, &s);
+	return s.p;
+}
+/* EOS.hpp:342-383 */
+static double eos_sound_speed(const qk_hydro_params *prm, double rho, double P)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.p = P;
+	eos_call(prm, EOS_RP, &s);
+	return s.cs;
+}
+/* EOS.hpp:159-198 */
+static double eos_eint_from_pres(const qk_hydro_params *prm, double rho, double P)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.p = P;
+	eos_call(prm, EOS_RP, &s);
+	return s.e * rho;
+}
+/* EOS.hpp:75-114 */
+static double eos_tgas_from_eint(const qk_hydro_params *prm, double rho, double Eint)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.e = Eint / rho;
+	eos_call(prm, EOS_RE, &s);
+	return s.T * C_k_B / prm->boltzmann_constant;
+}
+/* EOS.hpp:116-157 */
+static double eos_eint_from_tgas(const qk_hydro_params *prm, double rho, double Tgas)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.T = Tgas;
+	eos_call(prm, EOS_RT, &s);
+	return s.e * rho * prm->boltzmann_constant / C_k_B;
+}
+/* EOS.hpp:242-297 */
+static void eos_other_derivatives(const qk_hydro_params *prm, double rho, double P, double *dedr, double *dedp, double *drdp, double *dpdr_s,
+				  double *G)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.p = P;
+	eos_call(prm, EOS_RP, &s);
+	*dedr = s.dedr;
+	*dedp = 1.0 / s.dpde;
+	*drdp = 1.0 / (s.dpdr * C_k_B / prm->boltzmann_constant);
+	*dpdr_s = s.cs * s.cs;
+	*G = s.G;
+}
+
+double orc_eos_pressure(const qk_hydro_params *prm, double rho, double Eint) { return eos_pressure(prm, rho, Eint); }
+double orc_eos_sound_speed(const qk_hydro_params *prm, double rho, double P) { return eos_sound_speed(prm, rho, P); }
+double orc_eos_eint_from_pres(const qk_hydro_params *prm, double rho, double P) { return eos_eint_from_pres(prm, rho, P); }
+double orc_eos_tgas_from_eint(const qk_hydro_params *prm, double rho, double Eint) { return eos_tgas_from_eint(prm, rho, Eint); }
+double orc_eos_eint_from_tgas(const qk_hydro_params *prm, double rho, double T) { return eos_eint_from_tgas(prm, rho, T); }
+
+/* HydroSystem::ComputePressure(cons,i,j,k)  src/hydro/hydro_system.hpp:349-372 */
+static double cons_pressure(const qk_hydro_params *prm, const qk_array4 *c, int i, int j, int k)
+{
+	const double rho = A4(c, i, j, k, RHO), px = A4(c, i, j, k, MX), py = A4(c, i, j, k, MY), pz = A4(c, i, j, k, MZ);
+	const double E = A4(c, i, j, k, EN);
+	const double vx = px / rho, vy = py / rho, vz = pz / rho;
+	const double ke = 0.5 * rho * (vx * vx + vy * vy + vz * vz);
+	const double thermal = E - ke;
+	return eos_pressure(prm, rho, thermal);
+}
+/* HydroSystem::ComputeSoundSpeed(cons,i,j,k)  hydro_system.hpp:374-394 */
+static double cons_sound_speed(const qk_hydro_params *prm, const qk_array4 *c, int i, int j, int k)
+{
+	const double rho = A4(c, i, j, k, RHO);
+	const double P = cons_pressure(prm, c, i, j, k);
+	return eos_sound_speed(prm, rho, P);
+}
+
+/* HydroSystem::ConservedToPrimitive  hydro_system.hpp:138-196 */
+void orc_conserved_to_primitive(const qk_hydro_params *prm, const qk_array4 *cons, const qk_array4 *prim, const qk_box *bx)
+{
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(cons, i, j, k, RHO), px = A4(cons, i, j, k, MX), py = A4(cons, i, j, k, MY);
+				const double pz = A4(cons, i, j, k, MZ), E = A4(cons, i, j, k, EN), Eint_aux = A4(cons, i, j, k, EI);
+				const double vx = px / rho, vy = py / rho, vz = pz / rho;
+				const double ke = 0.5 * rho * (vx * vx + vy * vy + vz * vz);
+				const double Eint_cons = E - ke;
+				const double Pgas = cons_pressure(prm, cons, i, j, k);
+				const double eint_cons = Eint_cons / rho;
+				const double eint_aux = Eint_aux / rho;
+				A4(prim, i, j, k, 0) = rho;
+				A4(prim, i, j, k, 1) = vx;
+				A4(prim, i, j, k, 2) = vy;
+				A4(prim, i, j, k, 3) = vz;
+				if (prm->reconstruct_eint) {
+					A4(prim, i, j, k, 4) = eint_cons;
+					A4(prim, i, j, k, 5) = eint_aux;
+				} else {
+					A4(prim, i, j, k, 4) = Pgas;
+					A4(prim, i, j, k, 5) = Eint_aux;
+				}
+				for (int n = 0; n < prm->nscalars; ++n)
+					A4(prim, i, j, k, SC0 + n) = A4(cons, i, j, k, SC0 + n);
+			}
+}
+
+/* HydroSystem::ComputeFlatteningCoefficients<DIR>  hydro_system.hpp:531-626 */
+void orc_flattening_coefficients(const qk_hydro_params *prm, int dir, const qk_array4 *q, const qk_array4 *chi_out, const qk_box *bx)
+{
+	const double beta_max = 0.85, beta_min = 0.75, Zmax = 0.75, Zmin = 0.25;
+	const int e[3] = {dir == 0, dir == 1, dir == 2};
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				double P[5]; /* P(i-2..i+2) along dir */
+				for (int s = -2; s <= 2; ++s) {
+					const int ii = i + s * e[0], jj = j + s * e[1], kk = k + s * e[2];
+					double v = A4(q, ii, jj, kk, 4);
+					if (prm->reconstruct_eint) {
+						const double r = A4(q, ii, jj, kk, 0);
+						v = eos_pressure(prm, r, r * v);
+					}
+					P[s + 2] = v;
+				}
+				const double Pplus2 = P[4], Pplus1 = P[3], Pc = P[2], Pminus1 = P[1], Pminus2 = P[0];
+				const double beta_denom = fabs(Pplus2 - Pminus2);
+				const double beta = (beta_denom != 0) ? (fabs(Pplus1 - Pminus1) / beta_denom) : 0;
+				const double chi_min = dmax(0., dmin(1., (beta_max - beta) / (beta_max - beta_min)));
+				const double rho = A4(q, i, j, k, 0);
+				const double cs = eos_sound_speed(prm, rho, Pc);
+				const double K_S = (cs * cs) * rho; /* std::pow(cs,2)*rho */
+				const double Z = fabs(Pplus1 - Pminus1) / K_S;
+				const int vn = 1 + dir;
+				double chi = 1.0;
+				if (A4(q, i + e[0], j + e[1], k + e[2], vn) < A4(q, i - e[0], j - e[1], k - e[2], vn)) {
+					chi = dmax(chi_min, dmin(1., (Zmax - Z) / (Zmax - Zmin)));
+				}
+				A4(chi_out, i, j, k, 0) = chi;
+			}
+}
+
+/* HyperbolicSystem::MC / minmod  src/hyperbolic_system.hpp:58-66 */
+static inline double lim_MC(double a, double b) { return 0.5 * (sgnd(a) + sgnd(b)) * dmin(0.5 * fabs(a + b), dmin(2.0 * fabs(a), 2.0 * fabs(b))); }
+static inline double lim_minmod(double a, double b) { return 0.5 * (sgnd(a) + sgnd(b)) * dmin(fabs(a), fabs(b)); }
+
+/* HyperbolicSystem::ReconstructStates{Constant :164-181, PLM :218-247, PPM :337-433} */
+void orc_reconstruct_states(int order, int limiter, int dir, const qk_array4 *q, const qk_array4 *left, const qk_array4 *right, const qk_box *bx,
+			    int nvars)
+{
+	const int e0 = (dir == 0), e1 = (dir == 1), e2 = (dir == 2);
+	for (int n = 0; n < nvars; ++n)
+		for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+			for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+				for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+#define Q(s) A4(q, i + (s) * e0, j + (s) * e1, k + (s) * e2, n)
+					if (order == 1) {
+						A4(left, i, j, k, n) = Q(-1);
+						A4(right, i, j, k, n) = Q(0);
+					} else if (order == 2) {
+						double lslope, rslope;
+						if (limiter == QK_MC) {
+							lslope = lim_MC(Q(0) - Q(-1), Q(-1) - Q(-2));
+							rslope = lim_MC(Q(1) - Q(0), Q(0) - Q(-1));
+						} else {
+							lslope = lim_minmod(Q(0) - Q(-1), Q(-1) - Q(-2));
+							rslope = lim_minmod(Q(1) - Q(0), Q(0) - Q(-1));
+						}
+						A4(left, i, j, k, n) = Q(-1) + 0.25 * lslope;
+						A4(right, i, j, k, n) = Q(0) - 0.25 * rslope;
+					} else {
+						/* bounds = std::minmax({q(i), q(i-1), q(i+1)}) :365 */
+						double lo = Q(0), hi = Q(0);
+						if (Q(-1) < lo) lo = Q(-1);
+						if (Q(1) < lo) lo = Q(1);
+						if (!(Q(-1) < hi)) hi = Q(-1);
+						if (!(Q(1) < hi)) hi = Q(1);
+						const double coef_1 = (7. / 12.);
+						const double coef_2 = (-1. / 12.);
+						const double a_minus = (coef_1 * Q(0) + coef_2 * Q(1)) + (coef_1 * Q(-1) + coef_2 * Q(-2));
+						const double a_plus = (coef_1 * Q(1) + coef_2 * Q(2)) + (coef_1 * Q(0) + coef_2 * Q(-1));
+						double new_a_minus = clampd(a_minus, lo, hi);
+						double new_a_plus = clampd(a_plus, lo, hi);
+						const double a = Q(0);
+						const double dq_minus = (a - new_a_minus);
+						const double dq_plus = (new_a_plus - a);
+						const double qa = dq_plus * dq_minus;
+						if (qa <= 0.0) {
+							const double dq0 = lim_MC(Q(1) - Q(0), Q(0) - Q(-1));
+							new_a_minus = a - 0.5 * dq0;
+							new_a_plus = a + 0.5 * dq0;
+						} else {
+							if (fabs(dq_minus) >= 2.0 * fabs(dq_plus)) {
+								new_a_minus = a - 2.0 * dq_plus;
+							}
+							if (fabs(dq_plus) >= 2.0 * fabs(dq_minus)) {
+								new_a_plus = a + 2.0 * dq_minus;
+							}
+						}
+						A4(right, i, j, k, n) = new_a_minus;
+						A4(left, i + e0, j + e1, k + e2, n) = new_a_plus;
+					}
+#undef Q
+				}
+}
+
+/* HydroSystem::FlattenShocks<DIR>  hydro_system.hpp:628-694 */
+void orc_flatten_shocks(int dir, const qk_array4 *q, const qk_array4 *c1, const qk_array4 *c2, const qk_array4 *c3, const qk_array4 *left,
+			const qk_array4 *right, const qk_box *bx, int nvars)
+{
+	const int e0 = (dir == 0), e1 = (dir == 1), e2 = (dir == 2);
+	for (int n = 0; n < nvars; ++n)
+		for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+			for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+				for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+					double chi = A4(c1, i - 1, j, k, 0);
+					chi = dmin(chi, A4(c1, i, j, k, 0));
+					chi = dmin(chi, A4(c1, i + 1, j, k, 0));
+					chi = dmin(chi, A4(c2, i, j - 1, k, 0));
+					chi = dmin(chi, A4(c2, i, j, k, 0));
+					chi = dmin(chi, A4(c2, i, j + 1, k, 0));
+					chi = dmin(chi, A4(c3, i, j, k - 1, 0));
+					chi = dmin(chi, A4(c3, i, j, k, 0));
+					chi = dmin(chi, A4(c3, i, j, k + 1, 0));
+					const double a_minus = A4(right, i, j, k, n);
+					const double a_plus = A4(left, i + e0, j + e1, k + e2, n);
+					const double a_mean = A4(q, i, j, k, n);
+					A4(right, i, j, k, n) = chi * a_minus + (1. - chi) * a_mean;
+					A4(left, i + e0, j + e1, k + e2, n) = chi * a_plus + (1. - chi) * a_mean;
+				}
+}
+
+/* quokka::HydroState  src/hydro/HydroState.hpp:10-23 */
+typedef struct {
+	double rho, u, v, w, P, cs, E, Eint;
+	double scalar[QK_MAX_SCALARS];
+} hstate;
+
+/* quokka::Riemann::HLLC  src/hydro/HLLC.hpp:21-153 */
+static void riemann_hllc(const qk_hydro_params *prm, const hstate *sL, const hstate *sR, double du, double dw, int ns, double *F)
+{
+	const int nv = 6 + ns;
+	const double wl = sqrt(sL->rho);
+	const double wr = sqrt(sR->rho);
+	const double norm = 1. / (wl + wr);
+	const double u_tilde = (wl * sL->u + wr * sR->u) * norm;
+	const double v_tilde = (wl * sL->v + wr * sR->v) * norm;
+	const double w_tilde = (wl * sL->w + wr * sR->w) * norm;
+	const double vsq_tilde = u_tilde * u_tilde + v_tilde * v_tilde + w_tilde * w_tilde;
+	const double H_L = (sL->E + sL->P) / sL->rho;
+	const double H_R = (sR->E + sR->P) / sR->rho;
+	const double H_tilde = (wl * H_L + wr * H_R) * norm;
+	double cs_tilde;
+	const double dU = sL->u - sR->u;
+	double S_L, S_R;
+	if (prm->gamma != 1.0) {
+		double dedr_L, dedp_L, drdp_L, dpdr_s_L, G_L, dedr_R, dedp_R, drdp_R, dpdr_s_R, G_R;
+		eos_other_derivatives(prm, sL->rho, sL->P, &dedr_L, &dedp_L, &drdp_L, &dpdr_s_L, &G_L);
+		eos_other_derivatives(prm, sR->rho, sR->P, &dedr_R, &dedp_R, &drdp_R, &dpdr_s_R, &G_R);
+		const double C_tilde_rho = 0.5 * ((sL->Eint / sL->rho) + (sR->Eint / sR->rho) + sL->rho * dedr_L + sR->rho * dedr_R);
+		const double C_tilde_P = 0.5 * ((sL->Eint / sL->rho) * drdp_L + (sR->Eint / sR->rho) * drdp_R + sL->rho * dedp_L + sR->rho * dedp_R);
+		const double cs_exp = H_tilde - 0.5 * vsq_tilde - C_tilde_rho;
+		if (cs_exp <= 0) {
+			cs_tilde = 0.5 * (sL->cs + sR->cs);
+		} else {
+			cs_tilde = sqrt(cs_exp / C_tilde_P);
+		}
+		const double s_NL = 0.5 * G_L * dmax(dU, 0.);
+		const double s_NR = 0.5 * G_R * dmax(dU, 0.);
+		S_L = dmin(sL->u - (sL->cs + s_NL), u_tilde - (cs_tilde + s_NL));
+		S_R = dmax(sR->u + (sR->cs + s_NR), u_tilde + (cs_tilde + s_NR));
+	} else {
+		cs_tilde = 0.5 * (sL->cs + sR->cs);
+		const double G_L = 0.5 * (1.0 + 1.), G_R = 0.5 * (1.0 + 1.);
+		const double s_NL = 0.5 * G_L * dmax(dU, 0.);
+		const double s_NR = 0.5 * G_R * dmax(dU, 0.);
+		S_L = dmin(sL->u - (sL->cs + s_NL), u_tilde - (cs_tilde + s_NL));
+		S_R = dmax(sR->u + (sR->cs + s_NR), u_tilde + (cs_tilde + s_NR));
+	}
+	const double cs_max = dmax(sL->cs, sR->cs);
+	const double tp = dmin(1., (cs_max - dmin(du, 0.)) / (cs_max - dmin(dw, 0.)));
+	const double theta = tp * tp * tp * tp;
+	const double S_star = (theta * (sR->P - sL->P) + (sL->rho * sL->u * (S_L - sL->u) - sR->rho * sR->u * (S_R - sR->u))) /
+			      (sL->rho * (S_L - sL->u) - sR->rho * (S_R - sR->u));
+	const double vmag_L = sqrt(sL->u * sL->u + sL->v * sL->v + sL->w * sL->w);
+	const double vmag_R = sqrt(sR->u * sR->u + sR->v * sR->v + sR->w * sR->w);
+	const double chi = dmin(1., dmax(vmag_L, vmag_R) / cs_max);
+	const double phi = chi * (2. - chi);
+	const double P_LR = 0.5 * (sL->P + sR->P) + 0.5 * phi * (sL->rho * (S_L - sL->u) * (S_star - sL->u) + sR->rho * (S_R - sR->u) * (S_star - sR->u));
+
+	double D_L[MAXV] = {0., 1., 0., 0., sL->u, 0.};
+	double D_R[MAXV] = {0., 1., 0., 0., sR->u, 0.};
+	double D_star[MAXV] = {0., 1., 0., 0., S_star, 0.};
+	double U_L[MAXV] = {sL->rho, sL->rho * sL->u, sL->rho * sL->v, sL->rho * sL->w, sL->E, sL->Eint};
+	double U_R[MAXV] = {sR->rho, sR->rho * sR->u, sR->rho * sR->v, sR->rho * sR->w, sR->E, sR->Eint};
+	for (int n = 0; n < ns; ++n) {
+		U_L[6 + n] = sL->scalar[n];
+		U_R[6 + n] = sR->scalar[n];
+	}
+	for (int n = 0; n < nv; ++n) {
+		const double F_L = sL->u * U_L[n] + sL->P * D_L[n];
+		const double F_R = sR->u * U_R[n] + sR->P * D_R[n];
+		const double F_starL = (S_star * (S_L * U_L[n] - F_L) + S_L * P_LR * D_star[n]) / (S_L - S_star);
+		const double F_starR = (S_star * (S_R * U_R[n] - F_R) + S_R * P_LR * D_star[n]) / (S_R - S_star);
+		if (S_L > 0.0) {
+			F[n] = F_L;
+		} else if ((S_star > 0.0) && (S_L <= 0.0)) {
+			F[n] = F_starL;
+		} else if ((S_star <= 0.0) && (S_R >= 0.0)) {
+			F[n] = F_starR;
+		} else {
+			F[n] = F_R;
+		}
+	}
+}
+
+/* quokka::Riemann::LLF  src/hydro/LLF.hpp:15-43 */
+static void riemann_llf(const hstate *sL, const hstate *sR, int ns, double *F)
+{
+	const int nv = 6 + ns;
+	const double Sp = dmax(fabs(sL->u) + sL->cs, fabs(sR->u) + sR->cs);
+	double U_L[MAXV] = {sL->rho, sL->rho * sL->u, sL->rho * sL->v, sL->rho * sL->w, sL->E, sL->Eint};
+	double U_R[MAXV] = {sR->rho, sR->rho * sR->u, sR->rho * sR->v, sR->rho * sR->w, sR->E, sR->Eint};
+	for (int n = 0; n < ns; ++n) {
+		U_L[6 + n] = sL->scalar[n];
+		U_R[6 + n] = sR->scalar[n];
+	}
+	double D_L[MAXV] = {0., 1., 0., 0., sL->u, 0.};
+	double D_R[MAXV] = {0., 1., 0., 0., sR->u, 0.};
+	for (int n = 0; n < nv; ++n) {
+		const double F_L = sL->u * U_L[n] + sL->P * D_L[n];
+		const double F_R = sR->u * U_R[n] + sR->P * D_R[n];
+		F[n] = 0.5 * (F_L + F_R) - 0.5 * Sp * (U_R[n] - U_L[n]);
+	}
+}
+
+/* HydroSystem::ComputeFluxes<RIEMANN,DIR>  hydro_system.hpp:852-1112 */
+void orc_compute_fluxes(const qk_hydro_params *prm, int solver, int dir, const qk_array4 *flux, const qk_array4 *facevel, const qk_array4 *L,
+			const qk_array4 *R, const qk_array4 *q, const qk_box *fbx)
+{
+	const int ns = prm->nscalars, nms = prm->nmscalars, nv = 6 + ns;
+	const int aN = dir, aV = (dir + 1) % 3, aW = (dir + 2) % 3; /* array axes of the permuted (i,j,k), ArrayView_3d.hpp:18-113 */
+	const int velN = 1 + aN, velV = 1 + aV, velW = 1 + aW;	    /* hydro_system.hpp:954-976 */
+	int eN[3] = {0, 0, 0}, eV[3] = {0, 0, 0}, eW[3] = {0, 0, 0};
+	eN[aN] = 1;
+	eV[aV] = 1;
+	eW[aW] = 1;
+	for (int k = fbx->lo[2]; k <= fbx->hi[2]; ++k)
+		for (int j = fbx->lo[1]; j <= fbx->hi[1]; ++j)
+			for (int i = fbx->lo[0]; i <= fbx->hi[0]; ++i) {
+				const double rho_L = A4(L, i, j, k, 0), rho_R = A4(R, i, j, k, 0);
+				const double vx_L = A4(L, i, j, k, 1), vx_R = A4(R, i, j, k, 1);
+				const double vy_L = A4(L, i, j, k, 2), vy_R = A4(R, i, j, k, 2);
+				const double vz_L = A4(L, i, j, k, 3), vz_R = A4(R, i, j, k, 3);
+				const double ke_L = 0.5 * rho_L * (vx_L * vx_L + vy_L * vy_L + vz_L * vz_L);
+				const double ke_R = 0.5 * rho_R * (vx_R * vx_R + vy_R * vy_R + vz_R * vz_R);
+				double Eint_L, Eint_R, P_L, P_R;
+				if (prm->reconstruct_eint) {
+					const double eint_L = A4(L, i, j, k, 4), eint_R = A4(R, i, j, k, 4);
+					P_L = eos_pressure(prm, rho_L, eint_L * rho_L);
+					P_R = eos_pressure(prm, rho_R, eint_R * rho_R);
+					Eint_L = rho_L * A4(L, i, j, k, 5);
+					Eint_R = rho_R * A4(R, i, j, k, 5);
+				} else {
+					P_L = A4(L, i, j, k, 4);
+					P_R = A4(R, i, j, k, 4);
+					Eint_L = A4(L, i, j, k, 5);
+					Eint_R = A4(R, i, j, k, 5);
+				}
+				const double cs_L = eos_sound_speed(prm, rho_L, P_L);
+				const double E_L = eos_eint_from_pres(prm, rho_L, P_L) + ke_L;
+				const double cs_R = eos_sound_speed(prm, rho_R, P_R);
+				const double E_R = eos_eint_from_pres(prm, rho_R, P_R) + ke_R;
+				hstate sL, sR;
+				sL.rho = rho_L;
+				sL.u = A4(L, i, j, k, velN);
+				sL.v = A4(L, i, j, k, velV);
+				sL.w = A4(L, i, j, k, velW);
+				sL.P = P_L;
+				sL.cs = cs_L;
+				sL.E = E_L;
+				sL.Eint = Eint_L;
+				sR.rho = rho_R;
+				sR.u = A4(R, i, j, k, velN);
+				sR.v = A4(R, i, j, k, velV);
+				sR.w = A4(R, i, j, k, velW);
+				sR.P = P_R;
+				sR.cs = cs_R;
+				sR.E = E_R;
+				sR.Eint = Eint_R;
+				for (int n = 0; n < ns; ++n) {
+					sL.scalar[n] = A4(L, i, j, k, SC0 + n);
+					sR.scalar[n] = A4(R, i, j, k, SC0 + n);
+				}
+#define QC(di, dj, dk, n) A4(q, i + (di) * eN[0] + (dj) * eV[0] + (dk) * eW[0], j + (di) * eN[1] + (dj) * eV[1] + (dk) * eW[1], k + (di) * eN[2] + (dj) * eV[2] + (dk) * eW[2], n)
+				const double du = QC(0, 0, 0, velN) - QC(-1, 0, 0, velN);
+				const double dvl = dmin(QC(-1, 1, 0, velV) - QC(-1, 0, 0, velV), QC(-1, 0, 0, velV) - QC(-1, -1, 0, velV));
+				const double dvr = dmin(QC(0, 1, 0, velV) - QC(0, 0, 0, velV), QC(0, 0, 0, velV) - QC(0, -1, 0, velV));
+				double dw = dmin(dvl, dvr);
+				const double dwl = dmin(QC(-1, 0, 1, velW) - QC(-1, 0, 0, velW), QC(-1, 0, 0, velW) - QC(-1, 0, -1, velW));
+				const double dwr = dmin(QC(0, 0, 1, velW) - QC(0, 0, 0, velW), QC(0, 0, 0, velW) - QC(0, 0, -1, velW));
+				dw = dmin(dmin(dwl, dwr), dw);
+#undef QC
+				double Fc[MAXV], F[MAXV];
+				if (solver == QK_HLLC) {
+					riemann_hllc(prm, &sL, &sR, du, dw, ns, Fc);
+				} else {
+					riemann_llf(&sL, &sR, ns, Fc);
+				}
+				/* artificial viscosity :1052-1076 */
+				const double div_v = du + 0.5 * (dvl + dvr) + 0.5 * (dwl + dwr);
+				const double viscosity = prm->K_visc * dmax(-div_v, 0.);
+				double U_L[MAXV] = {sL.rho, sL.rho * sL.u, sL.rho * sL.v, sL.rho * sL.w, sL.E, sL.Eint};
+				double U_R[MAXV] = {sR.rho, sR.rho * sR.u, sR.rho * sR.v, sR.rho * sR.w, sR.E, sR.Eint};
+				double fluxSum_U_L = 0, fluxSum_U_R = 0;
+				for (int n = 0; n < ns; ++n) {
+					U_L[6 + n] = sL.scalar[n];
+					U_R[6 + n] = sR.scalar[n];
+					if (n < nms) {
+						fluxSum_U_L += U_L[6 + n];
+						fluxSum_U_R += U_R[6 + n];
+					}
+				}
+				for (int n = 0; n < nv; ++n)
+					F[n] = Fc[n] + viscosity * (U_L[n] - U_R[n]);
+				F[velN] = Fc[1];
+				F[velV] = Fc[2];
+				F[velW] = Fc[3];
+				const double v_norm = (F[0] >= 0.) ? (F[0] / rho_R) : (F[0] / rho_L);
+				A4(facevel, i, j, k, 0) = v_norm;
+				if (F[0] >= 0.) {
+					for (int n = 0; n < nms; ++n)
+						F[6 + n] = F[0] * U_L[6 + n] / fluxSum_U_L;
+				} else {
+					for (int n = 0; n < nms; ++n)
+						F[6 + n] = F[0] * U_R[6 + n] / fluxSum_U_R;
+				}
+				for (int n = 0; n < nv; ++n)
+					A4(flux, i, j, k, n) = F[n];
+			}
+}
+
+/* MultiFab::Saxpy: dst += a*src (extern/amrex/Src/Base/AMReX_MultiFab.cpp Saxpy -> FabArray::Saxpy) */
+void orc_saxpy(const qk_array4 *dst, double a, const qk_array4 *src, const qk_box *bx, int ncomp)
+{
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+			for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+				for (int i = bx->lo[0]; i <= bx->hi[0]; ++i)
+					A4(dst, i, j, k, n) += a * A4(src, i, j, k, n);
+}
+
+/* HydroSystem::ComputeRhsFromFluxes  hydro_system.hpp:448-473 */
+void orc_rhs_from_fluxes(const qk_array4 *rhs, const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz, const double dx[3], const qk_box *bx,
+			 int nvars)
+{
+	for (int n = 0; n < nvars; ++n)
+		for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+			for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+				for (int i = bx->lo[0]; i <= bx->hi[0]; ++i)
+					A4(rhs, i, j, k, n) = (1.0 / dx[0]) * (A4(fx, i, j, k, n) - A4(fx, i + 1, j, k, n)) +
+							      (1.0 / dx[1]) * (A4(fy, i, j, k, n) - A4(fy, i, j + 1, k, n)) +
+							      (1.0 / dx[2]) * (A4(fz, i, j, k, n) - A4(fz, i, j, k + 1, n));
+}
+
+#define IA4(a, i, j, k) ((a)->p[((int64_t)(i) - (a)->begin[0]) + ((int64_t)(j) - (a)->begin[1]) * (a)->jstride + ((int64_t)(k) - (a)->begin[2]) * (a)->kstride])
+
+/* HydroSystem::AddInternalEnergyPdV  hydro_system.hpp:775-814 */
+void orc_add_internal_energy_pdv(const qk_hydro_params *prm, const qk_array4 *rhs, const qk_array4 *c, const double dx[3], const qk_array4 *vx,
+				 const qk_array4 *vy, const qk_array4 *vz, const qk_iarray4 *redo, const qk_box *bx)
+{
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double Pgas = cons_pressure(prm, c, i, j, k);
+				double div_v;
+				if (IA4(redo, i, j, k) == 0) {
+					div_v = (A4(vx, i + 1, j, k, 0) - A4(vx, i, j, k, 0)) / dx[0] + (A4(vy, i, j + 1, k, 0) - A4(vy, i, j, k, 0)) / dx[1] +
+						(A4(vz, i, j, k + 1, 0) - A4(vz, i, j, k, 0)) / dx[2];
+				} else {
+					div_v = 0.5 * ((A4(c, i + 1, j, k, MX) / A4(c, i + 1, j, k, RHO) - A4(c, i - 1, j, k, MX) / A4(c, i - 1, j, k, RHO)) / dx[0] +
+						       (A4(c, i, j + 1, k, MY) / A4(c, i, j + 1, k, RHO) - A4(c, i, j - 1, k, MY) / A4(c, i, j - 1, k, RHO)) / dx[1] +
+						       (A4(c, i, j, k + 1, MZ) / A4(c, i, j, k + 1, RHO) - A4(c, i, j, k - 1, MZ) / A4(c, i, j, k - 1, RHO)) / dx[2]);
+				}
+				A4(rhs, i, j, k, EI) += -Pgas * div_v;
+			}
+}
+
+/* HydroSystem::isStateValid  hydro_system.hpp:423-446 */
+static int state_valid(const qk_hydro_params *prm, const qk_array4 *c, int i, int j, int k)
+{
+	int ok = (A4(c, i, j, k, RHO) > 0.);
+	for (int n = 0; n < prm->nmscalars; ++n)
+		if (A4(c, i, j, k, SC0 + n) < 0.0) {
+			ok = 0;
+			break;
+		}
+	return ok;
+}
+
+/* HydroSystem::PredictStep  hydro_system.hpp:475-497; returns redoFlag.sum() over bx */
+int64_t orc_predict_step(const qk_hydro_params *prm, const qk_array4 *uo, const qk_array4 *un, const qk_array4 *rhs, double dt, int nvars,
+			 const qk_iarray4 *redo, const qk_box *bx)
+{
+	int64_t nbad = 0;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				for (int n = 0; n < nvars; ++n)
+					A4(un, i, j, k, n) = A4(uo, i, j, k, n) + dt * A4(rhs, i, j, k, n);
+				const int bad = !state_valid(prm, un, i, j, k);
+				IA4(redo, i, j, k) = bad;
+				nbad += bad;
+			}
+	return nbad;
+}
+
+/* HydroSystem::EnforceLimits  hydro_system.hpp:698-773 */
+void orc_enforce_limits(const qk_hydro_params *prm, const qk_array4 *s, const qk_box *bx)
+{
+	const int ns = prm->nscalars, nms = prm->nmscalars;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(s, i, j, k, RHO);
+				double rho_new = rho;
+				if (rho < prm->density_floor) {
+					rho_new = prm->density_floor;
+					A4(s, i, j, k, RHO) = rho_new;
+					for (int n = 0; n < ns; ++n) {
+						if (rho_new == 0.0)
+							A4(s, i, j, k, SC0 + n) = 0.0;
+						else
+							A4(s, i, j, k, SC0 + n) *= rho / rho_new;
+					}
+				}
+				if (nms > 0) {
+					double sp_sum = 0.0;
+					for (int n = 0; n < nms; ++n) {
+						if (A4(s, i, j, k, SC0 + n) < 0.0)
+							A4(s, i, j, k, SC0 + n) = prm->small_x * rho_new;
+						sp_sum += A4(s, i, j, k, SC0 + n);
+					}
+					if ((sp_sum > DBL_MIN) && (rho_new > DBL_MIN)) {
+						sp_sum /= rho_new;
+						for (int n = 0; n < nms; ++n)
+							A4(s, i, j, k, SC0 + n) /= sp_sum;
+					}
+				}
+				if ((rho_new > DBL_MIN) && prm->gamma != 1.0) {
+					const double vx1 = A4(s, i, j, k, MX) / rho_new;
+					const double vx2 = A4(s, i, j, k, MY) / rho_new;
+					const double vx3 = A4(s, i, j, k, MZ) / rho_new;
+					const double Ekin = 0.5 * rho_new * (vx1 * vx1 + vx2 * vx2 + vx3 * vx3);
+					const double Etot = A4(s, i, j, k, EN);
+					const double primTemp = eos_tgas_from_eint(prm, rho_new, (Etot - Ekin));
+					if (primTemp < prm->temp_floor) {
+						const double prim_eint = eos_eint_from_tgas(prm, rho_new, prm->temp_floor);
+						A4(s, i, j, k, EN) = Ekin + prim_eint;
+					}
+					const double auxEint = A4(s, i, j, k, EI);
+					const double auxTemp = eos_tgas_from_eint(prm, rho_new, auxEint);
+					if (auxTemp < prm->temp_floor) {
+						A4(s, i, j, k, EI) = eos_eint_from_tgas(prm, rho_new, prm->temp_floor);
+					}
+				}
+			}
+}
+
+/* HydroSystem::SyncDualEnergy  hydro_system.hpp:816-850; returns the number of cells with rho<=0
+ * (where the reference aborts; those cells are left untouched here) */
+int64_t orc_sync_dual_energy(const qk_hydro_params *prm, const qk_array4 *s, const qk_box *bx)
+{
+	(void)prm;
+	const double eta = 1.0e-3;
+	int64_t nabort = 0;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(s, i, j, k, RHO), px = A4(s, i, j, k, MX), py = A4(s, i, j, k, MY), pz = A4(s, i, j, k, MZ);
+				const double Etot = A4(s, i, j, k, EN), Eint_aux = A4(s, i, j, k, EI);
+				if (rho <= 0.) {
+					++nabort;
+					continue;
+				}
+				const double Ekin = (px * px + py * py + pz * pz) / (2.0 * rho);
+				const double Eint_cons = Etot - Ekin;
+				if (Eint_cons > eta * Etot) {
+					A4(s, i, j, k, EI) = Eint_cons;
+				} else {
+					A4(s, i, j, k, EI) = Eint_aux;
+					A4(s, i, j, k, EN) = Eint_aux + Ekin;
+				}
+			}
+	return nabort;
+}
+
+static inline int a4_contains(const qk_array4 *a, int i, int j, int k)
+{
+	return i >= a->begin[0] && i < a->end[0] && j >= a->begin[1] && j < a->end[1] && k >= a->begin[2] && k < a->end[2];
+}
+
+/* QuokkaSimulation::replaceFluxes (one direction)  src/QuokkaSimulation.hpp:1324-1368 */
+void orc_replace_fluxes(int dir, const qk_array4 *flux, const qk_array4 *fo, const qk_iarray4 *redo, const qk_box *valid, int ncomp)
+{
+	const int e0 = (dir == 0), e1 = (dir == 1), e2 = (dir == 2);
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = valid->lo[2] - 1; k <= valid->hi[2] + 1; ++k)
+			for (int j = valid->lo[1] - 1; j <= valid->hi[1] + 1; ++j)
+				for (int i = valid->lo[0] - 1; i <= valid->hi[0] + 1; ++i) {
+					if (IA4(redo, i, j, k) == 1) {
+						if (a4_contains(flux, i, j, k))
+							A4(flux, i, j, k, n) = A4(fo, i, j, k, n);
+						if (a4_contains(flux, i + e0, j + e1, k + e2))
+							A4(flux, i + e0, j + e1, k + e2, n) = A4(fo, i + e0, j + e1, k + e2, n);
+					}
+				}
+}
+
+/* which=0: HydroSystem::ComputeMaxSignalSpeed + norminf (hydro_system.hpp:223-252);
+ * which=1: HydroSystem::maxSignalSpeedLocal (hydro_system.hpp:198-221) */
+double orc_max_signal_speed(const qk_hydro_params *prm, int which, const qk_array4 *c, const qk_box *bx)
+{
+	double m = (which == 0) ? 0.0 : -DBL_MAX; /* norminf starts from 0 (abs), ParReduce max from lowest */
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(c, i, j, k, RHO), px = A4(c, i, j, k, MX), py = A4(c, i, j, k, MY), pz = A4(c, i, j, k, MZ);
+				const double cs = cons_sound_speed(prm, c, i, j, k);
+				double sig;
+				if (which == 0) {
+					const double vx = px / rho, vy = py / rho, vz = pz / rho;
+					const double vel_mag = sqrt(vx * vx + vy * vy + vz * vz);
+					sig = fabs(cs + vel_mag);
+				} else {
+					const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+					const double abs_vel = sqrt(2.0 * kinetic_energy / rho);
+					sig = cs + abs_vel;
+				}
+				m = dmax(m, sig);
+			}
+	return m;
+}
+
+/* ================================================================================================
+ * Level driver (uniform single level, all boxes in this process)
+ * ============================================================================================== */
+struct orc_level {
+	qk_level_desc d;
+	qk_box *boxes;
+	int32_t *bc_lo, *bc_hi;
+	int nb;
+	double **snew, **sold; /* per box storage, ncomp x grown box */
+	double dt_prev;
+	double t;
+};
+
+static int64_t box_len(const qk_box *b, int d) { return (int64_t)b->hi[d] - b->lo[d] + 1; }
+static qk_box grow(qk_box b, int n)
+{
+	for (int d = 0; d < 3; ++d) {
+		b.lo[d] -= n;
+		b.hi[d] += n;
+	}
+	return b;
+}
+static qk_box grow_hi(qk_box b, int dir, int n)
+{
+	b.hi[dir] += n;
+	return b;
+}
+static qk_array4 mk_a4(double *p, qk_box b, int ncomp)
+{
+	qk_array4 a;
+	a.p = p;
+	a.jstride = box_len(&b, 0);
+	a.kstride = a.jstride * box_len(&b, 1);
+	a.nstride = a.kstride * box_len(&b, 2);
+	for (int d = 0; d < 3; ++d) {
+		a.begin[d] = b.lo[d];
+		a.end[d] = b.hi[d] + 1;
+	}
+	a.ncomp = ncomp;
+	return a;
+}
+static qk_array4 alloc_a4(qk_box b, int ncomp)
+{
+	int64_t n = box_len(&b, 0) * box_len(&b, 1) * box_len(&b, 2) * ncomp;
+	double *p = (double *)calloc((size_t)n, sizeof(double));
+	return mk_a4(p, b, ncomp);
+}
+static qk_iarray4 alloc_ia4(qk_box b)
+{
+	qk_iarray4 a;
+	int64_t n = box_len(&b, 0) * box_len(&b, 1) * box_len(&b, 2);
+	a.p = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+	a.jstride = box_len(&b, 0);
+	a.kstride = a.jstride * box_len(&b, 1);
+	a.nstride = a.kstride * box_len(&b, 2);
+	for (int d = 0; d < 3; ++d) {
+		a.begin[d] = b.lo[d];
+		a.end[d] = b.hi[d] + 1;
+	}
+	a.ncomp = 1;
+	return a;
+}
+
+orc_level *orc_level_create(const qk_level_desc *desc)
+{
+	orc_level *L = (orc_level *)calloc(1, sizeof(orc_level));
+	L->d = *desc;
+	L->nb = desc->nboxes_global;
+	L->boxes = (qk_box *)malloc(sizeof(qk_box) * L->nb);
+	memcpy(L->boxes, desc->boxes_global, sizeof(qk_box) * L->nb);
+	L->bc_lo = (int32_t *)malloc(sizeof(int32_t) * 3 * desc->ncomp);
+	L->bc_hi = (int32_t *)malloc(sizeof(int32_t) * 3 * desc->ncomp);
+	memcpy(L->bc_lo, desc->bc_lo, sizeof(int32_t) * 3 * desc->ncomp);
+	memcpy(L->bc_hi, desc->bc_hi, sizeof(int32_t) * 3 * desc->ncomp);
+	L->snew = (double **)malloc(sizeof(double *) * L->nb);
+	L->sold = (double **)malloc(sizeof(double *) * L->nb);
+	for (int b = 0; b < L->nb; ++b) {
+		qk_box g = grow(L->boxes[b], desc->nghost);
+		L->snew[b] = alloc_a4(g, desc->ncomp).p;
+		L->sold[b] = alloc_a4(g, desc->ncomp).p;
+	}
+	L->dt_prev = 1.e100; /* dt_.resize(nlevs_max, 1.e100)  src/simulation.hpp:448 */
+	L->t = 0.0;
+	return L;
+}
+void orc_level_destroy(orc_level *L)
+{
+	if (!L)
+		return;
+	for (int b = 0; b < L->nb; ++b) {
+		free(L->snew[b]);
+		free(L->sold[b]);
+	}
+	free(L->snew);
+	free(L->sold);
+	free(L->boxes);
+	free(L->bc_lo);
+	free(L->bc_hi);
+	free(L);
+}
+int orc_level_nboxes(const orc_level *L) { return L->nb; }
+qk_box orc_level_box(const orc_level *L, int b) { return L->boxes[b]; }
+qk_array4 orc_level_state(orc_level *L, int which, int b)
+{
+	return mk_a4(which == 0 ? L->snew[b] : L->sold[b], grow(L->boxes[b], L->d.nghost), L->d.ncomp);
+}
+
+/* fillBoundaryConditions, level 0  src/simulation.hpp:1752-1765:
+ *  (1) FabArray::FillBoundary(periodicity): ghost cells that lie (after a periodic shift) inside
+ *      another box's VALID region are copied from it (corners included, cross=false);
+ *  (2) PhysBCFunct + amrex::FilccCell (extern/amrex/Src/Base/AMReX_FilCC_3D_C.H:38-41,66-75 ...):
+ *      ghost cells outside the domain: per-axis mirror (reflect_even/odd) or clamp (foextrap),
+ *      applied x then y then z over faces -> edges -> corners (AMReX_PhysBCFunct.H:406-470), i.e.
+ *      the composition of the per-axis maps; sources are cells of the same FAB. */
+void orc_fill_boundary(orc_level *L, qk_array4 *arrs, int scomp, int ncomp)
+{
+	const qk_box dom = L->d.domain;
+	const int ng = L->d.nghost;
+	/* (1) */
+	for (int b = 0; b < L->nb; ++b) {
+		const qk_box g = grow(L->boxes[b], ng);
+		for (int s = 0; s < L->nb; ++s) {
+			int smin[3], smax[3];
+			for (int d = 0; d < 3; ++d) {
+				smin[d] = L->d.periodic[d] ? -1 : 0;
+				smax[d] = L->d.periodic[d] ? 1 : 0;
+			}
+			for (int sz = smin[2]; sz <= smax[2]; ++sz)
+				for (int sy = smin[1]; sy <= smax[1]; ++sy)
+					for (int sx = smin[0]; sx <= smax[0]; ++sx) {
+						if (s == b && sx == 0 && sy == 0 && sz == 0)
+							continue;
+						const int sh[3] = {sx * (int)box_len(&dom, 0), sy * (int)box_len(&dom, 1), sz * (int)box_len(&dom, 2)};
+						/* region (in dst index space) = g ∩ (box_s + sh) */
+						qk_box r;
+						int empty = 0;
+						for (int d = 0; d < 3; ++d) {
+							r.lo[d] = g.lo[d] > L->boxes[s].lo[d] + sh[d] ? g.lo[d] : L->boxes[s].lo[d] + sh[d];
+							r.hi[d] = g.hi[d] < L->boxes[s].hi[d] + sh[d] ? g.hi[d] : L->boxes[s].hi[d] + sh[d];
+							if (r.lo[d] > r.hi[d])
+								empty = 1;
+						}
+						if (empty)
+							continue;
+						for (int n = scomp; n < scomp + ncomp; ++n)
+							for (int k = r.lo[2]; k <= r.hi[2]; ++k)
+								for (int j = r.lo[1]; j <= r.hi[1]; ++j)
+									for (int i = r.lo[0]; i <= r.hi[0]; ++i)
+										A4(&arrs[b], i, j, k, n) = A4(&arrs[s], i - sh[0], j - sh[1], k - sh[2], n);
+					}
+		}
+	}
+	/* (2) */
+	for (int b = 0; b < L->nb; ++b) {
+		const qk_box g = grow(L->boxes[b], ng);
+		for (int n = scomp; n < scomp + ncomp; ++n)
+			for (int k = g.lo[2]; k <= g.hi[2]; ++k)
+				for (int j = g.lo[1]; j <= g.hi[1]; ++j)
+					for (int i = g.lo[0]; i <= g.hi[0]; ++i) {
+						int idx[3] = {i, j, k};
+						int src[3] = {i, j, k};
+						double sign = 1.0;
+						int outside = 0, skip = 0;
+						for (int d = 0; d < 3; ++d) {
+							if (L->d.periodic[d])
+								continue;
+							if (idx[d] < dom.lo[d]) {
+								outside = 1;
+								const int bc = L->bc_lo[n * 3 + d];
+								if (bc == QK_BC_REFLECT_EVEN || bc == QK_BC_REFLECT_ODD) {
+									src[d] = 2 * dom.lo[d] - idx[d] - 1;
+									if (bc == QK_BC_REFLECT_ODD)
+										sign = -sign;
+								} else if (bc == QK_BC_FOEXTRAP) {
+									src[d] = dom.lo[d];
+								} else {
+									skip = 1;
+								}
+							} else if (idx[d] > dom.hi[d]) {
+								outside = 1;
+								const int bc = L->bc_hi[n * 3 + d];
+								if (bc == QK_BC_REFLECT_EVEN || bc == QK_BC_REFLECT_ODD) {
+									src[d] = 2 * dom.hi[d] - idx[d] + 1;
+									if (bc == QK_BC_REFLECT_ODD)
+										sign = -sign;
+								} else if (bc == QK_BC_FOEXTRAP) {
+									src[d] = dom.hi[d];
+								} else {
+									skip = 1;
+								}
+							}
+						}
+						if (!outside || skip)
+							continue;
+						const double v = A4(&arrs[b], src[0], src[1], src[2], n);
+						A4(&arrs[b], i, j, k, n) = (sign < 0) ? -v : v;
+					}
+	}
+}
+
+static void free_a4(qk_array4 *a) { free(a->p); }
+
+/* QuokkaSimulation::advanceHydroAtLevel  src/QuokkaSimulation.hpp:1032-1322 (uniform level: no
+ * flux registers, no Strang sources, no tracers).  Operates state_old (ghost cells are filled in
+ * place, as the reference does on state_old_cc_tmp) -> state_new. */
+int orc_advance_hydro_level(orc_level *L, const qk_hydro_params *prm, double dt, double cfl, int64_t *bad1, int64_t *bad2)
+{
+	const int nb = L->nb, ng = L->d.nghost, nv = 6 + prm->nscalars, nc = L->d.ncomp;
+	const double *dx = L->d.dx;
+	int success = 1;
+	if (bad1)
+		*bad1 = 0;
+	if (bad2)
+		*bad2 = 0;
+
+	qk_array4 *Uold = malloc(sizeof(qk_array4) * nb), *Unew = malloc(sizeof(qk_array4) * nb), *Uint = malloc(sizeof(qk_array4) * nb);
+	qk_array4 *prim = malloc(sizeof(qk_array4) * nb), *rhs = malloc(sizeof(qk_array4) * nb);
+	qk_array4 *chi[3], *lft[3], *rgt[3], *flx[3], *fvl[3], *fof[3], *fov[3], *frk[3], *avg[3];
+	qk_iarray4 *redo = malloc(sizeof(qk_iarray4) * nb);
+	for (int d = 0; d < 3; ++d) {
+		chi[d] = malloc(sizeof(qk_array4) * nb);
+		lft[d] = malloc(sizeof(qk_array4) * nb);
+		rgt[d] = malloc(sizeof(qk_array4) * nb);
+		flx[d] = malloc(sizeof(qk_array4) * nb);
+		fvl[d] = malloc(sizeof(qk_array4) * nb);
+		fof[d] = malloc(sizeof(qk_array4) * nb);
+		fov[d] = malloc(sizeof(qk_array4) * nb);
+		frk[d] = malloc(sizeof(qk_array4) * nb);
+		avg[d] = malloc(sizeof(qk_array4) * nb);
+	}
+	for (int b = 0; b < nb; ++b) {
+		const qk_box vb = L->boxes[b];
+		Uold[b] = orc_level_state(L, 1, b);
+		Unew[b] = orc_level_state(L, 0, b);
+		Uint[b] = alloc_a4(grow(vb, ng), nc); /* state_inter_cc_, setVal(0) :1056-1057 */
+		prim[b] = alloc_a4(grow(vb, ng), nv);
+		rhs[b] = alloc_a4(vb, nv);
+		redo[b] = alloc_ia4(grow(vb, 1));
+		for (int d = 0; d < 3; ++d) {
+			chi[d][b] = alloc_a4(grow(vb, 2), 1);
+			lft[d][b] = alloc_a4(grow(grow_hi(vb, d, 1), 1), nv);
+			rgt[d][b] = alloc_a4(grow(grow_hi(vb, d, 1), 1), nv);
+			flx[d][b] = alloc_a4(grow_hi(vb, d, 1), nv);
+			fvl[d][b] = alloc_a4(grow_hi(vb, d, 1), 1);
+			fof[d][b] = alloc_a4(grow_hi(vb, d, 1), nv);
+			fov[d][b] = alloc_a4(grow_hi(vb, d, 1), 1);
+			frk[d][b] = alloc_a4(grow_hi(vb, d, 1), nv); /* flux_rk2, setVal(0) :1067-1068 */
+			avg[d][b] = alloc_a4(grow(grow_hi(vb, d, 1), 2), 1); /* avgFaceVel ng=2 :1070-1071 */
+		}
+	}
+
+	/* :1076 */
+	orc_fill_boundary(L, Uold, 0, nc);
+
+	/* computeFOHydroFluxes :1096 -> :1519-1568 */
+	for (int b = 0; b < nb; ++b) {
+		const qk_box vb = L->boxes[b], g4 = grow(vb, ng), g1 = grow(vb, 1);
+		orc_conserved_to_primitive(prm, &Uold[b], &prim[b], &g4);
+		for (int d = 0; d < 3; ++d) {
+			const qk_box fb = grow_hi(vb, d, 1);
+			orc_reconstruct_states(1, 0, d, &prim[b], &lft[d][b], &rgt[d][b], &g1, nv);
+			orc_compute_fluxes(prm, QK_LLF, d, &fof[d][b], &fov[d][b], &lft[d][b], &rgt[d][b], &prim[b], &fb);
+		}
+	}
+
+	for (int stage = 1; stage <= prm->integrator_order && success; ++stage) {
+		qk_array4 *Uin = (stage == 1) ? Uold : Uint;
+		qk_array4 *Uout = (stage == 1 && prm->integrator_order == 2) ? Uint : Unew;
+		if (stage == 1 && prm->integrator_order == 1)
+			Uout = Uint; /* forward Euler writes state_inter then copies :1286-1287 */
+		if (stage == 2)
+			orc_fill_boundary(L, Uint, 0, nc); /* :1204 */
+		int64_t nbad_total = 0;
+		/* computeHydroFluxes :1403-1490 */
+		for (int b = 0; b < nb; ++b) {
+			const qk_box vb = L->boxes[b], g4 = grow(vb, ng), g2 = grow(vb, 2), g1 = grow(vb, 1);
+			orc_conserved_to_primitive(prm, &Uin[b], &prim[b], &g4);
+			for (int d = 0; d < 3; ++d)
+				orc_flattening_coefficients(prm, d, &prim[b], &chi[d][b], &g2);
+			for (int d = 0; d < 3; ++d) {
+				const qk_box fb = grow_hi(vb, d, 1);
+				orc_reconstruct_states(prm->reconstruction_order, QK_MINMOD, d, &prim[b], &lft[d][b], &rgt[d][b], &g1, nv);
+				orc_flatten_shocks(d, &prim[b], &chi[0][b], &chi[1][b], &chi[2][b], &lft[d][b], &rgt[d][b], &g1, nv);
+				orc_compute_fluxes(prm, QK_HLLC, d, &flx[d][b], &fvl[d][b], &lft[d][b], &rgt[d][b], &prim[b], &fb);
+				/* Saxpy :1105-1108 / :1219-1222 */
+				orc_saxpy(&frk[d][b], 0.5, &flx[d][b], &fb, nv);
+				orc_saxpy(&avg[d][b], 0.5, &fvl[d][b], &fb, 1);
+			}
+		}
+		/* stage 1 uses (fluxArrays, faceVel); stage 2 uses (flux_rk2, avgFaceVel) :1114-1116, :1228-1230 */
+		qk_array4 **F = (stage == 1) ? flx : frk;
+		qk_array4 **V = (stage == 1) ? fvl : avg;
+		for (int b = 0; b < nb; ++b) {
+			const qk_box vb = L->boxes[b];
+			memset(redo[b].p, 0, sizeof(int32_t) * (size_t)redo[b].nstride); /* redoFlag.setVal(none) */
+			orc_rhs_from_fluxes(&rhs[b], &F[0][b], &F[1][b], &F[2][b], dx, &vb, nv);
+			orc_add_internal_energy_pdv(prm, &rhs[b], &Uold[b], dx, &V[0][b], &V[1][b], &V[2][b], &redo[b], &vb);
+			nbad_total += orc_predict_step(prm, &Uold[b], &Uout[b], &rhs[b], dt, nv, &redo[b], &vb);
+		}
+		if (stage == 1 && bad1)
+			*bad1 = nbad_total;
+		if (stage == 2 && bad2)
+			*bad2 = nbad_total;
+		if (nbad_total > 0) {
+			/* redoFlag.FillBoundary(periodicity) :1157: exchange the 1-cell ghost layer of the flags */
+			for (int b = 0; b < nb; ++b) {
+				const qk_box g = grow(L->boxes[b], 1);
+				const qk_box dom = L->d.domain;
+				for (int s = 0; s < nb; ++s)
+					for (int sz = -1; sz <= 1; ++sz)
+						for (int sy = -1; sy <= 1; ++sy)
+							for (int sx = -1; sx <= 1; ++sx) {
+								if ((sx && !L->d.periodic[0]) || (sy && !L->d.periodic[1]) || (sz && !L->d.periodic[2]))
+									continue;
+								if (s == b && !sx && !sy && !sz)
+									continue;
+								const int sh[3] = {sx * (int)box_len(&dom, 0), sy * (int)box_len(&dom, 1), sz * (int)box_len(&dom, 2)};
+								qk_box r;
+								int empty = 0;
+								for (int d = 0; d < 3; ++d) {
+									r.lo[d] = g.lo[d] > L->boxes[s].lo[d] + sh[d] ? g.lo[d] : L->boxes[s].lo[d] + sh[d];
+									r.hi[d] = g.hi[d] < L->boxes[s].hi[d] + sh[d] ? g.hi[d] : L->boxes[s].hi[d] + sh[d];
+									if (r.lo[d] > r.hi[d])
+										empty = 1;
+								}
+								if (empty)
+									continue;
+								for (int k = r.lo[2]; k <= r.hi[2]; ++k)
+									for (int j = r.lo[1]; j <= r.hi[1]; ++j)
+										for (int i = r.lo[0]; i <= r.hi[0]; ++i)
+											IA4(&redo[b], i, j, k) = IA4(&redo[s], i - sh[0], j - sh[1], k - sh[2]);
+							}
+			}
+			nbad_total = 0;
+			for (int b = 0; b < nb; ++b) {
+				const qk_box vb = L->boxes[b];
+				for (int d = 0; d < 3; ++d) {
+					orc_replace_fluxes(d, &F[d][b], &fof[d][b], &redo[b], &vb, nv);
+					orc_replace_fluxes(d, &V[d][b], &fov[d][b], &redo[b], &vb, 1);
+				}
+			}
+			for (int b = 0; b < nb; ++b) {
+				const qk_box vb = L->boxes[b];
+				orc_rhs_from_fluxes(&rhs[b], &F[0][b], &F[1][b], &F[2][b], dx, &vb, nv);
+				orc_add_internal_energy_pdv(prm, &rhs[b], &Uold[b], dx, &V[0][b], &V[1][b], &V[2][b], &redo[b], &vb);
+				nbad_total += orc_predict_step(prm, &Uold[b], &Uout[b], &rhs[b], dt, nv, &redo[b], &vb);
+			}
+			if (nbad_total > 0 && prm->abort_on_fofc_failure) {
+				success = 0;
+			}
+		}
+		if (success) {
+			for (int b = 0; b < nb; ++b) {
+				const qk_box vb = L->boxes[b];
+				orc_enforce_limits(prm, &Uout[b], &vb);
+				if (prm->use_dual_energy)
+					orc_sync_dual_energy(prm, &Uout[b], &vb);
+			}
+		}
+	}
+	if (success && prm->integrator_order == 1) {
+		for (int b = 0; b < nb; ++b) {
+			const qk_box vb = L->boxes[b];
+			for (int n = 0; n < nv; ++n)
+				for (int k = vb.lo[2]; k <= vb.hi[2]; ++k)
+					for (int j = vb.lo[1]; j <= vb.hi[1]; ++j)
+						for (int i = vb.lo[0]; i <= vb.hi[0]; ++i)
+							A4(&Unew[b], i, j, k, n) = A4(&Uint[b], i, j, k, n);
+		}
+	}
+	/* isCflViolated :992-1013 */
+	if (success) {
+		double max_signal = -DBL_MAX;
+		for (int b = 0; b < nb; ++b) {
+			const qk_box vb = L->boxes[b];
+			max_signal = dmax(max_signal, orc_max_signal_speed(prm, 1, &Unew[b], &vb));
+		}
+		const double dx_min = dmin(dmin(dx[0], dx[1]), dx[2]);
+		const double dt_cfl = cfl * (dx_min / max_signal);
+		if (dt > (1.1 * dt_cfl))
+			success = 0;
+	}
+
+	for (int b = 0; b < nb; ++b) {
+		free_a4(&Uint[b]);
+		free_a4(&prim[b]);
+		free_a4(&rhs[b]);
+		free(redo[b].p);
+		for (int d = 0; d < 3; ++d) {
+			free_a4(&chi[d][b]);
+			free_a4(&lft[d][b]);
+			free_a4(&rgt[d][b]);
+			free_a4(&flx[d][b]);
+			free_a4(&fvl[d][b]);
+			free_a4(&fof[d][b]);
+			free_a4(&fov[d][b]);
+			free_a4(&frk[d][b]);
+			free_a4(&avg[d][b]);
+		}
+	}
+	for (int d = 0; d < 3; ++d) {
+		free(chi[d]);
+		free(lft[d]);
+		free(rgt[d]);
+		free(flx[d]);
+		free(fvl[d]);
+		free(fof[d]);
+		free(fov[d]);
+		free(frk[d]);
+		free(avg[d]);
+	}
+	free(Uold);
+	free(Unew);
+	free(Uint);
+	free(prim);
+	free(rhs);
+	free(redo);
+	return success;
+}
+
+/* AMRSimulation::computeTimestep, single level  src/simulation.hpp:703-818 */
+double orc_compute_timestep(orc_level *L, const qk_hydro_params *prm, double cfl, double t_now, double stop_time)
+{
+	double smax = 0.0;
+	for (int b = 0; b < L->nb; ++b) {
+		qk_array4 s = orc_level_state(L, 0, b);
+		smax = dmax(smax, orc_max_signal_speed(prm, 0, &s, &L->boxes[b]));
+	}
+	const double *dx = L->d.dx;
+	const double dx_min = dmin(dmin(dx[0], dx[1]), dx[2]);
+	const double hydro_dt = cfl * (dx_min / smax);
+	double dt_tmp = dmin(hydro_dt, DBL_MAX); /* computeExtraPhysicsTimestep -> max() */
+	dt_tmp = dmin(dt_tmp, 1.1 * L->dt_prev);
+	double dt_0 = dt_tmp;
+	dt_0 = dmin(dt_0, 1.0 * dt_tmp);
+	dt_0 = dmin(dt_0, DBL_MAX); /* maxDt_ */
+	if (t_now == 0.0)
+		dt_0 = dmin(dt_0, DBL_MAX); /* initDt_ */
+	const double eps = 1.e-3 * dt_0;
+	if (t_now + dt_0 > stop_time - eps)
+		dt_0 = stop_time - t_now;
+	L->dt_prev = dt_0;
+	return dt_0;
+}
+
+/* advanceSingleTimestepAtLevel + advanceHydroAtLevelWithRetries  src/QuokkaSimulation.hpp:653-707,885-990 */
+int orc_step_with_retries(orc_level *L, const qk_hydro_params *prm, double dt, double cfl)
+{
+	const int nb = L->nb, ng = L->d.nghost, nc = L->d.ncomp, nv = 6 + prm->nscalars;
+	/* std::swap(state_old, state_new) :671 */
+	double **tmp = L->sold;
+	L->sold = L->snew;
+	L->snew = tmp;
+	/* keep a pristine copy of state_old (the reference copies it into state_old_cc_tmp each retry :939-940) */
+	double **save = malloc(sizeof(double *) * nb);
+	int64_t *len = malloc(sizeof(int64_t) * nb);
+	for (int b = 0; b < nb; ++b) {
+		qk_box g = grow(L->boxes[b], ng);
+		len[b] = box_len(&g, 0) * box_len(&g, 1) * box_len(&g, 2) * nc;
+		save[b] = malloc(sizeof(double) * (size_t)len[b]);
+		memcpy(save[b], L->sold[b], sizeof(double) * (size_t)len[b]);
+	}
+	int result = -1;
+	for (int retry = 0; retry <= 6; ++retry) {
+		const int nsub = 1 << retry;
+		const double dt_step = dt / nsub;
+		for (int b = 0; b < nb; ++b)
+			memcpy(L->sold[b], save[b], sizeof(double) * (size_t)len[b]);
+		int ok = 1;
+		for (int sub = 0; sub < nsub; ++sub) {
+			if (sub > 0) { /* amrex::Copy(state_old_cc_tmp, state_new, 0,0,ncompHydro_, nghost) :948 */
+				for (int b = 0; b < nb; ++b) {
+					qk_box g = grow(L->boxes[b], ng);
+					int64_t per = box_len(&g, 0) * box_len(&g, 1) * box_len(&g, 2);
+					memcpy(L->sold[b], L->snew[b], sizeof(double) * (size_t)(per * nv));
+				}
+			}
+			ok = orc_advance_hydro_level(L, prm, dt_step, cfl, NULL, NULL);
+			if (!ok)
+				break;
+		}
+		if (ok) {
+			result = retry;
+			break;
+		}
+	}
+	/* state_old keeps the pre-step state without filled ghosts, as in the reference */
+	for (int b = 0; b < nb; ++b) {
+		memcpy(L->sold[b], save[b], sizeof(double) * (size_t)len[b]);
+		free(save[b]);
+	}
+	free(save);
+	free(len);
+	if (result >= 0)
+		L->t += dt;
+	return result;
+}

@@ -1,0 +1,174 @@
+"""Test-side loader of the CPU oracle (oracle/liboracle.so) and, where it was built, of the reference
+itself (oracle/_ref/libquokka_ref.so).  TEST INFRASTRUCTURE: never imported by the product package.
+
+Host arrays are numpy float64 of shape (ncomp, nz, ny, nx), C-contiguous == AMReX FAB order
+(x fastest, component-major; extern/amrex/Src/Base/AMReX_Array4.H:59-68).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from quokka_b200.capi import (qk_array4, qk_box, qk_hydro_params, qk_iarray4, qk_level_desc)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libquokka_ref.so")
+
+_A4P = C.POINTER(qk_array4)
+_IA4P = C.POINTER(qk_iarray4)
+_BXP = C.POINTER(qk_box)
+_PRM = C.POINTER(qk_hydro_params)
+_D3 = C.POINTER(C.c_double)
+_I64P = C.POINTER(C.c_int64)
+
+
+def build_oracle() -> str:
+    src = os.path.join(ROOT, "oracle", "quokka_oracle.c")
+    if (not os.path.exists(ORACLE_SO)) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+_oracle = None
+
+
+def oracle() -> C.CDLL:
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    lib = C.CDLL(build_oracle())
+    sig = {
+        "orc_conserved_to_primitive": (None, [_PRM, _A4P, _A4P, _BXP]),
+        "orc_flattening_coefficients": (None, [_PRM, C.c_int, _A4P, _A4P, _BXP]),
+        "orc_reconstruct_states": (None, [C.c_int, C.c_int, C.c_int, _A4P, _A4P, _A4P, _BXP, C.c_int]),
+        "orc_flatten_shocks": (None, [C.c_int, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _BXP, C.c_int]),
+        "orc_compute_fluxes": (None, [_PRM, C.c_int, C.c_int, _A4P, _A4P, _A4P, _A4P, _A4P, _BXP]),
+        "orc_saxpy": (None, [_A4P, C.c_double, _A4P, _BXP, C.c_int]),
+        "orc_rhs_from_fluxes": (None, [_A4P, _A4P, _A4P, _A4P, _D3, _BXP, C.c_int]),
+        "orc_add_internal_energy_pdv": (None, [_PRM, _A4P, _A4P, _D3, _A4P, _A4P, _A4P, _IA4P, _BXP]),
+        "orc_predict_step": (C.c_int64, [_PRM, _A4P, _A4P, _A4P, C.c_double, C.c_int, _IA4P, _BXP]),
+        "orc_enforce_limits": (None, [_PRM, _A4P, _BXP]),
+        "orc_sync_dual_energy": (C.c_int64, [_PRM, _A4P, _BXP]),
+        "orc_replace_fluxes": (None, [C.c_int, _A4P, _A4P, _IA4P, _BXP, C.c_int]),
+        "orc_max_signal_speed": (C.c_double, [_PRM, C.c_int, _A4P, _BXP]),
+        "orc_eos_pressure": (C.c_double, [_PRM, C.c_double, C.c_double]),
+        "orc_eos_sound_speed": (C.c_double, [_PRM, C.c_double, C.c_double]),
+        "orc_eos_eint_from_pres": (C.c_double, [_PRM, C.c_double, C.c_double]),
+        "orc_eos_tgas_from_eint": (C.c_double, [_PRM, C.c_double, C.c_double]),
+        "orc_eos_eint_from_tgas": (C.c_double, [_PRM, C.c_double, C.c_double]),
+        "orc_level_create": (C.c_void_p, [C.POINTER(qk_level_desc)]),
+        "orc_level_destroy": (None, [C.c_void_p]),
+        "orc_level_nboxes": (C.c_int, [C.c_void_p]),
+        "orc_level_state": (qk_array4, [C.c_void_p, C.c_int, C.c_int]),
+        "orc_level_box": (qk_box, [C.c_void_p, C.c_int]),
+        "orc_fill_boundary": (None, [C.c_void_p, _A4P, C.c_int, C.c_int]),
+        "orc_advance_hydro_level": (C.c_int, [C.c_void_p, _PRM, C.c_double, C.c_double, _I64P, _I64P]),
+        "orc_compute_timestep": (C.c_double, [C.c_void_p, _PRM, C.c_double, C.c_double, C.c_double]),
+        "orc_step_with_retries": (C.c_int, [C.c_void_p, _PRM, C.c_double, C.c_double]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _oracle = lib
+    return lib
+
+
+_ref = None
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref() -> C.CDLL:
+    """The reference's own templates behind extern "C" (oracle/ref_build/ref_harness.cpp)."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    lib = C.CDLL(REF_SO)
+    lib.ref_nvar.argtypes = [C.c_int]
+    lib.ref_cons_to_prim.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_int]
+    lib.ref_flattening_coefficients.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_int, C.c_int]
+    lib.ref_reconstruct.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, C.c_int, C.c_int, C.c_int]
+    lib.ref_flatten_shocks.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int, C.c_int, C.c_int]
+    lib.ref_compute_fluxes.argtypes = [C.c_int, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int, C.c_double]
+    lib.ref_update_op.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _IA4P, _D3, C.c_double, C.c_double, C.c_double, _D3]
+    _ref = lib
+    return lib
+
+
+# ---- numpy <-> qk_array4 ---------------------------------------------------------------------------
+class HostFab:
+    """A numpy-backed FAB over an index box (inclusive lo/hi)."""
+
+    def __init__(self, box: qk_box, ncomp: int, dtype=np.float64, fill=0.0):
+        self.box = box
+        self.ncomp = ncomp
+        nz, ny, nx = box.shape()
+        self.a = np.full((ncomp, nz, ny, nx), fill, dtype=dtype)
+
+    def desc(self):
+        d = qk_array4() if self.a.dtype == np.float64 else qk_iarray4()
+        nz, ny, nx = self.box.shape()
+        d.p = self.a.ctypes.data
+        d.jstride = nx
+        d.kstride = nx * ny
+        d.nstride = nx * ny * nz
+        d.begin[:] = list(self.box.lo)
+        d.end[:] = [self.box.hi[i] + 1 for i in range(3)]
+        d.ncomp = self.ncomp
+        return d
+
+    def view(self, box: qk_box):
+        """numpy view (ncomp, nz, ny, nx) of the sub-box."""
+        o = [box.lo[d] - self.box.lo[d] for d in range(3)]
+        s = [box.hi[d] - box.lo[d] + 1 for d in range(3)]
+        return self.a[:, o[2]:o[2] + s[2], o[1]:o[1] + s[1], o[0]:o[0] + s[0]]
+
+
+def face_box(valid: qk_box, d: int, ng: int = 0) -> qk_box:
+    """amrex::convert(box, e_d) grown by ng (cell-index convention: hi[d]+1 is the last face)."""
+    lo = [valid.lo[i] - ng for i in range(3)]
+    hi = [valid.hi[i] + ng for i in range(3)]
+    hi[d] += 1
+    return qk_box.make(lo, hi)
+
+
+def grow(valid: qk_box, ng: int) -> qk_box:
+    return valid.grown(ng)
+
+
+def random_cons(box: qk_box, nscalars=0, seed=12345, kind="smooth"):
+    """Seeded conserved states (rho, m, E, Eaux [, scalars]) on `box`: SURVEY.md 8(d) microbenchmark
+    inputs (rho in U(0.1,10), v in U(-1,1)^3, P in U(0.1,10)); kind='shocked' adds jumps."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = box.shape()
+    shp = (nz, ny, nx)
+    rho = rng.uniform(0.1, 10.0, shp)
+    v = rng.uniform(-1.0, 1.0, (3,) + shp)
+    P = rng.uniform(0.1, 10.0, shp)
+    if kind == "smooth":
+        # low-pass so that PPM takes the smooth branches too
+        for arr in (rho, P, v[0], v[1], v[2]):
+            for ax in range(3):
+                arr[...] = (np.roll(arr, 1, ax) + 2 * arr + np.roll(arr, -1, ax)) / 4
+    elif kind == "shocked":
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        m = (x + y + z) % 7 < 3
+        P[m] *= 50.0
+        rho[m] *= 4.0
+    return rho, v, P, rng
+
+
+def cons_from_prim(rho, v, P, gamma, rng, nscalars=0, eaux_jitter=True):
+    ke = 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
+    eint = P / (gamma - 1.0)
+    comps = [rho, rho * v[0], rho * v[1], rho * v[2], eint + ke, eint * (1 + (1e-3 * rng.standard_normal(rho.shape) if eaux_jitter else 0))]
+    for _ in range(nscalars):
+        comps.append(rho * rng.uniform(0.0, 1.0, rho.shape))
+    return np.stack(comps)
