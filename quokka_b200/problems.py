@@ -1,0 +1,94 @@
+"""Problem set-ups of the reference's hot-path configs, as host-side data (no numerics of the path).
+
+Sedov blast: src/problems/HydroBlast3D/test_hydro3d_blast.cpp (octant symmetry, reflecting walls,
+gamma = 1.4, reconstruct_eint = false, cfl 0.3) with tests/blast_unigrid_*.in geometry.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .capi import (QK_BC_REFLECT_EVEN, QK_BC_REFLECT_ODD, hydro_params, qk_box)
+
+
+def chop_domain(ncell, max_grid_size):
+    """amrex::BoxArray(domain).maxSize(max_grid_size): boxes in x-fastest order
+    (extern/amrex/Src/Base/AMReX_BoxArray.cpp maxSize -> BoxList::maxSize)."""
+    n = [int(c) for c in (ncell if hasattr(ncell, "__len__") else (ncell,) * 3)]
+    m = [int(c) for c in (max_grid_size if hasattr(max_grid_size, "__len__") else (max_grid_size,) * 3)]
+    cuts = []
+    for d in range(3):
+        nb = -(-n[d] // m[d])
+        # AMReX chops into nb nearly-equal chunks; for the power-of-two configs they are equal
+        base, rem = divmod(n[d], nb)
+        edges = [0]
+        for i in range(nb):
+            edges.append(edges[-1] + base + (1 if i < rem else 0))
+        cuts.append(edges)
+    boxes = []
+    for kz in range(len(cuts[2]) - 1):
+        for jy in range(len(cuts[1]) - 1):
+            for ix in range(len(cuts[0]) - 1):
+                boxes.append(qk_box.make((cuts[0][ix], cuts[1][jy], cuts[2][kz]), (cuts[0][ix + 1] - 1, cuts[1][jy + 1] - 1, cuts[2][kz + 1] - 1)))
+    return boxes
+
+
+def distribute(boxes, nranks):
+    """Box -> rank map.  The reference uses AMReX's SFC strategy (AMReX_DistributionMapping.cpp:42); for the
+    uniform power-of-two configs (equal-weight boxes in Morton order) SFC assigns contiguous Z-order
+    chunks, which is what this reproduces."""
+    def morton(b):
+        x, y, z = (b.lo[0] // max(1, b.hi[0] - b.lo[0] + 1), b.lo[1] // max(1, b.hi[1] - b.lo[1] + 1), b.lo[2] // max(1, b.hi[2] - b.lo[2] + 1))
+        code = 0
+        for bit in range(10):
+            code |= ((x >> bit) & 1) << (3 * bit) | ((y >> bit) & 1) << (3 * bit + 1) | ((z >> bit) & 1) << (3 * bit + 2)
+        return code
+    order = sorted(range(len(boxes)), key=lambda i: morton(boxes[i]))
+    owner = [0] * len(boxes)
+    per = len(boxes) / nranks
+    for pos, i in enumerate(order):
+        owner[i] = min(nranks - 1, int(pos / per))
+    return owner
+
+
+class SedovProblem:
+    """HydroBlast3D (test_hydro3d_blast.cpp:22-116,222-262)."""
+
+    gamma = 1.4
+    cfl = 0.3
+    stop_time = 1.0
+    ncomp = 6
+    nghost = 4
+    E_blast = 0.851072 / 8.0  # octant (test_hydro3d_blast.cpp:56-60)
+    rho0 = 1.0
+
+    def __init__(self, ncell, max_grid_size, prob_hi=1.2):
+        self.ncell = [int(c) for c in (ncell if hasattr(ncell, "__len__") else (ncell,) * 3)]
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in self.ncell))
+        hi = prob_hi if hasattr(prob_hi, "__len__") else (prob_hi,) * 3
+        self.dx = [(float(hi[d]) - 0.0) / self.ncell[d] for d in range(3)]
+        self.boxes = chop_domain(self.ncell, max_grid_size)
+        self.periodic = (0, 0, 0)
+        # reflect_odd on the normal momentum, reflect_even otherwise (test_hydro3d_blast.cpp:224-254)
+        lo = []
+        for n in range(self.ncomp):
+            for d in range(3):
+                lo.append(QK_BC_REFLECT_ODD if n == 1 + d else QK_BC_REFLECT_EVEN)
+        self.bc_lo = lo
+        self.bc_hi = list(lo)
+
+    def params(self, **kw):
+        return hydro_params(gamma=self.gamma, reconstruct_eint=0, **kw)
+
+    def initial_state(self, box: qk_box, ng=None) -> np.ndarray:
+        """(ncomp, nz, ny, nx) on the grown box; ghost cells zero (filled later by the BC fill)."""
+        ng = self.nghost if ng is None else ng
+        g = box.grown(ng)
+        nz, ny, nx = g.shape()
+        a = np.zeros((self.ncomp, nz, ny, nx))
+        cell_vol = self.dx[0] * self.dx[1] * self.dx[2]
+        v = a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng]
+        v[0] = self.rho0
+        v[4] = 1.0e-10 * (self.E_blast / cell_vol)
+        if box.lo[0] <= 0 <= box.hi[0] and box.lo[1] <= 0 <= box.hi[1] and box.lo[2] <= 0 <= box.hi[2]:
+            v[4, 0 - box.lo[2], 0 - box.lo[1], 0 - box.lo[0]] = self.E_blast / cell_vol
+        return a
