@@ -233,8 +233,59 @@ int qk_fill_physical_bc(qk_level *lev, const qk_array4 *state, int scomp, int nc
 int qk_hydro_advance_stage(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
 			   const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
 
+/* The same stage through the FAITHFUL path only: one kernel per reference operator, fluxes materialised as
+ * MultiFabs exactly as QuokkaSimulation.hpp:1403-1490 does.  qk_hydro_advance_stage runs the fused sweep kernels
+ * and falls back to this path when a cell is flagged (FOFC); both produce identical bits. */
+int qk_hydro_advance_stage_faithful(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
+				    const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
+
 /* bytes of device scratch currently held by the level */
 int64_t qk_level_scratch_bytes(const qk_level *lev);
+
+/* ---- rank <-> rank transport: NCCL over NVLink/NVSwitch in place of AMReX's MPI calls --------------------
+ * (FabArray::FillBoundary MPI_Isend/Irecv: extern/amrex/Src/Base/AMReX_FabArrayCommI.H:7-165;
+ *  ParallelDescriptor::ReduceRealMax / ReduceLongSum: AMReX_ParallelDescriptor.cpp:1091,1659,1746).
+ * One process per GPU.  The 128-byte id is created on rank 0 (qk_comm_unique_id) and handed to the other ranks by
+ * whatever bootstrap the host application has (MPI_Bcast in Quokka; torch.distributed in bench.py). */
+typedef struct qk_comm qk_comm; /* opaque */
+int qk_comm_unique_id(void *id128);
+int qk_comm_create(const void *id128, int rank, int nranks, qk_comm **out);
+void qk_comm_destroy(qk_comm *comm);
+int qk_comm_rank(const qk_comm *comm);
+int qk_comm_nranks(const qk_comm *comm);
+/* attach (or detach with NULL) the communicator used by qk_fill_boundary and the stage's ncells_bad sum */
+int qk_level_set_comm(qk_level *lev, qk_comm *comm);
+
+/* AMRSimulation::fillBoundaryConditions on level 0 (src/simulation.hpp:1752-1765): FillBoundary(periodicity)
+ * = same-rank copies + packed neighbour messages over the communicator, then the physical BC fill. */
+int qk_fill_boundary(qk_level *lev, const qk_array4 *state, int scomp, int ncomp, void *stream);
+
+/* ---- single-level time-step driver (C++ host code inside the library) ---------------------------------------
+ * The uniform-grid image of AMRSimulation::evolve/computeTimestep (src/simulation.hpp:722-977) and
+ * QuokkaSimulation::advanceSingleTimestepAtLevel/advanceHydroAtLevelWithRetries/advanceHydroAtLevel
+ * (src/QuokkaSimulation.hpp:653-707,885-990,1032-1322).  It owns state_new/state_old/state_inter on the device
+ * in AMReX FAB layout (ghost cells included) and is what bench.py and the whole-run parity tests drive. */
+typedef struct qk_sim qk_sim; /* opaque */
+int qk_sim_create(const qk_level_desc *desc, const qk_hydro_params *prm, double cfl, qk_comm *comm, qk_sim **out);
+void qk_sim_destroy(qk_sim *sim);
+int qk_sim_nlocal(const qk_sim *sim);
+qk_level *qk_sim_level(qk_sim *sim);
+void *qk_sim_stream(qk_sim *sim);
+double qk_sim_time(const qk_sim *sim);
+int64_t qk_sim_cell_updates(const qk_sim *sim); /* cellUpdates_, simulation.hpp:1285 */
+int64_t qk_sim_retries(const qk_sim *sim);
+int64_t qk_sim_box_doubles(const qk_sim *sim, int local_box);
+/* descriptor of state_new (which=0), state_old (1), state_inter (2) of a local box (device pointer) */
+int qk_sim_state_desc(qk_sim *sim, int which, int local_box, qk_array4 *out);
+/* host <-> device copy of state_new of one local box (whole FAB incl. ghosts); stream-ordered, see qk_sim_sync */
+int qk_sim_set_state(qk_sim *sim, int local_box, const double *host);
+int qk_sim_get_state(qk_sim *sim, int local_box, double *host);
+int qk_sim_sync(qk_sim *sim);
+void qk_sim_reset_clock(qk_sim *sim, double t, double dt_prev);
+int qk_sim_compute_timestep(qk_sim *sim, double stop_time, double *dt_out);
+/* one coarse step; *retries = number of dt-halving retries used, -1 if all 6 failed (the reference aborts there) */
+int qk_sim_step(qk_sim *sim, double dt, int *retries);
+int qk_sim_evolve(qk_sim *sim, int max_steps, double stop_time, int *steps_done, double *elapsed_s, double *device_ms);
 
 #ifdef __cplusplus
 }

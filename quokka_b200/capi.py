@@ -12,6 +12,7 @@ import os
 QK_MAX_SCALARS = 8
 QK_OK = 0
 QK_ERR_NO_DEVICE = -1
+QK_ERR_BAD_ARG, QK_ERR_UNSUPPORTED, QK_ERR_NOMEM = -2, -3, -4
 QK_X1, QK_X2, QK_X3 = 0, 1, 2
 QK_HLLC, QK_LLF = 0, 1
 QK_MINMOD, QK_MC = 0, 1
@@ -201,7 +202,32 @@ SYMBOLS = {
     "qk_unpack_ghosts": (C.c_int, [_VP, C.c_int, _A4P, C.c_int, C.c_int, _VP, _VP]),
     "qk_fill_physical_bc": (C.c_int, [_VP, _A4P, C.c_int, C.c_int, _VP]),
     "qk_hydro_advance_stage": (C.c_int, [_VP, _PRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _I64P, _VP]),
+    "qk_hydro_advance_stage_faithful": (C.c_int, [_VP, _PRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _I64P, _VP]),
     "qk_level_scratch_bytes": (C.c_int64, [_VP]),
+    "qk_comm_unique_id": (C.c_int, [_VP]),
+    "qk_comm_create": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "qk_comm_destroy": (None, [_VP]),
+    "qk_comm_rank": (C.c_int, [_VP]),
+    "qk_comm_nranks": (C.c_int, [_VP]),
+    "qk_level_set_comm": (C.c_int, [_VP, _VP]),
+    "qk_fill_boundary": (C.c_int, [_VP, _A4P, C.c_int, C.c_int, _VP]),
+    "qk_sim_create": (C.c_int, [C.POINTER(qk_level_desc), _PRM, C.c_double, _VP, C.POINTER(_VP)]),
+    "qk_sim_destroy": (None, [_VP]),
+    "qk_sim_nlocal": (C.c_int, [_VP]),
+    "qk_sim_level": (_VP, [_VP]),
+    "qk_sim_stream": (_VP, [_VP]),
+    "qk_sim_time": (C.c_double, [_VP]),
+    "qk_sim_cell_updates": (C.c_int64, [_VP]),
+    "qk_sim_retries": (C.c_int64, [_VP]),
+    "qk_sim_box_doubles": (C.c_int64, [_VP, C.c_int]),
+    "qk_sim_state_desc": (C.c_int, [_VP, C.c_int, C.c_int, _A4P]),
+    "qk_sim_set_state": (C.c_int, [_VP, C.c_int, _VP]),
+    "qk_sim_get_state": (C.c_int, [_VP, C.c_int, _VP]),
+    "qk_sim_sync": (C.c_int, [_VP]),
+    "qk_sim_reset_clock": (None, [_VP, C.c_double, C.c_double]),
+    "qk_sim_compute_timestep": (C.c_int, [_VP, C.c_double, _D3]),
+    "qk_sim_step": (C.c_int, [_VP, C.c_double, C.POINTER(C.c_int)]),
+    "qk_sim_evolve": (C.c_int, [_VP, C.c_int, C.c_double, C.POINTER(C.c_int), _D3, _D3]),
 }
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libquokka_b200.so")

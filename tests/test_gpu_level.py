@@ -1,0 +1,256 @@
+"""GPU parity of the level path: ghost fill (FillBoundary + physical BCs), one RK stage of
+advanceHydroAtLevel (production entry and the faithful per-operator path), the FOFC fallback, and
+whole runs through the C++ driver (qk_sim) against (a) the oracle level driver on the same inputs and
+(b) the committed state dumps of the reference's own Sedov executable (tests/golden/*.npz).
+Bar: BIT-EXACT on all conserved components, identical time, dt sequence and retry count.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from quokka_b200 import capi
+from quokka_b200.capi import check, make_level_desc, qk_array4, qk_box
+from quokka_b200.problems import SedovProblem, chop_domain
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load()
+
+
+def exact(a, b, what=""):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape
+    bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} mismatches, max abs diff {np.nanmax(np.abs(a - b))}"
+
+
+class GenericProblem:
+    """a seeded random state on an arbitrary box layout / BC set (ghost-fill and stage tests)"""
+
+    cfl = 0.3
+    stop_time = 1.0
+    nghost = 4
+
+    def __init__(self, ncell, max_grid, periodic, bc_kind, nscalars=0, gamma=1.4):
+        self.ncell = list(ncell)
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in ncell))
+        self.dx = [1.0 / c for c in ncell]
+        self.boxes = chop_domain(ncell, max_grid)
+        self.periodic = periodic
+        self.ncomp = 6 + nscalars
+        self.nscalars = nscalars
+        self.gamma = gamma
+        lo = []
+        for n in range(self.ncomp):
+            for d in range(3):
+                if bc_kind == "reflect":
+                    lo.append(capi.QK_BC_REFLECT_ODD if n == 1 + d else capi.QK_BC_REFLECT_EVEN)
+                elif bc_kind == "outflow":
+                    lo.append(capi.QK_BC_FOEXTRAP)
+                else:
+                    lo.append(capi.QK_BC_INT_DIR)
+        self.bc_lo = lo
+        self.bc_hi = list(lo)
+
+    def params(self, **kw):
+        return capi.hydro_params(gamma=self.gamma, nscalars=self.nscalars, **kw)
+
+    def states(self, seed=1, kind="shocked"):
+        rho, v, P, rng = ol.random_cons(self.domain, self.nscalars, seed, kind)
+        U = ol.cons_from_prim(rho, v, P, self.gamma, rng, self.nscalars)
+        out = []
+        ng = self.nghost
+        for bx in self.boxes:
+            g = bx.grown(ng)
+            nz, ny, nx = g.shape()
+            a = np.full((self.ncomp, nz, ny, nx), np.nan)
+            a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng] = U[:, bx.lo[2]:bx.hi[2] + 1, bx.lo[1]:bx.hi[1] + 1, bx.lo[0]:bx.hi[0] + 1]
+            out.append(a)
+        return out
+
+
+def level_desc(p, owner=None, rank=0):
+    return make_level_desc(p.domain, p.periodic, p.dx, p.nghost, p.ncomp, p.boxes, owner or [0] * len(p.boxes), rank, p.bc_lo, p.bc_hi)
+
+
+def oracle_level(p, states):
+    desc, keep = level_desc(p)
+    o = ol.oracle()
+    L = o.orc_level_create(C.byref(desc))
+    for b in range(len(p.boxes)):
+        for which in (0, 1):
+            d = o.orc_level_state(L, which, b)
+            buf = np.ctypeslib.as_array(C.cast(d.p, C.POINTER(C.c_double)), shape=states[b].shape)
+            buf[...] = states[b]
+    return L, (desc, keep)
+
+
+def oracle_state(p, L, which, b):
+    o = ol.oracle()
+    d = o.orc_level_state(L, which, b)
+    g = p.boxes[b].grown(p.nghost)
+    nz, ny, nx = g.shape()
+    return np.ctypeslib.as_array(C.cast(d.p, C.POINTER(C.c_double)), shape=(p.ncomp, nz, ny, nx))
+
+
+@pytest.mark.parametrize("periodic,bc", [((0, 0, 0), "reflect"), ((1, 1, 1), "periodic"), ((1, 0, 0), "outflow"), ((0, 1, 0), "reflect")])
+@pytest.mark.parametrize("grid", [((32, 32, 32), 16), ((24, 16, 8), 8), ((16, 16, 16), 16)])
+def test_fill_boundary(lib, periodic, bc, grid):
+    from quokka_b200.device import DevMultiFab
+
+    p = GenericProblem(grid[0], grid[1], periodic, bc, nscalars=1)
+    st = p.states()
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    arrs = (qk_array4 * len(p.boxes))(*[o.orc_level_state(L, 0, b) for b in range(len(p.boxes))])
+    o.orc_fill_boundary(L, arrs, 0, p.ncomp)
+    desc, keep2 = level_desc(p)
+    lev = C.c_void_p()
+    check(lib.qk_level_create(C.byref(desc), C.byref(lev)))
+    mf = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    check(lib.qk_fill_boundary(lev, mf.descs, 0, p.ncomp, None))
+    got = mf.numpy()
+    for b in range(len(p.boxes)):
+        exact(got[b], oracle_state(p, L, 0, b), f"box {b}")
+    # the three-call form (local copies, then BCs) gives the same result on one rank
+    mf2 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    check(lib.qk_fill_boundary_local(lev, mf2.descs, 0, p.ncomp, None))
+    check(lib.qk_fill_physical_bc(lev, mf2.descs, 0, p.ncomp, None))
+    for b in range(len(p.boxes)):
+        exact(mf2.numpy()[b], got[b], f"box {b} (split calls)")
+    lib.qk_level_destroy(lev)
+    o.orc_level_destroy(L)
+
+
+def run_stage_pair(lib, p, prm, st, dt, entry):
+    """two RK stages through `entry` (qk_hydro_advance_stage or ..._faithful); returns (Unew list, bad1, bad2)"""
+    from quokka_b200.device import DevMultiFab
+
+    desc, keep = level_desc(p)
+    lev = C.c_void_p()
+    check(lib.qk_level_create(C.byref(desc), C.byref(lev)))
+    U0 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    U1 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost)
+    U2 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost)
+    b1, b2 = C.c_int64(-1), C.c_int64(-1)
+    check(lib.qk_fill_boundary(lev, U0.descs, 0, p.ncomp, None))
+    check(entry(lev, C.byref(prm), 1, U0.descs, U0.descs, U1.descs, dt, C.byref(b1), None))
+    check(lib.qk_fill_boundary(lev, U1.descs, 0, p.ncomp, None))
+    check(entry(lev, C.byref(prm), 2, U0.descs, U1.descs, U2.descs, dt, C.byref(b2), None))
+    out = U2.numpy()
+    lib.qk_level_destroy(lev)
+    return out, b1.value, b2.value
+
+
+@pytest.mark.parametrize("which", ["production", "faithful"])
+@pytest.mark.parametrize("case", ["reflect_multi", "periodic_scalars", "single_box", "eint"])
+def test_advance_two_stages(lib, which, case):
+    if case == "reflect_multi":
+        p = GenericProblem((32, 32, 32), 16, (0, 0, 0), "reflect")
+        prm = p.params()
+    elif case == "periodic_scalars":
+        p = GenericProblem((32, 16, 16), 16, (1, 1, 1), "periodic", nscalars=2, gamma=5.0 / 3.0)
+        prm = p.params(nmscalars=0)
+    elif case == "single_box":
+        p = GenericProblem((24, 20, 12), 32, (0, 0, 0), "outflow")
+        prm = p.params()
+    else:
+        p = GenericProblem((32, 32, 16), 16, (0, 1, 0), "reflect")
+        prm = p.params(reconstruct_eint=1)
+    st = p.states(seed=5, kind="smooth")
+    dt = 2.0e-4
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    bo1, bo2 = C.c_int64(), C.c_int64()
+    ok = o.orc_advance_hydro_level(L, C.byref(prm), dt, 1.0e9, C.byref(bo1), C.byref(bo2))
+    entry = lib.qk_hydro_advance_stage if which == "production" else lib.qk_hydro_advance_stage_faithful
+    got, b1, b2 = run_stage_pair(lib, p, prm, st, dt, entry)
+    assert (b1, b2) == (bo1.value, bo2.value)
+    assert ok == 1
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        ref = oracle_state(p, L, 0, b)
+        exact(got[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng], f"{case} box {b}")
+    o.orc_level_destroy(L)
+
+
+@pytest.mark.parametrize("which", ["production", "faithful"])
+def test_fofc_fallback(lib, which):
+    """a violent state + large dt makes PredictStep flag cells: first-order flux correction must reproduce the
+    reference's replaceFluxes/redo sequence (QuokkaSimulation.hpp:1146-1184) bit for bit"""
+    p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic")
+    prm = p.params()
+    prm.abort_on_fofc_failure = 0
+    st = p.states(seed=9, kind="shocked")
+    dt = 4.0e-3
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    bo1, bo2 = C.c_int64(), C.c_int64()
+    o.orc_advance_hydro_level(L, C.byref(prm), dt, 1.0e9, C.byref(bo1), C.byref(bo2))
+    assert bo1.value > 0 or bo2.value > 0, "test input does not trigger FOFC"
+    entry = lib.qk_hydro_advance_stage if which == "production" else lib.qk_hydro_advance_stage_faithful
+    # NB the oracle reports the count seen at the FIRST check; the C ABI reports what survived FOFC
+    got, b1, b2 = run_stage_pair(lib, p, prm, st, dt, entry)
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        ref = oracle_state(p, L, 0, b)
+        exact(got[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng], f"box {b}")
+    o.orc_level_destroy(L)
+
+
+def run_gpu_sedov(ncell, box, nsteps):
+    from quokka_b200.simulation import HydroSimulation
+
+    prob = SedovProblem(ncell, box)
+    sim = HydroSimulation(prob)
+    sim.setInitialConditions()
+    dts = []
+    for _ in range(nsteps):
+        dt = sim.computeTimestep()
+        r = sim.advanceSingleTimestepAtLevel(dt)
+        assert r >= 0
+        dts.append(dt)
+    out = sim.gather_global()
+    t, retries, upd = sim.time, sim.retries, sim.cellUpdates
+    sim.close()
+    return out, t, retries, upd, dts
+
+
+@pytest.mark.parametrize("name", ["sedov16_b16_s5", "sedov32_b16_s10", "sedov32_b32_s30"])
+def test_sedov_matches_reference_run(name):
+    """C2/C3 in miniature: the library's own time loop reproduces the reference executable's state dump."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    state, t, retries, upd, _ = run_gpu_sedov(int(g["ncell"]), int(g["box"]), int(g["nsteps"]))
+    assert t == float(g["time"])
+    assert retries == int(g["retries"])
+    assert upd == int(g["ncell"]) ** 3 * int(g["nsteps"])
+    exact(state, g["state"], name)
+
+
+def test_sedov64_100_steps_vs_oracle():
+    """north_star tolerance: L_inf on conserved variables after 100 steps < 1e-12 (relative to max|U_n|);
+    the bar here is stricter -- bit-exact against the oracle driver, 64^3 in 8 boxes."""
+    from test_oracle_golden import run_oracle_sedov
+
+    n, box, steps = 64, 32, 100
+    ref, t_ref, r_ref = run_oracle_sedov(n, box, steps)
+    got, t, r, upd, _ = run_gpu_sedov(n, box, steps)
+    assert t == t_ref and r == r_ref
+    for c in range(6):
+        scale = np.abs(ref[c]).max()
+        err = np.abs(got[c] - ref[c]).max() / (scale if scale > 0 else 1.0)
+        assert err < 1e-12, f"component {c}: rel L_inf {err}"
+    exact(got, ref, "sedov64")
+    # the reference's own pass criterion: total energy conserved (test_hydro3d_blast.cpp:199-205)
+    prob = SedovProblem(n, box)
+    vol = prob.dx[0] * prob.dx[1] * prob.dx[2]
+    E0 = sum(prob.initial_state(b, 0)[4].sum() for b in prob.boxes) * vol
+    assert abs(got[4].sum() * vol - E0) / E0 < 1e-13
