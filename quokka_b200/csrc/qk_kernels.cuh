@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(TPB) k_flatten(int dir, Iter it, int nvars, A4
 }
 
 // transverse velocity-difference terms of the carbuncle fix at a face (hydro_system.hpp:1018-1034)
-__device__ __forceinline__ void face_du_dw(const A4 &q, int dir, int64_t o, int64_t sN, double &du, double &dw)
+__device__ __forceinline__ void face_du_dw(const A4 &q, int dir, int64_t o, int64_t sN, double &du, double &dw, double &div_v)
 {
 	const int aV = (dir + 1) % 3, aW = (dir + 2) % 3;
 	const int64_t sV = (aV == 0) ? 1 : (aV == 1) ? q.js : q.ks;
@@ -156,6 +156,7 @@ __device__ __forceinline__ void face_du_dw(const A4 &q, int dir, int64_t o, int6
 	const double dwl = dmin(vW[-sN + sW] - vW[-sN], vW[-sN] - vW[-sN - sW]);
 	const double dwr = dmin(vW[sW] - vW[0], vW[0] - vW[-sW]);
 	dw = dmin(dmin(dwl, dwr), dw);
+	div_v = du + 0.5 * (dvl + dvr) + 0.5 * (dwl + dwr); // hydro_system.hpp:1054
 }
 
 // HydroSystem::ComputeFluxes<RIEMANN,DIR>  hydro_system.hpp:852-1112
@@ -170,9 +171,9 @@ template <int SOLVER> __global__ void __launch_bounds__(TPB) k_compute_fluxes(Hy
 		R[n] = right(i, j, k, n);
 	}
 	const int64_t sN = (dir == 0) ? 1 : (dir == 1) ? q.js : q.ks;
-	double du, dw, vface;
-	face_du_dw(q, dir, q.off(i, j, k), sN, du, dw);
-	face_flux<SOLVER>(c, dir, L, R, du, dw, F, vface);
+	double du, dw, vface, div_v;
+	face_du_dw(q, dir, q.off(i, j, k), sN, du, dw, div_v);
+	face_flux<SOLVER, true>(c, dir, L, R, du, dw, F, vface, div_v);
 	for (int n = 0; n < c.nv; ++n)
 		flux(i, j, k, n) = F[n];
 	fvel(i, j, k, 0) = vface;
@@ -229,9 +230,9 @@ __global__ void __launch_bounds__(TPB) k_flux_function(HydroConst c, int dir, It
 			R[n] = chiR * amR + (1. - chiR) * q0;
 		}
 	}
-	double du, dw, vface;
-	face_du_dw(q, dir, o, sN, du, dw);
-	face_flux<SOLVER>(c, dir, L, R, du, dw, F, vface);
+	double du, dw, vface, div_v;
+	face_du_dw(q, dir, o, sN, du, dw, div_v);
+	face_flux<SOLVER, true>(c, dir, L, R, du, dw, F, vface, div_v);
 	for (int n = 0; n < c.nv; ++n)
 		flux(i, j, k, n) = F[n];
 	fvel(i, j, k, 0) = vface;

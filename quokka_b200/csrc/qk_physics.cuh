@@ -12,6 +12,11 @@
 //     dropped: they can only turn a -0.0 into +0.0, never change a non-zero value;
 //   * the unlimited PPM interface value is shared between a_plus(i) and a_minus(i+1), which the
 //     reference computes twice with the same grouping (hyperbolic_system.hpp:380-385).
+// The dropped zero terms matter only for NON-FINITE intermediates (inf*0 = NaN): face_flux<.., SPECIAL=true>
+// keeps every one of them (and the K_visc=0 artificial-viscosity term, hydro_system.hpp:1052-1076) so that
+// unphysical states (rho <= 0 surviving a failed FOFC) propagate NaN/Inf exactly as the reference does; the
+// faithful path uses SPECIAL=true, the fused sweeps SPECIAL=false and are only run on states whose previous
+// stage reported ncells_bad == 0 (qk_sweep.cu).
 #pragma once
 #include "qk_common.cuh"
 
@@ -210,9 +215,9 @@ struct FaceState { // quokka::HydroState, src/hydro/HydroState.hpp:10-23 (canoni
 // HydroSystem::ComputeFluxes<HLLC,DIR> body after the L/R gather (hydro_system.hpp:879-1104) + Riemann::HLLC (HLLC.hpp:21-153).
 // prims: L[*], R[*] hold the reconstructed primitive components in ARRAY order (rho, vx, vy, vz, P|eint, Eaux|eaux, scalars..).
 // Returns F in ARRAY component order and the face velocity.
-template <int SOLVER>
+template <int SOLVER, bool SPECIAL = false>
 __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const double *__restrict__ L, const double *__restrict__ R, double du,
-					  double dw, double *__restrict__ F, double &vface)
+					  double dw, double *__restrict__ F, double &vface, double div_v = 0.0)
 {
 	const int iN = 1 + dir, iV = 1 + (dir + 1) % 3, iW = 1 + (dir + 2) % 3; // hydro_system.hpp:954-976
 	const double rho_L = L[0], rho_R = R[0];
@@ -250,10 +255,12 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 			if (n == 1) {
 				FL = FL + P_L;
 				FR = FR + P_R;
-			}
-			if (n == 4) {
+			} else if (n == 4) {
 				FL = FL + P_L * uL;
 				FR = FR + P_R * uR;
+			} else if (SPECIAL) {
+				FL = FL + P_L * 0.;
+				FR = FR + P_R * 0.;
 			}
 			Fc[n] = 0.5 * (FL + FR) - hS * (UR[n] - UL[n]);
 		}
@@ -264,7 +271,10 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		F[4] = Fc[4];
 		F[5] = Fc[5];
 		for (int n = 0; n < c.ns; ++n) {
-			F[6 + n] = 0.5 * (uL * L[6 + n] + uR * R[6 + n]) - hS * (R[6 + n] - L[6 + n]);
+			if (SPECIAL)
+				F[6 + n] = 0.5 * ((uL * L[6 + n] + P_L * 0.) + (uR * R[6 + n] + P_R * 0.)) - hS * (R[6 + n] - L[6 + n]);
+			else
+				F[6 + n] = 0.5 * (uL * L[6 + n] + uR * R[6 + n]) - hS * (R[6 + n] - L[6 + n]);
 		}
 	} else { // HLLC
 		const double wl = sqrt(rho_L);
@@ -280,7 +290,7 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		const double dU = uL - uR;
 		// gamma != 1 branch (HLLC.hpp:47-73); dedr = 0 for the gamma law (actual_eos.H:230)
 		const double eiL = Eint_L / rho_L, eiR = Eint_R / rho_R;
-		const double C_tilde_rho = 0.5 * (eiL + eiR);
+		const double C_tilde_rho = SPECIAL ? 0.5 * (eiL + eiR + rho_L * 0. + rho_R * 0.) : 0.5 * (eiL + eiR);
 		const double C_tilde_P = 0.5 * (eiL * eL.drdp + eiR * eR.drdp + rho_L * eL.dedp + rho_R * eR.dedp);
 		const double cs_exp = H_tilde - 0.5 * vsq_tilde - C_tilde_rho;
 		double cs_tilde;
@@ -327,18 +337,20 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 			double FK = uK * UK[n];
 			if (n == 1) {
 				FK = FK + PK;
-			}
-			if (n == 4) {
+			} else if (n == 4) {
 				FK = FK + PK * uK;
+			} else if (SPECIAL) {
+				FK = FK + PK * 0.;
 			}
 			double Fs = FK;
 			if (star) {
 				double num = S_star * (SK * UK[n] - FK);
 				if (n == 1) {
 					num = num + SP;
-				}
-				if (n == 4) {
+				} else if (n == 4) {
 					num = num + SP * S_star;
+				} else if (SPECIAL) {
+					num = num + SP * 0.;
 				}
 				Fs = num / den;
 			}
@@ -352,9 +364,23 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		F[5] = Fc[5];
 		for (int n = 0; n < c.ns; ++n) {
 			const double Un = left ? L[6 + n] : R[6 + n];
-			const double FK = uK * Un;
-			F[6 + n] = star ? (S_star * (SK * Un - FK)) / den : FK;
+			const double FK = SPECIAL ? (uK * Un + PK * 0.) : (uK * Un);
+			if (SPECIAL)
+				F[6 + n] = star ? (S_star * (SK * Un - FK) + SP * 0.) / den : FK;
+			else
+				F[6 + n] = star ? (S_star * (SK * Un - FK)) / den : FK;
 		}
+	}
+	if (SPECIAL) {
+		// artificial viscosity with K_visc = 0 (hydro_system.hpp:1052-1076): adds +0 to every non-momentum component
+		// unless the velocity divergence or a state difference is not finite
+		const double viscosity = c.K_visc * dmax(-div_v, 0.);
+		const double E_Lv = eL.Eint + ke_L, E_Rv = eR.Eint + ke_R;
+		F[0] = F[0] + viscosity * (rho_L - rho_R);
+		F[4] = F[4] + viscosity * (E_Lv - E_Rv);
+		F[5] = F[5] + viscosity * (Eint_L - Eint_R);
+		for (int n = 0; n < c.ns; ++n)
+			F[6 + n] = F[6 + n] + viscosity * (L[6 + n] - R[6 + n]);
 	}
 	// face-centred normal velocity (hydro_system.hpp:1089-1091)
 	vface = (F[0] >= 0.) ? (F[0] / rho_R) : (F[0] / rho_L);
