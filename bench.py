@@ -1,0 +1,343 @@
+#!/usr/bin/env python3
+"""bench.py -- Mcell-updates/s of the hydro hot path on the Sedov blast (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one coarse time step of the whole level: a full RK2-SSP update of every cell (2 ghost fills, 2 x
+(prim + flattening + PPM + HLLC in x,y,z + update), dt and CFL reductions) -- exactly what the reference counts in
+its figure of merit (src/simulation.hpp:972-977, cellUpdates_ += CountCells(lev) :1285).
+N = 1: configs[1], Sedov 256^3 in eight 128^3 boxes.  N > 1: weak scaling, 256^3 cells (8 boxes) per GPU
+(N = 8 is configs[2], Sedov 512^3), boxes mapped to ranks as AMReX's SFC DistributionMapping does, ghost exchange
+over the library's NCCL transport.  `value` is timed with CUDA events around the C++ driver's loop with the state
+resident in HBM; `e2e` drives the same steps through the C ABI from HOST buffers (pinned): state upload, step,
+state download inside the timed region.  The state (0.8 GB per GPU) is far larger than L2, so no explicit flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mcell-updates/s (Sedov 3D PPM+HLLC)"
+UNIT = "Mcell-updates/s"
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "test_hydro3d_blast")
+
+REF_INPUT = """
+geometry.prob_lo     =  0.0  0.0  0.0
+geometry.prob_hi     =  1.2  1.2  1.2
+geometry.is_periodic =  0    0    0
+amr.v = 0
+amr.max_level = 0
+amr.n_error_buf = 3
+amr.grid_eff = 0.7
+do_reflux = 0
+do_subcycle = 0
+plotfile_interval = -1
+checkpoint_interval = -1
+"""
+
+
+def ncell_for(ngpus):
+    """256^3 cells per GPU: 1 -> 256^3, 2 -> 512x256x256, 4 -> 512x512x256, 8 -> 512^3"""
+    n = [256, 256, 256]
+    d = 0
+    g = ngpus
+    while g > 1:
+        n[d] *= 2
+        d = (d + 1) % 3
+        g //= 2
+    return n
+
+
+def make_config(world, ncell):
+    which = "configs[1]" if world == 1 else "configs[2]" if world == 8 else "weak-scaled configs[1]"
+    return {"workload": f"Sedov blast {ncell[0]}x{ncell[1]}x{ncell[2]} uniform ({which}), 128^3 boxes (8 per GPU), PPM+HLLC RK2, gamma=1.4, "
+                        "reflecting BCs, cfl 0.3",
+            "cells": ncell[0] * ncell[1] * ncell[2], "l2": "state per GPU (0.8 GB) >> 126 MB L2, no flush needed",
+            "arith": "exact (IEEE order, no FMA contraction)",
+            "parallelism": f"dp{world} (boxes over ranks, NCCL ghost exchange)" if world > 1 else "1 GPU"}
+
+
+# ---- clocks --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- the reference's own CPU implementation ---------------------------------------------------------------------
+def run_reference_cpu(ncell, box, nsteps, threads):
+    """the UNMODIFIED reference executable (oracle/_ref/test_hydro3d_blast, built from /root/reference by
+    oracle/ref_build/Makefile) on the host cores; returns (Mupdates/s from its own FOM line, elapsed s)"""
+    tmp = tempfile.mkdtemp(prefix="qkref_")
+    try:
+        with open(os.path.join(tmp, "in"), "w") as f:
+            f.write(REF_INPUT)
+            f.write(f"amr.n_cell = {ncell[0]} {ncell[1]} {ncell[2]}\namr.max_grid_size = {box}\namr.blocking_factor = {box}\nmax_timesteps = {nsteps}\n")
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        out = subprocess.run([REF_EXE, "in"], cwd=tmp, env=env, capture_output=True, text=True).stdout
+        el = time.time() - t0
+        m = re.search(r"figure-of-merit:\s*([0-9.eE+-]+)\s*\S+/zone-update\s*\[([0-9.eE+-]+)\s*Mupdates/s\]", out)
+        me = re.search(r"elapsed time:\s*([0-9.eE+-]+)", out)
+        if not m:
+            raise RuntimeError("reference run printed no figure of merit:\n" + out[-2000:])
+        return float(m.group(2)), (float(me.group(1)) if me else el)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def run_oracle_port(ncell, box, nsteps):
+    """fallback CPU baseline when oracle/_ref did not travel: the single-core C restatement (oracle/liboracle.so)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_golden import run_oracle_sedov
+
+    t0 = time.time()
+    run_oracle_sedov(ncell, box, nsteps)
+    el = time.time() - t0
+    return ncell ** 3 * nsteps / el / 1e6, el
+
+
+def cpu_baseline(steps):
+    cores = os.cpu_count() or 1
+    if os.path.exists(REF_EXE):
+        v, el = run_reference_cpu([128, 128, 128], 64, steps, cores)
+        return {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"reference executable (OpenMP, {cores} threads), Sedov 128^3 in 64^3 boxes, {steps} steps, {el:.1f} s"}
+    v, el = run_oracle_port(48, 48, steps)
+    return {"value": round(v, 4), "unit": UNIT, "cores": 1, "kind": "port", "sample": f"C oracle, 1 thread, Sedov 48^3, {steps} steps, {el:.1f} s"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = args.steps + args.warmup
+    cores = os.cpu_count() or 1
+    ncell = ncell_for(args.gpus)
+    if os.path.exists(REF_EXE):
+        # bounded sample of the workload: one 128^3 box-sized domain (the configs' building block) per "GPU"
+        sample = [c // 2 for c in ncell]
+        v, el = run_reference_cpu(sample, 64, steps, cores)
+        kind, sample_txt = "reference", f"reference executable (OpenMP, {cores} threads), Sedov {sample[0]}x{sample[1]}x{sample[2]} in 64^3 boxes, {steps} steps, {el:.1f} s"
+        ms = el * 1e3 / steps
+    else:
+        v, el = run_oracle_port(48, 48, steps)
+        cores, kind, sample_txt = 1, "port", f"C oracle, 1 thread, Sedov 48^3, {steps} steps, {el:.1f} s"
+        ms = el * 1e3 / steps
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": make_config(args.gpus, ncell),
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_txt},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libquokka_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from quokka_b200 import capi
+    from quokka_b200.problems import SedovProblem
+    from quokka_b200.simulation import Communicator, HydroSimulation
+
+    lib = capi.load()
+    ncell = ncell_for(world)
+    prob = SedovProblem(ncell, 128)
+    comm = None
+    if world > 1:
+        def bcast(b):
+            obj = [b]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        comm = Communicator(rank, world, bcast)
+    sim = HydroSimulation(prob, nranks=world, rank=rank, comm=comm)
+    sim.setInitialConditions()
+    ncells_total = ncell[0] * ncell[1] * ncell[2]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up (also builds the scratch pools)
+    sim.evolve(args.warmup)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.qk_prof_enable(1)
+    l0 = lib.qk_launch_count()
+    barrier()
+    nd, elapsed, dev_ms = sim.evolve(args.steps)
+    barrier()
+    launches = lib.qk_launch_count() - l0
+    lib.qk_prof_enable(0)
+    clk = clocks.stop() if rank == 0 else None
+    assert nd == args.steps, (nd, args.steps)
+    ms_total = max_over_ranks(dev_ms)
+    value = ncells_total * args.steps / (ms_total * 1e-3) / 1e6
+
+    # per-kernel-class device time (CUDA events on the sim's stream inside the timed region)
+    buf = (capi.C.c_char * 8192)()
+    lib.qk_prof_report(buf, 8192)
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        nm, cnt, ms = ln.split()
+        prof[nm] = (int(cnt), float(ms))
+    ncell_local = sum(b.ncells() for b in sim.local_boxes)
+    roof = roofline(prof, ncell_local, args.steps, ms_total)
+
+    if args.no_extras:  # profiling runs (ncu): kernels only
+        if rank == 0:
+            print(json.dumps({"value": round(value, 2), "ms_per_step": round(ms_total / args.steps, 4), "gpu_launches": int(launches), "roofline": roof}))
+        sim.close()
+        return 0
+    # end to end through the C ABI from host buffers: upload, one step, download -- every step
+    e2e_steps = max(1, min(args.steps, 5))
+    sim.download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.upload()
+        dt = sim.computeTimestep()
+        r = sim.advanceSingleTimestepAtLevel(dt)
+        assert r >= 0
+        sim.download()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_val = ncells_total * e2e_steps / e2e_s / 1e6
+    hb = sim.h2d_bytes()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": make_config(world, ncell),
+                "clocks": clk, "gpu_launches": int(launches),
+                "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": hb, "steps": e2e_steps,
+                        "note": "host-buffer plugin call: pinned state upload + step + state download per step"},
+                "roofline": roof, "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(3)
+            except Exception as e:  # never lose the GPU line to a CPU-side problem
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    sim.close()
+    if comm:
+        comm.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def roofline(prof, ncell_local, steps, ms_total):
+    """dominant kernel class vs the measured HBM copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
+    Algorithmic bytes per cell per launch are documented in DESIGN.md section 4."""
+    peak, src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    ALG = {  # bytes per cell per launch-set of the class (one direction / one pass)
+        "flux_function": 48 + 24 + 56,  # faithful path: read prim 6 + chi 3, write flux 6 + facevel 1
+        "sweep_x": 56 + 56 + 56, "sweep_y": 56 + 56 + 112, "sweep_z": 56 + 56 + 56 + 48 + 48,
+    }
+    cand = [(v[1], k) for k, v in prof.items() if k in ALG]
+    if not cand:
+        return None
+    ms, name = max(cand)
+    nl = prof[name][0]
+    # every launch set of the class covers all local cells once per direction-pass; passes per step = launches / boxes...
+    passes = {"flux_function": 6, "sweep_x": 2, "sweep_y": 2, "sweep_z": 2}[name] * steps
+    bytes_per_pass = ALG[name] * ncell_local
+    achieved = bytes_per_pass * passes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": None, "algorithmic_bytes_per_cell": ALG[name], "avg_pass_ms": round(ms / passes, 4), "launches": nl,
+            "share_of_step": round(ms / ms_total, 4)}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the e2e and cpu_baseline legs (profiling runs)")
+    a = ap.parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

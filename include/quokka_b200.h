@@ -105,6 +105,14 @@ int qk_device_count(void);
 const char *qk_error_string(int code);
 /* total kernels launched by this library since load (for bench.py "gpu_launches") */
 int64_t qk_launch_count(void);
+/* optional device timing per kernel class (CUDA events on the launching stream; used by bench.py for the roofline
+ * line).  qk_prof_report writes "name launches total_ms" lines and returns the bytes needed. */
+int qk_prof_enable(int on);
+int qk_prof_report(char *buf, int buflen);
+/* device self-test of the shared-reciprocal FP64 division used by the fused sweeps (csrc/qk_div.cuh): compares
+ * npairs quotients bit for bit with the compiler's IEEE division; mode 0 random bit patterns, 1 moderate exponents,
+ * 2 with zeros / subnormals / infinities / NaNs mixed in.  *bad_rcp counts refined reciprocals != 1.0/b. */
+int qk_selftest_division(uint64_t seed, int mode, int64_t npairs, int64_t *bad_div, int64_t *bad_rcp);
 
 /* ---- per-operator entry points (one per reference operator; parity harness + drop-in) ------ */
 

@@ -178,6 +178,9 @@ SYMBOLS = {
     "qk_device_count": (C.c_int, []),
     "qk_error_string": (C.c_char_p, [C.c_int]),
     "qk_launch_count": (C.c_int64, []),
+    "qk_prof_enable": (C.c_int, [C.c_int]),
+    "qk_prof_report": (C.c_int, [C.c_char_p, C.c_int]),
+    "qk_selftest_division": (C.c_int, [C.c_uint64, C.c_int, C.c_int64, _I64P, _I64P]),
     "qk_hydro_conserved_to_primitive": (C.c_int, [_PRM, C.c_int, _BXP, _A4P, _A4P, C.c_int, _VP]),
     "qk_hydro_flattening_coefficients": (C.c_int, [_PRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_int, _VP]),
     "qk_reconstruct_states": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, C.c_int, C.c_int, _VP]),

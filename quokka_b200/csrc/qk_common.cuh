@@ -84,3 +84,22 @@ extern int64_t g_qk_launches;
 	} while (0)
 
 int qk_require_device();
+
+// ---- optional per-kernel-class device timing (bench.py roofline): CUDA events on the launching stream ----
+extern bool g_qk_prof_on;
+void qk_prof_mark(const char *name, int launches, cudaStream_t s, bool begin);
+struct ProfScope {
+	const char *name;
+	cudaStream_t s;
+	int64_t l0;
+	ProfScope(const char *n, cudaStream_t st) : name(n), s(st), l0(g_qk_launches)
+	{
+		if (g_qk_prof_on)
+			qk_prof_mark(name, 0, s, true);
+	}
+	~ProfScope()
+	{
+		if (g_qk_prof_on)
+			qk_prof_mark(name, (int)(g_qk_launches - l0), s, false);
+	}
+};

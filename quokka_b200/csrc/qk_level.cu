@@ -612,6 +612,7 @@ extern "C" int qk_fill_boundary(qk_level *L, const qk_array4 *state, int scomp, 
 
 int qk_level::fill_boundary_tab(const A4 *tab, int scomp, int nc, cudaStream_t s)
 {
+	ProfScope prof_("fill_boundary", s);
 	// pack + post the remote messages first so that NVLink traffic overlaps the local copies
 	const bool remote = !plan.peers.empty();
 	if (remote) {

@@ -3,9 +3,77 @@
 // The fused, tuned path lives in qk_level.cu / qk_sweep.cuh; both share qk_physics.cuh.
 // Compiled with --fmad=false (exact arithmetic contract, see qk_physics.cuh).
 #include "qk_kernels.cuh"
+#include "qk_div.cuh"
 #include <string.h>
 
+#include <map>
+#include <string>
+#include <vector>
+
 int64_t g_qk_launches = 0;
+bool g_qk_prof_on = false;
+
+// per-class event pairs; resolved (synchronised + summed) only when the report is read
+namespace
+{
+struct ProfClass {
+	std::vector<cudaEvent_t> ev; // begin,end,begin,end...
+	size_t used = 0;
+	int64_t launches = 0;
+};
+std::map<std::string, ProfClass> g_prof;
+} // namespace
+
+void qk_prof_mark(const char *name, int launches, cudaStream_t s, bool begin)
+{
+	ProfClass &c = g_prof[name];
+	if (c.used == c.ev.size()) {
+		cudaEvent_t e;
+		if (cudaEventCreate(&e) != cudaSuccess)
+			return;
+		c.ev.push_back(e);
+	}
+	cudaEventRecord(c.ev[c.used++], s);
+	if (!begin)
+		c.launches += launches;
+}
+
+extern "C" int qk_prof_enable(int on)
+{
+	g_qk_prof_on = (on != 0);
+	if (on)
+		for (auto &kv : g_prof) {
+			kv.second.used = 0;
+			kv.second.launches = 0;
+		}
+	return 0;
+}
+
+// "name launches total_ms\n" per class into buf; returns the number of bytes needed
+extern "C" int qk_prof_report(char *buf, int buflen)
+{
+	std::string out;
+	for (auto &kv : g_prof) {
+		ProfClass &c = kv.second;
+		if (c.used < 2)
+			continue;
+		double ms = 0;
+		for (size_t i = 0; i + 1 < c.used; i += 2) {
+			cudaEventSynchronize(c.ev[i + 1]);
+			float t = 0;
+			if (cudaEventElapsedTime(&t, c.ev[i], c.ev[i + 1]) == cudaSuccess)
+				ms += t;
+		}
+		char line[256];
+		snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), (long long)c.launches, ms);
+		out += line;
+	}
+	if (buf && buflen > 0) {
+		strncpy(buf, out.c_str(), (size_t)buflen - 1);
+		buf[buflen - 1] = 0;
+	}
+	return (int)out.size() + 1;
+}
 
 namespace
 {
@@ -75,6 +143,7 @@ extern "C" int qk_hydro_conserved_to_primitive(const qk_hydro_params *prm, int n
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("cons_to_prim", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).grown(nghost));
 		k_cons_to_prim<<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(cons[b]), A4(prim[b]));
@@ -88,6 +157,7 @@ extern "C" int qk_hydro_flattening_coefficients(const qk_hydro_params *prm, int 
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("flatten_coefs", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).grown(nghost));
 		k_flat_coefs<<<it.blocks(), TPB, 0, S(stream)>>>(c, dir, it, A4(prim[b]), A4(chi[b]));
@@ -100,6 +170,7 @@ extern "C" int qk_reconstruct_states(int order, int limiter, int dir, int nboxes
 				     const qk_array4 *right, int nghost, int nvars, void *stream)
 {
 	QK_TRY(qk_require_device());
+	ProfScope prof_("reconstruct", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).grown(nghost));
 		if (order == 3)
@@ -121,6 +192,7 @@ extern "C" int qk_hydro_flatten_shocks(int dir, int nboxes, const qk_box *valid,
 				       const qk_array4 *chi3, const qk_array4 *left, const qk_array4 *right, int nghost, int nvars, void *stream)
 {
 	QK_TRY(qk_require_device());
+	ProfScope prof_("flatten_shocks", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).grown(nghost));
 		k_flatten<<<it.blocks(), TPB, 0, S(stream)>>>(dir, it, nvars, A4(q[b]), A4(chi1[b]), A4(chi2[b]), A4(chi3[b]), A4(left[b]), A4(right[b]));
@@ -134,6 +206,7 @@ extern "C" int qk_hydro_compute_fluxes(const qk_hydro_params *prm, int solver, i
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("compute_fluxes", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).face(dir));
 		if (solver == QK_HLLC)
@@ -151,6 +224,7 @@ extern "C" int qk_hydro_flux_function(const qk_hydro_params *prm, int fo, int di
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("flux_function", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).face(dir));
 		const A4 q(prim[b]), f(flux[b]), v(facevel[b]);
@@ -173,6 +247,7 @@ extern "C" int qk_hydro_flux_function(const qk_hydro_params *prm, int fo, int di
 extern "C" int qk_saxpy(int nboxes, const qk_box *region, const qk_array4 *dst, double a, const qk_array4 *src, int ncomp, void *stream)
 {
 	QK_TRY(qk_require_device());
+	ProfScope prof_("saxpy", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(region[b])));
 		k_saxpy<<<it.blocks(), TPB, 0, S(stream)>>>(it, ncomp, A4(dst[b]), a, A4(src[b]));
@@ -185,6 +260,7 @@ extern "C" int qk_hydro_rhs_from_fluxes(int nboxes, const qk_box *valid, const q
 					const qk_array4 *fz, const double dx[3], int nvars, void *stream)
 {
 	QK_TRY(qk_require_device());
+	ProfScope prof_("rhs_from_fluxes", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_rhs<<<it.blocks(), TPB, 0, S(stream)>>>(it, nvars, A4(rhs[b]), A4(fx[b]), A4(fy[b]), A4(fz[b]), dx[0], dx[1], dx[2]);
@@ -199,6 +275,7 @@ extern "C" int qk_hydro_add_internal_energy_pdv(const qk_hydro_params *prm, int 
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("pdv", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_pdv<<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(rhs[b]), A4(cons[b]), A4(vx[b]), A4(vy[b]), A4(vz[b]), IA4(redo[b]), dx[0], dx[1], dx[2]);
@@ -215,6 +292,7 @@ extern "C" int qk_hydro_predict_step(const qk_hydro_params *prm, int nboxes, con
 	QK_TRY(ensure_scalars());
 	const HydroConst c = make_hydro_const(prm);
 	QK_CUDA(cudaMemsetAsync(g_scalar_dev, 0, 8, S(stream)));
+	ProfScope prof_("predict_step", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_predict<<<it.blocks(), TPB, 0, S(stream)>>>(c, it, nvars, A4(cons_old[b]), A4(cons_new[b]), A4(rhs[b]), dt, IA4(redo[b]), g_scalar_dev);
@@ -232,6 +310,7 @@ extern "C" int qk_hydro_enforce_limits(const qk_hydro_params *prm, int nboxes, c
 {
 	QK_TRY(check_params(prm));
 	const HydroConst c = make_hydro_const(prm);
+	ProfScope prof_("enforce_limits", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_enforce<<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(state[b]));
@@ -246,6 +325,7 @@ extern "C" int qk_hydro_sync_dual_energy(const qk_hydro_params *prm, int nboxes,
 	QK_TRY(check_params(prm));
 	QK_TRY(ensure_scalars());
 	QK_CUDA(cudaMemsetAsync(g_scalar_dev, 0, 8, S(stream)));
+	ProfScope prof_("sync_dual_energy", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_sync<<<it.blocks(), TPB, 0, S(stream)>>>(it, A4(state[b]), g_scalar_dev);
@@ -263,6 +343,7 @@ extern "C" int qk_hydro_replace_fluxes(int dir, int nboxes, const qk_box *valid,
 				       const qk_iarray4 *redo, int ncomp, void *stream)
 {
 	QK_TRY(qk_require_device());
+	ProfScope prof_("replace_fluxes", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it(Box3(valid[b]).grown(1));
 		k_replace<<<it.blocks(), TPB, 0, S(stream)>>>(dir, it, ncomp, A4(flux[b]), A4(fo_flux[b]), IA4(redo[b]), Box3(valid[b]).face(dir));
@@ -278,6 +359,7 @@ extern "C" int qk_hydro_max_signal_speed(const qk_hydro_params *prm, int which, 
 	QK_TRY(ensure_scalars());
 	const HydroConst c = make_hydro_const(prm);
 	QK_CUDA(cudaMemsetAsync(g_scalar_dev, 0, 8, S(stream)));
+	ProfScope prof_("max_signal_speed", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
 		Iter it((Box3(valid[b])));
 		k_max_signal<<<it.blocks(), TPB, 0, S(stream)>>>(c, which, it, A4(cons[b]), g_scalar_dev);
@@ -286,5 +368,72 @@ extern "C" int qk_hydro_max_signal_speed(const qk_hydro_params *prm, int which, 
 	QK_CUDA(cudaMemcpyAsync(g_scalar_host, g_scalar_dev, 8, cudaMemcpyDeviceToHost, S(stream)));
 	QK_CUDA(cudaStreamSynchronize(S(stream)));
 	*max_out = (g_scalar_host[0] == 0ull) ? ((which == 0) ? 0.0 : -1.7976931348623157e308) : key2d(g_scalar_host[0]);
+	return 0;
+}
+
+
+// ---- self-test of qk_div.cuh on the device (tests/test_gpu_division.py) ------------------------------------------
+namespace
+{
+__device__ __forceinline__ unsigned long long sm64(unsigned long long &s)
+{
+	s += 0x9E3779B97F4A7C15ull;
+	unsigned long long z = s;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+// mode 0: full-range random bit patterns; 1: random mantissas, exponents within +-40 of 1; 2: specials mixed in
+__global__ void k_div_selftest(unsigned long long seed, int mode, int per_thread, unsigned long long *out)
+{
+	unsigned long long s = seed + 0x1234567ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x);
+	unsigned long long bad_div = 0, bad_rcp = 0;
+	const double specials[12] = {0.0, -0.0, 1.0, -1.0, 4.9406564584124654e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
+				     __longlong_as_double(0x7ff0000000000000ll), __longlong_as_double(0xfff0000000000000ll),
+				     __longlong_as_double(0x7ff8000000000000ll), 1e-300, 1e300};
+	for (int it = 0; it < per_thread; ++it) {
+		unsigned long long ua = sm64(s), ub = sm64(s);
+		if (mode == 1) {
+			ua = (ua & 0x800fffffffffffffull) | ((0x3ffull - 40 + (sm64(s) % 81)) << 52);
+			ub = (ub & 0x800fffffffffffffull) | ((0x3ffull - 40 + (sm64(s) % 81)) << 52);
+		}
+		double a = __longlong_as_double((long long)ua), b = __longlong_as_double((long long)ub);
+		if (mode == 2) {
+			const unsigned long long pick = sm64(s);
+			if ((pick & 3) == 0)
+				a = specials[(pick >> 8) % 12];
+			if ((pick & 12) == 0)
+				b = specials[(pick >> 16) % 12];
+		}
+		const QkRcp r = qk_rcp(b);
+		const double q1 = qk_div(a, r);
+		const double q2 = a / b;
+		if (__double_as_longlong(q1) != __double_as_longlong(q2) && !((q1 != q1) && (q2 != q2)))
+			++bad_div;
+		// is the division's refined reciprocal the correctly rounded 1/b wherever the fast path applies?
+		const double y = 1.0 / b;
+		if (r.ok && __double_as_longlong(r.y) != __double_as_longlong(y) && !((r.y != r.y) && (y != y)))
+			++bad_rcp;
+	}
+	if (bad_div)
+		atomicAdd(out, bad_div);
+	if (bad_rcp)
+		atomicAdd(out + 1, bad_rcp);
+}
+} // namespace
+
+extern "C" int qk_selftest_division(uint64_t seed, int mode, int64_t npairs, int64_t *bad_div, int64_t *bad_rcp)
+{
+	QK_TRY(qk_require_device());
+	QK_TRY(ensure_scalars());
+	QK_CUDA(cudaMemset(g_scalar_dev, 0, 16));
+	const int threads = 256, blocks = 148 * 8, per = (int)((npairs + (int64_t)threads * blocks - 1) / ((int64_t)threads * blocks));
+	k_div_selftest<<<blocks, threads>>>(seed, mode, per, g_scalar_dev);
+	QK_KERNEL_CHECK();
+	QK_CUDA(cudaMemcpy(g_scalar_host, g_scalar_dev, 16, cudaMemcpyDeviceToHost));
+	if (bad_div)
+		*bad_div = (int64_t)g_scalar_host[0];
+	if (bad_rcp)
+		*bad_rcp = (int64_t)g_scalar_host[1];
 	return 0;
 }
