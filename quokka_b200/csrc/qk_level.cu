@@ -374,6 +374,7 @@ extern "C" void qk_level_destroy(qk_level *L)
 		return;
 	L->plan.destroy();
 	L->plan1.destroy();
+	qk_fused_free(L);
 	L->free_scratch();
 	if (L->d_bc_lo)
 		cudaFree(L->d_bc_lo);
@@ -937,35 +938,52 @@ int qk_level::fofc_redo(const qk_hydro_params *prm, std::vector<qk_array4> *F, s
 	return update_from_fluxes(prm, F, V, U0, Uout, dt, nbad, s);
 }
 
-int qk_level::faithful_stage(const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
-			     int64_t *ncells_bad, cudaStream_t s)
+// computeHydroFluxes (QuokkaSimulation.hpp:1403-1490) of state U into flx/fvl, then flux_rk2 += 0.5 F, avgFaceVel += 0.5 v (:1105-1108)
+int qk_level::faithful_fluxes(const qk_hydro_params *prm, const qk_array4 *U, bool zero_rk, cudaStream_t s)
 {
 	const int nb = (int)valid.size();
-	const int nv = 6 + prm->nscalars;
-	QK_TRY(ensure_faithful_scratch(nv));
-	if (stage == 1)
-		scr.fo_valid = false;
-	// computeHydroFluxes (QuokkaSimulation.hpp:1403-1490): K1, K2 x3, then K3+K4+K5 fused per direction
-	QK_TRY(qk_hydro_conserved_to_primitive(prm, nb, valid.data(), Ustage, scr.prim.data(), nghost, s));
+	const int nv = scr.nv;
+	QK_TRY(qk_hydro_conserved_to_primitive(prm, nb, valid.data(), U, scr.prim.data(), nghost, s));
 	for (int d = 0; d < 3; ++d)
 		QK_TRY(qk_hydro_flattening_coefficients(prm, d, nb, valid.data(), scr.prim.data(), scr.chi[d].data(), 2, s));
 	for (int d = 0; d < 3; ++d)
 		QK_TRY(qk_hydro_flux_function(prm, 0, d, nb, valid.data(), scr.prim.data(), scr.chi[0].data(), scr.chi[1].data(), scr.chi[2].data(),
 					      scr.flx[d].data(), scr.fvl[d].data(), s));
-	// flux_rk2 / avgFaceVel accumulate 0.5 F (QuokkaSimulation.hpp:1060-1073 setVal(0); :1105-1108, :1219-1222 Saxpy)
 	for (int d = 0; d < 3; ++d) {
-		if (stage == 1) {
+		if (zero_rk) { // flux_rk2.setVal(0), avgFaceVel.setVal(0) (:1060-1073)
 			QK_CUDA(cudaMemsetAsync(scr.frk[d][0].p, 0, (size_t)((char *)(scr.frk[d][nb - 1].p + scr.frk[d][nb - 1].nstride * nv) - (char *)scr.frk[d][0].p), s));
 			QK_CUDA(cudaMemsetAsync(scr.avg[d][0].p, 0, (size_t)((char *)(scr.avg[d][nb - 1].p + scr.avg[d][nb - 1].nstride) - (char *)scr.avg[d][0].p), s));
 		}
 		QK_TRY(qk_saxpy(nb, scr.faces[d].data(), scr.frk[d].data(), 0.5, scr.flx[d].data(), nv, s));
 		QK_TRY(qk_saxpy(nb, scr.faces[d].data(), scr.avg[d].data(), 0.5, scr.fvl[d].data(), 1, s));
 	}
+	return 0;
+}
+
+int qk_level::faithful_stage(const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
+			     int64_t *ncells_bad, cudaStream_t s)
+{
+	const int nb = (int)valid.size();
+	const int nv = 6 + prm->nscalars;
+	QK_TRY(ensure_faithful_scratch(nv));
+	if (stage == 1) {
+		scr.fo_valid = false;
+		QK_TRY(faithful_fluxes(prm, Ustage, true, s));
+		scr.rk_valid = true;
+	} else {
+		if (!scr.rk_valid) { // stage 1 of this step ran on the fused path: rebuild 0.5 F(U0) first
+			scr.fo_valid = false;
+			QK_TRY(faithful_fluxes(prm, U0, true, s));
+		}
+		QK_TRY(faithful_fluxes(prm, Ustage, false, s));
+		scr.rk_valid = false; // consumed
+	}
 	std::vector<qk_array4> *F = (stage == 1) ? scr.flx : scr.frk;
 	std::vector<qk_array4> *V = (stage == 1) ? scr.fvl : scr.avg;
 	QK_CUDA(cudaMemsetAsync(scr.redo_base, 0, scr.redo_count * 4, s)); // redoFlag.setVal(quokka::redoFlag::none)
 	int64_t bad = 0;
 	QK_TRY(update_from_fluxes(prm, F, V, U0, Uout, dt, &bad, s));
+	scr.first_check_bad = bad;
 	if (bad > 0)
 		QK_TRY(fofc_redo(prm, F, V, U0, Uout, dt, &bad, s));
 	if (bad == 0 || !prm->abort_on_fofc_failure) {
@@ -1001,5 +1019,13 @@ extern "C" int qk_hydro_advance_stage(qk_level *L, const qk_hydro_params *prm, i
 	QK_TRY(qk_fused_stage(L, prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream), &handled));
 	if (handled)
 		return 0;
-	return L->faithful_stage(prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream));
+	int64_t bad = 0;
+	if (stage == 1)
+		L->scr.rk_valid = false;
+	QK_TRY(L->faithful_stage(prm, stage, U0, Ustage, Uout, dt, &bad, S(stream)));
+	if (L->scr.first_check_bad == 0)
+		qk_fused_untaint(L); // every cell of Uout has rho > 0 again: the fused kernels may take the next stage
+	if (ncells_bad)
+		*ncells_bad = bad;
+	return 0;
 }

@@ -77,6 +77,8 @@ struct FaithfulScratch {
 	int32_t *redo_base = nullptr;
 	size_t redo_count = 0;
 	bool fo_valid = false;
+	bool rk_valid = false;	      // frk/avg hold 0.5*F(U0), 0.5*faceVel(U0) of the CURRENT step (set by a faithful stage 1)
+	int64_t first_check_bad = 0; // redoFlag.sum() before FOFC in the last faithful stage
 };
 
 struct FusedState; // qk_sweep.cu
@@ -120,11 +122,14 @@ struct qk_level {
 			       double dt, int64_t *nbad, cudaStream_t s);
 	int fofc_redo(const qk_hydro_params *prm, std::vector<qk_array4> *F, std::vector<qk_array4> *V, const qk_array4 *U0, const qk_array4 *Uout, double dt,
 		      int64_t *nbad, cudaStream_t s);
+	int faithful_fluxes(const qk_hydro_params *prm, const qk_array4 *U, bool zero_rk, cudaStream_t s);
 	int faithful_stage(const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
 			   int64_t *ncells_bad, cudaStream_t s);
 };
 
 void qk_plan_tags(const qk_level &L, int ng, std::vector<HostTag> &out);
+void qk_fused_free(qk_level *L);
+void qk_fused_untaint(qk_level *L);
 
 // ---- communicator (qk_comm.cpp): NCCL resolved at run time with dlopen, so the library loads on machines
 // without NCCL and never conflicts with the copy a host application (or torch) already loaded ----

@@ -1,9 +1,648 @@
-// qk_sweep.cu -- fused sweep path (placeholder until the tuned kernels land: reports "not handled").
+// qk_sweep.cu -- the FUSED stage of QuokkaSimulation::advanceHydroAtLevel (src/QuokkaSimulation.hpp:1099-1198,
+// 1202-1285): per RK stage
+//
+//   k_fprim    HydroSystem::ConservedToPrimitive (ng = 4)                                     hydro_system.hpp:138-196
+//   k_fchi     ComputeFlatteningCoefficients<X1,X2,X3> in ONE pass (ng = 2), sharing rho c_s^2  :531-626
+//   k_fchimin  the 9-point min of FlattenShocks, once per cell instead of once per direction    :655-669
+//   k_sweep_x  PPM -> flatten -> HLLC -> flux difference along x; lane <-> cell, neighbour states and fluxes
+//              exchanged with warp shuffles; nothing but 0.5*F (RK2 average) and the RHS is written
+//   k_sweep_m  the same along y / z by MARCHING: lane <-> x (coalesced), each thread walks a pencil segment and
+//              keeps the previous face's flux and the previous cell's right state in registers, so every PPM
+//              parabola and every Riemann problem is evaluated exactly once; the z sweep carries the epilogue
+//              (ComputeRhsFromFluxes sum, AddInternalEnergyPdV, PredictStep, redoFlag count, EnforceLimits,
+//              SyncDualEnergy) and writes the new state -- no rhs / flux / face-velocity MultiFabs exist.
+//
+// All local boxes go into one launch per kernel.  Arithmetic is the reference's (see qk_fast.cuh); the association
+// order of the three directional contributions is that of ComputeRhsFromFluxes (x, then +y, then +z) and of
+// AddInternalEnergyPdV's div v.  A stage whose result flags a cell (redoFlag) or contains a non-finite value is
+// REDONE by the faithful path of qk_level.cu, which owns the first-order flux correction.
+#include "qk_fast.cuh"
 #include "qk_level.h"
 
-int qk_fused_stage(qk_level *, const qk_hydro_params *, int, const qk_array4 *, const qk_array4 *, const qk_array4 *, double, int64_t *, cudaStream_t,
-		   bool *handled)
+#include <algorithm>
+#include <string.h>
+
+namespace
+{
+constexpr int SEG = 32; // cells per marching segment
+
+struct SweepBox {
+	A4 U0, Us, Uo; // state_old (ghost-filled), stage input (ghost-filled), stage output
+	A4 prim;       // 6+NS primitives + chi_min as the last component; same index space as the state (ng ghosts)
+	A4 chi3;       // chi_x, chi_y, chi_z (ng = 2)
+	A4 rhs;        // 6+NS RHS components + div v as the last component (valid cells)
+	A4 hF[3];      // per direction: 0.5*F(U0) (6+NS) + 0.5*faceVel(U0), nodal in that direction
+	int lo[3], hi[3];
+};
+
+__device__ __forceinline__ bool nonfinite(double v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u; }
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fprim(FastConst c, const SweepBox *__restrict__ boxes, int ng)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 1 + 2 * ng, ny = B.hi[1] - B.lo[1] + 1 + 2 * ng, nz = B.hi[2] - B.lo[2] + 1 + 2 * ng;
+	const int64_t total = (int64_t)nx * ny * nz;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - ng + (int)(t - jk * nx);
+		const int k = B.lo[2] - ng + (int)(jk / ny);
+		const int j = B.lo[1] - ng + (int)(jk - (jk / ny) * ny);
+		const int64_t o = B.Us.off(i, j, k), op = B.prim.off(i, j, k);
+		double U[6 + NS], q[6 + NS];
+#pragma unroll
+		for (int n = 0; n < 6 + NS; ++n)
+			U[n] = B.Us.p[o + n * B.Us.ns];
+		f_cons_to_prim<NS, REINT>(c, U, q);
+#pragma unroll
+		for (int n = 0; n < 6 + NS; ++n)
+			B.prim.p[op + n * B.prim.ns] = q[n];
+	}
+}
+
+// chi along the three directions of one cell; rho c_s^2 is evaluated once (the reference recomputes it per direction)
+template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi(FastConst c, const SweepBox *__restrict__ boxes)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 5, ny = B.hi[1] - B.lo[1] + 5, nz = B.hi[2] - B.lo[2] + 5;
+	const int64_t total = (int64_t)nx * ny * nz;
+	const A4 &q = B.prim;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - 2 + (int)(t - jk * nx);
+		const int k = B.lo[2] - 2 + (int)(jk / ny);
+		const int j = B.lo[1] - 2 + (int)(jk - (jk / ny) * ny);
+		const int64_t o = q.off(i, j, k);
+		const int64_t st[3] = {1, q.js, q.ks};
+		const double rho = q.p[o];
+		double P0 = q.p[o + 4 * q.ns];
+		if (REINT)
+			P0 = f_pressure_from_e(c, rho, (rho == 0.0) ? 0.0 : div_d(rho * P0, rho));
+		const double cs = f_sound_speed(c, rho, P0);
+		const QkRcp RKS = qk_rcp((cs * cs) * rho);
+		const int64_t oc = B.chi3.off(i, j, k);
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			double P[5];
+#pragma unroll
+			for (int m = -2; m <= 2; ++m) {
+				if (m == 0)
+					continue;
+				double v = q.p[o + m * st[d] + 4 * q.ns];
+				if (REINT) {
+					const double r = q.p[o + m * st[d]];
+					v = f_pressure_from_e(c, r, (r == 0.0) ? 0.0 : div_d(r * v, r));
+				}
+				P[m + 2] = v;
+			}
+			const double vm1 = q.p[o - st[d] + (1 + d) * q.ns], vp1 = q.p[o + st[d] + (1 + d) * q.ns];
+			B.chi3.p[oc + d * B.chi3.ns] = f_flatten_chi(c, P[0], P[1], P[3], P[4], RKS, vm1, vp1);
+		}
+	}
+}
+
+// min over chi_x(i-1,i,i+1), chi_y(j-1,j,j+1), chi_z(k-1,k,k+1) in the reference's order (hydro_system.hpp:655-669)
+template <int NS> __global__ void __launch_bounds__(256) k_fchimin(const SweepBox *__restrict__ boxes)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 3, ny = B.hi[1] - B.lo[1] + 3, nz = B.hi[2] - B.lo[2] + 3;
+	const int64_t total = (int64_t)nx * ny * nz;
+	const A4 &x = B.chi3;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - 1 + (int)(t - jk * nx);
+		const int k = B.lo[2] - 1 + (int)(jk / ny);
+		const int j = B.lo[1] - 1 + (int)(jk - (jk / ny) * ny);
+		const int64_t o = x.off(i, j, k);
+		double chi = x.p[o - 1];
+		chi = dmin(chi, x.p[o]);
+		chi = dmin(chi, x.p[o + 1]);
+		chi = dmin(chi, x.p[o - x.js + x.ns]);
+		chi = dmin(chi, x.p[o + x.ns]);
+		chi = dmin(chi, x.p[o + x.js + x.ns]);
+		chi = dmin(chi, x.p[o - x.ks + 2 * x.ns]);
+		chi = dmin(chi, x.p[o + 2 * x.ns]);
+		chi = dmin(chi, x.p[o + x.ks + 2 * x.ns]);
+		B.prim.p[B.prim.off(i, j, k) + (6 + NS) * B.prim.ns] = chi;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-cell pieces shared by the two sweep kernels
+// ---------------------------------------------------------------------------------------------------------------
+// transverse velocity-difference minima of one cell (hydro_system.hpp:1022-1033): mV = min(vV(+V)-vV, vV-vV(-V)), mW likewise
+template <int DIR> __device__ __forceinline__ void cell_trans_min(const A4 &q, int64_t o, double &mV, double &mW)
+{
+	constexpr int aV = (DIR + 1) % 3, aW = (DIR + 2) % 3;
+	const int64_t sV = (aV == 0) ? 1 : (aV == 1) ? q.js : q.ks;
+	const int64_t sW = (aW == 0) ? 1 : (aW == 1) ? q.js : q.ks;
+	const double *vV = q.p + o + (1 + aV) * q.ns;
+	const double *vW = q.p + o + (1 + aW) * q.ns;
+	const double v0 = vV[0], w0 = vW[0];
+	mV = dmin(vV[sV] - v0, v0 - vV[-sV]);
+	mW = dmin(vW[sW] - w0, w0 - vW[-sW]);
+}
+
+// stage epilogue of one cell: rhs (all three directions summed) -> new state (hydro_system.hpp:775-814, 475-497, 698-773, 816-850)
+template <int NS, int NMS>
+__device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *U0, double *r, double divv, double *Un, int &bad, int &nonfin)
+{
+	// AddInternalEnergyPdV: P from the OLD state; redoFlag is none on this path
+	const QkRcp Rr = qk_rcp(U0[0]);
+	const double vx = div_r(U0[1], Rr), vy = div_r(U0[2], Rr), vz = div_r(U0[3], Rr);
+	const double ke = 0.5 * U0[0] * (vx * vx + vy * vy + vz * vz);
+	const double Eint = U0[4] - ke;
+	const double P = f_pressure_from_e(c, U0[0], (U0[0] == 0.0) ? 0.0 : div_r(Eint, Rr));
+	r[5] = r[5] + (-P * divv);
+	// PredictStep
+#pragma unroll
+	for (int n = 0; n < 6 + NS; ++n)
+		Un[n] = U0[n] + c.dt * r[n];
+	bad = !(Un[0] > 0.);
+#pragma unroll
+	for (int n = 0; n < NMS; ++n)
+		if (Un[6 + n] < 0.0)
+			bad = 1;
+	nonfin = 0;
+#pragma unroll
+	for (int n = 0; n < 6 + NS; ++n)
+		nonfin |= nonfinite(Un[n]);
+	// EnforceLimits
+	const double rho = Un[0];
+	double rho_new = rho;
+	if (rho < c.h.dfloor) {
+		rho_new = c.h.dfloor;
+		Un[0] = rho_new;
+#pragma unroll
+		for (int n = 0; n < NS; ++n) {
+			if (rho_new == 0.0)
+				Un[6 + n] = 0.0;
+			else
+				Un[6 + n] *= rho / rho_new;
+		}
+	}
+	if (NMS > 0) {
+		double sp_sum = 0.0;
+#pragma unroll
+		for (int n = 0; n < NMS; ++n) {
+			if (Un[6 + n] < 0.0)
+				Un[6 + n] = c.h.small_x * rho_new;
+			sp_sum += Un[6 + n];
+		}
+		if ((sp_sum > 2.2250738585072014e-308) && (rho_new > 2.2250738585072014e-308)) {
+			sp_sum /= rho_new;
+#pragma unroll
+			for (int n = 0; n < NMS; ++n)
+				Un[6 + n] /= sp_sum;
+		}
+	}
+	// the temperature floors compare T >= small_temp > 0 (or NaN) with tempFloor: never taken unless tempFloor > 0
+	if (c.h.tfloor > 0. && rho_new > 2.2250738585072014e-308) {
+		const double v1 = Un[1] / rho_new, v2 = Un[2] / rho_new, v3 = Un[3] / rho_new;
+		const double Ekin = 0.5 * rho_new * (v1 * v1 + v2 * v2 + v3 * v3);
+		const double primTemp = eos_tgas_from_eint(c.h, rho_new, (Un[4] - Ekin));
+		if (primTemp < c.h.tfloor)
+			Un[4] = Ekin + eos_eint_from_tgas(c.h, rho_new, c.h.tfloor);
+		const double auxTemp = eos_tgas_from_eint(c.h, rho_new, Un[5]);
+		if (auxTemp < c.h.tfloor)
+			Un[5] = eos_eint_from_tgas(c.h, rho_new, c.h.tfloor);
+	}
+	// SyncDualEnergy (cells with rho <= 0 are flagged above and the stage is redone by the faithful path)
+	if (Un[0] > 0.) {
+		const double Ekin = div_d(Un[1] * Un[1] + Un[2] * Un[2] + Un[3] * Un[3], 2.0 * Un[0]);
+		const double Eint_cons = Un[4] - Ekin;
+		if (Eint_cons > 1.0e-3 * Un[4])
+			Un[5] = Eint_cons;
+		else
+			Un[4] = Un[5] + Ekin;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x sweep: one warp per 30 cells of a row (lane l <-> cell x0 - 1 + l)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+__global__ void __launch_bounds__(128) k_sweep_x(FastConst c, const SweepBox *__restrict__ boxes, int tiles_x, int rows_per_box_max)
+{
+	constexpr int NV = 6 + NS;
+	const SweepBox &B = boxes[blockIdx.z];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int row = blockIdx.y * 4 + warp;
+	if (row >= ny * nz)
+		return; // whole warp
+	const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+	const int x0 = B.lo[0] + blockIdx.x * 30;
+	if (x0 > B.hi[0])
+		return;
+	const int i = x0 - 1 + lane;
+	const bool cell_ok = (i <= B.hi[0] + 1); // cells lo-1 .. hi+1 carry a parabola
+	const int ic = cell_ok ? i : B.hi[0] + 1;
+	const A4 &q = B.prim;
+	const int64_t o = q.off(ic, j, k);
+
+	// PPM + flattening of the own cell, all variables
+	const double chi = q.p[o + NV * q.ns], omchi = 1. - chi;
+	double am[NV], ap[NV], q0v[NV];
+#pragma unroll
+	for (int n = 0; n < NV; ++n) {
+		const double *p = q.p + o + n * q.ns;
+		const double qm2 = p[-2], qm1 = p[-1], q0 = p[0], qp1 = p[1], qp2 = p[2];
+		q0v[n] = q0;
+		f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+	}
+	double mV, mW;
+	cell_trans_min<0>(q, o, mV, mW);
+
+	// face between lane-1 and lane: L = ap(lane-1), R = am(lane)
+	double Ls[NV];
+#pragma unroll
+	for (int n = 0; n < NV; ++n)
+		Ls[n] = shfl_up1(ap[n]);
+	const double mVl = shfl_up1(mV), mWl = shfl_up1(mW);
+	const double du = q0v[1] - shfl_up1(q0v[1]);
+	double dw = dmin(mVl, mV);
+	dw = dmin(dmin(mWl, mW), dw);
+	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
+	double G[NV + 1];
+	if (face_ok) {
+		double F[NV], vf;
+		f_hllc<0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
+		const A4 &h = B.hF[0];
+		const int64_t oh = h.off(i, j, k);
+		if (STAGE == 1) {
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				G[n] = F[n];
+			G[NV] = vf;
+			if (DUAL && (lane <= 30 || i == B.hi[0] + 1)) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					h.p[oh + n * h.ns] = 0.0 + 0.5 * F[n];
+				h.p[oh + NV * h.ns] = 0.0 + 0.5 * vf;
+			}
+		} else {
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				G[n] = h.p[oh + n * h.ns] + 0.5 * F[n];
+			G[NV] = h.p[oh + NV * h.ns] + 0.5 * vf;
+		}
+	} else {
+#pragma unroll
+		for (int n = 0; n <= NV; ++n)
+			G[n] = 0.0;
+	}
+	// cell update needs the flux of the next face (lane+1)
+	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
+	const A4 &r = B.rhs;
+	const int64_t orr = upd ? r.off(i, j, k) : 0;
+#pragma unroll
+	for (int n = 0; n < NV; ++n) {
+		const double Gn = shfl_dn1(G[n]);
+		if (upd)
+			r.p[orr + n * r.ns] = c.inv_dx[0] * (G[n] - Gn);
+	}
+	const double Vn = shfl_dn1(G[NV]);
+	if (upd)
+		r.p[orr + NV * r.ns] = div_c(Vn - G[NV], c.dx[0], c.y_dx[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y / z sweeps by marching; LAST carries the stage epilogue
+// ---------------------------------------------------------------------------------------------------------------
+template <int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
+__global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
+{
+	constexpr int NV = 6 + NS;
+	constexpr int TD = (DIR == 1) ? 2 : 1; // the transverse (non-x) axis a warp is pinned to
+	const int box = blockIdx.z / nseg, seg = blockIdx.z - box * nseg;
+	const SweepBox &B = boxes[box];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int i = B.lo[0] + blockIdx.x * 32 + lane;
+	const int t = B.lo[TD] + blockIdx.y * 4 + warp;
+	const int s0 = B.lo[DIR] + seg * SEG;
+	int bad_cnt = 0, nf_cnt = 0;
+	if (i <= B.hi[0] && t <= B.hi[TD] && s0 <= B.hi[DIR]) {
+		const int s1 = min(s0 + SEG, B.hi[DIR] + 1); // cells s0 .. s1-1 are updated, faces s0 .. s1 evaluated
+		const A4 &q = B.prim;
+		const int64_t sN = (DIR == 1) ? q.js : q.ks;
+		int idx[3];
+		idx[0] = i;
+		idx[TD] = t;
+		idx[DIR] = s0 - 1;
+		int64_t o = q.off(idx[0], idx[1], idx[2]);
+		const A4 &h = B.hF[DIR];
+		const int64_t shN = (DIR == 1) ? h.js : h.ks;
+		int64_t oh = h.off(idx[0], idx[1], idx[2]); // face index == cell index of the cell on its high side
+		const A4 &r = B.rhs;
+		const int64_t srN = (DIR == 1) ? r.js : r.ks;
+		int64_t orr = r.off(idx[0], idx[1], idx[2]);
+		const A4 &u0 = B.U0, &uo = B.Uo;
+		const int64_t suN = (DIR == 1) ? u0.js : u0.ks, soN = (DIR == 1) ? uo.js : uo.ks;
+		int64_t ou = u0.off(idx[0], idx[1], idx[2]), oo = uo.off(idx[0], idx[1], idx[2]);
+
+		double apL[NV], ifl[NV], Gp[NV + 1];
+		double mVp = 0, mWp = 0, vNp = 0;
+		// unlimited interface value at the low face of the first cell
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double *p = q.p + o + n * q.ns;
+			ifl[n] = ppm_iface(p[-2 * sN], p[-sN], p[0], p[sN]);
+		}
+		for (int s = s0 - 1; s <= s1; ++s) {
+			const double chi = q.p[o + NV * q.ns], omchi = 1. - chi;
+			double am[NV], ap[NV];
+			double vN0 = 0;
+#pragma unroll
+			for (int n = 0; n < NV; ++n) {
+				const double *p = q.p + o + n * q.ns;
+				const double qm1 = p[-sN], q0 = p[0], qp1 = p[sN], qp2 = p[2 * sN];
+				if (n == 1 + DIR)
+					vN0 = q0;
+				const double ifh = ppm_iface(qm1, q0, qp1, qp2);
+				f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
+				ifl[n] = ifh;
+			}
+			double mV, mW;
+			cell_trans_min<DIR>(q, o, mV, mW);
+			if (s >= s0) {
+				const double du = vN0 - vNp;
+				double dw = dmin(mVp, mV);
+				dw = dmin(dmin(mWp, mW), dw);
+				double F[NV], vf, G[NV + 1];
+				f_hllc<DIR, NS, NMS, REINT>(c, apL, am, du, dw, F, vf);
+				if (STAGE == 1) {
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						G[n] = F[n];
+					G[NV] = vf;
+					if (DUAL) {
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							h.p[oh + n * h.ns] = 0.0 + 0.5 * F[n];
+						h.p[oh + NV * h.ns] = 0.0 + 0.5 * vf;
+					}
+				} else {
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						G[n] = h.p[oh + n * h.ns] + 0.5 * F[n];
+					G[NV] = h.p[oh + NV * h.ns] + 0.5 * vf;
+				}
+				if (s > s0) { // cell s-1: both faces known
+					const int64_t orc = orr - srN;
+					double rr[NV];
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						rr[n] = r.p[orc + n * r.ns] + c.inv_dx[DIR] * (Gp[n] - G[n]);
+					const double divv = r.p[orc + NV * r.ns] + div_c(G[NV] - Gp[NV], c.dx[DIR], c.y_dx[DIR]);
+					if (!LAST) {
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							r.p[orc + n * r.ns] = rr[n];
+						r.p[orc + NV * r.ns] = divv;
+					} else {
+						double U0[NV], Un[NV];
+						const int64_t ouc = ou - suN;
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							U0[n] = u0.p[ouc + n * u0.ns];
+						int bad, nf;
+						cell_epilogue<NS, NMS>(c, U0, rr, divv, Un, bad, nf);
+						bad_cnt += bad;
+						nf_cnt += nf;
+						const int64_t ooc = oo - soN;
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							uo.p[ooc + n * uo.ns] = Un[n];
+					}
+				}
+#pragma unroll
+				for (int n = 0; n <= NV; ++n)
+					Gp[n] = G[n];
+			}
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				apL[n] = ap[n];
+			mVp = mV;
+			mWp = mW;
+			vNp = vN0;
+			o += sN;
+			oh += shN;
+			orr += srN;
+			ou += suN;
+			oo += soN;
+		}
+	}
+	if (LAST) {
+		// one atomic per block that saw a flagged / non-finite cell (none in a healthy run)
+		const int any = __syncthreads_or(bad_cnt | nf_cnt);
+		if (any) {
+			if (bad_cnt)
+				atomicAdd(counters, (unsigned long long)bad_cnt);
+			if (nf_cnt)
+				atomicAdd(counters + 1, (unsigned long long)nf_cnt);
+		}
+	}
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedState {
+	int nv = 0; // 6 + nscalars the scratch was built for
+	std::vector<qk_array4> prim, chi3, rhs, hF[3];
+	SweepBox *d_boxes = nullptr;
+	SweepBox *h_boxes = nullptr; // pinned staging, one table per in-flight stage (ring of 8)
+	int ring = 0;
+	cudaEvent_t ev[8];
+	bool ev_used[8];
+	bool tainted = false; // a previous stage left flagged cells in the state: stay on the faithful path
+};
+
+void qk_fused_free(qk_level *L)
+{
+	if (!L->fused)
+		return;
+	FusedState *F = L->fused;
+	if (F->d_boxes)
+		cudaFree(F->d_boxes);
+	if (F->h_boxes) {
+		cudaFreeHost(F->h_boxes);
+		for (int i = 0; i < 8; ++i)
+			cudaEventDestroy(F->ev[i]);
+	}
+	delete F;
+	L->fused = nullptr;
+}
+
+void qk_fused_untaint(qk_level *L)
+{
+	if (L->fused)
+		L->fused->tainted = false;
+}
+
+static int fused_setup(qk_level *L, int nv)
+{
+	if (L->fused && L->fused->nv == nv)
+		return 0;
+	if (L->fused)
+		return QK_ERR_UNSUPPORTED;
+	FusedState *F = new FusedState();
+	L->fused = F;
+	const int nb = (int)L->valid.size();
+	int rc = 0;
+	rc = rc ? rc : L->alloc_fabs(F->prim, nv + 1, L->nghost, -1);
+	rc = rc ? rc : L->alloc_fabs(F->chi3, 3, 2, -1);
+	rc = rc ? rc : L->alloc_fabs(F->rhs, nv + 1, 0, -1);
+	for (int d = 0; d < 3 && !rc; ++d)
+		rc = L->alloc_fabs(F->hF[d], nv + 1, 0, d);
+	if (rc)
+		return rc;
+	QK_CUDA(cudaMalloc(&F->d_boxes, sizeof(SweepBox) * nb * 8));
+	QK_CUDA(cudaMallocHost(&F->h_boxes, sizeof(SweepBox) * nb * 8));
+	for (int i = 0; i < 8; ++i) {
+		QK_CUDA(cudaEventCreateWithFlags(&F->ev[i], cudaEventDisableTiming));
+		F->ev_used[i] = false;
+	}
+	F->nv = nv;
+	return 0;
+}
+
+#define QK_TRY(x)                                                                                                                                    \
+	do {                                                                                                                                         \
+		int r_ = (x);                                                                                                                        \
+		if (r_ != 0)                                                                                                                         \
+			return r_;                                                                                                                   \
+	} while (0)
+
+template <int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], cudaStream_t s)
+{
+	const int ng = L->nghost;
+	{
+		ProfScope p("fused_prim", s);
+		const int64_t cells = (int64_t)(maxn[0] + 2 * ng) * (maxn[1] + 2 * ng) * (maxn[2] + 2 * ng);
+		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+		k_fprim<NS, REINT><<<grid, 256, 0, s>>>(c, d_tab, ng);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("fused_chi", s);
+		const int64_t cells = (int64_t)(maxn[0] + 4) * (maxn[1] + 4) * (maxn[2] + 4);
+		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+		k_fchi<NS, REINT><<<grid, 256, 0, s>>>(c, d_tab);
+		QK_KERNEL_CHECK();
+		k_fchimin<NS><<<grid, 256, 0, s>>>(d_tab);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_x", s);
+		const int tiles_x = (maxn[0] + 29) / 30;
+		const int rows = maxn[1] * maxn[2];
+		dim3 grid(tiles_x, (rows + 3) / 4, nb);
+		k_sweep_x<NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_y", s);
+		const int nseg = (maxn[1] + SEG - 1) / SEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[2] + 3) / 4, nb * nseg);
+		k_sweep_m<1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_z", s);
+		const int nseg = (maxn[2] + SEG - 1) / SEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
+		k_sweep_m<2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+template <int NS, int NMS, bool REINT> static int dispatch_stage(qk_level *L, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, cudaStream_t s)
+{
+	if (stage == 1)
+		return dual ? launch_stage<NS, NMS, REINT, 1, true>(L, c, t, nb, maxn, s) : launch_stage<NS, NMS, REINT, 1, false>(L, c, t, nb, maxn, s);
+	return launch_stage<NS, NMS, REINT, 2, true>(L, c, t, nb, maxn, s);
+}
+
+int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
+		   int64_t *ncells_bad, cudaStream_t s, bool *handled)
 {
 	*handled = false;
+	// configurations the fused kernels are instantiated for; anything else runs the faithful path
+	const int ns = prm->nscalars, nms = prm->nmscalars;
+	const bool inst = (ns == 0 && nms == 0) || (ns == 1 && nms == 0) || (ns == 3 && nms == 2);
+	if (prm->reconstruction_order != 3 || !inst || !prm->use_dual_energy || L->nghost < 4)
+		return 0;
+	if (L->fused && L->fused->tainted)
+		return 0;
+	FastConst c;
+	if (!make_fast_const(prm, L->dx, dt, &c))
+		return 0;
+	const int nv = 6 + ns;
+	QK_TRY(fused_setup(L, nv));
+	QK_TRY(L->ensure_counters());
+	FusedState *F = L->fused;
+	const int nb = (int)L->valid.size();
+	// box table through the pinned ring
+	const int slot = F->ring;
+	F->ring = (F->ring + 1) % 8;
+	if (F->ev_used[slot])
+		QK_CUDA(cudaEventSynchronize(F->ev[slot]));
+	SweepBox *hb = F->h_boxes + (size_t)slot * nb;
+	int maxn[3] = {1, 1, 1};
+	for (int b = 0; b < nb; ++b) {
+		SweepBox &B = hb[b];
+		B.U0 = A4(U0[b]);
+		B.Us = A4(Ustage[b]);
+		B.Uo = A4(Uout[b]);
+		B.prim = A4(F->prim[b]);
+		B.chi3 = A4(F->chi3[b]);
+		B.rhs = A4(F->rhs[b]);
+		for (int d = 0; d < 3; ++d) {
+			B.hF[d] = A4(F->hF[d][b]);
+			B.lo[d] = L->valid[b].lo[d];
+			B.hi[d] = L->valid[b].hi[d];
+			maxn[d] = std::max(maxn[d], B.hi[d] - B.lo[d] + 1);
+		}
+	}
+	SweepBox *db = F->d_boxes + (size_t)slot * nb;
+	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(SweepBox) * nb, cudaMemcpyHostToDevice, s));
+	QK_CUDA(cudaEventRecord(F->ev[slot], s));
+	F->ev_used[slot] = true;
+	QK_CUDA(cudaMemsetAsync(L->d_counters, 0, 16, s));
+
+	const bool dual = (prm->integrator_order == 2);
+	int rc;
+	if (ns == 0)
+		rc = prm->reconstruct_eint ? dispatch_stage<0, 0, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<0, 0, false>(L, c, db, nb, maxn, stage, dual, s);
+	else if (ns == 1)
+		rc = prm->reconstruct_eint ? dispatch_stage<1, 0, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<1, 0, false>(L, c, db, nb, maxn, stage, dual, s);
+	else
+		rc = prm->reconstruct_eint ? dispatch_stage<3, 2, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<3, 2, false>(L, c, db, nb, maxn, stage, dual, s);
+	QK_TRY(rc);
+	QK_CUDA(cudaMemcpyAsync(L->h_counters, L->d_counters, 16, cudaMemcpyDeviceToHost, s));
+	QK_CUDA(cudaStreamSynchronize(s));
+	int64_t flagged = (int64_t)(L->h_counters[0] + L->h_counters[1]);
+	QK_TRY(L->global_sum(&flagged, s));
+	if (flagged > 0) {
+		// redo the whole stage with the faithful path (FOFC lives there); it recomputes F(U0) itself in stage 2
+		L->scr.rk_valid = false;
+		int64_t bad = 0;
+		QK_TRY(L->faithful_stage(prm, stage, U0, Ustage, Uout, dt, &bad, s));
+		if (bad > 0)
+			F->tainted = true;
+		if (ncells_bad)
+			*ncells_bad = bad;
+	} else if (ncells_bad) {
+		*ncells_bad = 0;
+	}
+	*handled = true;
 	return 0;
 }

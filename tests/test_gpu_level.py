@@ -151,7 +151,7 @@ def run_stage_pair(lib, p, prm, st, dt, entry):
 
 
 @pytest.mark.parametrize("which", ["production", "faithful"])
-@pytest.mark.parametrize("case", ["reflect_multi", "periodic_scalars", "single_box", "eint"])
+@pytest.mark.parametrize("case", ["reflect_multi", "periodic_scalars", "mass_scalars", "single_box", "eint"])
 def test_advance_two_stages(lib, which, case):
     if case == "reflect_multi":
         p = GenericProblem((32, 32, 32), 16, (0, 0, 0), "reflect")
@@ -159,6 +159,9 @@ def test_advance_two_stages(lib, which, case):
     elif case == "periodic_scalars":
         p = GenericProblem((32, 16, 16), 16, (1, 1, 1), "periodic", nscalars=2, gamma=5.0 / 3.0)
         prm = p.params(nmscalars=0)
+    elif case == "mass_scalars":
+        p = GenericProblem((16, 32, 16), 16, (1, 0, 1), "reflect", nscalars=3, gamma=5.0 / 3.0)
+        prm = p.params(nmscalars=2, reconstruct_eint=1)
     elif case == "single_box":
         p = GenericProblem((24, 20, 12), 32, (0, 0, 0), "outflow")
         prm = p.params()
