@@ -263,7 +263,8 @@ def main_ours(args):
 
     if args.no_extras:  # profiling runs (ncu): kernels only
         if rank == 0:
-            print(json.dumps({"value": round(value, 2), "ms_per_step": round(ms_total / args.steps, 4), "gpu_launches": int(launches), "roofline": roof}))
+            print(json.dumps({"value": round(value, 2), "ms_per_step": round(ms_total / args.steps, 4), "gpu_launches": int(launches), "roofline": roof,
+                              "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}))
         sim.close()
         return 0
     # end to end through the C ABI from host buffers: upload, one step, download -- every step

@@ -37,6 +37,9 @@ struct SweepBox {
 
 __device__ __forceinline__ bool nonfinite(double v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u; }
 
+// ---- plain-`/` fallback for isolated quotients (taken when a fast quotient left its domain) ----
+__device__ __noinline__ double slow_div(double a, double b) { return a / b; }
+
 // ---------------------------------------------------------------------------------------------------------------
 template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fprim(FastConst c, const SweepBox *__restrict__ boxes, int ng)
 {
@@ -53,7 +56,10 @@ template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fprim(Fas
 #pragma unroll
 		for (int n = 0; n < 6 + NS; ++n)
 			U[n] = B.Us.p[o + n * B.Us.ns];
-		f_cons_to_prim<NS, REINT>(c, U, q);
+		unsigned slow = 0;
+		f_cons_to_prim<NS, REINT, true>(c, U, q, slow);
+		if (slow)
+			f_cons_to_prim<NS, REINT, false>(c, U, q, slow);
 #pragma unroll
 		for (int n = 0; n < 6 + NS; ++n)
 			B.prim.p[op + n * B.prim.ns] = q[n];
@@ -75,29 +81,53 @@ template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi(Fast
 		const int64_t o = q.off(i, j, k);
 		const int64_t st[3] = {1, q.js, q.ks};
 		const double rho = q.p[o];
-		double P0 = q.p[o + 4 * q.ns];
-		if (REINT)
-			P0 = f_pressure_from_e(c, rho, (rho == 0.0) ? 0.0 : div_d(rho * P0, rho));
-		const double cs = f_sound_speed(c, rho, P0);
-		const QkRcp RKS = qk_rcp((cs * cs) * rho);
-		const int64_t oc = B.chi3.off(i, j, k);
+		double Pc[3][5];
+		double vm1[3], vp1[3];
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
-			double P[5];
 #pragma unroll
-			for (int m = -2; m <= 2; ++m) {
-				if (m == 0)
-					continue;
-				double v = q.p[o + m * st[d] + 4 * q.ns];
-				if (REINT) {
-					const double r = q.p[o + m * st[d]];
-					v = f_pressure_from_e(c, r, (r == 0.0) ? 0.0 : div_d(r * v, r));
-				}
-				P[m + 2] = v;
-			}
-			const double vm1 = q.p[o - st[d] + (1 + d) * q.ns], vp1 = q.p[o + st[d] + (1 + d) * q.ns];
-			B.chi3.p[oc + d * B.chi3.ns] = f_flatten_chi(c, P[0], P[1], P[3], P[4], RKS, vm1, vp1);
+			for (int m = -2; m <= 2; ++m)
+				Pc[d][m + 2] = q.p[o + m * st[d] + 4 * q.ns];
+			vm1[d] = q.p[o - st[d] + (1 + d) * q.ns];
+			vp1[d] = q.p[o + st[d] + (1 + d) * q.ns];
 		}
+		unsigned slow = 0;
+		if (REINT) { // pressures from the specific internal energies (hydro_system.hpp:577-586)
+#pragma unroll
+			for (int d = 0; d < 3; ++d)
+#pragma unroll
+				for (int m = -2; m <= 2; ++m) {
+					if (d > 0 && m == 0) {
+						Pc[d][2] = Pc[0][2];
+						continue;
+					}
+					const double r = q.p[o + m * st[d]];
+					Pc[d][m + 2] = f_pressure_from_e<true>(c, r, (r == 0.0) ? 0.0 : div_d<true>(r * Pc[d][m + 2], r, slow), slow);
+				}
+		}
+		const double cs = f_sound_speed<true>(c, rho, Pc[0][2], slow);
+		const QkRcp RKS = rcp_f<true>((cs * cs) * rho, slow);
+		double chi[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d)
+			chi[d] = f_flatten_chi<true>(c, Pc[d][0], Pc[d][1], Pc[d][3], Pc[d][4], RKS, vm1[d], vp1[d], slow);
+		if (slow) { // plain-division fallback (qk_physics.cuh)
+			if (REINT) {
+				for (int d = 0; d < 3; ++d)
+					for (int m = -2; m <= 2; ++m) {
+						const double r = q.p[o + m * st[d]];
+						Pc[d][m + 2] = eos_pressure(c.h, r, r * q.p[o + m * st[d] + 4 * q.ns]);
+					}
+			}
+			const double cs2 = eos_sound_speed(c.h, rho, Pc[0][2]);
+			const double KS = (cs2 * cs2) * rho;
+			for (int d = 0; d < 3; ++d)
+				chi[d] = flatten_chi(Pc[d][0], Pc[d][1], Pc[d][3], Pc[d][4], KS, vm1[d], vp1[d]);
+		}
+		const int64_t oc = B.chi3.off(i, j, k);
+#pragma unroll
+		for (int d = 0; d < 3; ++d)
+			B.chi3.p[oc + d * B.chi3.ns] = chi[d];
 	}
 }
 
@@ -148,11 +178,14 @@ template <int NS, int NMS>
 __device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *U0, double *r, double divv, double *Un, int &bad, int &nonfin)
 {
 	// AddInternalEnergyPdV: P from the OLD state; redoFlag is none on this path
-	const QkRcp Rr = qk_rcp(U0[0]);
-	const double vx = div_r(U0[1], Rr), vy = div_r(U0[2], Rr), vz = div_r(U0[3], Rr);
+	unsigned slow = 0;
+	const QkRcp Rr = rcp_f<true>(U0[0], slow);
+	const double vx = div_r<true>(U0[1], Rr, slow), vy = div_r<true>(U0[2], Rr, slow), vz = div_r<true>(U0[3], Rr, slow);
 	const double ke = 0.5 * U0[0] * (vx * vx + vy * vy + vz * vz);
 	const double Eint = U0[4] - ke;
-	const double P = f_pressure_from_e(c, U0[0], (U0[0] == 0.0) ? 0.0 : div_r(Eint, Rr));
+	double P = f_pressure_from_e<true>(c, U0[0], (U0[0] == 0.0) ? 0.0 : div_r<true>(Eint, Rr, slow), slow);
+	if (slow)
+		P = cons_pressure(c.h, U0[0], U0[1], U0[2], U0[3], U0[4]);
 	r[5] = r[5] + (-P * divv);
 	// PredictStep
 #pragma unroll
@@ -209,7 +242,11 @@ __device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *
 	}
 	// SyncDualEnergy (cells with rho <= 0 are flagged above and the stage is redone by the faithful path)
 	if (Un[0] > 0.) {
-		const double Ekin = div_d(Un[1] * Un[1] + Un[2] * Un[2] + Un[3] * Un[3], 2.0 * Un[0]);
+		unsigned s2 = 0;
+		const double num = Un[1] * Un[1] + Un[2] * Un[2] + Un[3] * Un[3], den = 2.0 * Un[0];
+		double Ekin = div_d<true>(num, den, s2);
+		if (s2)
+			Ekin = slow_div(num, den);
 		const double Eint_cons = Un[4] - Ekin;
 		if (Eint_cons > 1.0e-3 * Un[4])
 			Un[5] = Eint_cons;
@@ -270,7 +307,10 @@ __global__ void __launch_bounds__(128) k_sweep_x(FastConst c, const SweepBox *__
 	double G[NV + 1];
 	if (face_ok) {
 		double F[NV], vf;
-		f_hllc<0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
+		unsigned slow = 0;
+		f_hllc<0, NS, NMS, REINT, true>(c, Ls, am, du, dw, F, vf, slow);
+		if (slow)
+			f_hllc<0, NS, NMS, REINT, false>(c, Ls, am, du, dw, F, vf, slow);
 		const A4 &h = B.hF[0];
 		const int64_t oh = h.off(i, j, k);
 		if (STAGE == 1) {
@@ -307,7 +347,13 @@ __global__ void __launch_bounds__(128) k_sweep_x(FastConst c, const SweepBox *__
 	}
 	const double Vn = shfl_dn1(G[NV]);
 	if (upd)
-		r.p[orr + NV * r.ns] = div_c(Vn - G[NV], c.dx[0], c.y_dx[0]);
+	{
+			unsigned s3 = 0;
+			double dv = div_c<true>(Vn - G[NV], c.dx[0], c.y_dx[0], s3);
+			if (s3)
+				dv = slow_div(Vn - G[NV], c.dx[0]);
+			r.p[orr + NV * r.ns] = dv;
+		}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -373,7 +419,10 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 				double dw = dmin(mVp, mV);
 				dw = dmin(dmin(mWp, mW), dw);
 				double F[NV], vf, G[NV + 1];
-				f_hllc<DIR, NS, NMS, REINT>(c, apL, am, du, dw, F, vf);
+				unsigned slow = 0;
+				f_hllc<DIR, NS, NMS, REINT, true>(c, apL, am, du, dw, F, vf, slow);
+				if (slow)
+					f_hllc<DIR, NS, NMS, REINT, false>(c, apL, am, du, dw, F, vf, slow);
 				if (STAGE == 1) {
 #pragma unroll
 					for (int n = 0; n < NV; ++n)
@@ -397,7 +446,11 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 #pragma unroll
 					for (int n = 0; n < NV; ++n)
 						rr[n] = r.p[orc + n * r.ns] + c.inv_dx[DIR] * (Gp[n] - G[n]);
-					const double divv = r.p[orc + NV * r.ns] + div_c(G[NV] - Gp[NV], c.dx[DIR], c.y_dx[DIR]);
+					unsigned s3 = 0;
+					double dv = div_c<true>(G[NV] - Gp[NV], c.dx[DIR], c.y_dx[DIR], s3);
+					if (s3)
+						dv = slow_div(G[NV] - Gp[NV], c.dx[DIR]);
+					const double divv = r.p[orc + NV * r.ns] + dv;
 					if (!LAST) {
 #pragma unroll
 						for (int n = 0; n < NV; ++n)
