@@ -767,18 +767,21 @@ static qk_box face_of(qk_box b, int d)
 	return b;
 }
 
-int qk_level::alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int face_dir)
+// pad_x: round the x pitch up to an even number of doubles so that every row starts 16-byte aligned (TMA bulk copies)
+int qk_level::alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int face_dir, bool pad_x)
 {
 	const int nb = (int)valid.size();
 	out.resize(nb);
 	size_t total = 0;
 	std::vector<size_t> off(nb);
+	auto pitch = [&](const qk_box &bx) { return pad_x ? (size_t)((blen(bx, 0) + 1) & ~1) : (size_t)blen(bx, 0); };
 	for (int b = 0; b < nb; ++b) {
 		qk_box bx = bgrow(face_dir >= 0 ? face_of(valid[b], face_dir) : valid[b], grow);
 		off[b] = total;
-		size_t n = (size_t)blen(bx, 0) * blen(bx, 1) * blen(bx, 2) * ncomp;
+		size_t n = pitch(bx) * blen(bx, 1) * blen(bx, 2) * ncomp;
 		total += (n + 31) & ~(size_t)31; // keep every FAB 256-byte aligned
 	}
+	total += 64; // slack: a bulk row copy may run a few elements past the last row
 	double *p = nullptr;
 	if (cudaMalloc(&p, total * sizeof(double)) != cudaSuccess) {
 		cudaGetLastError();
@@ -789,6 +792,11 @@ int qk_level::alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int f
 	for (int b = 0; b < nb; ++b) {
 		qk_box bx = bgrow(face_dir >= 0 ? face_of(valid[b], face_dir) : valid[b], grow);
 		out[b] = mk_desc(p + off[b], bx, ncomp);
+		if (pad_x) {
+			out[b].jstride = (int64_t)pitch(bx);
+			out[b].kstride = out[b].jstride * blen(bx, 1);
+			out[b].nstride = out[b].kstride * blen(bx, 2);
+		}
 	}
 	return 0;
 }

@@ -112,7 +112,7 @@ struct qk_level {
 	int fill_bc(const qk_exchange_plan &P, const A4 *tab, int scomp, int nc, cudaStream_t s);
 	int fill_boundary_tab(const A4 *tab, int scomp, int nc, cudaStream_t s);
 	int fill_redo_flags(cudaStream_t s);
-	int alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int face_dir);
+	int alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int face_dir, bool pad_x = false);
 	int ensure_counters();
 	int ensure_faithful_scratch(int nv);
 	int ensure_fo_scratch();

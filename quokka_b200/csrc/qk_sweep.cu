@@ -20,6 +20,7 @@
 #include "qk_level.h"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 namespace
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 		}
 	}
 }
+#include "qk_march.cuh"
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -548,11 +550,11 @@ static int fused_setup(qk_level *L, int nv)
 	L->fused = F;
 	const int nb = (int)L->valid.size();
 	int rc = 0;
-	rc = rc ? rc : L->alloc_fabs(F->prim, nv + 1, L->nghost, -1);
+	rc = rc ? rc : L->alloc_fabs(F->prim, nv + 1, L->nghost, -1, true);
 	rc = rc ? rc : L->alloc_fabs(F->chi3, 3, 2, -1);
-	rc = rc ? rc : L->alloc_fabs(F->rhs, nv + 1, 0, -1);
+	rc = rc ? rc : L->alloc_fabs(F->rhs, nv + 1, 0, -1, true);
 	for (int d = 0; d < 3 && !rc; ++d)
-		rc = L->alloc_fabs(F->hF[d], nv + 1, 0, d);
+		rc = L->alloc_fabs(F->hF[d], nv + 1, 0, d, true);
 	if (rc)
 		return rc;
 	QK_CUDA(cudaMalloc(&F->d_boxes, sizeof(SweepBox) * nb * 8));
@@ -573,7 +575,7 @@ static int fused_setup(qk_level *L, int nv)
 	} while (0)
 
 template <int NS, int NMS, bool REINT, int STAGE, bool DUAL>
-static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], cudaStream_t s)
+static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], bool tma, cudaStream_t s)
 {
 	const int ng = L->nghost;
 	{
@@ -604,24 +606,44 @@ static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, 
 		ProfScope p("sweep_y", s);
 		const int nseg = (maxn[1] + SEG - 1) / SEG;
 		dim3 grid((maxn[0] + 31) / 32, (maxn[2] + 3) / 4, nb * nseg);
-		k_sweep_m<1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		if (tma) {
+			auto kern = k_march_t<1, NS, NMS, REINT, STAGE, DUAL, false>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			kern<<<grid, 128, MarchSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
+		} else {
+			k_sweep_m<1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		}
 		QK_KERNEL_CHECK();
 	}
 	{
 		ProfScope p("sweep_z", s);
 		const int nseg = (maxn[2] + SEG - 1) / SEG;
 		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
-		k_sweep_m<2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		if (tma) {
+			auto kern = k_march_t<2, NS, NMS, REINT, STAGE, DUAL, true>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			kern<<<grid, 128, MarchSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
+		} else {
+			k_sweep_m<2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
+		}
 		QK_KERNEL_CHECK();
 	}
 	return 0;
 }
 
-template <int NS, int NMS, bool REINT> static int dispatch_stage(qk_level *L, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, cudaStream_t s)
+template <int NS, int NMS, bool REINT> static int dispatch_stage(qk_level *L, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma, cudaStream_t s)
 {
 	if (stage == 1)
-		return dual ? launch_stage<NS, NMS, REINT, 1, true>(L, c, t, nb, maxn, s) : launch_stage<NS, NMS, REINT, 1, false>(L, c, t, nb, maxn, s);
-	return launch_stage<NS, NMS, REINT, 2, true>(L, c, t, nb, maxn, s);
+		return dual ? launch_stage<NS, NMS, REINT, 1, true>(L, c, t, nb, maxn, tma, s) : launch_stage<NS, NMS, REINT, 1, false>(L, c, t, nb, maxn, tma, s);
+	return launch_stage<NS, NMS, REINT, 2, true>(L, c, t, nb, maxn, tma, s);
 }
 
 int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
@@ -650,7 +672,12 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		QK_CUDA(cudaEventSynchronize(F->ev[slot]));
 	SweepBox *hb = F->h_boxes + (size_t)slot * nb;
 	int maxn[3] = {1, 1, 1};
+	bool tma = (getenv("QK_NO_TMA") == nullptr);
+	auto rows16 = [](const qk_array4 &a, int lo0) {
+		return ((uintptr_t)a.p % 16 == 0) && (a.jstride % 2 == 0) && (a.kstride % 2 == 0) && (a.nstride % 2 == 0) && ((lo0 - a.begin[0]) % 2 == 0);
+	};
 	for (int b = 0; b < nb; ++b) {
+		tma = tma && rows16(U0[b], L->valid[b].lo[0]) && rows16(F->prim[b], L->valid[b].lo[0]);
 		SweepBox &B = hb[b];
 		B.U0 = A4(U0[b]);
 		B.Us = A4(Ustage[b]);
@@ -674,11 +701,11 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	const bool dual = (prm->integrator_order == 2);
 	int rc;
 	if (ns == 0)
-		rc = prm->reconstruct_eint ? dispatch_stage<0, 0, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<0, 0, false>(L, c, db, nb, maxn, stage, dual, s);
+		rc = prm->reconstruct_eint ? dispatch_stage<0, 0, true>(L, c, db, nb, maxn, stage, dual, tma, s) : dispatch_stage<0, 0, false>(L, c, db, nb, maxn, stage, dual, tma, s);
 	else if (ns == 1)
-		rc = prm->reconstruct_eint ? dispatch_stage<1, 0, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<1, 0, false>(L, c, db, nb, maxn, stage, dual, s);
+		rc = prm->reconstruct_eint ? dispatch_stage<1, 0, true>(L, c, db, nb, maxn, stage, dual, tma, s) : dispatch_stage<1, 0, false>(L, c, db, nb, maxn, stage, dual, tma, s);
 	else
-		rc = prm->reconstruct_eint ? dispatch_stage<3, 2, true>(L, c, db, nb, maxn, stage, dual, s) : dispatch_stage<3, 2, false>(L, c, db, nb, maxn, stage, dual, s);
+		rc = prm->reconstruct_eint ? dispatch_stage<3, 2, true>(L, c, db, nb, maxn, stage, dual, tma, s) : dispatch_stage<3, 2, false>(L, c, db, nb, maxn, stage, dual, tma, s);
 	QK_TRY(rc);
 	QK_CUDA(cudaMemcpyAsync(L->h_counters, L->d_counters, 16, cudaMemcpyDeviceToHost, s));
 	QK_CUDA(cudaStreamSynchronize(s));

@@ -1,0 +1,40 @@
+// qk_tma.cuh -- sm_100a async-copy primitives used by the staged sweep kernels: 1-D bulk copies by the TMA engine
+// (cp.async.bulk, SASS UBLKCP) completing on shared-memory mbarriers.  One elected lane of a warp arms the barrier
+// with the byte count and issues the copies; every lane of that warp waits on the barrier's phase parity.
+#pragma once
+#include <stdint.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "QK_WAIT_%=:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "@p bra QK_DONE_%=;\n"
+		     "bra QK_WAIT_%=;\n"
+		     "QK_DONE_%=:\n"
+		     "}\n" ::"r"(smem_u32(bar)),
+		     "r"(parity)
+		     : "memory");
+}
+
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+		     "r"(smem_u32(bar))
+		     : "memory");
+}
