@@ -37,7 +37,8 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 	using SM = MarchSmem<NV>;
 	constexpr int TD = (DIR == 1) ? 2 : 1;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform in the compiler's eyes
 	double *const prim_s = reinterpret_cast<double *>(smem_raw + (size_t)warp * SM::WARP_BYTES);
 	double *const trans_s = prim_s + SM::NR * SM::PR;
 	double *const aux_s = trans_s + 2 * SM::TR;
@@ -72,29 +73,35 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 		}
 		__syncwarp();
 
-		auto issue_prim = [&](int row) {
-			const int slot = (row - (s0 - 3)) % SM::NR;
+		// running source pointers (warp-uniform): row r+3 of prim, the transverse rows of r+1, face r / cell r-1 of the aux arrays
+		const int64_t sN = (DIR == 1) ? q.js : q.ks;
+		const int64_t sT = (DIR == 1) ? q.ks : q.js; // y sweep: V = z; z sweep: W = y
+		const int64_t shN = (DIR == 1) ? h.js : h.ks, srN = (DIR == 1) ? rh.js : rh.ks, soN = (DIR == 1) ? uo.js : uo.ks,
+			      suN = (DIR == 1) ? u0.js : u0.ks;
+		const double *src_q = q.p + off_row(q, s0 - 3);
+		const double *src_t = q.p + off_row(q, s0 - 1) + ((DIR == 1) ? 3 : 2) * q.ns; // vz | vy
+		const double *src_h = h.p + off_row(h, s0 - 1);
+		const double *src_r = rh.p + off_row(rh, s0 - 2);
+		const double *src_u = u0.p + off_row(u0, s0 - 2);
+
+		auto issue_prim = [&](int slot) { // copies the row at src_q
 			double *dst = prim_s + slot * SM::PR;
 			uint64_t *bar = &bars[slot];
-			const double *src = q.p + off_row(q, row);
 			mbar_arrive_expect_tx(bar, (unsigned)NV * rowb + wideb);
 #pragma unroll
 			for (int n = 0; n <= NV; ++n) {
 				if (n == 1)
 					continue;
-				bulk_g2s(dst + n * 32, src + n * q.ns, rowb, bar);
+				bulk_g2s(dst + n * 32, src_q + n * q.ns, rowb, bar);
 			}
-			bulk_g2s(dst + SM::WIDE, src - 2 + q.ns, wideb, bar);
+			bulk_g2s(dst + SM::WIDE, src_q - 2 + q.ns, wideb, bar);
 		};
-		auto issue_trans = [&](int row) {
-			const int slot = (row - (s0 - 1)) & 1;
+		auto issue_trans = [&](int slot) { // the two transverse rows at src_t
 			double *dst = trans_s + slot * SM::TR;
 			uint64_t *bar = &bars[5 + slot];
-			const int64_t sT = (DIR == 1) ? q.ks : q.js;	      // y sweep: V = z; z sweep: W = y
-			const double *src = q.p + off_row(q, row) + ((DIR == 1) ? 3 : 2) * q.ns; // vz | vy
 			mbar_arrive_expect_tx(bar, 2u * rowb);
-			bulk_g2s(dst, src - sT, rowb, bar);
-			bulk_g2s(dst + 32, src + sT, rowb, bar);
+			bulk_g2s(dst, src_t - sT, rowb, bar);
+			bulk_g2s(dst + 32, src_t + sT, rowb, bar);
 		};
 		// what the end of step r reads: hF of face r (stage 2), rhs (+U0) of cell r-1
 		auto aux_bytes = [&](int r) -> unsigned {
@@ -107,39 +114,37 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			}
 			return b;
 		};
-		auto issue_aux = [&](int r) {
+		auto issue_aux = [&](int r) { // src_h at face r, src_r / src_u at cell r-1
 			uint64_t *bar = &bars[7];
 			mbar_arrive_expect_tx(bar, aux_bytes(r));
 			if (STAGE == 2) {
-				const double *src = h.p + off_row(h, r);
 #pragma unroll
 				for (int n = 0; n <= NV; ++n)
-					bulk_g2s(aux_s + SM::AUX_HF + n * 32, src + n * h.ns, rowb, bar);
+					bulk_g2s(aux_s + SM::AUX_HF + n * 32, src_h + n * h.ns, rowb, bar);
 			}
 			if (r > s0) {
-				const double *src = rh.p + off_row(rh, r - 1);
 #pragma unroll
 				for (int n = 0; n <= NV; ++n)
-					bulk_g2s(aux_s + SM::AUX_RHS + n * 32, src + n * rh.ns, rowb, bar);
+					bulk_g2s(aux_s + SM::AUX_RHS + n * 32, src_r + n * rh.ns, rowb, bar);
 				if (LAST) {
-					const double *su = u0.p + off_row(u0, r - 1);
 #pragma unroll
 					for (int n = 0; n < NV; ++n)
-						bulk_g2s(aux_s + SM::AUX_U0 + n * 32, su + n * u0.ns, rowb, bar);
+						bulk_g2s(aux_s + SM::AUX_U0 + n * 32, src_u + n * u0.ns, rowb, bar);
 				}
 			}
 		};
-		// value of component n (n = NV: chi) of the cell (lane, row)
-		auto P = [&](int row, int n) -> double {
-			const double *sl = prim_s + ((row - (s0 - 3)) % SM::NR) * SM::PR;
-			return (n == 1) ? sl[SM::WIDE + lane + 2] : sl[n * 32 + lane];
-		};
+		// component n (n = NV: chi) of this lane's cell in a prim slot
+		auto PV = [&](const double *sl, int n) -> double { return (n == 1) ? sl[SM::WIDE + lane + 2] : sl[n * 32 + lane]; };
 
-		if (lane == 0) {
-			for (int row = s0 - 3; row <= s0 + 1; ++row)
-				issue_prim(row);
-			issue_trans(s0 - 1);
+		// prologue: rows s0-3 .. s0+1 into slots 0 .. 4, transverse rows of cell s0-1 into trans slot 0
+		for (int sl = 0; sl < SM::NR; ++sl) {
+			if (lane == 0)
+				issue_prim(sl);
+			src_q += sN;
 		}
+		if (lane == 0)
+			issue_trans(0);
+		src_t += sN;
 		// rows s0-3 .. s0 -> unlimited interface value at the low face of cell s0-1
 #pragma unroll
 		for (int b = 0; b < 4; ++b)
@@ -149,36 +154,45 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 		if (active) {
 #pragma unroll
 			for (int n = 0; n < NV; ++n)
-				ifl[n] = ppm_iface(P(s0 - 3, n), P(s0 - 2, n), P(s0 - 1, n), P(s0, n));
+				ifl[n] = ppm_iface(PV(prim_s, n), PV(prim_s + SM::PR, n), PV(prim_s + 2 * SM::PR, n), PV(prim_s + 3 * SM::PR, n));
 		}
 		unsigned aux_phase = 0;
 		int64_t o_h = h.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_r = rh.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_o = uo.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
-		const int64_t shN = (DIR == 1) ? h.js : h.ks, srN = (DIR == 1) ? rh.js : rh.ks, soN = (DIR == 1) ? uo.js : uo.ks;
+		// slot of row r+2 (the newest row a step reads) and its phase parity; rows r+1, r, r-1 sit in the slots before it
+		int k5 = 4;
+		unsigned par5 = 0, tslot = 0, tpar = 0;
 
 		for (int r = s0 - 1; r <= s1; ++r) {
 			__syncwarp(); // every lane is done with the slots about to be refilled
 			const bool have_aux = aux_bytes(r) != 0;
+			const int kfree = (k5 == 4) ? 0 : k5 + 1; // held row r-2: free now
 			if (lane == 0) {
 				if (r + 3 <= s1 + 2)
-					issue_prim(r + 3);
+					issue_prim(kfree);
 				if (r + 1 <= s1)
-					issue_trans(r + 1);
+					issue_trans((int)(tslot ^ 1u));
 				if (have_aux)
 					issue_aux(r);
 			}
-			{ // row r+2 is the newest one this step reads
-				const int k = r + 2 - (s0 - 3);
-				mbar_wait(&bars[k % SM::NR], (unsigned)(k / SM::NR) & 1u);
-			}
+			src_q += sN;
+			src_t += sN;
+			src_h += shN;
+			src_r += srN;
+			src_u += suN;
+			const double *s_p2 = prim_s + k5 * SM::PR;
+			const double *s_p1 = prim_s + ((k5 >= 1) ? k5 - 1 : k5 + 4) * SM::PR;
+			const double *s_0 = prim_s + ((k5 >= 2) ? k5 - 2 : k5 + 3) * SM::PR;
+			const double *s_m1 = prim_s + ((k5 >= 3) ? k5 - 3 : k5 + 2) * SM::PR;
+			mbar_wait(&bars[k5], par5);
 			double am[NV], ap[NV];
 			double vN0 = 0, mV = 0, mW = 0;
 			if (active) {
-				const double chi = P(r, NV), omchi = 1. - chi;
+				const double chi = s_0[NV * 32 + lane], omchi = 1. - chi;
 #pragma unroll
 				for (int n = 0; n < NV; ++n) {
-					const double qm1 = P(r - 1, n), q0 = P(r, n), qp1 = P(r + 1, n), qp2 = P(r + 2, n);
+					const double qm1 = PV(s_m1, n), q0 = PV(s_0, n), qp1 = PV(s_p1, n), qp2 = PV(s_p2, n);
 					if (n == 1 + DIR)
 						vN0 = q0;
 					const double ifh = ppm_iface(qm1, q0, qp1, qp2);
@@ -186,16 +200,12 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 					ifl[n] = ifh;
 				}
 			}
-			{
-				const int k = r - (s0 - 1);
-				mbar_wait(&bars[5 + (k & 1)], (unsigned)(k >> 1) & 1u);
-			}
+			mbar_wait(&bars[5 + tslot], tpar);
 			if (active) { // transverse velocity-difference minima of cell r (hydro_system.hpp:1022-1033)
-				const double *sl = prim_s + ((r - (s0 - 3)) % SM::NR) * SM::PR;
-				const double *tr = trans_s + ((r - (s0 - 1)) & 1) * SM::TR;
-				const double x0 = sl[SM::WIDE + lane + 2], xm = sl[SM::WIDE + lane + 1], xp = sl[SM::WIDE + lane + 3];
+				const double *tr = trans_s + tslot * SM::TR;
+				const double x0 = s_0[SM::WIDE + lane + 2], xm = s_0[SM::WIDE + lane + 1], xp = s_0[SM::WIDE + lane + 3];
 				const double mx = dmin(xp - x0, x0 - xm); // along x
-				const double t0 = sl[((DIR == 1) ? 3 : 2) * 32 + lane];
+				const double t0 = s_0[((DIR == 1) ? 3 : 2) * 32 + lane];
 				const double mt = dmin(tr[32 + lane] - t0, t0 - tr[lane]); // along the other transverse axis
 				if (DIR == 1) { // V = z, W = x
 					mV = mt;
@@ -284,6 +294,15 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			o_h += shN;
 			o_r += srN;
 			o_o += soN;
+			// rotate the rings
+			if (k5 == 4) {
+				k5 = 0;
+				par5 ^= 1u;
+			} else {
+				++k5;
+			}
+			tpar ^= tslot; // the parity of a trans slot flips every second step
+			tslot ^= 1u;
 		}
 	}
 	if (LAST) {
@@ -293,6 +312,158 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 				atomicAdd(counters, (unsigned long long)bad_cnt);
 			if (nf_cnt)
 				atomicAdd(counters + 1, (unsigned long long)nf_cnt);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x sweep with TMA-staged rows: one warp owns a 30-cell tile in x (lane l <-> cell x0-1+l, parabola for every lane,
+// flux for lanes 1..31, update for lanes 1..30; neighbour states and fluxes by warp shuffle, as in k_sweep_x) and
+// walks XROWS consecutive rows; the rows of row m+1 are bulk-copied into the other stage while row m is computed.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int XROWS = 8;
+template <int NV> struct XSmem {
+	static constexpr int PW = 38;			    // cells x0-4 .. x0+33 of every component (+ chi)
+	static constexpr int PRIM = (NV + 1) * PW;	    // 16-byte multiple for every NV
+	static constexpr int TW = 34;			    // cells x0-2 .. x0+31 of the transverse velocity rows
+	static constexpr int TRANS = 4 * TW;		    // vy(j-1), vy(j+1), vz(k-1), vz(k+1)
+	static constexpr int AUX = (NV + 1) * 32;	    // 0.5 F(U0) at faces x0 .. x0+31 (stage 2)
+	static constexpr int STAGE_DOUBLES = PRIM + TRANS + AUX;
+	static constexpr int WARP_BYTES = 2 * STAGE_DOUBLES * 8 + 16; // two stages + two mbarriers
+	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
+};
+
+template <int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+__global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
+{
+	constexpr int NV = 6 + NS;
+	using SM = XSmem<NV>;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+	double *const st0 = reinterpret_cast<double *>(smem_raw + (size_t)warp * SM::WARP_BYTES);
+	uint64_t *const bars = reinterpret_cast<uint64_t *>(st0 + 2 * SM::STAGE_DOUBLES);
+	const SweepBox &B = boxes[blockIdx.z];
+	const int ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int nrows = ny * nz;
+	const int row0 = (blockIdx.y * 4 + warp) * XROWS;
+	const int x0 = B.lo[0] + blockIdx.x * 30;
+	if (row0 >= nrows || x0 > B.hi[0])
+		return; // whole warp
+	const int rows = min(XROWS, nrows - row0);
+	const int i = x0 - 1 + lane;
+	const A4 &q = B.prim;
+	const A4 &h = B.hF[0];
+	const A4 &r = B.rhs;
+	if (lane == 0) {
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		mbar_init_fence();
+	}
+	__syncwarp();
+	constexpr unsigned PB = SM::PW * 8, TB = SM::TW * 8, AB = 32 * 8;
+	auto issue = [&](int m) { // stage row row0+m
+		const int row = row0 + m;
+		const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+		double *dst = st0 + (m & 1) * SM::STAGE_DOUBLES;
+		uint64_t *bar = &bars[m & 1];
+		mbar_arrive_expect_tx(bar, (unsigned)(NV + 1) * PB + 4u * TB + ((STAGE == 2) ? (unsigned)(NV + 1) * AB : 0u));
+		const double *src = q.p + q.off(x0 - 4, j, k);
+#pragma unroll
+		for (int n = 0; n <= NV; ++n)
+			bulk_g2s(dst + n * SM::PW, src + n * q.ns, PB, bar);
+		const double *sy = src + 2 + 2 * q.ns, *sz = src + 2 + 3 * q.ns; // vy, vz rows starting at x0-2
+		bulk_g2s(dst + SM::PRIM, sy - q.js, TB, bar);
+		bulk_g2s(dst + SM::PRIM + SM::TW, sy + q.js, TB, bar);
+		bulk_g2s(dst + SM::PRIM + 2 * SM::TW, sz - q.ks, TB, bar);
+		bulk_g2s(dst + SM::PRIM + 3 * SM::TW, sz + q.ks, TB, bar);
+		if (STAGE == 2) {
+			const double *sh = h.p + h.off(x0, j, k);
+#pragma unroll
+			for (int n = 0; n <= NV; ++n)
+				bulk_g2s(dst + SM::PRIM + SM::TRANS + n * 32, sh + n * h.ns, AB, bar);
+		}
+	};
+	if (lane == 0)
+		issue(0);
+	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
+	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
+	for (int m = 0; m < rows; ++m) {
+		__syncwarp();
+		if (lane == 0 && m + 1 < rows)
+			issue(m + 1);
+		const double *sp = st0 + (m & 1) * SM::STAGE_DOUBLES;
+		mbar_wait(&bars[m & 1], (unsigned)(m >> 1) & 1u);
+		const int row = row0 + m;
+		const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+		// PPM + flattening of the own cell (x0-1+lane sits at index lane+3 of a prim row)
+		const double chi = sp[NV * SM::PW + lane + 3], omchi = 1. - chi;
+		double am[NV], ap[NV], q0v1 = 0;
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double *p = sp + n * SM::PW + lane + 3;
+			const double qm2 = p[-2], qm1 = p[-1], q0 = p[0], qp1 = p[1], qp2 = p[2];
+			if (n == 1)
+				q0v1 = q0;
+			f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+		}
+		// transverse minima: V = y, W = z (cell x0-1+lane sits at index lane+1 of a transverse row)
+		const double *tr = sp + SM::PRIM;
+		const double vy0 = sp[2 * SM::PW + lane + 3], vz0 = sp[3 * SM::PW + lane + 3];
+		const double mV = dmin(tr[SM::TW + lane + 1] - vy0, vy0 - tr[lane + 1]);
+		const double mW = dmin(tr[3 * SM::TW + lane + 1] - vz0, vz0 - tr[2 * SM::TW + lane + 1]);
+		double Ls[NV];
+#pragma unroll
+		for (int n = 0; n < NV; ++n)
+			Ls[n] = shfl_up1(ap[n]);
+		const double mVl = shfl_up1(mV), mWl = shfl_up1(mW);
+		const double du = q0v1 - shfl_up1(q0v1);
+		double dw = dmin(mVl, mV);
+		dw = dmin(dmin(mWl, mW), dw);
+		double G[NV + 1];
+		if (face_ok) {
+			double F[NV], vf;
+			unsigned slow = 0;
+			f_hllc<0, NS, NMS, REINT, true>(c, Ls, am, du, dw, F, vf, slow);
+			if (slow)
+				f_hllc<0, NS, NMS, REINT, false>(c, Ls, am, du, dw, F, vf, slow);
+			if (STAGE == 1) {
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					G[n] = F[n];
+				G[NV] = vf;
+				if (DUAL && (lane <= 30 || i == B.hi[0] + 1)) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
+					const int64_t oh = h.off(i, j, k);
+#pragma unroll
+					for (int n = 0; n <= NV; ++n)
+						h.p[oh + n * h.ns] = 0.0 + 0.5 * G[n];
+				}
+			} else {
+				const double *ax = sp + SM::PRIM + SM::TRANS + lane - 1; // face i = x0-1+lane sits at index lane-1
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					G[n] = ax[n * 32] + 0.5 * F[n];
+				G[NV] = ax[NV * 32] + 0.5 * vf;
+			}
+		} else {
+#pragma unroll
+			for (int n = 0; n <= NV; ++n)
+				G[n] = 0.0;
+		}
+		const int64_t orr = upd ? r.off(i, j, k) : 0;
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double Gn = shfl_dn1(G[n]);
+			if (upd)
+				r.p[orr + n * r.ns] = c.inv_dx[0] * (G[n] - Gn);
+		}
+		const double Vn = shfl_dn1(G[NV]);
+		if (upd) {
+			unsigned s3 = 0;
+			double dv = div_c<true>(Vn - G[NV], c.dx[0], c.y_dx[0], s3);
+			if (s3)
+				dv = slow_div(Vn - G[NV], c.dx[0]);
+			r.p[orr + NV * r.ns] = dv;
 		}
 	}
 }

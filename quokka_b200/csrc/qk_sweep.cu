@@ -598,8 +598,19 @@ static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, 
 		ProfScope p("sweep_x", s);
 		const int tiles_x = (maxn[0] + 29) / 30;
 		const int rows = maxn[1] * maxn[2];
-		dim3 grid(tiles_x, (rows + 3) / 4, nb);
-		k_sweep_x<NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
+		if (tma) {
+			auto kern = k_sweep_xt<NS, NMS, REINT, STAGE, DUAL>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
+			kern<<<grid, 128, XSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab);
+		} else {
+			dim3 grid(tiles_x, (rows + 3) / 4, nb);
+			k_sweep_x<NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
+		}
 		QK_KERNEL_CHECK();
 	}
 	{
