@@ -18,31 +18,33 @@
 #pragma once
 #include "qk_tma.cuh"
 
-template <int NV> struct MarchSmem {
-	static constexpr int NR = 5;
+template <int NV, int STAGE, bool LAST> struct MarchSmem {
+	static constexpr int NR = 4;
 	static constexpr int PR = (NV + 1) * 32 + 36; // rows n*32 for n = 0..NV (n = NV: chi; n = 1 unused) + wide vx row
 	static constexpr int WIDE = (NV + 1) * 32;
 	static constexpr int TR = 64;
-	static constexpr int AUX_HF = 0, AUX_RHS = (NV + 1) * 32, AUX_U0 = 2 * (NV + 1) * 32;
-	static constexpr int AUX = 2 * (NV + 1) * 32 + NV * 32;
-	static constexpr int WARP_DOUBLES = NR * PR + 2 * TR + AUX;
-	static constexpr int WARP_BYTES = WARP_DOUBLES * 8 + 64; // + 8 mbarriers
+	static constexpr int AUX_HF = 0;
+	static constexpr int AUX_RHS = (STAGE == 2) ? (NV + 1) * 32 : 0;
+	static constexpr int AUX_U0 = AUX_RHS + (NV + 1) * 32;
+	static constexpr int AUX = AUX_U0 + (LAST ? NV * 32 : 0);
+	static constexpr int WARP_DOUBLES = NR * PR + TR + AUX;
+	static constexpr int WARP_BYTES = WARP_DOUBLES * 8 + 64; // + mbarriers: [0..3] prim, [4] trans, [5] aux
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
 template <int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
-__global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
+__global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
-	using SM = MarchSmem<NV>;
+	using SM = MarchSmem<NV, STAGE, LAST>;
 	constexpr int TD = (DIR == 1) ? 2 : 1;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); // warp-uniform in the compiler's eyes
 	double *const prim_s = reinterpret_cast<double *>(smem_raw + (size_t)warp * SM::WARP_BYTES);
 	double *const trans_s = prim_s + SM::NR * SM::PR;
-	double *const aux_s = trans_s + 2 * SM::TR;
-	uint64_t *const bars = reinterpret_cast<uint64_t *>(aux_s + SM::AUX); // [0..4] prim, [5..6] trans, [7] aux
+	double *const aux_s = trans_s + SM::TR;
+	uint64_t *const bars = reinterpret_cast<uint64_t *>(aux_s + SM::AUX); // [0..3] prim, [4] trans, [5] aux
 
 	const int box = blockIdx.z / nseg, seg = blockIdx.z - box * nseg;
 	const SweepBox &B = boxes[box];
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 		};
 		if (lane == 0) {
 #pragma unroll
-			for (int b = 0; b < 8; ++b)
+			for (int b = 0; b < 6; ++b)
 				mbar_init(&bars[b], 1);
 			mbar_init_fence();
 		}
@@ -96,9 +98,9 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			}
 			bulk_g2s(dst + SM::WIDE, src_q - 2 + q.ns, wideb, bar);
 		};
-		auto issue_trans = [&](int slot) { // the two transverse rows at src_t
-			double *dst = trans_s + slot * SM::TR;
-			uint64_t *bar = &bars[5 + slot];
+		auto issue_trans = [&]() { // the two transverse rows at src_t
+			double *dst = trans_s;
+			uint64_t *bar = &bars[4];
 			mbar_arrive_expect_tx(bar, 2u * rowb);
 			bulk_g2s(dst, src_t - sT, rowb, bar);
 			bulk_g2s(dst + 32, src_t + sT, rowb, bar);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			return b;
 		};
 		auto issue_aux = [&](int r) { // src_h at face r, src_r / src_u at cell r-1
-			uint64_t *bar = &bars[7];
+			uint64_t *bar = &bars[5];
 			mbar_arrive_expect_tx(bar, aux_bytes(r));
 			if (STAGE == 2) {
 #pragma unroll
@@ -136,14 +138,14 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 		// component n (n = NV: chi) of this lane's cell in a prim slot
 		auto PV = [&](const double *sl, int n) -> double { return (n == 1) ? sl[SM::WIDE + lane + 2] : sl[n * 32 + lane]; };
 
-		// prologue: rows s0-3 .. s0+1 into slots 0 .. 4, transverse rows of cell s0-1 into trans slot 0
+		// prologue: rows s0-3 .. s0 into slots 0 .. 3, transverse rows of cell s0-1
 		for (int sl = 0; sl < SM::NR; ++sl) {
 			if (lane == 0)
 				issue_prim(sl);
 			src_q += sN;
 		}
 		if (lane == 0)
-			issue_trans(0);
+			issue_trans();
 		src_t += sN;
 		// rows s0-3 .. s0 -> unlimited interface value at the low face of cell s0-1
 #pragma unroll
@@ -156,36 +158,31 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			for (int n = 0; n < NV; ++n)
 				ifl[n] = ppm_iface(PV(prim_s, n), PV(prim_s + SM::PR, n), PV(prim_s + 2 * SM::PR, n), PV(prim_s + 3 * SM::PR, n));
 		}
+		__syncwarp();
+		if (lane == 0)
+			issue_prim(0); // row s0+1 replaces row s0-3
+		src_q += sN;
 		unsigned aux_phase = 0;
 		int64_t o_h = h.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_r = rh.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_o = uo.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
-		// slot of row r+2 (the newest row a step reads) and its phase parity; rows r+1, r, r-1 sit in the slots before it
-		int k5 = 4;
-		unsigned par5 = 0, tslot = 0, tpar = 0;
+		// k4: slot of row r+2 (the newest row a step reads), par4 its phase parity; rows r+1, r, r-1 sit in the slots before it
+		int k4 = 0;
+		unsigned par4 = 1, tpar = 0;
 
 		for (int r = s0 - 1; r <= s1; ++r) {
-			__syncwarp(); // every lane is done with the slots about to be refilled
+			__syncwarp(); // the aux slot is free again
 			const bool have_aux = aux_bytes(r) != 0;
-			const int kfree = (k5 == 4) ? 0 : k5 + 1; // held row r-2: free now
-			if (lane == 0) {
-				if (r + 3 <= s1 + 2)
-					issue_prim(kfree);
-				if (r + 1 <= s1)
-					issue_trans((int)(tslot ^ 1u));
-				if (have_aux)
-					issue_aux(r);
-			}
-			src_q += sN;
-			src_t += sN;
+			if (lane == 0 && have_aux)
+				issue_aux(r);
 			src_h += shN;
 			src_r += srN;
 			src_u += suN;
-			const double *s_p2 = prim_s + k5 * SM::PR;
-			const double *s_p1 = prim_s + ((k5 >= 1) ? k5 - 1 : k5 + 4) * SM::PR;
-			const double *s_0 = prim_s + ((k5 >= 2) ? k5 - 2 : k5 + 3) * SM::PR;
-			const double *s_m1 = prim_s + ((k5 >= 3) ? k5 - 3 : k5 + 2) * SM::PR;
-			mbar_wait(&bars[k5], par5);
+			const double *s_p2 = prim_s + k4 * SM::PR;
+			const double *s_p1 = prim_s + ((k4 + 3) & 3) * SM::PR;
+			const double *s_0 = prim_s + ((k4 + 2) & 3) * SM::PR;
+			const double *s_m1 = prim_s + ((k4 + 1) & 3) * SM::PR;
+			mbar_wait(&bars[k4], par4);
 			double am[NV], ap[NV];
 			double vN0 = 0, mV = 0, mW = 0;
 			if (active) {
@@ -200,9 +197,9 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 					ifl[n] = ifh;
 				}
 			}
-			mbar_wait(&bars[5 + tslot], tpar);
+			mbar_wait(&bars[4], tpar);
 			if (active) { // transverse velocity-difference minima of cell r (hydro_system.hpp:1022-1033)
-				const double *tr = trans_s + tslot * SM::TR;
+				const double *tr = trans_s;
 				const double x0 = s_0[SM::WIDE + lane + 2], xm = s_0[SM::WIDE + lane + 1], xp = s_0[SM::WIDE + lane + 3];
 				const double mx = dmin(xp - x0, x0 - xm); // along x
 				const double t0 = s_0[((DIR == 1) ? 3 : 2) * 32 + lane];
@@ -215,6 +212,15 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 					mW = mt;
 				}
 			}
+			__syncwarp(); // row r-1 and the transverse rows have been consumed by every lane: refill them for step r+1
+			if (lane == 0) {
+				if (r + 3 <= s1 + 2)
+					issue_prim((k4 + 1) & 3);
+				if (r + 1 <= s1)
+					issue_trans();
+			}
+			src_q += sN;
+			src_t += sN;
 			if (r >= s0) {
 				double G[NV + 1];
 				if (active) {
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 					G[NV] = vf;
 				}
 				if (have_aux) {
-					mbar_wait(&bars[7], aux_phase);
+					mbar_wait(&bars[5], aux_phase);
 					aux_phase ^= 1u;
 				}
 				if (active) {
@@ -294,15 +300,11 @@ __global__ void __launch_bounds__(128) k_march_t(FastConst c, const SweepBox *__
 			o_h += shN;
 			o_r += srN;
 			o_o += soN;
-			// rotate the rings
-			if (k5 == 4) {
-				k5 = 0;
-				par5 ^= 1u;
-			} else {
-				++k5;
-			}
-			tpar ^= tslot; // the parity of a trans slot flips every second step
-			tslot ^= 1u;
+			// rotate the ring
+			k4 = (k4 + 1) & 3;
+			if (k4 == 0)
+				par4 ^= 1u;
+			tpar ^= 1u;
 		}
 	}
 	if (LAST) {

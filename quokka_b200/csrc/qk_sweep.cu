@@ -621,10 +621,10 @@ static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, 
 			auto kern = k_march_t<1, NS, NMS, REINT, STAGE, DUAL, false>;
 			static bool attr_set = false;
 			if (!attr_set) {
-				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS>::BLOCK_BYTES));
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
+			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
 		} else {
 			k_sweep_m<1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
 		}
@@ -638,10 +638,10 @@ static int launch_stage(qk_level *L, const FastConst &c, const SweepBox *d_tab, 
 			auto kern = k_march_t<2, NS, NMS, REINT, STAGE, DUAL, true>;
 			static bool attr_set = false;
 			if (!attr_set) {
-				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS>::BLOCK_BYTES));
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
+			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES, s>>>(c, d_tab, nseg, L->d_counters);
 		} else {
 			k_sweep_m<2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, L->d_counters);
 		}
