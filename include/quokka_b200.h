@@ -219,6 +219,8 @@ int qk_level_nlocal(const qk_level *lev);
 int qk_level_local_ids(const qk_level *lev, int32_t *ids);
 /* copy tags whose src or dst is this rank and src_rank != dst_rank; returns count (tags may be NULL) */
 int qk_level_remote_tags(const qk_level *lev, qk_copy_tag *tags, int max_tags);
+/* copy tags whose src and dst boxes both live on this rank (offset is unused); returns count */
+int qk_level_local_tags(const qk_level *lev, qk_copy_tag *tags, int max_tags);
 
 /* FabArray::FillBoundary, same-rank part (FB_local_copy_gpu, extern/amrex/Src/Base/AMReX_FBI.H:272) */
 int qk_fill_boundary_local(qk_level *lev, const qk_array4 *state, int scomp, int ncomp, void *stream);

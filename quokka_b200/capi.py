@@ -200,6 +200,7 @@ SYMBOLS = {
     "qk_level_nlocal": (C.c_int, [_VP]),
     "qk_level_local_ids": (C.c_int, [_VP, C.POINTER(C.c_int32)]),
     "qk_level_remote_tags": (C.c_int, [_VP, C.POINTER(qk_copy_tag), C.c_int]),
+    "qk_level_local_tags": (C.c_int, [_VP, C.POINTER(qk_copy_tag), C.c_int]),
     "qk_fill_boundary_local": (C.c_int, [_VP, _A4P, C.c_int, C.c_int, _VP]),
     "qk_pack_ghosts": (C.c_int, [_VP, C.c_int, _A4P, C.c_int, C.c_int, _VP, _I64P, _VP]),
     "qk_unpack_ghosts": (C.c_int, [_VP, C.c_int, _A4P, C.c_int, C.c_int, _VP, _VP]),

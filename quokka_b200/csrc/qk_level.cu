@@ -401,14 +401,12 @@ extern "C" int qk_level_local_ids(const qk_level *L, int32_t *ids)
 		ids[i] = L->local_ids[i];
 	return 0;
 }
-extern "C" int qk_level_remote_tags(const qk_level *L, qk_copy_tag *tags, int max_tags)
+static int export_tags(const std::vector<HostTag> &src, qk_copy_tag *tags, int max_tags)
 {
-	if (!L)
-		return QK_ERR_BAD_ARG;
-	const int n = (int)L->plan.remote.size();
+	const int n = (int)src.size();
 	if (tags) {
 		for (int i = 0; i < n && i < max_tags; ++i) {
-			const HostTag &t = L->plan.remote[i];
+			const HostTag &t = src[i];
 			qk_copy_tag &o = tags[i];
 			o.src_box = t.src_box;
 			o.dst_box = t.dst_box;
@@ -424,6 +422,14 @@ extern "C" int qk_level_remote_tags(const qk_level *L, qk_copy_tag *tags, int ma
 		}
 	}
 	return n;
+}
+extern "C" int qk_level_remote_tags(const qk_level *L, qk_copy_tag *tags, int max_tags)
+{
+	return L ? export_tags(L->plan.remote, tags, max_tags) : QK_ERR_BAD_ARG;
+}
+extern "C" int qk_level_local_tags(const qk_level *L, qk_copy_tag *tags, int max_tags)
+{
+	return L ? export_tags(L->plan.local, tags, max_tags) : QK_ERR_BAD_ARG;
 }
 
 // ---- descriptor ring: per-call Array4 tables travel host -> device through pinned slots ----------------

@@ -2,6 +2,11 @@
 """dynamic opcode mix + hottest stall lines from `ncu --page source --csv`: python scripts/ncu_opmix.py src.csv [nwarps]"""
 import csv, sys, collections, re
 rows = list(csv.reader(open(sys.argv[1])))
+# the source page concatenates kernels: keep the first one ("Kernel Name" row, header row, instructions...)
+starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rows = rows[starts[which]:(starts[which + 1] if which + 1 < len(starts) else len(rows))]
+print(rows[0][1][:120])
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 ops = collections.Counter(); samples = collections.Counter(); tot = 0; stot = 0
