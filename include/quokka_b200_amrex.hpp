@@ -1,0 +1,392 @@
+// quokka_b200_amrex.hpp -- header-only C++17 shim between Quokka's operator surface and the C ABI of
+// libquokka_b200.so (include/quokka_b200.h).
+//
+// `quokka::b200::HydroSystemB200<problem_t>` has the same static-function surface as the reference's
+// `HydroSystem<problem_t>` / `HyperbolicSystem<problem_t>` (src/hydro/hydro_system.hpp:66-135,
+// src/hyperbolic_system.hpp:85-125) for every operator `QuokkaSimulation<problem_t>::advanceHydroAtLevel` calls
+// (src/QuokkaSimulation.hpp:1096-1278, 1403-1568): same names, same argument order and meaning, MultiFabs in and out.
+// A maintainer switches a call site by replacing `HydroSystem<problem_t>::` with `HydroSystemB200<problem_t>::`
+// (INTEGRATION.md shows the patch).  The compile-time traits of the problem become the run-time qk_hydro_params.
+//
+// Nothing here computes: every function builds Array4 views of the local FABs and forwards to the library.  AMReX must
+// be built with GPU support for the pointers to be device pointers; kernels are enqueued on amrex::Gpu::gpuStream().
+// This file is written for this repository; it includes the reference's headers only for the trait/enum declarations.
+#pragma once
+
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "AMReX_Array4.H"
+#include "AMReX_BCRec.H"
+#include "AMReX_Geometry.H"
+#include "AMReX_GpuDevice.H"
+#include "AMReX_MultiFab.H"
+#include "AMReX_iMultiFab.H"
+
+#include "hydro/hydro_system.hpp" // RiemannSolver, FluxDir, SlopeLimiter, EOS_Traits, HydroSystem_Traits, Physics_Traits
+#include "quokka_b200.h"
+
+namespace quokka::b200
+{
+
+inline void check(int rc, const char *what)
+{
+	if (rc != QK_OK) {
+		// the reference reports operator failures with amrex::Abort
+		amrex::Abort(std::string("libquokka_b200: ") + what + " failed: " + qk_error_string(rc));
+	}
+}
+
+// amrex::Array4<T> and qk_array4 have the same members in the same order; copy field by field so that no layout
+// assumption beyond the names is needed
+template <typename T> inline auto view(amrex::Array4<T> const &a) -> qk_array4
+{
+	qk_array4 v;
+	v.p = const_cast<double *>(reinterpret_cast<double const *>(a.p));
+	v.jstride = a.jstride;
+	v.kstride = a.kstride;
+	v.nstride = a.nstride;
+	v.begin[0] = a.begin.x;
+	v.begin[1] = a.begin.y;
+	v.begin[2] = a.begin.z;
+	v.end[0] = a.end.x;
+	v.end[1] = a.end.y;
+	v.end[2] = a.end.z;
+	v.ncomp = a.ncomp;
+	return v;
+}
+template <typename T> inline auto iview(amrex::Array4<T> const &a) -> qk_iarray4
+{
+	qk_iarray4 v;
+	v.p = const_cast<int32_t *>(reinterpret_cast<int32_t const *>(a.p));
+	v.jstride = a.jstride;
+	v.kstride = a.kstride;
+	v.nstride = a.nstride;
+	v.begin[0] = a.begin.x;
+	v.begin[1] = a.begin.y;
+	v.begin[2] = a.begin.z;
+	v.end[0] = a.end.x;
+	v.end[1] = a.end.y;
+	v.end[2] = a.end.z;
+	v.ncomp = a.ncomp;
+	return v;
+}
+
+inline auto to_box(amrex::Box const &b) -> qk_box
+{
+	const amrex::Box c = amrex::enclosedCells(b);
+	qk_box q;
+	for (int d = 0; d < 3; ++d) {
+		q.lo[d] = (d < AMREX_SPACEDIM) ? c.smallEnd(d) : 0;
+		q.hi[d] = (d < AMREX_SPACEDIM) ? c.bigEnd(d) : 0;
+	}
+	return q;
+}
+
+// the local part of a MultiFab as the (descriptors, valid boxes) pair the ABI takes, in MFIter order
+struct MFView {
+	std::vector<qk_array4> arr;
+	std::vector<qk_box> valid;
+	explicit MFView(amrex::MultiFab const &mf)
+	{
+		for (amrex::MFIter mfi(mf); mfi.isValid(); ++mfi) {
+			arr.push_back(view(mf.const_array(mfi)));
+			valid.push_back(to_box(mfi.validbox()));
+		}
+	}
+	[[nodiscard]] auto n() const -> int { return static_cast<int>(arr.size()); }
+};
+struct iMFView {
+	std::vector<qk_iarray4> arr;
+	explicit iMFView(amrex::iMultiFab const &mf)
+	{
+		for (amrex::MFIter mfi(mf); mfi.isValid(); ++mfi) {
+			arr.push_back(iview(mf.const_array(mfi)));
+		}
+	}
+};
+
+inline auto stream() -> void *
+{
+#ifdef AMREX_USE_GPU
+	return static_cast<void *>(amrex::Gpu::gpuStream());
+#else
+	return nullptr; // host-only AMReX build: the library refuses with QK_ERR_NO_DEVICE unless the FABs live in device memory
+#endif
+}
+
+// run-time image of the problem's traits (include/quokka_b200.h qk_hydro_params); the simulation-level knobs
+// (floors, reconstruction order, ...) are filled by the caller from QuokkaSimulation's members
+template <typename problem_t> inline auto make_params() -> qk_hydro_params
+{
+	qk_hydro_params p{};
+	p.gamma = quokka::EOS_Traits<problem_t>::gamma;
+	p.mean_molecular_weight = quokka::EOS_Traits<problem_t>::mean_molecular_weight;
+	p.boltzmann_constant = quokka::EOS_Traits<problem_t>::boltzmann_constant;
+	p.small_temp = 1e-10;  // eos_init arguments, src/QuokkaSimulation.hpp:165-166
+	p.small_dens = 1e-100;
+	p.density_floor = 0.0;
+	p.temp_floor = 0.0;
+	p.K_visc = 0.0;
+	p.small_x = network_rp::small_x;
+	p.reconstruct_eint = HydroSystem_Traits<problem_t>::reconstruct_eint ? 1 : 0;
+	p.nscalars = Physics_Traits<problem_t>::numPassiveScalars;
+	p.nmscalars = Physics_Traits<problem_t>::numMassScalars;
+	p.reconstruction_order = 3;
+	p.use_dual_energy = 1;
+	p.integrator_order = 2;
+	p.abort_on_fofc_failure = 1;
+	p.arith = QK_ARITH_EXACT;
+	return p;
+}
+
+template <typename problem_t> class HydroSystemB200
+{
+      public:
+	static constexpr int nvar_ = HydroSystem<problem_t>::nvar_;
+
+	// HydroSystem::ConservedToPrimitive  src/hydro/hydro_system.hpp:138-196
+	static void ConservedToPrimitive(amrex::MultiFab const &cons_mf, amrex::MultiFab &primVar_mf, int nghost)
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView c(cons_mf);
+		MFView q(primVar_mf);
+		check(qk_hydro_conserved_to_primitive(&prm, c.n(), c.valid.data(), c.arr.data(), q.arr.data(), nghost, stream()), "ConservedToPrimitive");
+	}
+
+	// HydroSystem::ComputeFlatteningCoefficients<DIR>  :531-626
+	template <FluxDir DIR> static void ComputeFlatteningCoefficients(amrex::MultiFab const &primVar_mf, amrex::MultiFab &x1Chi_mf, int nghost)
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView q(primVar_mf);
+		MFView chi(x1Chi_mf);
+		check(qk_hydro_flattening_coefficients(&prm, static_cast<int>(DIR), q.n(), q.valid.data(), q.arr.data(), chi.arr.data(), nghost, stream()),
+		      "ComputeFlatteningCoefficients");
+	}
+
+	// HyperbolicSystem::ReconstructStatesConstant / PLM<limiter> / PPM  src/hyperbolic_system.hpp:129-181,183-247,295-433
+	template <FluxDir DIR>
+	static void ReconstructStatesConstant(amrex::MultiFab const &q_mf, amrex::MultiFab &leftState_mf, amrex::MultiFab &rightState_mf, int nghost, int nvars)
+	{
+		reconstruct<DIR>(1, QK_MINMOD, q_mf, leftState_mf, rightState_mf, nghost, nvars);
+	}
+	template <FluxDir DIR, SlopeLimiter limiter>
+	static void ReconstructStatesPLM(amrex::MultiFab const &q_mf, amrex::MultiFab &leftState_mf, amrex::MultiFab &rightState_mf, int nghost, int nvars)
+	{
+		reconstruct<DIR>(2, limiter == SlopeLimiter::MC ? QK_MC : QK_MINMOD, q_mf, leftState_mf, rightState_mf, nghost, nvars);
+	}
+	template <FluxDir DIR>
+	static void ReconstructStatesPPM(amrex::MultiFab const &q_mf, amrex::MultiFab &leftState_mf, amrex::MultiFab &rightState_mf, int nghost, int nvars)
+	{
+		reconstruct<DIR>(3, QK_MINMOD, q_mf, leftState_mf, rightState_mf, nghost, nvars);
+	}
+
+	// HydroSystem::FlattenShocks<DIR>  hydro_system.hpp:628-694
+	template <FluxDir DIR>
+	static void FlattenShocks(amrex::MultiFab const &q_mf, amrex::MultiFab const &x1Chi_mf, amrex::MultiFab const &x2Chi_mf, amrex::MultiFab const &x3Chi_mf,
+				  amrex::MultiFab &x1LeftState_mf, amrex::MultiFab &x1RightState_mf, int nghost, int nvars)
+	{
+		MFView q(q_mf);
+		MFView c1(x1Chi_mf);
+		MFView c2(x2Chi_mf);
+		MFView c3(x3Chi_mf);
+		MFView l(x1LeftState_mf);
+		MFView r(x1RightState_mf);
+		check(qk_hydro_flatten_shocks(static_cast<int>(DIR), q.n(), q.valid.data(), q.arr.data(), c1.arr.data(), c2.arr.data(), c3.arr.data(),
+					      l.arr.data(), r.arr.data(), nghost, nvars, stream()),
+		      "FlattenShocks");
+	}
+
+	// HydroSystem::ComputeFluxes<RIEMANN, DIR>  :852-1112 (HLLC, LLF; HLLD/MHD is out of scope)
+	template <RiemannSolver RIEMANN, FluxDir DIR>
+	static void ComputeFluxes(amrex::MultiFab &x1Flux_mf, amrex::MultiFab &x1FaceVel_mf, amrex::MultiFab const &x1LeftState_mf,
+				  amrex::MultiFab const &x1RightState_mf, amrex::MultiFab const &primVar_mf, amrex::Real K_visc)
+	{
+		static_assert(RIEMANN == RiemannSolver::HLLC || RIEMANN == RiemannSolver::LLF, "HLLD is not provided by libquokka_b200");
+		qk_hydro_params prm = make_params<problem_t>();
+		prm.K_visc = K_visc;
+		MFView q(primVar_mf);
+		MFView f(x1Flux_mf);
+		MFView v(x1FaceVel_mf);
+		MFView l(x1LeftState_mf);
+		MFView r(x1RightState_mf);
+		check(qk_hydro_compute_fluxes(&prm, RIEMANN == RiemannSolver::HLLC ? QK_HLLC : QK_LLF, static_cast<int>(DIR), q.n(), q.valid.data(),
+					      f.arr.data(), v.arr.data(), l.arr.data(), r.arr.data(), q.arr.data(), stream()),
+		      "ComputeFluxes");
+	}
+
+	// HydroSystem::ComputeRhsFromFluxes  :448-473
+	static void ComputeRhsFromFluxes(amrex::MultiFab &rhs_mf, std::array<amrex::MultiFab, AMREX_SPACEDIM> const &fluxArray,
+					 amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx, int nvars)
+	{
+		static_assert(AMREX_SPACEDIM == 3, "libquokka_b200 operates on 3-D FABs (1-D/2-D problems use one-cell-thick boxes)");
+		MFView rhs(rhs_mf);
+		MFView fx(fluxArray[0]);
+		MFView fy(fluxArray[1]);
+		MFView fz(fluxArray[2]);
+		const double d[3] = {dx[0], dx[1], dx[2]};
+		check(qk_hydro_rhs_from_fluxes(rhs.n(), rhs.valid.data(), rhs.arr.data(), fx.arr.data(), fy.arr.data(), fz.arr.data(), d, nvars, stream()),
+		      "ComputeRhsFromFluxes");
+	}
+
+	// HydroSystem::AddInternalEnergyPdV  :775-814
+	static void AddInternalEnergyPdV(amrex::MultiFab &rhs_mf, amrex::MultiFab const &consVar_mf, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx,
+					 std::array<amrex::MultiFab, AMREX_SPACEDIM> const &faceVelArray, amrex::iMultiFab const &redoFlag_mf)
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView rhs(rhs_mf);
+		MFView cons(consVar_mf);
+		MFView vx(faceVelArray[0]);
+		MFView vy(faceVelArray[1]);
+		MFView vz(faceVelArray[2]);
+		iMFView redo(redoFlag_mf);
+		const double d[3] = {dx[0], dx[1], dx[2]};
+		check(qk_hydro_add_internal_energy_pdv(&prm, rhs.n(), rhs.valid.data(), rhs.arr.data(), cons.arr.data(), d, vx.arr.data(), vy.arr.data(),
+						       vz.arr.data(), redo.arr.data(), stream()),
+		      "AddInternalEnergyPdV");
+	}
+
+	// HydroSystem::PredictStep  :475-497 (fills redoFlag; the caller sums it as the reference does, QuokkaSimulation.hpp:1146)
+	static void PredictStep(amrex::MultiFab const &consVarOld, amrex::MultiFab &consVarNew, amrex::MultiFab const &rhs, double dt, int nvars,
+				amrex::iMultiFab &redoFlag_mf)
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView u0(consVarOld);
+		MFView u1(consVarNew);
+		MFView r(rhs);
+		iMFView redo(redoFlag_mf);
+		check(qk_hydro_predict_step(&prm, u0.n(), u0.valid.data(), u0.arr.data(), u1.arr.data(), r.arr.data(), dt, nvars, redo.arr.data(), nullptr,
+					    stream()),
+		      "PredictStep");
+	}
+
+	// HydroSystem::EnforceLimits  :698-773
+	static void EnforceLimits(amrex::Real densityFloor, amrex::Real tempFloor, amrex::MultiFab &state_mf)
+	{
+		qk_hydro_params prm = make_params<problem_t>();
+		prm.density_floor = densityFloor;
+		prm.temp_floor = tempFloor;
+		MFView s(state_mf);
+		check(qk_hydro_enforce_limits(&prm, s.n(), s.valid.data(), s.arr.data(), stream()), "EnforceLimits");
+	}
+
+	// HydroSystem::SyncDualEnergy  :816-850
+	static void SyncDualEnergy(amrex::MultiFab &consVar_mf)
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView s(consVar_mf);
+		int64_t nabort = 0;
+		check(qk_hydro_sync_dual_energy(&prm, s.n(), s.valid.data(), s.arr.data(), &nabort, stream()), "SyncDualEnergy");
+		if (nabort > 0) {
+			amrex::Abort("density is negative in SyncDualEnergy! abort!!"); // hydro_system.hpp:832
+		}
+	}
+
+	// HydroSystem::maxSignalSpeedLocal  :198-221 (local max; the caller reduces over ranks as the reference does)
+	static auto maxSignalSpeedLocal(amrex::MultiFab const &cons) -> amrex::Real
+	{
+		const qk_hydro_params prm = make_params<problem_t>();
+		MFView c(cons);
+		double m = 0.0;
+		check(qk_hydro_max_signal_speed(&prm, 1, c.n(), c.valid.data(), c.arr.data(), &m, stream()), "maxSignalSpeedLocal");
+		return m;
+	}
+
+	// QuokkaSimulation::replaceFluxes for one direction  src/QuokkaSimulation.hpp:1324-1368
+	template <FluxDir DIR> static void ReplaceFluxes(amrex::MultiFab &flux, amrex::MultiFab const &FOflux, amrex::iMultiFab const &redoFlag_mf, int ncomp)
+	{
+		MFView f(flux);
+		MFView fo(FOflux);
+		iMFView redo(redoFlag_mf);
+		check(qk_hydro_replace_fluxes(static_cast<int>(DIR), f.n(), f.valid.data(), f.arr.data(), fo.arr.data(), redo.arr.data(), ncomp, stream()),
+		      "replaceFluxes");
+	}
+
+      private:
+	template <FluxDir DIR>
+	static void reconstruct(int order, int limiter, amrex::MultiFab const &q_mf, amrex::MultiFab &leftState_mf, amrex::MultiFab &rightState_mf, int nghost,
+				int nvars)
+	{
+		MFView q(q_mf);
+		MFView l(leftState_mf);
+		MFView r(rightState_mf);
+		check(qk_reconstruct_states(order, limiter, static_cast<int>(DIR), q.n(), q.valid.data(), q.arr.data(), l.arr.data(), r.arr.data(), nghost, nvars,
+					    stream()),
+		      "ReconstructStates");
+	}
+};
+
+// ---- stage-level drop-in -----------------------------------------------------------------------------------------
+// One qk_level per AMR level mirrors BoxArray + DistributionMapping + Geometry + BCRec; it is rebuilt when the grids
+// change (after regrid).  advanceStage replaces the body of one RK stage of advanceHydroAtLevel
+// (src/QuokkaSimulation.hpp:1099-1198 / :1202-1285): *all* of K1-K10 and the FOFC logic run inside the library.
+class LevelB200
+{
+      public:
+	LevelB200(amrex::BoxArray const &ba, amrex::DistributionMapping const &dm, amrex::Geometry const &geom, amrex::Vector<amrex::BCRec> const &bcs, int nghost,
+		  int ncomp)
+	{
+		const int nb = static_cast<int>(ba.size());
+		boxes_.resize(nb);
+		owner_.resize(nb);
+		for (int i = 0; i < nb; ++i) {
+			boxes_[i] = to_box(ba[i]);
+			owner_[i] = dm[i];
+		}
+		bc_lo_.resize(3 * ncomp);
+		bc_hi_.resize(3 * ncomp);
+		for (int n = 0; n < ncomp; ++n) {
+			for (int d = 0; d < 3; ++d) {
+				bc_lo_[3 * n + d] = (d < AMREX_SPACEDIM) ? bcs[n].lo(d) : QK_BC_INT_DIR;
+				bc_hi_[3 * n + d] = (d < AMREX_SPACEDIM) ? bcs[n].hi(d) : QK_BC_INT_DIR;
+			}
+		}
+		qk_level_desc d{};
+		d.domain = to_box(geom.Domain());
+		for (int k = 0; k < 3; ++k) {
+			d.periodic[k] = (k < AMREX_SPACEDIM) ? static_cast<int>(geom.isPeriodic(k)) : 1;
+			d.dx[k] = (k < AMREX_SPACEDIM) ? geom.CellSize(k) : 1.0;
+		}
+		d.nghost = nghost;
+		d.ncomp = ncomp;
+		d.nboxes_global = nb;
+		d.boxes_global = boxes_.data();
+		d.owner = owner_.data();
+		d.my_rank = amrex::ParallelDescriptor::MyProc();
+		d.bc_lo = bc_lo_.data();
+		d.bc_hi = bc_hi_.data();
+		check(qk_level_create(&d, &lev_), "qk_level_create");
+	}
+	~LevelB200() { qk_level_destroy(lev_); }
+	LevelB200(LevelB200 const &) = delete;
+	auto operator=(LevelB200 const &) -> LevelB200 & = delete;
+
+	// ghost fill of level 0 / a uniform level: FillBoundary + physical BCs (simulation.hpp:1752-1765)
+	void fillBoundary(amrex::MultiFab &state, int scomp, int ncomp)
+	{
+		MFView s(state);
+		check(qk_fill_boundary(lev_, s.arr.data(), scomp, ncomp, stream()), "fillBoundary");
+	}
+
+	// returns ncells_bad after the first-order flux correction (0 = success), as redoFlag.sum() does in the reference
+	auto advanceStage(qk_hydro_params const &prm, int stage, amrex::MultiFab const &U0, amrex::MultiFab const &Ustage, amrex::MultiFab &Uout, double dt)
+	    -> int64_t
+	{
+		MFView u0(U0);
+		MFView us(Ustage);
+		MFView uo(Uout);
+		int64_t bad = 0;
+		check(qk_hydro_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStage");
+		return bad;
+	}
+	[[nodiscard]] auto handle() const -> qk_level * { return lev_; }
+
+      private:
+	qk_level *lev_ = nullptr;
+	std::vector<qk_box> boxes_;
+	std::vector<int32_t> owner_, bc_lo_, bc_hi_;
+};
+
+} // namespace quokka::b200

@@ -1,0 +1,64 @@
+// Compile-only check (g++ -fsyntax-only against the reference's own headers under /root/reference): every static function of
+// HydroSystemB200<problem_t> instantiates with the argument lists QuokkaSimulation<problem_t> uses for HydroSystem<problem_t>.
+#include "quokka_b200_amrex.hpp"
+
+struct SedovLike {
+};
+template <> struct quokka::EOS_Traits<SedovLike> {
+	static constexpr double gamma = 1.4;
+	static constexpr double mean_molecular_weight = C::m_u;
+	static constexpr double boltzmann_constant = C::k_B;
+};
+template <> struct HydroSystem_Traits<SedovLike> {
+	static constexpr bool reconstruct_eint = false;
+};
+template <> struct Physics_Traits<SedovLike> {
+	static constexpr bool is_hydro_enabled = true;
+	static constexpr int numMassScalars = 0;
+	static constexpr int numPassiveScalars = numMassScalars + 0;
+	static constexpr bool is_radiation_enabled = false;
+	static constexpr bool is_mhd_enabled = false;
+	static constexpr int nGroups = 1;
+};
+
+// the call sequence of QuokkaSimulation::hydroFluxFunction / advanceHydroAtLevel (src/QuokkaSimulation.hpp:1403-1517, 1096-1198)
+template <typename Hydro> void stage(amrex::MultiFab &state_old, amrex::MultiFab &state_new, amrex::iMultiFab &redoFlag, amrex::Real dt,
+				     amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx)
+{
+	const int ng = 4;
+	const int nvars = Hydro::nvar_;
+	auto const &ba = state_old.boxArray();
+	auto const &dm = state_old.DistributionMap();
+	amrex::MultiFab prim(ba, dm, nvars, ng);
+	std::array<amrex::MultiFab, 3> chi, flux, fvel;
+	amrex::MultiFab left, right, rhs(ba, dm, nvars, 0);
+	Hydro::ConservedToPrimitive(state_old, prim, ng);
+	Hydro::template ComputeFlatteningCoefficients<FluxDir::X1>(prim, chi[0], 2);
+	Hydro::template ComputeFlatteningCoefficients<FluxDir::X2>(prim, chi[1], 2);
+	Hydro::template ComputeFlatteningCoefficients<FluxDir::X3>(prim, chi[2], 2);
+	Hydro::template ReconstructStatesPPM<FluxDir::X1>(prim, left, right, 1, nvars);
+	Hydro::template ReconstructStatesPLM<FluxDir::X2, SlopeLimiter::minmod>(prim, left, right, 1, nvars);
+	Hydro::template ReconstructStatesConstant<FluxDir::X3>(prim, left, right, 1, nvars);
+	Hydro::template FlattenShocks<FluxDir::X1>(prim, chi[0], chi[1], chi[2], left, right, 1, nvars);
+	Hydro::template ComputeFluxes<RiemannSolver::HLLC, FluxDir::X1>(flux[0], fvel[0], left, right, prim, 0.0);
+	Hydro::template ComputeFluxes<RiemannSolver::LLF, FluxDir::X2>(flux[1], fvel[1], left, right, prim, 0.0);
+	Hydro::ComputeRhsFromFluxes(rhs, flux, dx, nvars);
+	Hydro::AddInternalEnergyPdV(rhs, state_old, dx, fvel, redoFlag);
+	Hydro::PredictStep(state_old, state_new, rhs, dt, nvars, redoFlag);
+	Hydro::EnforceLimits(0.0, 0.0, state_new);
+	Hydro::SyncDualEnergy(state_new);
+}
+
+template void stage<HydroSystem<SedovLike>>(amrex::MultiFab &, amrex::MultiFab &, amrex::iMultiFab &, amrex::Real, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM>);
+template void stage<quokka::b200::HydroSystemB200<SedovLike>>(amrex::MultiFab &, amrex::MultiFab &, amrex::iMultiFab &, amrex::Real,
+							      amrex::GpuArray<amrex::Real, AMREX_SPACEDIM>);
+
+auto stage_level(quokka::b200::LevelB200 &lev, amrex::MultiFab &U0, amrex::MultiFab &U1, amrex::MultiFab &Unew, double dt) -> int64_t
+{
+	qk_hydro_params prm = quokka::b200::make_params<SedovLike>();
+	lev.fillBoundary(U0, 0, U0.nComp());
+	int64_t bad = lev.advanceStage(prm, 1, U0, U0, U1, dt);
+	lev.fillBoundary(U1, 0, U1.nComp());
+	bad += lev.advanceStage(prm, 2, U0, U1, Unew, dt);
+	return bad;
+}
