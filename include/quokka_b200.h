@@ -32,6 +32,7 @@ extern "C" {
 
 #define QK_ABI_VERSION 1
 #define QK_MAX_SCALARS 8
+#define QK_MAX_GROUPS 8
 
 enum { QK_OK = 0, QK_ERR_NO_DEVICE = -1, QK_ERR_BAD_ARG = -2, QK_ERR_UNSUPPORTED = -3, QK_ERR_NOMEM = -4 };
 
@@ -180,6 +181,38 @@ int qk_hydro_replace_fluxes(int dir, int nboxes, const qk_box *valid, const qk_a
 int qk_hydro_max_signal_speed(const qk_hydro_params *prm, int which, int nboxes, const qk_box *valid, const qk_array4 *cons, double *max_out,
 			      void *stream);
 
+/* ---- two-moment (M1) radiation transport sweep: RadSystem<problem_t>, src/radiation/radiation_system.hpp --------------
+ * run-time image of RadSystem_Traits<problem_t> (:73-82) + Physics_Indices<problem_t>::radFirstIndex (src/physics_info.hpp:40)
+ * + the radiation knobs of QuokkaSimulation (radiationReconstructionOrder_, src/QuokkaSimulation.hpp:125).  The state
+ * MultiFab holds, per photon group g, (E_r, F_x, F_y, F_z) at components nstart + 4 g .. nstart + 4 g + 3 (:181). */
+typedef struct qk_rad_params {
+	double c_light;		      /* RadSystem_Traits::c_light */
+	double c_hat;		      /* RadSystem_Traits::c_hat (reduced speed of light) */
+	double Erad_floor;	      /* RadSystem_Traits::Erad_floor (total; divided by ngroups inside, :211) */
+	int32_t ngroups;	      /* Physics_Traits::nGroups */
+	int32_t nstart;		      /* nstartHyperbolic_ = radFirstIndex = 6 + numPassiveScalars */
+	int32_t reconstruction_order; /* radiationReconstructionOrder_: 1 donor cell | 2 PLM(MC) | 3 PPM (QuokkaSimulation.hpp:1942-1957) */
+	int32_t integrator_order;     /* 1 forward Euler | 2 RK2 (IMEX PD-ARS transport part, IMEX_a32 = 0.5, :52) */
+} qk_rad_params;
+
+/* RadSystem::ConservedToPrimitive(cons, primVar, ghostRange)  radiation_system.hpp:589-614.  prim has 4*ngroups components
+ * (E_r, f_x, f_y, f_z per group, primVarIndex :183-188); computed on `valid` grown by nghost. */
+int qk_rad_conserved_to_primitive(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, const qk_array4 *prim, int nghost,
+				  void *stream);
+/* RadSystem::ComputeFluxes<DIR>(x1Flux, x1FluxDiffusive, left, right, x1FluxRange, consVar, dx, use_wavespeed_correction = false)
+ * :985-1139 (+ ComputeRadPressure :918-983, ComputeEddingtonTensor :873-916, ComputeEddingtonFactor :773-790).
+ * flux / flux_diffusive: 4*ngroups components, nodal in dir; flux_diffusive may be NULL (the reference computes it but no
+ * consumer reads it, :669,715-716). */
+int qk_rad_compute_fluxes(const qk_rad_params *prm, int dir, int nboxes, const qk_box *valid, const qk_array4 *flux, const qk_array4 *flux_diffusive,
+			  const qk_array4 *left, const qk_array4 *right, const qk_array4 *cons, void *stream);
+/* RadSystem::PredictStep(consVarOld, consVarNew, fluxArray, ., dt, dx, indexRange, .)  :667-710 (isStateValid / amendRadState :624-665) */
+int qk_rad_predict_step(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons_old, const qk_array4 *cons_new,
+			const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz, double dt, const double dx[3], void *stream);
+/* RadSystem::AddFluxesRK2(U_new, U0, U1, fluxArrayOld, fluxArray, ., ., dt, dx, indexRange, .)  :712-771 */
+int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *u_new, const qk_array4 *u0, const qk_array4 *u1,
+			  const qk_array4 *fx_old, const qk_array4 *fy_old, const qk_array4 *fz_old, const qk_array4 *fx, const qk_array4 *fy,
+			  const qk_array4 *fz, double dt, const double dx[3], void *stream);
+
 /* ---- level object: fused path + ghost fill -------------------------------------------------- */
 
 /* Description of the boxes of ONE AMR level owned by this rank (a MultiFab's local part) and of
@@ -242,6 +275,17 @@ int qk_fill_physical_bc(qk_level *lev, const qk_array4 *state, int scomp, int nc
  * redoFlag.sum() that survived FOFC (0 => success).  Synchronises `stream` once (for ncells_bad). */
 int qk_hydro_advance_stage(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
 			   const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
+
+/* One stage of the radiation transport substep for all local boxes, fused (no left/right/flux arrays exist):
+ *   stage 1 = advanceRadiationForwardEuler's transport part (src/QuokkaSimulation.hpp:1791-1822):
+ *             Uout = PredictStep(U0, F(U0))                          (Ustage == U0, ghost-filled)
+ *   stage 2 = advanceRadiationMidpointRK2's (:1824-1862):
+ *             Uout = AddFluxesRK2(U0, Ustage, F(U0), F(Ustage))       (Ustage = stage-1 result, ghost-filled)
+ * Only components nstart .. nstart + 4*ngroups - 1 are read and written.  The level keeps the stage-1 flux divergence
+ * between the two calls (the reference re-evaluates F(U0); its coefficient 0.5 - IMEX_a32 is exactly 0, the product is still
+ * formed so that non-finite values and signed zeros propagate identically). */
+int qk_rad_advance_stage(qk_level *lev, const qk_rad_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout,
+			 double dt, void *stream);
 
 /* The same stage through the FAITHFUL path only: one kernel per reference operator, fluxes materialised as
  * MultiFabs exactly as QuokkaSimulation.hpp:1403-1490 does.  qk_hydro_advance_stage runs the fused sweep kernels

@@ -764,6 +764,196 @@ double orc_max_signal_speed(const qk_hydro_params *prm, int which, const qk_arra
 }
 
 /* ================================================================================================
+ * Two-moment radiation transport  src/radiation/radiation_system.hpp
+ * ============================================================================================== */
+/* RadSystem::ConservedToPrimitive  :589-614 */
+void orc_rad_conserved_to_primitive(const qk_rad_params *prm, const qk_array4 *cons, const qk_array4 *prim, const qk_box *bx)
+{
+	const int ns = prm->nstart;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i)
+				for (int g = 0; g < prm->ngroups; ++g) {
+					const double E_r = A4(cons, i, j, k, ns + 4 * g);
+					const double Fx = A4(cons, i, j, k, ns + 4 * g + 1);
+					const double Fy = A4(cons, i, j, k, ns + 4 * g + 2);
+					const double Fz = A4(cons, i, j, k, ns + 4 * g + 3);
+					A4(prim, i, j, k, 4 * g) = E_r;
+					A4(prim, i, j, k, 4 * g + 1) = Fx / (prm->c_light * E_r);
+					A4(prim, i, j, k, 4 * g + 2) = Fy / (prm->c_light * E_r);
+					A4(prim, i, j, k, 4 * g + 3) = Fz / (prm->c_light * E_r);
+				}
+}
+
+/* RadSystem::ComputeEddingtonFactor  :773-790 (Levermore 1984 closure) */
+static double rad_eddington_factor(double f_in)
+{
+	const double f = clampd(f_in, 0., 1.);
+	const double f_fac = sqrt(4.0 - 3.0 * (f * f));
+	return (3.0 + 4.0 * (f * f)) / (5.0 + 2.0 * f_fac);
+}
+
+/* RadSystem::ComputeEddingtonTensor :873-916 + ComputeRadPressure<DIR> :918-983: F[4] = (F_n, T_nx E, T_ny E, T_nz E), S = max(0.1, sqrt(T_nn)) */
+static void rad_pressure(int dir, double erad, const double Fv[3], const double fv[3], double F[4], double *S)
+{
+	const double f = sqrt(fv[0] * fv[0] + fv[1] * fv[1] + fv[2] * fv[2]);
+	double n[3];
+	for (int ii = 0; ii < 3; ++ii)
+		n[ii] = (f > 0.) ? (fv[ii] / f) : 0.;
+	const double chi = rad_eddington_factor(f);
+	const double Tdiag = (1.0 - chi) / 2.0;
+	const double Tf = (3.0 * chi - 1.0) / 2.0;
+	double T[3][3];
+	for (int ii = 0; ii < 3; ++ii)
+		for (int jj = 0; jj < 3; ++jj) {
+			const double delta_ij = (ii == jj) ? 1 : 0;
+			T[ii][jj] = Tdiag * delta_ij + Tf * (n[ii] * n[jj]);
+		}
+	const double Tnormal = T[dir][dir];
+	F[0] = Fv[dir];
+	F[1] = T[dir][0] * erad;
+	F[2] = T[dir][1] * erad;
+	F[3] = T[dir][2] * erad;
+	const double sq = sqrt(Tnormal);
+	*S = (0.1 < sq) ? sq : 0.1; /* std::max(0.1, sqrt(Tnormal)) */
+}
+
+/* RadSystem::ComputeFluxes<DIR>  :985-1139, use_wavespeed_correction = false (epsilon = 1).  fdiff may be NULL. */
+void orc_rad_compute_fluxes(const qk_rad_params *prm, int dir, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left,
+			    const qk_array4 *right, const qk_array4 *cons, const qk_box *facebx)
+{
+	const int e0 = (dir == 0), e1 = (dir == 1), e2 = (dir == 2), ns = prm->nstart;
+	const double c = prm->c_light, chat = prm->c_hat;
+	for (int k = facebx->lo[2]; k <= facebx->hi[2]; ++k)
+		for (int j = facebx->lo[1]; j <= facebx->hi[1]; ++j)
+			for (int i = facebx->lo[0]; i <= facebx->hi[0]; ++i)
+				for (int g = 0; g < prm->ngroups; ++g) {
+					double erad_L = A4(left, i, j, k, 4 * g), erad_R = A4(right, i, j, k, 4 * g);
+					double fL[3], fR[3], FL[3], FR[3];
+					for (int m = 0; m < 3; ++m) {
+						fL[m] = A4(left, i, j, k, 4 * g + 1 + m);
+						fR[m] = A4(right, i, j, k, 4 * g + 1 + m);
+					}
+					double f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
+					double f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
+					for (int m = 0; m < 3; ++m) {
+						FL[m] = fL[m] * (c * erad_L);
+						FR[m] = fR[m] * (c * erad_R);
+					}
+					if ((erad_L <= 0.) || (erad_R <= 0.) || (f_L >= 1.) || (f_R >= 1.)) { /* first-order fallback :1054-1079 */
+						erad_L = A4(cons, i - e0, j - e1, k - e2, ns + 4 * g);
+						erad_R = A4(cons, i, j, k, ns + 4 * g);
+						for (int m = 0; m < 3; ++m) {
+							FL[m] = A4(cons, i - e0, j - e1, k - e2, ns + 4 * g + 1 + m);
+							FR[m] = A4(cons, i, j, k, ns + 4 * g + 1 + m);
+							fL[m] = FL[m] / (c * erad_L);
+							fR[m] = FR[m] / (c * erad_R);
+						}
+						f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
+						f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
+					}
+					double F_L[4], F_R[4], S_L, S_R;
+					rad_pressure(dir, erad_L, FL, fL, F_L, &S_L);
+					S_L *= -1.;
+					rad_pressure(dir, erad_R, FR, fR, F_R, &S_R);
+					F_L[0] *= chat / c;
+					F_R[0] *= chat / c;
+					for (int n = 1; n < 4; ++n) {
+						F_L[n] *= chat * c;
+						F_R[n] *= chat * c;
+					}
+					S_L *= chat;
+					S_R *= chat;
+					const double U_L[4] = {erad_L, FL[0], FL[1], FL[2]};
+					const double U_R[4] = {erad_R, FR[0], FR[1], FR[2]};
+					const double a = S_R / (S_R - S_L), b = S_L / (S_R - S_L), d = S_R * S_L / (S_R - S_L);
+					for (int n = 0; n < 4; ++n) {
+						const double eps = 1.0;
+						A4(flux, i, j, k, 4 * g + n) = a * F_L[n] - b * F_R[n] + (eps * d) * (U_R[n] - U_L[n]);
+						if (fdiff)
+							A4(fdiff, i, j, k, 4 * g + n) = a * F_L[n] - b * F_R[n] + d * (U_R[n] - U_L[n]);
+					}
+				}
+}
+
+/* RadSystem::isStateValid :624-643 / amendRadState :645-665 on the 4*ngroups hyperbolic variables of one cell */
+static void rad_validate(const qk_rad_params *prm, double *cons)
+{
+	const double c = prm->c_light, floor_g = prm->Erad_floor / prm->ngroups;
+	int valid = 1;
+	for (int g = 0; g < prm->ngroups; ++g) {
+		const double E_r = cons[4 * g], Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
+		const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+		const double f = Fnorm / (c * E_r);
+		valid = (valid && (E_r > 0.) && (f <= 1.));
+	}
+	if (valid)
+		return;
+	for (int g = 0; g < prm->ngroups; ++g) {
+		double E_r = cons[4 * g];
+		if (E_r < floor_g) {
+			E_r = floor_g;
+			cons[4 * g] = floor_g;
+		}
+		const double Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
+		if (Fx * Fx + Fy * Fy + Fz * Fz > c * c * E_r * E_r) {
+			const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+			cons[4 * g + 1] = Fx / Fnorm * c * E_r;
+			cons[4 * g + 2] = Fy / Fnorm * c * E_r;
+			cons[4 * g + 3] = Fz / Fnorm * c * E_r;
+		}
+	}
+}
+
+/* RadSystem::PredictStep  :667-710 */
+void orc_rad_predict_step(const qk_rad_params *prm, const qk_array4 *uo, const qk_array4 *un, const qk_array4 *fx, const qk_array4 *fy,
+			  const qk_array4 *fz, double dt, const double dx[3], const qk_box *bx)
+{
+	const int nh = 4 * prm->ngroups, ns = prm->nstart;
+	double cons[4 * QK_MAX_GROUPS];
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				for (int n = 0; n < nh; ++n)
+					cons[n] = A4(uo, i, j, k, ns + n) + ((dt / dx[0]) * (A4(fx, i, j, k, n) - A4(fx, i + 1, j, k, n)) +
+									     (dt / dx[1]) * (A4(fy, i, j, k, n) - A4(fy, i, j + 1, k, n)) +
+									     (dt / dx[2]) * (A4(fz, i, j, k, n) - A4(fz, i, j, k + 1, n)));
+				rad_validate(prm, cons);
+				for (int n = 0; n < nh; ++n)
+					A4(un, i, j, k, ns + n) = cons[n];
+			}
+}
+
+/* RadSystem::AddFluxesRK2  :712-771 (IMEX_a32 = 0.5 :52) */
+void orc_rad_add_fluxes_rk2(const qk_rad_params *prm, const qk_array4 *unew, const qk_array4 *u0, const qk_array4 *u1, const qk_array4 *fxo,
+			    const qk_array4 *fyo, const qk_array4 *fzo, const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz, double dt,
+			    const double dx[3], const qk_box *bx)
+{
+	const int nh = 4 * prm->ngroups, ns = prm->nstart;
+	const double IMEX_a32 = 0.5;
+	double cons[4 * QK_MAX_GROUPS];
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				for (int n = 0; n < nh; ++n) {
+					const double U_0 = A4(u0, i, j, k, ns + n);
+					const double U_1 = A4(u1, i, j, k, ns + n);
+					const double FxU_0 = (dt / dx[0]) * (A4(fxo, i, j, k, n) - A4(fxo, i + 1, j, k, n));
+					const double FxU_1 = (dt / dx[0]) * (A4(fx, i, j, k, n) - A4(fx, i + 1, j, k, n));
+					const double FyU_0 = (dt / dx[1]) * (A4(fyo, i, j, k, n) - A4(fyo, i, j + 1, k, n));
+					const double FyU_1 = (dt / dx[1]) * (A4(fy, i, j, k, n) - A4(fy, i, j + 1, k, n));
+					const double FzU_0 = (dt / dx[2]) * (A4(fzo, i, j, k, n) - A4(fzo, i, j, k + 1, n));
+					const double FzU_1 = (dt / dx[2]) * (A4(fz, i, j, k, n) - A4(fz, i, j, k + 1, n));
+					cons[n] = (1.0 - IMEX_a32) * U_0 + IMEX_a32 * U_1 + ((0.5 - IMEX_a32) * (FxU_0 + FyU_0 + FzU_0)) +
+						  (0.5 * (FxU_1 + FyU_1 + FzU_1));
+				}
+				rad_validate(prm, cons);
+				for (int n = 0; n < nh; ++n)
+					A4(unew, i, j, k, ns + n) = cons[n];
+			}
+}
+
+/* ================================================================================================
  * Level driver (uniform single level, all boxes in this process)
  * ============================================================================================== */
 struct orc_level {
@@ -1259,4 +1449,73 @@ int orc_step_with_retries(orc_level *L, const qk_hydro_params *prm, double dt, d
 	if (result >= 0)
 		L->t += dt;
 	return result;
+}
+
+/* ---- radiation transport of one level: the hyperbolic part of advanceRadiationSubstepAtLevel
+ * (src/QuokkaSimulation.hpp:1721-1862: advanceRadiationForwardEuler then advanceRadiationMidpointRK2, no source terms,
+ * no flux registers) with computeRadiationFluxes / fluxFunction<DIR> (:1903-1986) per box.  state_old -> state_new. */
+static void rad_fluxes_of_box(const qk_rad_params *prm, const qk_array4 *U, const qk_box vb, int ng, qk_array4 flx[3])
+{
+	const int nh = 4 * prm->ngroups;
+	const qk_box g4 = grow(vb, ng), g1 = grow(vb, 1);
+	qk_array4 prim = alloc_a4(g4, nh);
+	orc_rad_conserved_to_primitive(prm, U, &prim, &g4);
+	for (int d = 0; d < 3; ++d) {
+		const qk_box rb = grow_hi(g1, d, 1), fb = grow_hi(vb, d, 1);
+		qk_array4 l = alloc_a4(rb, nh), r = alloc_a4(rb, nh);
+		if (prm->reconstruction_order == 3)
+			orc_reconstruct_states(3, 0, d, &prim, &l, &r, &g1, nh);
+		else
+			orc_reconstruct_states(prm->reconstruction_order, QK_MC, d, &prim, &l, &r, &rb, nh);
+		flx[d] = alloc_a4(fb, nh);
+		orc_rad_compute_fluxes(prm, d, &flx[d], NULL, &l, &r, U, &fb);
+		free_a4(&l);
+		free_a4(&r);
+	}
+	free_a4(&prim);
+}
+
+void orc_rad_advance_level(orc_level *L, const qk_rad_params *prm, double dt)
+{
+	const int nb = L->nb, ng = L->d.nghost, nc = L->d.ncomp;
+	const double *dx = L->d.dx;
+	qk_array4 *Uold = malloc(sizeof(qk_array4) * nb), *Unew = malloc(sizeof(qk_array4) * nb);
+	for (int b = 0; b < nb; ++b) {
+		Uold[b] = orc_level_state(L, 1, b);
+		Unew[b] = orc_level_state(L, 0, b);
+	}
+	orc_fill_boundary(L, Uold, 0, nc); /* :1798 */
+	for (int b = 0; b < nb; ++b) {
+		qk_array4 f[3];
+		rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, f);
+		orc_rad_predict_step(prm, &Uold[b], &Unew[b], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
+		for (int d = 0; d < 3; ++d)
+			free_a4(&f[d]);
+	}
+	if (prm->integrator_order == 2) {
+		orc_fill_boundary(L, Unew, 0, nc); /* :1831 */
+		/* stateInter and stateNew alias in the reference (:1840-1841): every box's fluxes are computed from the intermediate
+		 * state before that box is overwritten, and ghost cells of other boxes are not touched by the update */
+		for (int b = 0; b < nb; ++b) {
+			qk_array4 fo[3], f[3];
+			rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, fo);
+			rad_fluxes_of_box(prm, &Unew[b], L->boxes[b], ng, f);
+			orc_rad_add_fluxes_rk2(prm, &Unew[b], &Uold[b], &Unew[b], &fo[0], &fo[1], &fo[2], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
+			for (int d = 0; d < 3; ++d) {
+				free_a4(&fo[d]);
+				free_a4(&f[d]);
+			}
+		}
+	}
+	free(Uold);
+	free(Unew);
+}
+
+/* swap state_new <-> state_old (the radiation subcycle copies new -> old, :1597-1600; a swap has the same effect for the
+ * components the transport overwrites and is what the tests drive) */
+void orc_level_swap(orc_level *L)
+{
+	double **t = L->snew;
+	L->snew = L->sold;
+	L->sold = t;
 }

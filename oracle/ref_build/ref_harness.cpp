@@ -77,6 +77,54 @@ template <> struct Physics_Traits<P2> {
 	static constexpr int nGroups = 1;
 };
 
+// radiation problem types (one photon group; hydro + radiation variables, radFirstIndex = 6)
+//   R0: c = c_hat = 1, Erad_floor = 0 (dimensionless, RadStreaming-like traits)
+//   R1: c = c_cgs, c_hat = c/30 (reduced speed of light), Erad_floor = 1e-12
+struct R0 {
+};
+struct R1 {
+};
+template <> struct quokka::EOS_Traits<R0> {
+	static constexpr double gamma = 5. / 3.;
+	static constexpr double mean_molecular_weight = C::m_u;
+	static constexpr double boltzmann_constant = C::k_B;
+};
+template <> struct Physics_Traits<R0> {
+	static constexpr bool is_hydro_enabled = true;
+	static constexpr int numMassScalars = 0;
+	static constexpr int numPassiveScalars = numMassScalars + 0;
+	static constexpr bool is_radiation_enabled = true;
+	static constexpr bool is_mhd_enabled = false;
+	static constexpr int nGroups = 1;
+};
+template <> struct RadSystem_Traits<R0> {
+	static constexpr double c_light = 1.0;
+	static constexpr double c_hat = 1.0;
+	static constexpr double radiation_constant = 1.0;
+	static constexpr double Erad_floor = 0.;
+	static constexpr int beta_order = 0;
+};
+template <> struct quokka::EOS_Traits<R1> {
+	static constexpr double gamma = 5. / 3.;
+	static constexpr double mean_molecular_weight = C::m_u;
+	static constexpr double boltzmann_constant = C::k_B;
+};
+template <> struct Physics_Traits<R1> {
+	static constexpr bool is_hydro_enabled = true;
+	static constexpr int numMassScalars = 0;
+	static constexpr int numPassiveScalars = numMassScalars + 0;
+	static constexpr bool is_radiation_enabled = true;
+	static constexpr bool is_mhd_enabled = false;
+	static constexpr int nGroups = 1;
+};
+template <> struct RadSystem_Traits<R1> {
+	static constexpr double c_light = c_light_cgs_;
+	static constexpr double c_hat = c_light_cgs_ / 30.0;
+	static constexpr double radiation_constant = radiation_constant_cgs_;
+	static constexpr double Erad_floor = 1.0e-12;
+	static constexpr int beta_order = 0;
+};
+
 namespace
 {
 bool g_init = false;
@@ -324,6 +372,80 @@ void update_ops(int op, const qk_box *valid, const qk_array4 *a0, const qk_array
 	}
 }
 
+// ---- radiation: RadSystem<P> static functions take Array4s of one box ----
+template <typename P> void rad_cons_to_prim(const qk_box *valid, const qk_array4 *cons, const qk_array4 *prim, int ng)
+{
+	auto c = make_mf(valid, -1, RadSystem<P>::nvar_, ng);
+	auto q = make_mf(valid, -1, RadSystem<P>::nvarHyperbolic_, ng);
+	copy_in(c, cons);
+	RadSystem<P>::ConservedToPrimitive(c.const_array(0), q.array(0), amrex::grow(to_box(valid), ng));
+	copy_out(q, prim);
+}
+template <typename P, FluxDir DIR>
+void rad_fluxes(const qk_box *valid, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left, const qk_array4 *right, const qk_array4 *cons,
+		int ngcons)
+{
+	const int nh = RadSystem<P>::nvarHyperbolic_;
+	auto c = make_mf(valid, -1, RadSystem<P>::nvar_, ngcons);
+	auto l = make_mf(valid, static_cast<int>(DIR), nh, 1);
+	auto r = make_mf(valid, static_cast<int>(DIR), nh, 1);
+	auto f = make_mf(valid, static_cast<int>(DIR), nh, 0);
+	auto fd = make_mf(valid, static_cast<int>(DIR), nh, 0);
+	copy_in(c, cons);
+	copy_in(l, left);
+	copy_in(r, right);
+	amrex::GpuArray<amrex::Real, 3> dx{1.0, 1.0, 1.0};
+	RadSystem<P>::template ComputeFluxes<DIR>(f.array(0), fd.array(0), l.const_array(0), r.const_array(0),
+						  amrex::surroundingNodes(to_box(valid), static_cast<int>(DIR)), c.const_array(0), dx, false);
+	copy_out(f, flux);
+	copy_out(fd, fdiff);
+}
+template <typename P>
+void rad_update(int op, const qk_box *valid, const qk_array4 *unew, const qk_array4 *u0, const qk_array4 *u1, const qk_array4 *const *fold,
+		const qk_array4 *const *fnew, double dt, const double *dx3)
+{
+	const int nh = RadSystem<P>::nvarHyperbolic_, nv = RadSystem<P>::nvar_;
+	amrex::GpuArray<amrex::Real, 3> dx{dx3[0], dx3[1], dx3[2]};
+	auto un = make_mf(valid, -1, nv, 0);
+	auto a0 = make_mf(valid, -1, nv, 0);
+	auto a1 = make_mf(valid, -1, nv, 0);
+	std::array<amrex::MultiFab, 3> FO{make_mf(valid, 0, nh, 0), make_mf(valid, 1, nh, 0), make_mf(valid, 2, nh, 0)};
+	std::array<amrex::MultiFab, 3> F{make_mf(valid, 0, nh, 0), make_mf(valid, 1, nh, 0), make_mf(valid, 2, nh, 0)};
+	copy_in(un, unew);
+	copy_in(a0, u0);
+	for (int d = 0; d < 3; ++d) {
+		copy_in(F[d], fnew[d]);
+	}
+	amrex::Box bx = to_box(valid);
+	if (op == 0) { // PredictStep
+		RadSystem<P>::PredictStep(a0.const_array(0), un.array(0), {F[0].const_array(0), F[1].const_array(0), F[2].const_array(0)},
+					  {F[0].const_array(0), F[1].const_array(0), F[2].const_array(0)}, dt, dx, bx, nh);
+	} else { // AddFluxesRK2
+		copy_in(a1, u1);
+		for (int d = 0; d < 3; ++d) {
+			copy_in(FO[d], fold[d]);
+		}
+		RadSystem<P>::AddFluxesRK2(un.array(0), a0.const_array(0), a1.const_array(0), {FO[0].const_array(0), FO[1].const_array(0), FO[2].const_array(0)},
+					   {F[0].const_array(0), F[1].const_array(0), F[2].const_array(0)},
+					   {FO[0].const_array(0), FO[1].const_array(0), FO[2].const_array(0)},
+					   {F[0].const_array(0), F[1].const_array(0), F[2].const_array(0)}, dt, dx, bx, nh);
+	}
+	copy_out(un, unew);
+}
+#define DISPATCH_R(problem, CALL)                                                                                                                    \
+	switch (problem) {                                                                                                                           \
+	case 0: {                                                                                                                                    \
+		using P = R0;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 1: {                                                                                                                                    \
+		using P = R1;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	default:                                                                                                                                     \
+		return -1;                                                                                                                           \
+	}
+
 #define DISPATCH_P(problem, CALL)                                                                                                                    \
 	switch (problem) {                                                                                                                           \
 	case 0: {                                                                                                                                    \
@@ -414,6 +536,43 @@ int ref_update_op(int problem, int op, const qk_box *valid, const qk_array4 *a0,
 {
 	ensure_init();
 	DISPATCH_P(problem, update_ops<P>(op, valid, a0, a1, a2, fx, fy, fz, redo, dx3, dt, dfloor, tfloor, scalar_out));
+	return 0;
+}
+
+// ---- radiation (problem = 0: R0, 1: R1) ----
+int ref_rad_params(int problem, qk_rad_params *out)
+{
+	DISPATCH_R(problem, {
+		out->c_light = RadSystem<P>::c_light_;
+		out->c_hat = RadSystem<P>::c_hat_;
+		out->Erad_floor = RadSystem_Traits<P>::Erad_floor;
+		out->ngroups = RadSystem<P>::nGroups_;
+		out->nstart = RadSystem<P>::nstartHyperbolic_;
+		out->reconstruction_order = 3;
+		out->integrator_order = 2;
+	});
+	return 0;
+}
+int ref_rad_cons_to_prim(int problem, const qk_box *valid, const qk_array4 *cons, const qk_array4 *prim, int ng)
+{
+	ensure_init();
+	DISPATCH_R(problem, rad_cons_to_prim<P>(valid, cons, prim, ng));
+	return 0;
+}
+int ref_rad_compute_fluxes(int problem, int dir, const qk_box *valid, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left,
+			   const qk_array4 *right, const qk_array4 *cons, int ngcons)
+{
+	ensure_init();
+	DISPATCH_R(problem, DISPATCH_D(dir, (rad_fluxes<P, D>(valid, flux, fdiff, left, right, cons, ngcons))));
+	return 0;
+}
+int ref_rad_update(int problem, int op, const qk_box *valid, const qk_array4 *unew, const qk_array4 *u0, const qk_array4 *u1, const qk_array4 *fxo,
+		   const qk_array4 *fyo, const qk_array4 *fzo, const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz, double dt, const double *dx3)
+{
+	ensure_init();
+	const qk_array4 *fo[3] = {fxo, fyo, fzo};
+	const qk_array4 *fn[3] = {fx, fy, fz};
+	DISPATCH_R(problem, rad_update<P>(op, valid, unew, u0, u1, fo, fn, dt, dx3));
 	return 0;
 }
 

@@ -85,6 +85,27 @@ class qk_hydro_params(C.Structure):
     ]
 
 
+class qk_rad_params(C.Structure):
+    """run-time image of RadSystem_Traits<problem_t> (src/radiation/radiation_system.hpp:73-82)"""
+
+    _fields_ = [
+        ("c_light", C.c_double),
+        ("c_hat", C.c_double),
+        ("Erad_floor", C.c_double),
+        ("ngroups", C.c_int32),
+        ("nstart", C.c_int32),
+        ("reconstruction_order", C.c_int32),
+        ("integrator_order", C.c_int32),
+    ]
+
+
+def rad_params(c_light=1.0, c_hat=1.0, Erad_floor=0.0, ngroups=1, nstart=6, recon_order=3, integrator_order=2) -> qk_rad_params:
+    p = qk_rad_params()
+    p.c_light, p.c_hat, p.Erad_floor = c_light, c_hat, Erad_floor
+    p.ngroups, p.nstart, p.reconstruction_order, p.integrator_order = ngroups, nstart, recon_order, integrator_order
+    return p
+
+
 K_B = 1.3806488e-16  # Microphysics constants/fundamental_constants.H:22
 M_U = 1.6605390666e-24  # :55
 
@@ -169,6 +190,7 @@ _IA4P = C.POINTER(qk_iarray4)
 _BXP = C.POINTER(qk_box)
 _PRM = C.POINTER(qk_hydro_params)
 _D3 = C.POINTER(C.c_double)
+_RPRM = C.POINTER(qk_rad_params)
 _I64P = C.POINTER(C.c_int64)
 _VP = C.c_void_p
 
@@ -195,6 +217,11 @@ SYMBOLS = {
     "qk_hydro_sync_dual_energy": (C.c_int, [_PRM, C.c_int, _BXP, _A4P, _I64P, _VP]),
     "qk_hydro_replace_fluxes": (C.c_int, [C.c_int, C.c_int, _BXP, _A4P, _A4P, _IA4P, C.c_int, _VP]),
     "qk_hydro_max_signal_speed": (C.c_int, [_PRM, C.c_int, C.c_int, _BXP, _A4P, _D3, _VP]),
+    "qk_rad_conserved_to_primitive": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, C.c_int, _VP]),
+    "qk_rad_compute_fluxes": (C.c_int, [_RPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _VP]),
+    "qk_rad_predict_step": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
+    "qk_rad_add_fluxes_rk2": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
+    "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),
     "qk_level_create": (C.c_int, [C.POINTER(qk_level_desc), C.POINTER(_VP)]),
     "qk_level_destroy": (None, [_VP]),
     "qk_level_nlocal": (C.c_int, [_VP]),

@@ -375,6 +375,7 @@ extern "C" void qk_level_destroy(qk_level *L)
 	L->plan.destroy();
 	L->plan1.destroy();
 	qk_fused_free(L);
+	qk_rad_free(L);
 	L->free_scratch();
 	if (L->d_bc_lo)
 		cudaFree(L->d_bc_lo);

@@ -82,6 +82,7 @@ struct FaithfulScratch {
 };
 
 struct FusedState; // qk_sweep.cu
+struct RadState;   // qk_rad.cu
 
 struct qk_level {
 	qk_box domain;
@@ -105,6 +106,7 @@ struct qk_level {
 	int64_t scratch_bytes = 0;
 	FaithfulScratch scr;
 	FusedState *fused = nullptr;
+	RadState *rad = nullptr;
 
 	const A4 *dev_table(const qk_array4 *arrs, cudaStream_t s, int *err);
 	const IA4 *dev_table_int(const qk_iarray4 *arrs, cudaStream_t s, int *err);
@@ -129,6 +131,7 @@ struct qk_level {
 
 void qk_plan_tags(const qk_level &L, int ng, std::vector<HostTag> &out);
 void qk_fused_free(qk_level *L);
+void qk_rad_free(qk_level *L);
 void qk_fused_untaint(qk_level *L);
 
 // ---- communicator (qk_comm.cpp): NCCL resolved at run time with dlopen, so the library loads on machines

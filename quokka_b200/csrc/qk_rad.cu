@@ -1,0 +1,660 @@
+// qk_rad.cu -- two-moment (M1) radiation transport sweep: RadSystem<problem_t> of src/radiation/radiation_system.hpp
+// as driven by QuokkaSimulation::advanceRadiationForwardEuler / advanceRadiationMidpointRK2 and fluxFunction<DIR>
+// (src/QuokkaSimulation.hpp:1791-1862, 1903-1986).
+//
+//   per-operator kernels (parity harness, operator-level drop-in): k_rad_prim_op, k_rad_flux_op<DIR>, k_rad_predict_op,
+//                                                                  k_rad_rk2_op
+//   fused stage (qk_rad_advance_stage):  k_rad_prim   (E_r, F) -> (E_r, f = F / (c E_r)) on the valid box grown by 3, all boxes
+//                                        k_rad_stage  one CTA per 32 x 4 x 4 tile of cells: every thread reconstructs and
+//                                                     solves the HLL problem of the three LOW faces of its cell (PPM /
+//                                                     PLM-MC / donor cell on the reduced-flux primitives, Levermore closure,
+//                                                     frozen Eddington tensor), the tile's high faces are done by a second
+//                                                     small pass, fluxes meet in shared memory, and the conservative
+//                                                     update (PredictStep or AddFluxesRK2 + isStateValid / amendRadState)
+//                                                     is written straight to the new state: no left/right/flux arrays.
+//
+// Arithmetic: the reference's IEEE operation order, --fmad=false.  Parity with the oracle is bit for bit
+// (tests/test_gpu_radiation.py).
+#include "qk_level.h"
+#include "qk_kernels.cuh"
+
+#include <algorithm>
+
+namespace
+{
+struct RadConst {
+	double c, chat;
+	double chat_over_c, chat_times_c; // c_hat_/c_light_ and c_hat_*c_light_ as the reference forms them (:1087-1093)
+	double floor_g;			   // Erad_floor_ = Erad_floor / nGroups (:211)
+	int ng, nstart;
+};
+
+RadConst make_rad_const(const qk_rad_params *p)
+{
+	RadConst c;
+	c.c = p->c_light;
+	c.chat = p->c_hat;
+	c.chat_over_c = p->c_hat / p->c_light;
+	c.chat_times_c = p->c_hat * p->c_light;
+	c.floor_g = p->Erad_floor / p->ngroups;
+	c.ng = p->ngroups;
+	c.nstart = p->nstart;
+	return c;
+}
+
+int check_rad(const qk_rad_params *p)
+{
+	if (!p)
+		return QK_ERR_BAD_ARG;
+	if (p->ngroups < 1 || p->ngroups > QK_MAX_GROUPS || p->nstart < 0 || p->reconstruction_order < 1 || p->reconstruction_order > 3)
+		return QK_ERR_UNSUPPORTED;
+	return qk_require_device();
+}
+
+// RadSystem::ComputeEddingtonFactor  :773-790 (Levermore 1984)
+__device__ __forceinline__ double rad_eddington_factor(double f_in)
+{
+	const double f = clampd(f_in, 0., 1.);
+	const double f_fac = sqrt(4.0 - 3.0 * (f * f));
+	return (3.0 + 4.0 * (f * f)) / (5.0 + 2.0 * f_fac);
+}
+
+// ComputeEddingtonTensor :873-916 + ComputeRadPressure<DIR> :918-983.  Only row DIR of the tensor is needed.
+template <int DIR> __device__ __forceinline__ void rad_pressure(double erad, double Fn, double fx, double fy, double fz, double *F, double &S)
+{
+	const double f = sqrt(fx * fx + fy * fy + fz * fz);
+	const double fv[3] = {fx, fy, fz};
+	double n[3];
+#pragma unroll
+	for (int ii = 0; ii < 3; ++ii)
+		n[ii] = (f > 0.) ? (fv[ii] / f) : 0.;
+	const double chi = rad_eddington_factor(f);
+	const double Tdiag = (1.0 - chi) / 2.0;
+	const double Tf = (3.0 * chi - 1.0) / 2.0;
+	double T[3];
+#pragma unroll
+	for (int jj = 0; jj < 3; ++jj) {
+		const double delta_ij = (DIR == jj) ? 1 : 0;
+		T[jj] = Tdiag * delta_ij + Tf * (n[DIR] * n[jj]);
+	}
+	F[0] = Fn;
+	F[1] = T[0] * erad;
+	F[2] = T[1] * erad;
+	F[3] = T[2] * erad;
+	const double sq = sqrt(T[DIR]);
+	S = (0.1 < sq) ? sq : 0.1; // std::max(0.1, std::sqrt(Tnormal)) :980
+}
+
+// HLL flux of one face of one group (ComputeFluxes<DIR> body :1028-1137, epsilon = 1).  L/R: reconstructed (E_r, fx, fy, fz);
+// consL/consR point at component radEnergy of the cells either side of the face (first-order fallback :1054-1079).
+template <int DIR>
+__device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
+					      double *F)
+{
+	double erad_L = L[0], erad_R = R[0];
+	double fL[3] = {L[1], L[2], L[3]}, fR[3] = {R[1], R[2], R[3]};
+	double f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
+	double f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
+	double FL[3], FR[3];
+#pragma unroll
+	for (int m = 0; m < 3; ++m) {
+		FL[m] = fL[m] * (c.c * erad_L);
+		FR[m] = fR[m] * (c.c * erad_R);
+	}
+	if ((erad_L <= 0.) || (erad_R <= 0.) || (f_L >= 1.) || (f_R >= 1.)) {
+		erad_L = consL[0];
+		erad_R = consR[0];
+#pragma unroll
+		for (int m = 0; m < 3; ++m) {
+			FL[m] = consL[(1 + m) * cns];
+			FR[m] = consR[(1 + m) * cns];
+			fL[m] = FL[m] / (c.c * erad_L);
+			fR[m] = FR[m] / (c.c * erad_R);
+		}
+		f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
+		f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
+	}
+	double F_L[4], F_R[4], S_L, S_R;
+	rad_pressure<DIR>(erad_L, FL[DIR], fL[0], fL[1], fL[2], F_L, S_L);
+	S_L *= -1.;
+	rad_pressure<DIR>(erad_R, FR[DIR], fR[0], fR[1], fR[2], F_R, S_R);
+	F_L[0] *= c.chat_over_c;
+	F_R[0] *= c.chat_over_c;
+#pragma unroll
+	for (int n = 1; n < 4; ++n) {
+		F_L[n] *= c.chat_times_c;
+		F_R[n] *= c.chat_times_c;
+	}
+	S_L *= c.chat;
+	S_R *= c.chat;
+	const double U_L[4] = {erad_L, FL[0], FL[1], FL[2]};
+	const double U_R[4] = {erad_R, FR[0], FR[1], FR[2]};
+	const double a = S_R / (S_R - S_L), b = S_L / (S_R - S_L), d = S_R * S_L / (S_R - S_L);
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+		F[n] = a * F_L[n] - b * F_R[n] + d * (U_R[n] - U_L[n]);
+}
+
+// isStateValid :624-643 + amendRadState :645-665 on the NG groups of one cell
+template <int NGMAX> __device__ __forceinline__ void rad_validate(const RadConst &c, int ng, double *cons)
+{
+	bool valid = true;
+#pragma unroll
+	for (int g = 0; g < NGMAX; ++g) {
+		if (g < ng) {
+			const double E_r = cons[4 * g], Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
+			const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+			const double f = Fnorm / (c.c * E_r);
+			valid = (valid && (E_r > 0.) && (f <= 1.));
+		}
+	}
+	if (valid)
+		return;
+#pragma unroll
+	for (int g = 0; g < NGMAX; ++g) {
+		if (g < ng) {
+			double E_r = cons[4 * g];
+			if (E_r < c.floor_g) {
+				E_r = c.floor_g;
+				cons[4 * g] = c.floor_g;
+			}
+			const double Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
+			if (Fx * Fx + Fy * Fy + Fz * Fz > c.c * c.c * E_r * E_r) {
+				const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
+				cons[4 * g + 1] = Fx / Fnorm * c.c * E_r;
+				cons[4 * g + 2] = Fy / Fnorm * c.c * E_r;
+				cons[4 * g + 3] = Fz / Fnorm * c.c * E_r;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-operator kernels
+// ---------------------------------------------------------------------------------------------------------------
+// RadSystem::ConservedToPrimitive  :589-614
+__global__ void __launch_bounds__(TPB) k_rad_prim_op(RadConst c, Iter it, A4 cons, A4 prim)
+{
+	int i, j, k;
+	if (!it.get((int64_t)blockIdx.x * TPB + threadIdx.x, i, j, k))
+		return;
+	const int64_t o = cons.off(i, j, k), op = prim.off(i, j, k);
+	for (int g = 0; g < c.ng; ++g) {
+		const double *u = cons.p + o + (c.nstart + 4 * g) * cons.ns;
+		const double E_r = u[0], Fx = u[cons.ns], Fy = u[2 * cons.ns], Fz = u[3 * cons.ns];
+		double *q = prim.p + op + 4 * g * prim.ns;
+		q[0] = E_r;
+		q[prim.ns] = Fx / (c.c * E_r);
+		q[2 * prim.ns] = Fy / (c.c * E_r);
+		q[3 * prim.ns] = Fz / (c.c * E_r);
+	}
+}
+
+// RadSystem::ComputeFluxes<DIR>  :985-1139 from materialised left/right states
+template <int DIR> __global__ void __launch_bounds__(TPB) k_rad_flux_op(RadConst c, Iter it, A4 flux, A4 fdiff, bool have_fdiff, A4 left, A4 right, A4 cons)
+{
+	int i, j, k;
+	if (!it.get((int64_t)blockIdx.x * TPB + threadIdx.x, i, j, k))
+		return;
+	const int64_t sc = (DIR == 0) ? 1 : (DIR == 1) ? cons.js : cons.ks;
+	for (int g = 0; g < c.ng; ++g) {
+		double L[4], R[4], F[4];
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			L[n] = left(i, j, k, 4 * g + n);
+			R[n] = right(i, j, k, 4 * g + n);
+		}
+		const double *cR = cons.p + cons.off(i, j, k) + (c.nstart + 4 * g) * cons.ns;
+		rad_face_flux<DIR>(c, L, R, cR - sc, cR, cons.ns, F);
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			flux(i, j, k, 4 * g + n) = F[n];
+			if (have_fdiff)
+				fdiff(i, j, k, 4 * g + n) = F[n]; // epsilon = 1: the "diffusive" flux is the same expression (:1130-1131)
+		}
+	}
+}
+
+// RadSystem::PredictStep :667-710 (RK2 = false) / AddFluxesRK2 :712-771 (RK2 = true)
+template <bool RK2>
+__global__ void __launch_bounds__(TPB) k_rad_update_op(RadConst c, Iter it, A4 unew, A4 u0, A4 u1, A4 fxo, A4 fyo, A4 fzo, A4 fx, A4 fy, A4 fz, double dtdx,
+						       double dtdy, double dtdz)
+{
+	int i, j, k;
+	if (!it.get((int64_t)blockIdx.x * TPB + threadIdx.x, i, j, k))
+		return;
+	double cons[4 * QK_MAX_GROUPS];
+	const int nh = 4 * c.ng;
+	for (int n = 0; n < nh; ++n) {
+		const double FxU_1 = dtdx * (fx(i, j, k, n) - fx(i + 1, j, k, n));
+		const double FyU_1 = dtdy * (fy(i, j, k, n) - fy(i, j + 1, k, n));
+		const double FzU_1 = dtdz * (fz(i, j, k, n) - fz(i, j, k + 1, n));
+		const double U_0 = u0(i, j, k, c.nstart + n);
+		if (!RK2) {
+			cons[n] = U_0 + (FxU_1 + FyU_1 + FzU_1);
+		} else {
+			const double IMEX_a32 = 0.5;
+			const double U_1 = u1(i, j, k, c.nstart + n);
+			const double FxU_0 = dtdx * (fxo(i, j, k, n) - fxo(i + 1, j, k, n));
+			const double FyU_0 = dtdy * (fyo(i, j, k, n) - fyo(i, j + 1, k, n));
+			const double FzU_0 = dtdz * (fzo(i, j, k, n) - fzo(i, j, k + 1, n));
+			cons[n] = (1.0 - IMEX_a32) * U_0 + IMEX_a32 * U_1 + ((0.5 - IMEX_a32) * (FxU_0 + FyU_0 + FzU_0)) + (0.5 * (FxU_1 + FyU_1 + FzU_1));
+		}
+	}
+	rad_validate<QK_MAX_GROUPS>(c, c.ng, cons);
+	for (int n = 0; n < nh; ++n)
+		unew(i, j, k, c.nstart + n) = cons[n];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused stage
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RTX = 32, RTY = 4, RTZ = 4;
+constexpr int RSX = RTX + 1, RSY = RTY + 1, RSZ = RTZ + 1;
+constexpr int RAD_SMEM_DOUBLES = 3 * 4 * RSX * RSY * RSZ;
+
+struct RadBox {
+	A4 U0, Us, Uo; // state_old, stage input (ghost-filled), stage output
+	A4 prim;       // 4*NG reduced-flux primitives of Us (valid box grown by 3)
+	A4 S0;	       // stage-1 flux divergence (FxU_0 + FyU_0 + FzU_0), 4*NG components on the valid cells
+	int lo[3], hi[3];
+};
+
+__global__ void __launch_bounds__(256) k_rad_prim(RadConst c, const RadBox *__restrict__ boxes, int halo)
+{
+	const RadBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 1 + 2 * halo, ny = B.hi[1] - B.lo[1] + 1 + 2 * halo, nz = B.hi[2] - B.lo[2] + 1 + 2 * halo;
+	const int64_t total = (int64_t)nx * ny * nz;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - halo + (int)(t - jk * nx);
+		const int k = B.lo[2] - halo + (int)(jk / ny);
+		const int j = B.lo[1] - halo + (int)(jk - (jk / ny) * ny);
+		const int64_t o = B.Us.off(i, j, k), op = B.prim.off(i, j, k);
+		for (int g = 0; g < c.ng; ++g) {
+			const double *u = B.Us.p + o + (c.nstart + 4 * g) * B.Us.ns;
+			const double E_r = u[0], Fx = u[B.Us.ns], Fy = u[2 * B.Us.ns], Fz = u[3 * B.Us.ns];
+			double *q = B.prim.p + op + 4 * g * B.prim.ns;
+			q[0] = E_r;
+			q[B.prim.ns] = Fx / (c.c * E_r);
+			q[2 * B.prim.ns] = Fy / (c.c * E_r);
+			q[3 * B.prim.ns] = Fz / (c.c * E_r);
+		}
+	}
+}
+
+// left state of face (cell-1 | cell) = a_plus of cell-1, right state = a_minus of cell; qp points at the cell on the high side
+template <int ORDER> __device__ __forceinline__ void rad_recon_face(const double *qp, int64_t s, double &L, double &R)
+{
+	if (ORDER == 1) {
+		L = qp[-s];
+		R = qp[0];
+	} else if (ORDER == 2) { // PLM, MC limiter, interface-centred (src/hyperbolic_system.hpp:243-246)
+		const double qm2 = qp[-2 * s], qm1 = qp[-s], q0 = qp[0], qp1 = qp[s];
+		L = qm1 + 0.25 * lim_MC(q0 - qm1, qm1 - qm2);
+		R = q0 - 0.25 * lim_MC(qp1 - q0, q0 - qm1);
+	} else {
+		const double qm3 = qp[-3 * s], qm2 = qp[-2 * s], qm1 = qp[-s], q0 = qp[0], qp1 = qp[s], qp2 = qp[2 * s];
+		const double if_m = ppm_iface(qm3, qm2, qm1, q0), if_0 = ppm_iface(qm2, qm1, q0, qp1), if_p = ppm_iface(qm1, q0, qp1, qp2);
+		double am, ap;
+		ppm_limit(qm2, qm1, q0, if_m, if_0, am, ap);
+		L = ap;
+		ppm_limit(qm1, q0, qp1, if_0, if_p, am, ap);
+		R = am;
+	}
+}
+
+template <int ORDER, int DIR> __device__ __forceinline__ void rad_face_of_cell(const RadConst &c, const RadBox &B, int g, int i, int j, int k, double *F)
+{
+	const A4 &q = B.prim;
+	const int64_t s = (DIR == 0) ? 1 : (DIR == 1) ? q.js : q.ks;
+	const double *qp = q.p + q.off(i, j, k) + 4 * g * q.ns;
+	double L[4], R[4];
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+		rad_recon_face<ORDER>(qp + n * q.ns, s, L[n], R[n]);
+	const A4 &u = B.Us;
+	const int64_t su = (DIR == 0) ? 1 : (DIR == 1) ? u.js : u.ks;
+	const double *cR = u.p + u.off(i, j, k) + (c.nstart + 4 * g) * u.ns;
+	rad_face_flux<DIR>(c, L, R, cR - su, cR, u.ns, F);
+}
+
+__device__ __forceinline__ int rs_idx(int d, int n, int lz, int ly, int lx) { return (((d * 4 + n) * RSZ + lz) * RSY + ly) * RSX + lx; }
+
+template <int ORDER, int STAGE, bool KEEP_S0, int NG>
+__global__ void __launch_bounds__(RTX *RTY *RTZ) k_rad_stage(RadConst c, const RadBox *__restrict__ boxes, int tiles_y, int tiles_z, double dtdx, double dtdy,
+							      double dtdz)
+{
+	extern __shared__ double sF[];
+	const int box = blockIdx.z / tiles_z, tz = blockIdx.z - box * tiles_z;
+	const RadBox &B = boxes[box];
+	const int lx = threadIdx.x & 31, ly = (threadIdx.x >> 5) & 3, lz = threadIdx.x >> 7;
+	const int i0 = B.lo[0] + blockIdx.x * RTX, j0 = B.lo[1] + blockIdx.y * RTY, k0 = B.lo[2] + tz * RTZ;
+	if (i0 > B.hi[0] || j0 > B.hi[1] || k0 > B.hi[2])
+		return; // whole CTA
+	const int i = i0 + lx, j = j0 + ly, k = k0 + lz;
+	const bool inx = (i <= B.hi[0]), iny = (j <= B.hi[1]), inz = (k <= B.hi[2]);
+	const bool cell = inx && iny && inz;
+	double cons[4 * NG];
+#pragma unroll
+	for (int g = 0; g < NG; ++g) {
+		if (g > 0)
+			__syncthreads(); // shared fluxes of the previous group have been consumed
+		// pass 1: the three low faces of this thread's cell (a cell one past the box edge along d still owns the box's last d-face)
+		double F[4];
+		if ((i <= B.hi[0] + 1) && iny && inz) {
+			rad_face_of_cell<ORDER, 0>(c, B, g, i, j, k, F);
+#pragma unroll
+			for (int n = 0; n < 4; ++n)
+				sF[rs_idx(0, n, lz, ly, lx)] = F[n];
+		}
+		if (inx && (j <= B.hi[1] + 1) && inz) {
+			rad_face_of_cell<ORDER, 1>(c, B, g, i, j, k, F);
+#pragma unroll
+			for (int n = 0; n < 4; ++n)
+				sF[rs_idx(1, n, lz, ly, lx)] = F[n];
+		}
+		if (inx && iny && (k <= B.hi[2] + 1)) {
+			rad_face_of_cell<ORDER, 2>(c, B, g, i, j, k, F);
+#pragma unroll
+			for (int n = 0; n < 4; ++n)
+				sF[rs_idx(2, n, lz, ly, lx)] = F[n];
+		}
+		// pass 2: the faces on the high side of the tile
+		const int t = threadIdx.x;
+		if (t < RTY * RTZ) { // x faces at i0 + RTX
+			const int py = t & 3, pz = t >> 2;
+			const int fi = i0 + RTX, fj = j0 + py, fk = k0 + pz;
+			if (fi <= B.hi[0] + 1 && fj <= B.hi[1] && fk <= B.hi[2]) {
+				rad_face_of_cell<ORDER, 0>(c, B, g, fi, fj, fk, F);
+#pragma unroll
+				for (int n = 0; n < 4; ++n)
+					sF[rs_idx(0, n, pz, py, RTX)] = F[n];
+			}
+		} else if (t >= 32 && t < 32 + RTX * RTZ) { // y faces at j0 + RTY
+			const int u = t - 32, px = u & 31, pz = u >> 5;
+			const int fi = i0 + px, fj = j0 + RTY, fk = k0 + pz;
+			if (fi <= B.hi[0] && fj <= B.hi[1] + 1 && fk <= B.hi[2]) {
+				rad_face_of_cell<ORDER, 1>(c, B, g, fi, fj, fk, F);
+#pragma unroll
+				for (int n = 0; n < 4; ++n)
+					sF[rs_idx(1, n, pz, RTY, px)] = F[n];
+			}
+		} else if (t >= 32 + RTX * RTZ && t < 32 + RTX * RTZ + RTX * RTY) { // z faces at k0 + RTZ
+			const int u = t - 32 - RTX * RTZ, px = u & 31, py = u >> 5;
+			const int fi = i0 + px, fj = j0 + py, fk = k0 + RTZ;
+			if (fi <= B.hi[0] && fj <= B.hi[1] && fk <= B.hi[2] + 1) {
+				rad_face_of_cell<ORDER, 2>(c, B, g, fi, fj, fk, F);
+#pragma unroll
+				for (int n = 0; n < 4; ++n)
+					sF[rs_idx(2, n, RTZ, py, px)] = F[n];
+			}
+		}
+		__syncthreads();
+		if (cell) {
+			const int64_t o0 = B.U0.off(i, j, k) + (c.nstart + 4 * g) * B.U0.ns;
+			const int64_t os = B.S0.off(i, j, k) + 4 * g * B.S0.ns;
+#pragma unroll
+			for (int n = 0; n < 4; ++n) {
+				const double FxU = dtdx * (sF[rs_idx(0, n, lz, ly, lx)] - sF[rs_idx(0, n, lz, ly, lx + 1)]);
+				const double FyU = dtdy * (sF[rs_idx(1, n, lz, ly, lx)] - sF[rs_idx(1, n, lz, ly + 1, lx)]);
+				const double FzU = dtdz * (sF[rs_idx(2, n, lz, ly, lx)] - sF[rs_idx(2, n, lz + 1, ly, lx)]);
+				const double div = FxU + FyU + FzU;
+				const double U_0 = B.U0.p[o0 + n * B.U0.ns];
+				if (STAGE == 1) {
+					cons[4 * g + n] = U_0 + div; // PredictStep :694-698
+					if (KEEP_S0)
+						B.S0.p[os + n * B.S0.ns] = div;
+				} else { // AddFluxesRK2 :757-759
+					const double IMEX_a32 = 0.5;
+					const double U_1 = B.Us.p[B.Us.off(i, j, k) + (c.nstart + 4 * g + n) * B.Us.ns];
+					const double div0 = B.S0.p[os + n * B.S0.ns];
+					cons[4 * g + n] = (1.0 - IMEX_a32) * U_0 + IMEX_a32 * U_1 + ((0.5 - IMEX_a32) * div0) + (0.5 * div);
+				}
+			}
+		}
+	}
+	if (cell) {
+		rad_validate<NG>(c, NG, cons);
+		const int64_t oo = B.Uo.off(i, j, k) + c.nstart * B.Uo.ns;
+#pragma unroll
+		for (int n = 0; n < 4 * NG; ++n)
+			B.Uo.p[oo + n * B.Uo.ns] = cons[n];
+	}
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+#define QK_TRY(x)                                                                                                                                    \
+	do {                                                                                                                                         \
+		int r_ = (x);                                                                                                                        \
+		if (r_ != 0)                                                                                                                         \
+			return r_;                                                                                                                   \
+	} while (0)
+
+extern "C" int qk_rad_conserved_to_primitive(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, const qk_array4 *prim,
+					     int nghost, void *stream)
+{
+	QK_TRY(check_rad(prm));
+	const RadConst c = make_rad_const(prm);
+	ProfScope prof_("rad_cons_to_prim", S(stream));
+	for (int b = 0; b < nboxes; ++b) {
+		Iter it(Box3(valid[b]).grown(nghost));
+		k_rad_prim_op<<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(cons[b]), A4(prim[b]));
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+extern "C" int qk_rad_compute_fluxes(const qk_rad_params *prm, int dir, int nboxes, const qk_box *valid, const qk_array4 *flux,
+				     const qk_array4 *flux_diffusive, const qk_array4 *left, const qk_array4 *right, const qk_array4 *cons, void *stream)
+{
+	QK_TRY(check_rad(prm));
+	if (dir < 0 || dir > 2)
+		return QK_ERR_BAD_ARG;
+	const RadConst c = make_rad_const(prm);
+	ProfScope prof_("rad_compute_fluxes", S(stream));
+	for (int b = 0; b < nboxes; ++b) {
+		Iter it(Box3(valid[b]).face(dir));
+		const bool hd = (flux_diffusive != nullptr);
+		const A4 fd = hd ? A4(flux_diffusive[b]) : A4(flux[b]);
+		if (dir == 0)
+			k_rad_flux_op<0><<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(flux[b]), fd, hd, A4(left[b]), A4(right[b]), A4(cons[b]));
+		else if (dir == 1)
+			k_rad_flux_op<1><<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(flux[b]), fd, hd, A4(left[b]), A4(right[b]), A4(cons[b]));
+		else
+			k_rad_flux_op<2><<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(flux[b]), fd, hd, A4(left[b]), A4(right[b]), A4(cons[b]));
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+extern "C" int qk_rad_predict_step(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons_old, const qk_array4 *cons_new,
+				   const qk_array4 *fx, const qk_array4 *fy, const qk_array4 *fz, double dt, const double dx[3], void *stream)
+{
+	QK_TRY(check_rad(prm));
+	const RadConst c = make_rad_const(prm);
+	ProfScope prof_("rad_predict_step", S(stream));
+	for (int b = 0; b < nboxes; ++b) {
+		Iter it{Box3(valid[b])};
+		k_rad_update_op<false><<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(cons_new[b]), A4(cons_old[b]), A4(cons_old[b]), A4(fx[b]), A4(fy[b]),
+									   A4(fz[b]), A4(fx[b]), A4(fy[b]), A4(fz[b]), dt / dx[0], dt / dx[1], dt / dx[2]);
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+extern "C" int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const qk_box *valid, const qk_array4 *u_new, const qk_array4 *u0,
+				     const qk_array4 *u1, const qk_array4 *fx_old, const qk_array4 *fy_old, const qk_array4 *fz_old, const qk_array4 *fx,
+				     const qk_array4 *fy, const qk_array4 *fz, double dt, const double dx[3], void *stream)
+{
+	QK_TRY(check_rad(prm));
+	const RadConst c = make_rad_const(prm);
+	ProfScope prof_("rad_add_fluxes_rk2", S(stream));
+	for (int b = 0; b < nboxes; ++b) {
+		Iter it{Box3(valid[b])};
+		k_rad_update_op<true><<<it.blocks(), TPB, 0, S(stream)>>>(c, it, A4(u_new[b]), A4(u0[b]), A4(u1[b]), A4(fx_old[b]), A4(fy_old[b]), A4(fz_old[b]),
+									  A4(fx[b]), A4(fy[b]), A4(fz[b]), dt / dx[0], dt / dx[1], dt / dx[2]);
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+// ---- fused stage ------------------------------------------------------------------------------------------------
+struct RadState {
+	int nh = 0; // 4 * ngroups the scratch was built for
+	std::vector<qk_array4> prim, S0;
+	RadBox *d_boxes = nullptr, *h_boxes = nullptr; // ring of 8 tables
+	int ring = 0;
+	cudaEvent_t ev[8];
+	bool ev_used[8];
+	bool s0_valid = false;
+};
+
+void qk_rad_free(qk_level *L)
+{
+	if (!L->rad)
+		return;
+	RadState *R = L->rad;
+	if (R->d_boxes)
+		cudaFree(R->d_boxes);
+	if (R->h_boxes) {
+		cudaFreeHost(R->h_boxes);
+		for (int i = 0; i < 8; ++i)
+			cudaEventDestroy(R->ev[i]);
+	}
+	delete R;
+	L->rad = nullptr;
+}
+
+static int rad_setup(qk_level *L, int nh)
+{
+	if (L->rad && L->rad->nh == nh)
+		return 0;
+	if (L->rad)
+		return QK_ERR_UNSUPPORTED;
+	RadState *R = new RadState();
+	L->rad = R;
+	const int nb = (int)L->valid.size();
+	QK_TRY(L->alloc_fabs(R->prim, nh, 3, -1));
+	QK_TRY(L->alloc_fabs(R->S0, nh, 0, -1));
+	QK_CUDA(cudaMalloc(&R->d_boxes, sizeof(RadBox) * nb * 8));
+	QK_CUDA(cudaMallocHost(&R->h_boxes, sizeof(RadBox) * nb * 8));
+	for (int i = 0; i < 8; ++i) {
+		QK_CUDA(cudaEventCreateWithFlags(&R->ev[i], cudaEventDisableTiming));
+		R->ev_used[i] = false;
+	}
+	R->nh = nh;
+	return 0;
+}
+
+template <int ORDER, int NG>
+static int launch_rad_stage(const RadConst &c, const RadBox *tab, int nb, const int maxn[3], int stage, bool keep, double dtdx, double dtdy, double dtdz,
+			    cudaStream_t s)
+{
+	const int tx = (maxn[0] + RTX - 1) / RTX, ty = (maxn[1] + RTY - 1) / RTY, tz = (maxn[2] + RTZ - 1) / RTZ;
+	dim3 grid(tx, ty, tz * nb);
+	const size_t smem = sizeof(double) * RAD_SMEM_DOUBLES;
+#define QK_RAD_LAUNCH(ST, KP)                                                                                                                        \
+	do {                                                                                                                                         \
+		auto kern = k_rad_stage<ORDER, ST, KP, NG>;                                                                                          \
+		static bool attr_set = false;                                                                                                        \
+		if (!attr_set) {                                                                                                                     \
+			QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                                 \
+			attr_set = true;                                                                                                             \
+		}                                                                                                                                    \
+		kern<<<grid, RTX * RTY * RTZ, smem, s>>>(c, tab, ty, tz, dtdx, dtdy, dtdz);                                                          \
+	} while (0)
+	if (stage == 1 && keep)
+		QK_RAD_LAUNCH(1, true);
+	else if (stage == 1)
+		QK_RAD_LAUNCH(1, false);
+	else
+		QK_RAD_LAUNCH(2, false);
+#undef QK_RAD_LAUNCH
+	QK_KERNEL_CHECK();
+	return 0;
+}
+
+template <int NG>
+static int dispatch_rad_order(int order, const RadConst &c, const RadBox *tab, int nb, const int maxn[3], int stage, bool keep, double dtdx, double dtdy,
+			      double dtdz, cudaStream_t s)
+{
+	if (order == 3)
+		return launch_rad_stage<3, NG>(c, tab, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+	if (order == 2)
+		return launch_rad_stage<2, NG>(c, tab, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+	return launch_rad_stage<1, NG>(c, tab, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+}
+
+extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout,
+				    double dt, void *stream)
+{
+	if (!L || !U0 || !Ustage || !Uout || (stage != 1 && stage != 2))
+		return QK_ERR_BAD_ARG;
+	QK_TRY(check_rad(prm));
+	if (!L->has_device)
+		return QK_ERR_NO_DEVICE;
+	const int ng = prm->ngroups;
+	if (ng != 1 && ng != 2 && ng != 4)
+		return QK_ERR_UNSUPPORTED; // instantiated group counts of the fused kernel
+	if (L->nghost < 3 || prm->nstart + 4 * ng > L->ncomp)
+		return QK_ERR_BAD_ARG;
+	cudaStream_t s = S(stream);
+	QK_TRY(rad_setup(L, 4 * ng));
+	RadState *R = L->rad;
+	const int nb = (int)L->valid.size();
+	if (stage == 2 && !R->s0_valid)
+		return QK_ERR_BAD_ARG; // stage 2 needs the stage-1 flux divergence of the same step
+	for (int b = 0; b < nb; ++b)
+		if (Uout[b].p == Ustage[b].p || Uout[b].p == U0[b].p)
+			return QK_ERR_BAD_ARG; // a tile reads its neighbours' cells of Ustage / U0 while other tiles write Uout
+	const int slot = R->ring;
+	R->ring = (R->ring + 1) % 8;
+	if (R->ev_used[slot])
+		QK_CUDA(cudaEventSynchronize(R->ev[slot]));
+	RadBox *hb = R->h_boxes + (size_t)slot * nb;
+	int maxn[3] = {1, 1, 1};
+	for (int b = 0; b < nb; ++b) {
+		RadBox &B = hb[b];
+		B.U0 = A4(U0[b]);
+		B.Us = A4(Ustage[b]);
+		B.Uo = A4(Uout[b]);
+		B.prim = A4(R->prim[b]);
+		B.S0 = A4(R->S0[b]);
+		for (int d = 0; d < 3; ++d) {
+			B.lo[d] = L->valid[b].lo[d];
+			B.hi[d] = L->valid[b].hi[d];
+			maxn[d] = std::max(maxn[d], B.hi[d] - B.lo[d] + 1);
+		}
+	}
+	RadBox *db = R->d_boxes + (size_t)slot * nb;
+	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(RadBox) * nb, cudaMemcpyHostToDevice, s));
+	QK_CUDA(cudaEventRecord(R->ev[slot], s));
+	R->ev_used[slot] = true;
+	const RadConst c = make_rad_const(prm);
+	{
+		ProfScope p("rad_prim", s);
+		const int64_t cells = (int64_t)(maxn[0] + 6) * (maxn[1] + 6) * (maxn[2] + 6);
+		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+		k_rad_prim<<<grid, 256, 0, s>>>(c, db, 3);
+		QK_KERNEL_CHECK();
+	}
+	const bool keep = (stage == 1 && prm->integrator_order == 2);
+	const double dtdx = dt / L->dx[0], dtdy = dt / L->dx[1], dtdz = dt / L->dx[2];
+	int rc;
+	{
+		ProfScope p("rad_stage", s);
+		if (ng == 1)
+			rc = dispatch_rad_order<1>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+		else if (ng == 2)
+			rc = dispatch_rad_order<2>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+		else
+			rc = dispatch_rad_order<4>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+	}
+	QK_TRY(rc);
+	R->s0_valid = (stage == 1 && keep);
+	return 0;
+}

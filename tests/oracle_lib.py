@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from quokka_b200.capi import (qk_array4, qk_box, qk_hydro_params, qk_iarray4, qk_level_desc)
+from quokka_b200.capi import (qk_array4, qk_box, qk_hydro_params, qk_iarray4, qk_level_desc, qk_rad_params)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -23,6 +23,7 @@ _IA4P = C.POINTER(qk_iarray4)
 _BXP = C.POINTER(qk_box)
 _PRM = C.POINTER(qk_hydro_params)
 _D3 = C.POINTER(C.c_double)
+_RPRM = C.POINTER(qk_rad_params)
 _I64P = C.POINTER(C.c_int64)
 
 
@@ -69,6 +70,12 @@ def oracle() -> C.CDLL:
         "orc_advance_hydro_level": (C.c_int, [C.c_void_p, _PRM, C.c_double, C.c_double, _I64P, _I64P]),
         "orc_compute_timestep": (C.c_double, [C.c_void_p, _PRM, C.c_double, C.c_double, C.c_double]),
         "orc_step_with_retries": (C.c_int, [C.c_void_p, _PRM, C.c_double, C.c_double]),
+        "orc_rad_conserved_to_primitive": (None, [_RPRM, _A4P, _A4P, _BXP]),
+        "orc_rad_compute_fluxes": (None, [_RPRM, C.c_int, _A4P, _A4P, _A4P, _A4P, _A4P, _BXP]),
+        "orc_rad_predict_step": (None, [_RPRM, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _BXP]),
+        "orc_rad_add_fluxes_rk2": (None, [_RPRM, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _BXP]),
+        "orc_rad_advance_level": (None, [C.c_void_p, _RPRM, C.c_double]),
+        "orc_level_swap": (None, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -98,6 +105,10 @@ def ref() -> C.CDLL:
     lib.ref_flatten_shocks.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int, C.c_int, C.c_int]
     lib.ref_compute_fluxes.argtypes = [C.c_int, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int, C.c_double]
     lib.ref_update_op.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _IA4P, _D3, C.c_double, C.c_double, C.c_double, _D3]
+    lib.ref_rad_params.argtypes = [C.c_int, _RPRM]
+    lib.ref_rad_cons_to_prim.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_int]
+    lib.ref_rad_compute_fluxes.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int]
+    lib.ref_rad_update.argtypes = [C.c_int, C.c_int, _BXP] + [_A4P] * 9 + [C.c_double, _D3]
     _ref = lib
     return lib
 
@@ -172,3 +183,36 @@ def cons_from_prim(rho, v, P, gamma, rng, nscalars=0, eaux_jitter=True):
     for _ in range(nscalars):
         comps.append(rho * rng.uniform(0.0, 1.0, rho.shape))
     return np.stack(comps)
+
+
+def random_rad_cons(box: qk_box, prm, seed=777, kind="smooth", ncomp=None):
+    """Seeded radiation states in a full state FAB (hydro components = 1): E_r log-uniform over 4 decades, reduced flux
+    |f| in [0, 0.95] with random directions; kind='beam' adds cells with |f| -> 1 and inadmissible cells (E_r <= 0,
+    |f| > 1) so that the first-order fallback, the wave-speed floor and amendRadState are exercised."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = box.shape()
+    shp = (nz, ny, nx)
+    nc = ncomp if ncomp is not None else prm.nstart + 4 * prm.ngroups
+    a = np.ones((nc,) + shp)
+    for g in range(prm.ngroups):
+        E = 10.0 ** rng.uniform(-2.0, 2.0, shp)
+        if kind == "smooth":
+            for ax in range(3):
+                E = (np.roll(E, 1, ax) + 2 * E + np.roll(E, -1, ax)) / 4
+        fmag = rng.uniform(0.0, 0.95, shp)
+        mu = rng.uniform(-1.0, 1.0, shp)
+        phi = rng.uniform(0.0, 2 * np.pi, shp)
+        n = np.stack([np.sqrt(1 - mu ** 2) * np.cos(phi), np.sqrt(1 - mu ** 2) * np.sin(phi), mu])
+        if kind == "beam":
+            z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+            m = (x + 2 * y + 3 * z) % 11 == 0
+            fmag[m] = 1.0 - 1e-12
+            fmag[(x + y + z) % 13 == 0] = 0.0
+            fmag[(x * y + z) % 17 == 0] = 1.3
+            E[(x + y * z) % 19 == 0] *= -1.0
+            n[:, (x + 3 * y + z) % 7 == 0] = np.array([1.0, 0.0, 0.0])[:, None]
+        s = prm.nstart + 4 * g
+        a[s] = E
+        for m_ in range(3):
+            a[s + 1 + m_] = fmag * n[m_] * prm.c_light * np.abs(E)
+    return a

@@ -1,0 +1,310 @@
+"""GPU parity of the two-moment radiation transport sweep (csrc/qk_rad.cu) through the C ABI against the oracle
+(oracle/quokka_oracle.c: orc_rad_*, pinned to the reference's RadSystem<problem_t> templates by
+tests/test_oracle_rad_vs_ref.py).  Bar: BIT-EXACT.  Operators: ConservedToPrimitive, ComputeFluxes<DIR> (all reconstruction
+orders, admissible and inadmissible states), PredictStep, AddFluxesRK2 (valid and amended states); fused stage pair on
+multi-box levels; a free-streaming pulse for size-independent properties (energy conservation, causality)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from quokka_b200 import capi
+from quokka_b200.capi import QK_MC, check, make_level_desc, qk_array4, qk_box, rad_params
+from quokka_b200.problems import chop_domain
+
+pytestmark = pytest.mark.gpu
+
+VALID = qk_box.make((2, -3, 4), (13, 6, 11))
+NG = 4
+DX3 = (0.1, 0.07, 0.13)
+C_CGS = 2.99792458e10
+TRAITS = {0: dict(c_light=1.0, c_hat=1.0, Erad_floor=0.0), 1: dict(c_light=C_CGS, c_hat=C_CGS / 30.0, Erad_floor=1.0e-12),
+          2: dict(c_light=10.0, c_hat=2.5, Erad_floor=1.0e-9, ngroups=2, nstart=7)}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return capi.load()
+
+
+def exact(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    bad = ~((a == b) | (np.isnan(a) & np.isnan(b)))
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} mismatches"
+
+
+def dev(hf):
+    from quokka_b200.device import DevFab
+
+    return DevFab(hf.box, hf.ncomp, host=hf.a)
+
+
+def one(x):
+    return C.byref(x)
+
+
+def make_cons(prm, kind, seed=777):
+    gb = VALID.grown(NG)
+    f = ol.HostFab(gb, prm.nstart + 4 * prm.ngroups)
+    f.a[...] = ol.random_rad_cons(gb, prm, seed, kind)
+    return f
+
+
+def oracle_prim(prm, cons):
+    gb = VALID.grown(NG)
+    q = ol.HostFab(gb, 4 * prm.ngroups)
+    with np.errstate(all="ignore"):
+        ol.oracle().orc_rad_conserved_to_primitive(one(prm), one(cons.desc()), one(q.desc()), one(gb))
+    return q
+
+
+def oracle_recon(prm, q, order, d):
+    g1 = VALID.grown(1)
+    fb = ol.face_box(VALID, d, 1)
+    l, r = ol.HostFab(fb, 4 * prm.ngroups), ol.HostFab(fb, 4 * prm.ngroups)
+    ol.oracle().orc_reconstruct_states(order, QK_MC, d, one(q.desc()), one(l.desc()), one(r.desc()), one(g1 if order == 3 else fb), 4 * prm.ngroups)
+    return l, r
+
+
+def oracle_fluxes(prm, cons, order):
+    q = oracle_prim(prm, cons)
+    out = []
+    for d in range(3):
+        l, r = oracle_recon(prm, q, order, d)
+        fb = ol.face_box(VALID, d)
+        f = ol.HostFab(fb, 4 * prm.ngroups)
+        with np.errstate(all="ignore"):
+            ol.oracle().orc_rad_compute_fluxes(one(prm), d, one(f.desc()), None, one(l.desc()), one(r.desc()), one(cons.desc()), one(fb))
+        out.append(f)
+    return out
+
+
+@pytest.mark.parametrize("traits", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["smooth", "beam"])
+def test_rad_cons_to_prim(lib, traits, kind):
+    prm = rad_params(**TRAITS[traits])
+    cons = make_cons(prm, kind)
+    qo = oracle_prim(prm, cons)
+    dc, dq = dev(cons), dev(ol.HostFab(VALID.grown(NG), 4 * prm.ngroups))
+    check(lib.qk_rad_conserved_to_primitive(one(prm), 1, one(VALID), one(dc.desc()), one(dq.desc()), NG, None))
+    exact(dq.numpy(), qo.a)
+
+
+@pytest.mark.parametrize("traits", [0, 1, 2])
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("d", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["smooth", "beam"])
+def test_rad_compute_fluxes(lib, traits, order, d, kind):
+    prm = rad_params(**TRAITS[traits])
+    cons = make_cons(prm, kind)
+    q = oracle_prim(prm, cons)
+    l, r = oracle_recon(prm, q, order, d)
+    fb = ol.face_box(VALID, d)
+    fo = ol.HostFab(fb, 4 * prm.ngroups)
+    with np.errstate(all="ignore"):
+        ol.oracle().orc_rad_compute_fluxes(one(prm), d, one(fo.desc()), None, one(l.desc()), one(r.desc()), one(cons.desc()), one(fb))
+    # the GPU reconstruction is the shared HyperbolicSystem kernel (also bit-compared in test_gpu_operators.py)
+    dq, dl, dr = dev(q), dev(ol.HostFab(l.box, l.ncomp)), dev(ol.HostFab(r.box, r.ncomp))
+    check(lib.qk_reconstruct_states(order, QK_MC, d, 1, one(VALID), one(dq.desc()), one(dl.desc()), one(dr.desc()), 1, 4 * prm.ngroups, None))
+    df, dfd, dc = dev(ol.HostFab(fb, fo.ncomp)), dev(ol.HostFab(fb, fo.ncomp)), dev(cons)
+    check(lib.qk_rad_compute_fluxes(one(prm), d, 1, one(VALID), one(df.desc()), one(dfd.desc()), one(dl.desc()), one(dr.desc()), one(dc.desc()), None))
+    exact(df.numpy(), fo.a)
+    exact(dfd.numpy(), fo.a)
+
+
+@pytest.mark.parametrize("traits", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["smooth", "beam"])
+@pytest.mark.parametrize("dtf", [0.02, 3.0])
+def test_rad_update_ops(lib, traits, kind, dtf):
+    prm = rad_params(**TRAITS[traits])
+    dt = dtf / prm.c_hat
+    nc = prm.nstart + 4 * prm.ngroups
+    dx = (C.c_double * 3)(*DX3)
+    u0, u1 = make_cons(prm, kind, 777), make_cons(prm, kind, 778)
+    f0, f1 = oracle_fluxes(prm, u0, 3), oracle_fluxes(prm, u1, 2)
+    a = ol.HostFab(VALID, nc, fill=-7.0)
+    with np.errstate(all="ignore"):
+        ol.oracle().orc_rad_predict_step(one(prm), one(u0.desc()), one(a.desc()), *[one(f.desc()) for f in f0], dt, dx, one(VALID))
+    du0, du1 = dev(u0), dev(u1)
+    df0, df1 = [dev(f) for f in f0], [dev(f) for f in f1]
+    da = dev(ol.HostFab(VALID, nc, fill=-7.0))
+    check(lib.qk_rad_predict_step(one(prm), 1, one(VALID), one(du0.desc()), one(da.desc()), *[one(f.desc()) for f in df0], dt, dx, None))
+    exact(da.numpy(), a.a, "PredictStep")
+    b = ol.HostFab(VALID, nc, fill=-7.0)
+    with np.errstate(all="ignore"):
+        ol.oracle().orc_rad_add_fluxes_rk2(one(prm), one(b.desc()), one(u0.desc()), one(u1.desc()), *[one(f.desc()) for f in f0],
+                                           *[one(f.desc()) for f in f1], dt, dx, one(VALID))
+    db = dev(ol.HostFab(VALID, nc, fill=-7.0))
+    check(lib.qk_rad_add_fluxes_rk2(one(prm), 1, one(VALID), one(db.desc()), one(du0.desc()), one(du1.desc()), *[one(f.desc()) for f in df0],
+                                    *[one(f.desc()) for f in df1], dt, dx, None))
+    exact(db.numpy(), b.a, "AddFluxesRK2")
+    if dtf > 1:  # amendRadState was exercised
+        assert not np.array_equal(b.a[prm.nstart:], u0.view(VALID)[prm.nstart:])
+
+
+# ---- fused stage pair on a level ----------------------------------------------------------------------------------
+class RadProblem:
+    nghost = 4
+
+    def __init__(self, ncell, max_grid, periodic, prm):
+        self.ncell = list(ncell)
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in ncell))
+        self.dx = [1.0 / ncell[0], 1.3 / ncell[1], 0.9 / ncell[2]]
+        self.boxes = chop_domain(ncell, max_grid)
+        self.periodic = periodic
+        self.prm = prm
+        self.ncomp = prm.nstart + 4 * prm.ngroups
+        lo = []
+        for n in range(self.ncomp):
+            for d in range(3):
+                g = (n - prm.nstart) % 4 if n >= prm.nstart else -1
+                # reflecting walls: the normal radiation flux (and gas momentum) is odd
+                odd = (n == 1 + d) or (g == 1 + d)
+                lo.append(capi.QK_BC_INT_DIR if periodic[d] else (capi.QK_BC_REFLECT_ODD if odd else capi.QK_BC_REFLECT_EVEN))
+        self.bc_lo, self.bc_hi = lo, list(lo)
+
+    def states(self, kind, seed=31):
+        U = ol.random_rad_cons(self.domain, self.prm, seed, kind, ncomp=self.ncomp)
+        out, ng = [], self.nghost
+        for bx in self.boxes:
+            g = bx.grown(ng)
+            nz, ny, nx = g.shape()
+            a = np.full((self.ncomp, nz, ny, nx), np.nan)
+            a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng] = U[:, bx.lo[2]:bx.hi[2] + 1, bx.lo[1]:bx.hi[1] + 1, bx.lo[0]:bx.hi[0] + 1]
+            out.append(a)
+        return out
+
+
+def level_desc(p):
+    return make_level_desc(p.domain, p.periodic, p.dx, p.nghost, p.ncomp, p.boxes, [0] * len(p.boxes), 0, p.bc_lo, p.bc_hi)
+
+
+def gpu_rad_steps(lib, p, st, dt, nsteps):
+    """nsteps transport substeps (fill, stage 1, fill, stage 2) through qk_rad_advance_stage; returns host states"""
+    from quokka_b200.device import DevMultiFab
+
+    desc, keep = level_desc(p)
+    lev = C.c_void_p()
+    check(lib.qk_level_create(C.byref(desc), C.byref(lev)))
+    U0 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    U1 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    U2 = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=st)
+    prm = p.prm
+    for _ in range(nsteps):
+        check(lib.qk_fill_boundary(lev, U0.descs, 0, p.ncomp, None))
+        if prm.integrator_order == 2:
+            check(lib.qk_rad_advance_stage(lev, C.byref(prm), 1, U0.descs, U0.descs, U1.descs, dt, None))
+            check(lib.qk_fill_boundary(lev, U1.descs, 0, p.ncomp, None))
+            check(lib.qk_rad_advance_stage(lev, C.byref(prm), 2, U0.descs, U1.descs, U2.descs, dt, None))
+        else:
+            check(lib.qk_rad_advance_stage(lev, C.byref(prm), 1, U0.descs, U0.descs, U2.descs, dt, None))
+        U0, U2 = U2, U0
+    out = U0.numpy()
+    lib.qk_level_destroy(lev)
+    return out
+
+
+def oracle_rad_steps(p, st, dt, nsteps):
+    desc, keep = level_desc(p)
+    o = ol.oracle()
+    L = o.orc_level_create(C.byref(desc))
+    shapes = [s.shape for s in st]
+
+    def view(which, b):
+        d = o.orc_level_state(L, which, b)
+        return np.ctypeslib.as_array(C.cast(d.p, C.POINTER(C.c_double)), shape=shapes[b])
+
+    for b in range(len(p.boxes)):
+        view(0, b)[...] = st[b]
+        view(1, b)[...] = st[b]
+    with np.errstate(all="ignore"):
+        for _ in range(nsteps):
+            o.orc_level_swap(L)  # state_new -> state_old
+            for b in range(len(p.boxes)):  # hydro components travel with the swap; keep both copies identical
+                view(0, b)[:p.prm.nstart] = view(1, b)[:p.prm.nstart]
+            o.orc_rad_advance_level(L, C.byref(p.prm), dt)
+    out = [view(0, b).copy() for b in range(len(p.boxes))]
+    o.orc_level_destroy(L)
+    return out
+
+
+CASES = {
+    "ppm_periodic": dict(ncell=(32, 16, 16), grid=16, periodic=(1, 1, 1), traits=0, order=3),
+    "plm_reflect": dict(ncell=(32, 32, 16), grid=16, periodic=(0, 0, 0), traits=1, order=2),
+    "donor_mixed": dict(ncell=(24, 16, 8), grid=8, periodic=(1, 0, 1), traits=0, order=1),
+    "ppm_single_ragged": dict(ncell=(40, 12, 9), grid=64, periodic=(0, 1, 0), traits=1, order=3),
+    "two_groups": dict(ncell=(32, 16, 16), grid=16, periodic=(1, 1, 0), traits=2, order=3),
+    "euler": dict(ncell=(16, 16, 16), grid=8, periodic=(1, 1, 1), traits=0, order=3, integrator=1),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("kind", ["smooth", "beam"])
+def test_fused_rad_stage_pair(lib, case, kind):
+    cfg = CASES[case]
+    prm = rad_params(recon_order=cfg["order"], integrator_order=cfg.get("integrator", 2), **TRAITS[cfg["traits"]])
+    p = RadProblem(cfg["ncell"], cfg["grid"], cfg["periodic"], prm)
+    st = p.states(kind)
+    dt = 0.3 * min(p.dx) / prm.c_hat
+    got = gpu_rad_steps(lib, p, st, dt, 3)
+    want = oracle_rad_steps(p, st, dt, 3)
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        exact(got[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], want[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], f"{case} box {b}")
+        exact(got[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], st[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], "hydro components untouched")
+
+
+def test_rad_stage_argument_checks(lib):
+    prm = rad_params()
+    p = RadProblem((16, 16, 16), 16, (1, 1, 1), prm)
+    from quokka_b200.device import DevMultiFab
+
+    desc, keep = level_desc(p)
+    lev = C.c_void_p()
+    check(lib.qk_level_create(C.byref(desc), C.byref(lev)))
+    U = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost, host=p.states("smooth"))
+    V = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost)
+    assert lib.qk_rad_advance_stage(lev, C.byref(prm), 1, U.descs, U.descs, U.descs, 1e-3, None) == capi.QK_ERR_BAD_ARG  # aliasing
+    assert lib.qk_rad_advance_stage(lev, C.byref(prm), 2, U.descs, U.descs, V.descs, 1e-3, None) == capi.QK_ERR_BAD_ARG  # no stage 1 yet
+    bad = rad_params(ngroups=3)
+    assert lib.qk_rad_advance_stage(lev, C.byref(bad), 1, U.descs, U.descs, V.descs, 1e-3, None) == capi.QK_ERR_UNSUPPORTED
+    lib.qk_level_destroy(lev)
+
+
+def test_streaming_pulse_properties(lib):
+    """a Gaussian pulse of radiation free-streaming in a periodic 64^3 box, 40 substeps: total E_r is conserved to round-off,
+    E_r stays positive and the flux causal (|F| <= c E_r) everywhere -- properties that hold at any size."""
+    prm = rad_params(c_light=1.0, c_hat=1.0, recon_order=3)
+    p = RadProblem((64, 64, 64), 32, (1, 1, 1), prm)
+    z, y, x = np.meshgrid(*[(np.arange(64) + 0.5) / 64 for _ in range(3)], indexing="ij")
+    E = 1.0e-3 + np.exp(-((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2) / (2 * 0.05 ** 2))
+    U = np.ones((p.ncomp, 64, 64, 64))
+    U[6] = E
+    U[7] = 0.9 * E  # streaming along +x
+    U[8] = 0.0
+    U[9] = 0.0
+    st, ng = [], p.nghost
+    for bx in p.boxes:
+        g = bx.grown(ng)
+        nz, ny, nx = g.shape()
+        a = np.zeros((p.ncomp, nz, ny, nx))
+        a[:, ng:-ng, ng:-ng, ng:-ng] = U[:, bx.lo[2]:bx.hi[2] + 1, bx.lo[1]:bx.hi[1] + 1, bx.lo[0]:bx.hi[0] + 1]
+        st.append(a)
+    dt = 0.3 * min(p.dx)
+    out = gpu_rad_steps(lib, p, st, dt, 40)
+    e1 = sum(a[6, ng:-ng, ng:-ng, ng:-ng].sum() for a in out)
+    assert abs(e1 - E.sum()) <= 1e-12 * E.sum()
+    for a in out:
+        v = a[:, ng:-ng, ng:-ng, ng:-ng]
+        assert (v[6] > 0).all()
+        assert (np.sqrt(v[7] ** 2 + v[8] ** 2 + v[9] ** 2) <= v[6] * (1 + 1e-14)).all()
+    # the pulse has moved along +x by about 0.9 c t (flux-weighted centroid, periodic box: use the phase of the first mode)
+    full = np.zeros((64, 64, 64))
+    for bx, a in zip(p.boxes, out):
+        full[bx.lo[2]:bx.hi[2] + 1, bx.lo[1]:bx.hi[1] + 1, bx.lo[0]:bx.hi[0] + 1] = a[6, ng:-ng, ng:-ng, ng:-ng]
+    prof = full.sum(axis=(0, 1)) - full.sum(axis=(0, 1)).min()
+    phase = np.angle((prof * np.exp(-2j * np.pi * (np.arange(64) + 0.5) / 64)).sum())
+    shift = (-phase / (2 * np.pi)) % 1.0 - 0.5
+    assert 0.5 * 0.9 * 40 * dt < shift % 1.0 < 1.2 * 0.9 * 40 * dt
