@@ -448,6 +448,45 @@ __global__ void __launch_bounds__(TPB) k_max_signal(HydroConst c, int which, Ite
 }
 
 
+// both maxima in one pass over a box (grid-stride): out[0] = ComputeMaxSignalSpeed + norminf, out[1] = maxSignalSpeedLocal.
+// The per-cell values are the ones k_max_signal forms; max is associative, so the result is identical.
+__global__ void __launch_bounds__(TPB) k_max_signal2(HydroConst c, Iter it, A4 u, unsigned long long *out)
+{
+	double s0 = 0.0, s1 = -1.7976931348623157e308;
+	for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < it.total; t += (int64_t)gridDim.x * TPB) {
+		int i, j, k;
+		it.get(t, i, j, k);
+		const int64_t o = u.off(i, j, k);
+		const double rho = u.p[o], px = u.p[o + u.ns], py = u.p[o + 2 * u.ns], pz = u.p[o + 3 * u.ns], E = u.p[o + 4 * u.ns];
+		const double P = cons_pressure(c, rho, px, py, pz, E);
+		const double cs = eos_sound_speed(c, rho, P);
+		const double vx = px / rho, vy = py / rho, vz = pz / rho;
+		s0 = dmax(s0, fabs(cs + sqrt(vx * vx + vy * vy + vz * vz)));
+		const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+		s1 = dmax(s1, cs + sqrt(2.0 * kinetic_energy / rho));
+	}
+	__shared__ double sm[2][TPB / 32];
+	for (int o = 16; o > 0; o >>= 1) {
+		s0 = dmax(s0, __shfl_xor_sync(0xffffffffu, s0, o));
+		s1 = dmax(s1, __shfl_xor_sync(0xffffffffu, s1, o));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		sm[0][threadIdx.x >> 5] = s0;
+		sm[1][threadIdx.x >> 5] = s1;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < TPB / 32; ++w) {
+			s0 = dmax(s0, sm[0][w]);
+			s1 = dmax(s1, sm[1][w]);
+		}
+		if (!(s0 != s0))
+			atomicMax(out, d2key(s0));
+		if (!(s1 != s1))
+			atomicMax(out + 1, d2key(s1));
+	}
+}
+
 inline double key2d(unsigned long long k)
 {
 	unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;

@@ -32,7 +32,7 @@ template <int NV, int STAGE, bool LAST> struct MarchSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
+template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
 __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
@@ -228,10 +228,7 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 					double dw = dmin(mVp, mV);
 					dw = dmin(dmin(mWp, mW), dw);
 					double F[NV], vf;
-					unsigned slow = 0;
-					f_hllc<DIR, NS, NMS, REINT, true>(c, apL, am, du, dw, F, vf, slow);
-					if (slow)
-						f_hllc<DIR, NS, NMS, REINT, false>(c, apL, am, du, dw, F, vf, slow);
+					hllc_face<ARITH, DIR, NS, NMS, REINT>(c, apL, am, du, dw, F, vf);
 #pragma unroll
 					for (int n = 0; n < NV; ++n)
 						G[n] = F[n];
@@ -259,10 +256,7 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 #pragma unroll
 						for (int n = 0; n < NV; ++n)
 							rr[n] = aux_s[SM::AUX_RHS + n * 32 + lane] + c.inv_dx[DIR] * (Gp[n] - G[n]);
-						unsigned s3 = 0;
-						double dv = div_c<true>(G[NV] - Gp[NV], c.dx[DIR], c.y_dx[DIR], s3);
-						if (s3)
-							dv = slow_div(G[NV] - Gp[NV], c.dx[DIR]);
+						const double dv = div_dx<ARITH>(c, DIR, G[NV] - Gp[NV]);
 						const double divv = aux_s[SM::AUX_RHS + NV * 32 + lane] + dv;
 						if (!LAST) {
 #pragma unroll
@@ -275,7 +269,7 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 							for (int n = 0; n < NV; ++n)
 								U0[n] = aux_s[SM::AUX_U0 + n * 32 + lane];
 							int bad, nf;
-							cell_epilogue<NS, NMS>(c, U0, rr, divv, Un, bad, nf);
+							cell_epilogue<ARITH, NS, NMS>(c, U0, rr, divv, Un, bad, nf);
 							bad_cnt += bad;
 							nf_cnt += nf;
 							const int64_t ooc = o_o - soN;
@@ -335,7 +329,7 @@ template <int NV> struct XSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
 __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
 {
 	constexpr int NV = 6 + NS;
@@ -425,10 +419,7 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 		double G[NV + 1];
 		if (face_ok) {
 			double F[NV], vf;
-			unsigned slow = 0;
-			f_hllc<0, NS, NMS, REINT, true>(c, Ls, am, du, dw, F, vf, slow);
-			if (slow)
-				f_hllc<0, NS, NMS, REINT, false>(c, Ls, am, du, dw, F, vf, slow);
+			hllc_face<ARITH, 0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
 			if (STAGE == 1) {
 #pragma unroll
 				for (int n = 0; n < NV; ++n)
@@ -461,10 +452,7 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 		}
 		const double Vn = shfl_dn1(G[NV]);
 		if (upd) {
-			unsigned s3 = 0;
-			double dv = div_c<true>(Vn - G[NV], c.dx[0], c.y_dx[0], s3);
-			if (s3)
-				dv = slow_div(Vn - G[NV], c.dx[0]);
+			const double dv = div_dx<ARITH>(c, 0, Vn - G[NV]);
 			r.p[orr + NV * r.ns] = dv;
 		}
 	}

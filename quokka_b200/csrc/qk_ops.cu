@@ -5,6 +5,7 @@
 #include "qk_kernels.cuh"
 #include "qk_div.cuh"
 #include <string.h>
+#include <algorithm>
 
 #include <map>
 #include <string>
@@ -371,6 +372,28 @@ extern "C" int qk_hydro_max_signal_speed(const qk_hydro_params *prm, int which, 
 	return 0;
 }
 
+
+// both reductions of a time step in ONE pass (internal; the driver caches out[0] for the next computeTimestep):
+// out[0] = ComputeMaxSignalSpeed + norminf (simulation.hpp:709-710), out[1] = maxSignalSpeedLocal (isCflViolated)
+int qk_hydro_max_signal_both(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, double out[2], cudaStream_t s)
+{
+	QK_TRY(check_params(prm));
+	QK_TRY(ensure_scalars());
+	const HydroConst c = make_hydro_const(prm);
+	QK_CUDA(cudaMemsetAsync(g_scalar_dev, 0, 16, s));
+	ProfScope prof_("max_signal_speed", s);
+	for (int b = 0; b < nboxes; ++b) {
+		Iter it((Box3(valid[b])));
+		const unsigned blocks = std::min<unsigned>(it.blocks(), 148u * 8u);
+		k_max_signal2<<<blocks, TPB, 0, s>>>(c, it, A4(cons[b]), g_scalar_dev);
+		QK_KERNEL_CHECK();
+	}
+	QK_CUDA(cudaMemcpyAsync(g_scalar_host, g_scalar_dev, 16, cudaMemcpyDeviceToHost, s));
+	QK_CUDA(cudaStreamSynchronize(s));
+	out[0] = (g_scalar_host[0] == 0ull) ? 0.0 : key2d(g_scalar_host[0]);
+	out[1] = (g_scalar_host[1] == 0ull) ? -1.7976931348623157e308 : key2d(g_scalar_host[1]);
+	return 0;
+}
 
 // ---- self-test of qk_div.cuh on the device (tests/test_gpu_division.py) ------------------------------------------
 namespace

@@ -29,7 +29,12 @@ struct qk_sim {
 	size_t pool_doubles = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// local ComputeMaxSignalSpeed maximum of state_new, computed in the same pass as isCflViolated's at the end of the last
+	// advance (the next computeTimestep reads the same state); invalidated whenever state_new is changed from outside
+	bool sig_valid = false;
+	double sig_local = 0.0;
 };
+int qk_hydro_max_signal_both(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, double out[2], cudaStream_t s);
 
 static inline int blen(const qk_box &b, int d) { return b.hi[d] - b.lo[d] + 1; }
 
@@ -154,6 +159,7 @@ extern "C" int qk_sim_set_state(qk_sim *s, int b, const double *host)
 {
 	if (!s || b < 0 || b >= s->nb || !host)
 		return QK_ERR_BAD_ARG;
+	s->sig_valid = false;
 	QK_CUDA(cudaMemcpyAsync(s->snew[b].p, host, (size_t)qk_sim_box_doubles(s, b) * sizeof(double), cudaMemcpyHostToDevice, s->stream));
 	return 0;
 }
@@ -175,6 +181,7 @@ extern "C" void qk_sim_reset_clock(qk_sim *s, double t, double dt_prev)
 {
 	s->t = t;
 	s->dt_prev = dt_prev;
+	s->sig_valid = false;
 	s->cell_updates = 0;
 	s->retries = 0;
 }
@@ -195,7 +202,10 @@ extern "C" int qk_sim_compute_timestep(qk_sim *s, double stop_time, double *dt_o
 	if (!s || !dt_out)
 		return QK_ERR_BAD_ARG;
 	double smax = 0.0;
-	QK_TRY(qk_hydro_max_signal_speed(&s->prm, 0, s->nb, s->lev->valid.data(), s->snew.data(), &smax, s->stream));
+	if (s->sig_valid)
+		smax = s->sig_local;
+	else
+		QK_TRY(qk_hydro_max_signal_speed(&s->prm, 0, s->nb, s->lev->valid.data(), s->snew.data(), &smax, s->stream));
 	QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
 	const double *dx = s->lev->dx;
 	const double dx_min = dminh(dminh(dx[0], dx[1]), dx[2]);
@@ -240,8 +250,11 @@ static int advance_hydro(qk_sim *s, std::vector<qk_array4> &Uold, double dt, int
 		return 0;
 	}
 	// isCflViolated (:992-1013)
-	double smax = -DBL_MAX;
-	QK_TRY(qk_hydro_max_signal_speed(&s->prm, 1, s->nb, L->valid.data(), s->snew.data(), &smax, s->stream));
+	double both[2];
+	QK_TRY(qk_hydro_max_signal_both(&s->prm, s->nb, L->valid.data(), s->snew.data(), both, s->stream));
+	s->sig_local = both[0];
+	s->sig_valid = true;
+	double smax = both[1];
 	QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
 	const double dx_min = dminh(dminh(L->dx[0], L->dx[1]), L->dx[2]);
 	const double dt_cfl = s->cfl * (dx_min / smax);
@@ -258,6 +271,7 @@ extern "C" int qk_sim_step(qk_sim *s, double dt, int *retries_out)
 {
 	if (!s)
 		return QK_ERR_BAD_ARG;
+	s->sig_valid = false;
 	std::swap(s->snew, s->sold); // :671
 	std::swap(s->pool[0], s->pool[1]);
 	int result = -1;

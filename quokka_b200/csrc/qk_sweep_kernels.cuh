@@ -1,0 +1,648 @@
+// qk_sweep_kernels.cuh -- kernels and launchers of the fused stage, templated on the arithmetic mode ARITH (0 exact,
+// 1 relaxed).  Included by exactly two translation units: qk_sweep.cu (ARITH = 0, compiled with --fmad=false) and
+// qk_sweep_relaxed.cu (ARITH = 1, compiled with FMA contraction on).  See qk_sweep.cu for the description of the kernels.
+#pragma once
+#include "qk_relaxed.cuh"
+#include "qk_level.h"
+
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
+
+namespace
+{
+constexpr int SEG = 32; // cells per marching segment
+
+struct SweepBox {
+	A4 U0, Us, Uo; // state_old (ghost-filled), stage input (ghost-filled), stage output
+	A4 prim;       // 6+NS primitives + chi_min as the last component; same index space as the state (ng ghosts)
+	A4 chi3;       // chi_x, chi_y, chi_z (ng = 2)
+	A4 rhs;        // 6+NS RHS components + div v as the last component (valid cells)
+	A4 hF[3];      // per direction: 0.5*F(U0) (6+NS) + 0.5*faceVel(U0), nodal in that direction
+	int lo[3], hi[3];
+};
+
+__device__ __forceinline__ bool nonfinite(double v) { return ((unsigned)__double2hiint(v) & 0x7ff00000u) == 0x7ff00000u; }
+
+// ---- plain-`/` fallback for isolated quotients (taken when a fast quotient left its domain) ----
+__device__ __noinline__ double slow_div(double a, double b) { return a / b; }
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int ARITH, int NS, bool REINT> __global__ void __launch_bounds__(256) k_fprim(FastConst c, const SweepBox *__restrict__ boxes, int ng)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 1 + 2 * ng, ny = B.hi[1] - B.lo[1] + 1 + 2 * ng, nz = B.hi[2] - B.lo[2] + 1 + 2 * ng;
+	const int64_t total = (int64_t)nx * ny * nz;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - ng + (int)(t - jk * nx);
+		const int k = B.lo[2] - ng + (int)(jk / ny);
+		const int j = B.lo[1] - ng + (int)(jk - (jk / ny) * ny);
+		const int64_t o = B.Us.off(i, j, k), op = B.prim.off(i, j, k);
+		double U[6 + NS], q[6 + NS];
+#pragma unroll
+		for (int n = 0; n < 6 + NS; ++n)
+			U[n] = B.Us.p[o + n * B.Us.ns];
+		if (ARITH == 0) {
+			unsigned slow = 0;
+			f_cons_to_prim<NS, REINT, true>(c, U, q, slow);
+			if (slow)
+				f_cons_to_prim<NS, REINT, false>(c, U, q, slow);
+		} else {
+			r_cons_to_prim<NS, REINT>(c, U, q);
+		}
+#pragma unroll
+		for (int n = 0; n < 6 + NS; ++n)
+			B.prim.p[op + n * B.prim.ns] = q[n];
+	}
+}
+
+// chi along the three directions of one cell; rho c_s^2 is evaluated once (the reference recomputes it per direction)
+template <int ARITH, int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi(FastConst c, const SweepBox *__restrict__ boxes)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 5, ny = B.hi[1] - B.lo[1] + 5, nz = B.hi[2] - B.lo[2] + 5;
+	const int64_t total = (int64_t)nx * ny * nz;
+	const A4 &q = B.prim;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - 2 + (int)(t - jk * nx);
+		const int k = B.lo[2] - 2 + (int)(jk / ny);
+		const int j = B.lo[1] - 2 + (int)(jk - (jk / ny) * ny);
+		const int64_t o = q.off(i, j, k);
+		const int64_t st[3] = {1, q.js, q.ks};
+		const double rho = q.p[o];
+		double Pc[3][5];
+		double vm1[3], vp1[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+#pragma unroll
+			for (int m = -2; m <= 2; ++m)
+				Pc[d][m + 2] = q.p[o + m * st[d] + 4 * q.ns];
+			vm1[d] = q.p[o - st[d] + (1 + d) * q.ns];
+			vp1[d] = q.p[o + st[d] + (1 + d) * q.ns];
+		}
+		if (ARITH != 0) { // relaxed arithmetic (qk_relaxed.cuh): rho c_s^2 = gamma p in closed form
+			if (REINT) {
+#pragma unroll
+				for (int d = 0; d < 3; ++d)
+#pragma unroll
+					for (int m = -2; m <= 2; ++m) {
+						if (d > 0 && m == 0) {
+							Pc[d][2] = Pc[0][2];
+							continue;
+						}
+						const double r = q.p[o + m * st[d]];
+						Pc[d][m + 2] = r_pressure_from_e(c, r, (r == 0.0) ? 0.0 : Pc[d][m + 2]);
+					}
+			}
+			const double yKS = r_rcp(c.h.gamma * r_p_of_p(c, rho, Pc[0][2]));
+			const int64_t ocr = B.chi3.off(i, j, k);
+#pragma unroll
+			for (int d = 0; d < 3; ++d)
+				B.chi3.p[ocr + d * B.chi3.ns] = r_flatten_chi(c, Pc[d][0], Pc[d][1], Pc[d][3], Pc[d][4], yKS, vm1[d], vp1[d]);
+			continue;
+		}
+		unsigned slow = 0;
+		if (REINT) { // pressures from the specific internal energies (hydro_system.hpp:577-586)
+#pragma unroll
+			for (int d = 0; d < 3; ++d)
+#pragma unroll
+				for (int m = -2; m <= 2; ++m) {
+					if (d > 0 && m == 0) {
+						Pc[d][2] = Pc[0][2];
+						continue;
+					}
+					const double r = q.p[o + m * st[d]];
+					Pc[d][m + 2] = f_pressure_from_e<true>(c, r, (r == 0.0) ? 0.0 : div_d<true>(r * Pc[d][m + 2], r, slow), slow);
+				}
+		}
+		const double cs = f_sound_speed<true>(c, rho, Pc[0][2], slow);
+		const QkRcp RKS = rcp_f<true>((cs * cs) * rho, slow);
+		double chi[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d)
+			chi[d] = f_flatten_chi<true>(c, Pc[d][0], Pc[d][1], Pc[d][3], Pc[d][4], RKS, vm1[d], vp1[d], slow);
+		if (slow) { // plain-division fallback (qk_physics.cuh)
+			if (REINT) {
+				for (int d = 0; d < 3; ++d)
+					for (int m = -2; m <= 2; ++m) {
+						const double r = q.p[o + m * st[d]];
+						Pc[d][m + 2] = eos_pressure(c.h, r, r * q.p[o + m * st[d] + 4 * q.ns]);
+					}
+			}
+			const double cs2 = eos_sound_speed(c.h, rho, Pc[0][2]);
+			const double KS = (cs2 * cs2) * rho;
+			for (int d = 0; d < 3; ++d)
+				chi[d] = flatten_chi(Pc[d][0], Pc[d][1], Pc[d][3], Pc[d][4], KS, vm1[d], vp1[d]);
+		}
+		const int64_t oc = B.chi3.off(i, j, k);
+#pragma unroll
+		for (int d = 0; d < 3; ++d)
+			B.chi3.p[oc + d * B.chi3.ns] = chi[d];
+	}
+}
+
+// min over chi_x(i-1,i,i+1), chi_y(j-1,j,j+1), chi_z(k-1,k,k+1) in the reference's order (hydro_system.hpp:655-669)
+template <int NS> __global__ void __launch_bounds__(256) k_fchimin(const SweepBox *__restrict__ boxes)
+{
+	const SweepBox &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 3, ny = B.hi[1] - B.lo[1] + 3, nz = B.hi[2] - B.lo[2] + 3;
+	const int64_t total = (int64_t)nx * ny * nz;
+	const A4 &x = B.chi3;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] - 1 + (int)(t - jk * nx);
+		const int k = B.lo[2] - 1 + (int)(jk / ny);
+		const int j = B.lo[1] - 1 + (int)(jk - (jk / ny) * ny);
+		const int64_t o = x.off(i, j, k);
+		double chi = x.p[o - 1];
+		chi = dmin(chi, x.p[o]);
+		chi = dmin(chi, x.p[o + 1]);
+		chi = dmin(chi, x.p[o - x.js + x.ns]);
+		chi = dmin(chi, x.p[o + x.ns]);
+		chi = dmin(chi, x.p[o + x.js + x.ns]);
+		chi = dmin(chi, x.p[o - x.ks + 2 * x.ns]);
+		chi = dmin(chi, x.p[o + 2 * x.ns]);
+		chi = dmin(chi, x.p[o + x.ks + 2 * x.ns]);
+		B.prim.p[B.prim.off(i, j, k) + (6 + NS) * B.prim.ns] = chi;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-cell pieces shared by the two sweep kernels
+// ---------------------------------------------------------------------------------------------------------------
+// transverse velocity-difference minima of one cell (hydro_system.hpp:1022-1033): mV = min(vV(+V)-vV, vV-vV(-V)), mW likewise
+template <int DIR> __device__ __forceinline__ void cell_trans_min(const A4 &q, int64_t o, double &mV, double &mW)
+{
+	constexpr int aV = (DIR + 1) % 3, aW = (DIR + 2) % 3;
+	const int64_t sV = (aV == 0) ? 1 : (aV == 1) ? q.js : q.ks;
+	const int64_t sW = (aW == 0) ? 1 : (aW == 1) ? q.js : q.ks;
+	const double *vV = q.p + o + (1 + aV) * q.ns;
+	const double *vW = q.p + o + (1 + aW) * q.ns;
+	const double v0 = vV[0], w0 = vW[0];
+	mV = dmin(vV[sV] - v0, v0 - vV[-sV]);
+	mW = dmin(vW[sW] - w0, w0 - vW[-sW]);
+}
+
+// stage epilogue of one cell: rhs (all three directions summed) -> new state (hydro_system.hpp:775-814, 475-497, 698-773, 816-850)
+template <int ARITH, int NS, int NMS>
+__device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *U0, double *r, double divv, double *Un, int &bad, int &nonfin)
+{
+	// AddInternalEnergyPdV: P from the OLD state; redoFlag is none on this path
+	double P;
+	if (ARITH == 0) {
+		unsigned slow = 0;
+		const QkRcp Rr = rcp_f<true>(U0[0], slow);
+		const double vx = div_r<true>(U0[1], Rr, slow), vy = div_r<true>(U0[2], Rr, slow), vz = div_r<true>(U0[3], Rr, slow);
+		const double ke = 0.5 * U0[0] * (vx * vx + vy * vy + vz * vz);
+		const double Eint = U0[4] - ke;
+		P = f_pressure_from_e<true>(c, U0[0], (U0[0] == 0.0) ? 0.0 : div_r<true>(Eint, Rr, slow), slow);
+		if (slow)
+			P = cons_pressure(c.h, U0[0], U0[1], U0[2], U0[3], U0[4]);
+	} else {
+		const double y = r_rcp(U0[0]);
+		const double vx = U0[1] * y, vy = U0[2] * y, vz = U0[3] * y;
+		const double Eint = U0[4] - 0.5 * U0[0] * (vx * vx + vy * vy + vz * vz);
+		P = r_pressure_from_e(c, U0[0], (U0[0] == 0.0) ? 0.0 : Eint * y);
+	}
+	r[5] = r[5] + (-P * divv);
+	// PredictStep
+#pragma unroll
+	for (int n = 0; n < 6 + NS; ++n)
+		Un[n] = U0[n] + c.dt * r[n];
+	bad = !(Un[0] > 0.);
+#pragma unroll
+	for (int n = 0; n < NMS; ++n)
+		if (Un[6 + n] < 0.0)
+			bad = 1;
+	nonfin = 0;
+#pragma unroll
+	for (int n = 0; n < 6 + NS; ++n)
+		nonfin |= nonfinite(Un[n]);
+	// EnforceLimits
+	const double rho = Un[0];
+	double rho_new = rho;
+	if (rho < c.h.dfloor) {
+		rho_new = c.h.dfloor;
+		Un[0] = rho_new;
+#pragma unroll
+		for (int n = 0; n < NS; ++n) {
+			if (rho_new == 0.0)
+				Un[6 + n] = 0.0;
+			else
+				Un[6 + n] *= rho / rho_new;
+		}
+	}
+	if (NMS > 0) {
+		double sp_sum = 0.0;
+#pragma unroll
+		for (int n = 0; n < NMS; ++n) {
+			if (Un[6 + n] < 0.0)
+				Un[6 + n] = c.h.small_x * rho_new;
+			sp_sum += Un[6 + n];
+		}
+		if ((sp_sum > 2.2250738585072014e-308) && (rho_new > 2.2250738585072014e-308)) {
+			sp_sum /= rho_new;
+#pragma unroll
+			for (int n = 0; n < NMS; ++n)
+				Un[6 + n] /= sp_sum;
+		}
+	}
+	// the temperature floors compare T >= small_temp > 0 (or NaN) with tempFloor: never taken unless tempFloor > 0
+	if (c.h.tfloor > 0. && rho_new > 2.2250738585072014e-308) {
+		const double v1 = Un[1] / rho_new, v2 = Un[2] / rho_new, v3 = Un[3] / rho_new;
+		const double Ekin = 0.5 * rho_new * (v1 * v1 + v2 * v2 + v3 * v3);
+		const double primTemp = eos_tgas_from_eint(c.h, rho_new, (Un[4] - Ekin));
+		if (primTemp < c.h.tfloor)
+			Un[4] = Ekin + eos_eint_from_tgas(c.h, rho_new, c.h.tfloor);
+		const double auxTemp = eos_tgas_from_eint(c.h, rho_new, Un[5]);
+		if (auxTemp < c.h.tfloor)
+			Un[5] = eos_eint_from_tgas(c.h, rho_new, c.h.tfloor);
+	}
+	// SyncDualEnergy (cells with rho <= 0 are flagged above and the stage is redone by the faithful path)
+	if (Un[0] > 0.) {
+		const double num = Un[1] * Un[1] + Un[2] * Un[2] + Un[3] * Un[3], den = 2.0 * Un[0];
+		double Ekin;
+		if (ARITH == 0) {
+			unsigned s2 = 0;
+			Ekin = div_d<true>(num, den, s2);
+			if (s2)
+				Ekin = slow_div(num, den);
+		} else {
+			Ekin = num * r_rcp(den);
+		}
+		const double Eint_cons = Un[4] - Ekin;
+		if (Eint_cons > 1.0e-3 * Un[4])
+			Un[5] = Eint_cons;
+		else
+			Un[4] = Un[5] + Ekin;
+	}
+}
+
+// ---- arithmetic-mode dispatch: ARITH = 0 exact (shared-reciprocal fast path + plain-division twin), 1 relaxed ----
+template <int ARITH, int DIR, int NS, int NMS, bool REINT>
+__device__ __forceinline__ void hllc_face(const FastConst &c, const double *__restrict__ L, const double *__restrict__ R, double du, double dw,
+					  double *__restrict__ F, double &vf)
+{
+	if (ARITH == 0) {
+		unsigned slow = 0;
+		f_hllc<DIR, NS, NMS, REINT, true>(c, L, R, du, dw, F, vf, slow);
+		if (slow)
+			f_hllc<DIR, NS, NMS, REINT, false>(c, L, R, du, dw, F, vf, slow);
+	} else {
+		r_hllc<DIR, NS, NMS, REINT>(c, L, R, du, dw, F, vf);
+	}
+}
+template <int ARITH> __device__ __forceinline__ double div_dx(const FastConst &c, int d, double a)
+{
+	if (ARITH == 0) {
+		unsigned s3 = 0;
+		double dv = div_c<true>(a, c.dx[d], c.y_dx[d], s3);
+		if (s3)
+			dv = slow_div(a, c.dx[d]);
+		return dv;
+	}
+	return a * c.y_dx[d];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x sweep: one warp per 30 cells of a row (lane l <-> cell x0 - 1 + l)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+__global__ void __launch_bounds__(128) k_sweep_x(FastConst c, const SweepBox *__restrict__ boxes, int tiles_x, int rows_per_box_max)
+{
+	constexpr int NV = 6 + NS;
+	const SweepBox &B = boxes[blockIdx.z];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int row = blockIdx.y * 4 + warp;
+	if (row >= ny * nz)
+		return; // whole warp
+	const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+	const int x0 = B.lo[0] + blockIdx.x * 30;
+	if (x0 > B.hi[0])
+		return;
+	const int i = x0 - 1 + lane;
+	const bool cell_ok = (i <= B.hi[0] + 1); // cells lo-1 .. hi+1 carry a parabola
+	const int ic = cell_ok ? i : B.hi[0] + 1;
+	const A4 &q = B.prim;
+	const int64_t o = q.off(ic, j, k);
+
+	// PPM + flattening of the own cell, all variables
+	const double chi = q.p[o + NV * q.ns], omchi = 1. - chi;
+	double am[NV], ap[NV], q0v[NV];
+#pragma unroll
+	for (int n = 0; n < NV; ++n) {
+		const double *p = q.p + o + n * q.ns;
+		const double qm2 = p[-2], qm1 = p[-1], q0 = p[0], qp1 = p[1], qp2 = p[2];
+		q0v[n] = q0;
+		f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+	}
+	double mV, mW;
+	cell_trans_min<0>(q, o, mV, mW);
+
+	// face between lane-1 and lane: L = ap(lane-1), R = am(lane)
+	double Ls[NV];
+#pragma unroll
+	for (int n = 0; n < NV; ++n)
+		Ls[n] = shfl_up1(ap[n]);
+	const double mVl = shfl_up1(mV), mWl = shfl_up1(mW);
+	const double du = q0v[1] - shfl_up1(q0v[1]);
+	double dw = dmin(mVl, mV);
+	dw = dmin(dmin(mWl, mW), dw);
+	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
+	double G[NV + 1];
+	if (face_ok) {
+		double F[NV], vf;
+		hllc_face<ARITH, 0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
+		const A4 &h = B.hF[0];
+		const int64_t oh = h.off(i, j, k);
+		if (STAGE == 1) {
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				G[n] = F[n];
+			G[NV] = vf;
+			if (DUAL && (lane <= 30 || i == B.hi[0] + 1)) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					h.p[oh + n * h.ns] = 0.0 + 0.5 * F[n];
+				h.p[oh + NV * h.ns] = 0.0 + 0.5 * vf;
+			}
+		} else {
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				G[n] = h.p[oh + n * h.ns] + 0.5 * F[n];
+			G[NV] = h.p[oh + NV * h.ns] + 0.5 * vf;
+		}
+	} else {
+#pragma unroll
+		for (int n = 0; n <= NV; ++n)
+			G[n] = 0.0;
+	}
+	// cell update needs the flux of the next face (lane+1)
+	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
+	const A4 &r = B.rhs;
+	const int64_t orr = upd ? r.off(i, j, k) : 0;
+#pragma unroll
+	for (int n = 0; n < NV; ++n) {
+		const double Gn = shfl_dn1(G[n]);
+		if (upd)
+			r.p[orr + n * r.ns] = c.inv_dx[0] * (G[n] - Gn);
+	}
+	const double Vn = shfl_dn1(G[NV]);
+	if (upd)
+	{
+			const double dv = div_dx<ARITH>(c, 0, Vn - G[NV]);
+			r.p[orr + NV * r.ns] = dv;
+		}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y / z sweeps by marching; LAST carries the stage epilogue
+// ---------------------------------------------------------------------------------------------------------------
+template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
+__global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
+{
+	constexpr int NV = 6 + NS;
+	constexpr int TD = (DIR == 1) ? 2 : 1; // the transverse (non-x) axis a warp is pinned to
+	const int box = blockIdx.z / nseg, seg = blockIdx.z - box * nseg;
+	const SweepBox &B = boxes[box];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int i = B.lo[0] + blockIdx.x * 32 + lane;
+	const int t = B.lo[TD] + blockIdx.y * 4 + warp;
+	const int s0 = B.lo[DIR] + seg * SEG;
+	int bad_cnt = 0, nf_cnt = 0;
+	if (i <= B.hi[0] && t <= B.hi[TD] && s0 <= B.hi[DIR]) {
+		const int s1 = min(s0 + SEG, B.hi[DIR] + 1); // cells s0 .. s1-1 are updated, faces s0 .. s1 evaluated
+		const A4 &q = B.prim;
+		const int64_t sN = (DIR == 1) ? q.js : q.ks;
+		int idx[3];
+		idx[0] = i;
+		idx[TD] = t;
+		idx[DIR] = s0 - 1;
+		int64_t o = q.off(idx[0], idx[1], idx[2]);
+		const A4 &h = B.hF[DIR];
+		const int64_t shN = (DIR == 1) ? h.js : h.ks;
+		int64_t oh = h.off(idx[0], idx[1], idx[2]); // face index == cell index of the cell on its high side
+		const A4 &r = B.rhs;
+		const int64_t srN = (DIR == 1) ? r.js : r.ks;
+		int64_t orr = r.off(idx[0], idx[1], idx[2]);
+		const A4 &u0 = B.U0, &uo = B.Uo;
+		const int64_t suN = (DIR == 1) ? u0.js : u0.ks, soN = (DIR == 1) ? uo.js : uo.ks;
+		int64_t ou = u0.off(idx[0], idx[1], idx[2]), oo = uo.off(idx[0], idx[1], idx[2]);
+
+		double apL[NV], ifl[NV], Gp[NV + 1];
+		double mVp = 0, mWp = 0, vNp = 0;
+		// unlimited interface value at the low face of the first cell
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double *p = q.p + o + n * q.ns;
+			ifl[n] = ppm_iface(p[-2 * sN], p[-sN], p[0], p[sN]);
+		}
+		for (int s = s0 - 1; s <= s1; ++s) {
+			const double chi = q.p[o + NV * q.ns], omchi = 1. - chi;
+			double am[NV], ap[NV];
+			double vN0 = 0;
+#pragma unroll
+			for (int n = 0; n < NV; ++n) {
+				const double *p = q.p + o + n * q.ns;
+				const double qm1 = p[-sN], q0 = p[0], qp1 = p[sN], qp2 = p[2 * sN];
+				if (n == 1 + DIR)
+					vN0 = q0;
+				const double ifh = ppm_iface(qm1, q0, qp1, qp2);
+				f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
+				ifl[n] = ifh;
+			}
+			double mV, mW;
+			cell_trans_min<DIR>(q, o, mV, mW);
+			if (s >= s0) {
+				const double du = vN0 - vNp;
+				double dw = dmin(mVp, mV);
+				dw = dmin(dmin(mWp, mW), dw);
+				double F[NV], vf, G[NV + 1];
+				hllc_face<ARITH, DIR, NS, NMS, REINT>(c, apL, am, du, dw, F, vf);
+				if (STAGE == 1) {
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						G[n] = F[n];
+					G[NV] = vf;
+					if (DUAL) {
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							h.p[oh + n * h.ns] = 0.0 + 0.5 * F[n];
+						h.p[oh + NV * h.ns] = 0.0 + 0.5 * vf;
+					}
+				} else {
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						G[n] = h.p[oh + n * h.ns] + 0.5 * F[n];
+					G[NV] = h.p[oh + NV * h.ns] + 0.5 * vf;
+				}
+				if (s > s0) { // cell s-1: both faces known
+					const int64_t orc = orr - srN;
+					double rr[NV];
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						rr[n] = r.p[orc + n * r.ns] + c.inv_dx[DIR] * (Gp[n] - G[n]);
+					const double dv = div_dx<ARITH>(c, DIR, G[NV] - Gp[NV]);
+					const double divv = r.p[orc + NV * r.ns] + dv;
+					if (!LAST) {
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							r.p[orc + n * r.ns] = rr[n];
+						r.p[orc + NV * r.ns] = divv;
+					} else {
+						double U0[NV], Un[NV];
+						const int64_t ouc = ou - suN;
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							U0[n] = u0.p[ouc + n * u0.ns];
+						int bad, nf;
+						cell_epilogue<ARITH, NS, NMS>(c, U0, rr, divv, Un, bad, nf);
+						bad_cnt += bad;
+						nf_cnt += nf;
+						const int64_t ooc = oo - soN;
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							uo.p[ooc + n * uo.ns] = Un[n];
+					}
+				}
+#pragma unroll
+				for (int n = 0; n <= NV; ++n)
+					Gp[n] = G[n];
+			}
+#pragma unroll
+			for (int n = 0; n < NV; ++n)
+				apL[n] = ap[n];
+			mVp = mV;
+			mWp = mW;
+			vNp = vN0;
+			o += sN;
+			oh += shN;
+			orr += srN;
+			ou += suN;
+			oo += soN;
+		}
+	}
+	if (LAST) {
+		// one atomic per block that saw a flagged / non-finite cell (none in a healthy run)
+		const int any = __syncthreads_or(bad_cnt | nf_cnt);
+		if (any) {
+			if (bad_cnt)
+				atomicAdd(counters, (unsigned long long)bad_cnt);
+			if (nf_cnt)
+				atomicAdd(counters + 1, (unsigned long long)nf_cnt);
+		}
+	}
+}
+#include "qk_march.cuh"
+} // namespace
+
+#define QK_TRY(x)                                                                                                                                    \
+	do {                                                                                                                                         \
+		int r_ = (x);                                                                                                                        \
+		if (r_ != 0)                                                                                                                         \
+			return r_;                                                                                                                   \
+	} while (0)
+
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], bool tma, cudaStream_t s)
+{
+	{
+		ProfScope p("fused_prim", s);
+		const int64_t cells = (int64_t)(maxn[0] + 2 * ng) * (maxn[1] + 2 * ng) * (maxn[2] + 2 * ng);
+		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+		k_fprim<ARITH, NS, REINT><<<grid, 256, 0, s>>>(c, d_tab, ng);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("fused_chi", s);
+		const int64_t cells = (int64_t)(maxn[0] + 4) * (maxn[1] + 4) * (maxn[2] + 4);
+		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+		k_fchi<ARITH, NS, REINT><<<grid, 256, 0, s>>>(c, d_tab);
+		QK_KERNEL_CHECK();
+		k_fchimin<NS><<<grid, 256, 0, s>>>(d_tab);
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_x", s);
+		const int tiles_x = (maxn[0] + 29) / 30;
+		const int rows = maxn[1] * maxn[2];
+		if (tma) {
+			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, STAGE, DUAL>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
+			kern<<<grid, 128, XSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab);
+		} else {
+			dim3 grid(tiles_x, (rows + 3) / 4, nb);
+			k_sweep_x<ARITH, NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
+		}
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_y", s);
+		const int nseg = (maxn[1] + SEG - 1) / SEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[2] + 3) / 4, nb * nseg);
+		if (tma) {
+			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+		} else {
+			k_sweep_m<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
+		}
+		QK_KERNEL_CHECK();
+	}
+	{
+		ProfScope p("sweep_z", s);
+		const int nseg = (maxn[2] + SEG - 1) / SEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
+		if (tma) {
+			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+		} else {
+			k_sweep_m<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
+		}
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
+template <int ARITH, int NS, int NMS, bool REINT> static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma, cudaStream_t s)
+{
+	if (stage == 1)
+		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true>(ng, d_counters, c, t, nb, maxn, tma, s) : launch_stage<ARITH, NS, NMS, REINT, 1, false>(ng, d_counters, c, t, nb, maxn, tma, s);
+	return launch_stage<ARITH, NS, NMS, REINT, 2, true>(ng, d_counters, c, t, nb, maxn, tma, s);
+}
+
+
+// entry of one translation unit: all instantiated trait sets of one arithmetic mode
+template <int ARITH>
+static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3],
+				int stage, bool dual, bool tma, cudaStream_t s)
+{
+	if (ns == 0)
+		return reint ? dispatch_stage<ARITH, 0, 0, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 0, 0, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+	if (ns == 1)
+		return reint ? dispatch_stage<ARITH, 1, 0, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 1, 0, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+	return reint ? dispatch_stage<ARITH, 3, 2, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+		     : dispatch_stage<ARITH, 3, 2, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+}
