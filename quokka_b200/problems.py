@@ -92,3 +92,50 @@ class SedovProblem:
         if box.lo[0] <= 0 <= box.hi[0] and box.lo[1] <= 0 <= box.hi[1] and box.lo[2] <= 0 <= box.hi[2]:
             v[4, 0 - box.lo[2], 0 - box.lo[1], 0 - box.lo[0]] = self.E_blast / cell_vol
         return a
+
+
+class SodProblem:
+    """HydroShocktube (src/problems/HydroShocktube/test_hydro_shocktube.cpp:28-91, tests/shocktube.in), config C1 of
+    BASELINE.json, on a uniform level.  The reference builds it with AMREX_SPACEDIM = 1; here the tube is 4 cells thick and
+    periodic in y and z (all transverse differences are exactly zero, so the bits are the 1-D build's).  The Dirichlet walls
+    (setCustomBoundaryConditions :93-141) hold the initial left/right states; until a wave reaches a wall (t = 0.4 ends before)
+    first-order extrapolation of the undisturbed boundary cell gives the same ghost values."""
+
+    gamma = 1.4
+    cfl = 0.6
+    stop_time = 0.4
+    ncomp = 6
+    nghost = 4
+    rho_L, P_L, rho_R, P_R = 10.0, 100.0, 1.0, 1.0
+
+    def __init__(self, ncell_x, max_grid_size=128, thickness=4):
+        from .capi import QK_BC_FOEXTRAP, QK_BC_INT_DIR
+
+        self.ncell = [int(ncell_x), thickness, thickness]
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in self.ncell))
+        self.dx = [5.0 / self.ncell[0], 1.0 / thickness, 1.0 / thickness]
+        self.boxes = chop_domain(self.ncell, (max_grid_size, thickness, thickness))
+        self.periodic = (0, 1, 1)
+        lo = []
+        for n in range(self.ncomp):
+            lo += [QK_BC_FOEXTRAP, QK_BC_INT_DIR, QK_BC_INT_DIR]
+        self.bc_lo = lo
+        self.bc_hi = list(lo)
+
+    def params(self, **kw):
+        return hydro_params(gamma=self.gamma, reconstruct_eint=1, **kw)
+
+    def initial_state(self, box: qk_box, ng=None) -> np.ndarray:
+        ng = self.nghost if ng is None else ng
+        g = box.grown(ng)
+        nz, ny, nx = g.shape()
+        a = np.zeros((self.ncomp, nz, ny, nx))
+        x = 0.0 + (np.arange(box.lo[0], box.hi[0] + 1) + 0.5) * self.dx[0]
+        left = x < 2.0
+        rho = np.where(left, self.rho_L, self.rho_R)
+        P = np.where(left, self.P_L, self.P_R)
+        v = a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng] if ng else a
+        v[0] = rho
+        v[4] = P / (self.gamma - 1.0) + 0.5 * rho * (0.0 * 0.0)
+        v[5] = P / (self.gamma - 1.0)
+        return a

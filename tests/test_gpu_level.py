@@ -257,3 +257,26 @@ def test_sedov64_100_steps_vs_oracle():
     vol = prob.dx[0] * prob.dx[1] * prob.dx[2]
     E0 = sum(prob.initial_state(b, 0)[4].sum() for b in prob.boxes) * vol
     assert abs(got[4].sum() * vol - E0) / E0 < 1e-13
+
+
+@pytest.mark.parametrize("name", ["sod256_s40", "sod256_full", "sod1024_full"])
+def test_sod_matches_reference_run(name):
+    """config C1: the Sod shock tube (reconstruct_eint = true: EOS calls inside flattening and flux kernels) through the
+    library's time loop == the state dump of the reference's own 1-D executable, bit for bit, same retries, same error norm"""
+    from quokka_b200.problems import SodProblem
+    from quokka_b200.simulation import HydroSimulation
+    from test_oracle_golden import check_sod, sod_error_norm
+
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    prob = SodProblem(int(g["ncell"]), int(g["box"]))
+    sim = HydroSimulation(prob)
+    sim.setInitialConditions()
+    nd, _, _ = sim.evolve(int(g["nsteps"]))
+    assert nd == int(g["nsteps"])
+    state, t, retries = sim.gather_global(), sim.time, sim.retries
+    sim.close()
+    check_sod(state, t, g, prob)
+    assert retries == int(g["retries"])
+    if "ref_l1_error" in g:
+        e = sod_error_norm(state[:, 0, 0, :], g, prob)
+        assert abs(e - float(g["ref_l1_error"])) < 1e-9
