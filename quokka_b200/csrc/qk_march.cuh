@@ -18,13 +18,17 @@
 #pragma once
 #include "qk_tma.cuh"
 
-template <int NV, int STAGE, bool LAST> struct MarchSmem {
+// R0 (relaxed arithmetic only): instead of the three 0.5*F(U0) face arrays, stage 1 keeps its complete right-hand side
+// R(U0) per cell (in the z-face scratch array) and stage 2 forms 0.5*R(U0) + 0.5*R(U1): algebraically the same update
+// (the RK2 flux average is linear), 120 B/cell less traffic in each stage, but not the reference's rounding order.
+template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 	static constexpr int NR = 4;
 	static constexpr int PR = (NV + 1) * 32 + 36; // rows n*32 for n = 0..NV (n = NV: chi; n = 1 unused) + wide vx row
 	static constexpr int WIDE = (NV + 1) * 32;
 	static constexpr int TR = 64;
 	static constexpr int AUX_HF = 0;
-	static constexpr int AUX_RHS = (STAGE == 2) ? (NV + 1) * 32 : 0;
+	static constexpr int HF_ROWS = (STAGE == 2) ? (R0 ? (LAST ? NV : 0) : NV + 1) : 0;
+	static constexpr int AUX_RHS = HF_ROWS * 32;
 	static constexpr int AUX_U0 = AUX_RHS + (NV + 1) * 32;
 	static constexpr int AUX = AUX_U0 + (LAST ? NV * 32 : 0);
 	static constexpr int WARP_DOUBLES = NR * PR + TR + AUX;
@@ -36,7 +40,8 @@ template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL,
 __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
-	using SM = MarchSmem<NV, STAGE, LAST>;
+	constexpr bool R0 = (ARITH == 1);
+	using SM = MarchSmem<NV, STAGE, LAST, R0>;
 	constexpr int TD = (DIR == 1) ? 2 : 1;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -109,22 +114,27 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 		auto aux_bytes = [&](int r) -> unsigned {
 			unsigned b = 0;
 			if (r >= s0) {
-				if (STAGE == 2)
+				if (STAGE == 2 && !R0)
 					b += (unsigned)(NV + 1) * rowb;
 				if (r > s0)
-					b += (unsigned)(NV + 1) * rowb + (LAST ? (unsigned)NV * rowb : 0u);
+					b += (unsigned)(NV + 1) * rowb + (LAST ? (unsigned)NV * rowb : 0u) + ((STAGE == 2 && R0 && LAST) ? (unsigned)NV * rowb : 0u);
 			}
 			return b;
 		};
 		auto issue_aux = [&](int r) { // src_h at face r, src_r / src_u at cell r-1
 			uint64_t *bar = &bars[5];
 			mbar_arrive_expect_tx(bar, aux_bytes(r));
-			if (STAGE == 2) {
+			if (STAGE == 2 && !R0) {
 #pragma unroll
 				for (int n = 0; n <= NV; ++n)
 					bulk_g2s(aux_s + SM::AUX_HF + n * 32, src_h + n * h.ns, rowb, bar);
 			}
 			if (r > s0) {
+				if (STAGE == 2 && R0 && LAST) { // R(U0) of cell r-1
+#pragma unroll
+					for (int n = 0; n < NV; ++n)
+						bulk_g2s(aux_s + SM::AUX_HF + n * 32, src_h - shN + n * h.ns, rowb, bar);
+				}
 #pragma unroll
 				for (int n = 0; n <= NV; ++n)
 					bulk_g2s(aux_s + SM::AUX_RHS + n * 32, src_r + n * rh.ns, rowb, bar);
@@ -240,12 +250,12 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 				}
 				if (active) {
 					if (STAGE == 1) {
-						if (DUAL) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
+						if (DUAL && !R0) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
 #pragma unroll
 							for (int n = 0; n <= NV; ++n)
 								h.p[o_h + n * h.ns] = 0.0 + 0.5 * G[n];
 						}
-					} else {
+					} else if (!R0) {
 #pragma unroll
 						for (int n = 0; n <= NV; ++n)
 							G[n] = aux_s[SM::AUX_HF + n * 32 + lane] + 0.5 * G[n];
@@ -269,7 +279,13 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 							for (int n = 0; n < NV; ++n)
 								U0[n] = aux_s[SM::AUX_U0 + n * 32 + lane];
 							int bad, nf;
-							cell_epilogue<ARITH, NS, NMS>(c, U0, rr, divv, Un, bad, nf);
+							cell_epilogue<ARITH, NS, NMS, (STAGE == 2 && R0)>(c, U0, rr, divv, Un, bad, nf, aux_s + SM::AUX_HF + lane);
+							if (STAGE == 1 && DUAL && R0) { // keep R(U0) of cell r-1 for stage 2
+								const int64_t ohc = o_h - shN;
+#pragma unroll
+								for (int n = 0; n < NV; ++n)
+									h.p[ohc + n * h.ns] = rr[n];
+							}
 							bad_cnt += bad;
 							nf_cnt += nf;
 							const int64_t ooc = o_o - soN;
@@ -318,12 +334,12 @@ __global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox 
 // walks XROWS consecutive rows; the rows of row m+1 are bulk-copied into the other stage while row m is computed.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int XROWS = 8;
-template <int NV> struct XSmem {
+template <int NV, int STAGE> struct XSmem {
 	static constexpr int PW = 38;			    // cells x0-4 .. x0+33 of every component (+ chi)
 	static constexpr int PRIM = (NV + 1) * PW;	    // 16-byte multiple for every NV
 	static constexpr int TW = 34;			    // cells x0-2 .. x0+31 of the transverse velocity rows
 	static constexpr int TRANS = 4 * TW;		    // vy(j-1), vy(j+1), vz(k-1), vz(k+1)
-	static constexpr int AUX = (NV + 1) * 32;	    // 0.5 F(U0) at faces x0 .. x0+31 (stage 2)
+	static constexpr int AUX = (STAGE == 2) ? (NV + 1) * 32 : 0; // 0.5 F(U0) at faces x0 .. x0+31 (stage 2 only; the relaxed mode never runs STAGE 2 here)
 	static constexpr int STAGE_DOUBLES = PRIM + TRANS + AUX;
 	static constexpr int WARP_BYTES = 2 * STAGE_DOUBLES * 8 + 16; // two stages + two mbarriers
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
@@ -333,7 +349,7 @@ template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
 __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
 {
 	constexpr int NV = 6 + NS;
-	using SM = XSmem<NV>;
+	using SM = XSmem<NV, STAGE>;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);

@@ -250,8 +250,14 @@ static int advance_hydro(qk_sim *s, std::vector<qk_array4> &Uold, double dt, int
 		return 0;
 	}
 	// isCflViolated (:992-1013)
+	// the final-stage epilogue of the fused path has already reduced both maxima of state_new; otherwise one pass does
 	double both[2];
-	QK_TRY(qk_hydro_max_signal_both(&s->prm, s->nb, L->valid.data(), s->snew.data(), both, s->stream));
+	if (!qk_fused_take_signal(L, s->snew.data(), both)) {
+		int rc = qk_fused_max_signal(L, &s->prm, s->snew.data(), both, s->stream);
+		if (rc == QK_ERR_UNSUPPORTED)
+			rc = qk_hydro_max_signal_both(&s->prm, s->nb, L->valid.data(), s->snew.data(), both, s->stream);
+		QK_TRY(rc);
+	}
 	s->sig_local = both[0];
 	s->sig_valid = true;
 	double smax = both[1];

@@ -35,6 +35,10 @@ struct FusedState {
 	cudaEvent_t ev[8];
 	bool ev_used[8];
 	bool tainted = false; // a previous stage left flagged cells in the state: stay on the faithful path
+	// signal speeds of the state the last final-stage epilogue wrote (local maxima), and the array they belong to
+	bool sig_valid = false;
+	const double *sig_of = nullptr;
+	double sig[2] = {0.0, 0.0};
 };
 
 void qk_fused_free(qk_level *L)
@@ -51,6 +55,60 @@ void qk_fused_free(qk_level *L)
 	}
 	delete F;
 	L->fused = nullptr;
+}
+
+// local signal-speed maxima reduced by the last final-stage epilogue, if they belong to `state` (and consume them)
+bool qk_fused_take_signal(qk_level *L, const qk_array4 *state, double out[2])
+{
+	FusedState *F = L->fused;
+	if (!F || !F->sig_valid || L->valid.empty() || F->sig_of != state[0].p)
+		return false;
+	out[0] = F->sig[0];
+	out[1] = F->sig[1];
+	F->sig_valid = false;
+	return true;
+}
+
+// one pass over the local boxes: out[0] = ComputeMaxSignalSpeed + norminf (simulation.hpp:709-710), out[1] = maxSignalSpeedLocal
+// (isCflViolated); returns QK_ERR_UNSUPPORTED when the constants leave the shared-reciprocal domain (caller uses qk_ops.cu's kernels)
+int qk_fused_max_signal(qk_level *L, const qk_hydro_params *prm, const qk_array4 *state, double out[2], cudaStream_t s)
+{
+	FastConst c;
+	if (!make_fast_const(prm, L->dx, 0.0, &c))
+		return QK_ERR_UNSUPPORTED;
+	QK_TRY(L->ensure_counters());
+	QK_CUDA(cudaMemsetAsync(L->d_counters + 4, 0, 16, s));
+	{
+		ProfScope p("max_signal_speed", s);
+		const int nb = (int)L->valid.size();
+		for (int b0 = 0; b0 < nb; b0 += SigBoxes::MAXB) {
+			SigBoxes sb;
+			const int n = std::min(SigBoxes::MAXB, nb - b0);
+			int64_t maxcells = 1;
+			for (int b = 0; b < n; ++b) {
+				sb.u[b] = A4(state[b0 + b]);
+				sb.bx[b] = Box3(L->valid[b0 + b]);
+				maxcells = std::max(maxcells, sb.bx[b].ncells());
+			}
+			const unsigned per_box = (unsigned)std::max<int64_t>(1, std::min<int64_t>((maxcells + 255) / 256, (148 * 16 + n - 1) / n));
+			if (prm->arith == QK_ARITH_FAST) // closed-form EOS, as the relaxed sweeps (this unit is compiled without FMA contraction)
+				k_signal<1><<<dim3(per_box, n), 256, 0, s>>>(c, sb, L->d_counters + 4);
+			else
+				k_signal<0><<<dim3(per_box, n), 256, 0, s>>>(c, sb, L->d_counters + 4);
+			QK_KERNEL_CHECK();
+		}
+	}
+	QK_CUDA(cudaMemcpyAsync(L->h_counters + 4, L->d_counters + 4, 16, cudaMemcpyDeviceToHost, s));
+	QK_CUDA(cudaStreamSynchronize(s));
+	auto key2d = [](unsigned long long k) {
+		unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+		double v;
+		memcpy(&v, &b, 8);
+		return v;
+	};
+	out[0] = (L->h_counters[4] == 0ull) ? 0.0 : key2d(L->h_counters[4]);
+	out[1] = (L->h_counters[5] == 0ull) ? -1.7976931348623157e308 : key2d(L->h_counters[5]);
+	return 0;
 }
 
 void qk_fused_untaint(qk_level *L)
@@ -136,16 +194,20 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(SweepBox) * nb, cudaMemcpyHostToDevice, s));
 	QK_CUDA(cudaEventRecord(F->ev[slot], s));
 	F->ev_used[slot] = true;
-	QK_CUDA(cudaMemsetAsync(L->d_counters, 0, 16, s));
+	QK_CUDA(cudaMemsetAsync(L->d_counters, 0, 32, s));
+	F->sig_valid = false;
+	// (folding the dt / CFL reductions into the final-stage epilogue was measured: +0.40 ms per step at 256^3 from register
+	// pressure in the marching loop, against 0.12 ms for the one-pass k_signal kernel -- qk_fused_max_signal)
+	c.want_sig = 0;
 
 	const bool dual = (prm->integrator_order == 2);
 	int rc;
-	if (prm->arith == QK_ARITH_FAST)
+	if (prm->arith == QK_ARITH_FAST && tma) // the relaxed kernels exist in the TMA-staged form only
 		rc = qk_sweep_stage_relaxed(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
 	else
 		rc = sweep_stage_dispatch<0>(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
 	QK_TRY(rc);
-	QK_CUDA(cudaMemcpyAsync(L->h_counters, L->d_counters, 16, cudaMemcpyDeviceToHost, s));
+	QK_CUDA(cudaMemcpyAsync(L->h_counters, L->d_counters, 32, cudaMemcpyDeviceToHost, s));
 	QK_CUDA(cudaStreamSynchronize(s));
 	int64_t flagged = (int64_t)(L->h_counters[0] + L->h_counters[1]);
 	QK_TRY(L->global_sum(&flagged, s));
@@ -158,8 +220,21 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 			F->tainted = true;
 		if (ncells_bad)
 			*ncells_bad = bad;
-	} else if (ncells_bad) {
-		*ncells_bad = 0;
+	} else {
+		if (ncells_bad)
+			*ncells_bad = 0;
+		if (c.want_sig && nb > 0) {
+			auto key2d = [](unsigned long long k) {
+				unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+				double v;
+				memcpy(&v, &b, 8);
+				return v;
+			};
+			F->sig[0] = (L->h_counters[2] == 0ull) ? 0.0 : key2d(L->h_counters[2]);
+			F->sig[1] = (L->h_counters[3] == 0ull) ? -1.7976931348623157e308 : key2d(L->h_counters[3]);
+			F->sig_of = Uout[0].p;
+			F->sig_valid = true;
+		}
 	}
 	*handled = true;
 	return 0;

