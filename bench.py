@@ -261,7 +261,7 @@ def main_ours(args):
         nm, cnt, ms = ln.split()
         prof[nm] = (int(cnt), float(ms))
     ncell_local = sum(b.ncells() for b in sim.local_boxes)
-    roof = roofline(prof, ncell_local, args.steps, ms_total)
+    roof = roofline(prof, ncell_local, args.steps, ms_total, args.arith)
 
     if args.no_extras:  # profiling runs (ncu): kernels only
         if rank == 0:
@@ -323,9 +323,122 @@ def main_ours(args):
     return 0
 
 
-def roofline(prof, ncell_local, steps, ms_total):
+# ---- radiation transport sweep (SURVEY.md section 8(a) RadSystem rows; not the headline metric) ----------------------------------
+def main_radiation(args):
+    """python bench.py --workload radiation: one step = one two-moment transport substep (ghost fill, stage 1, ghost fill,
+    stage 2 through qk_rad_advance_stage) of a free-streaming pulse on 256^3 in eight 128^3 boxes, one photon group, PPM."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from quokka_b200 import capi
+    from quokka_b200.capi import check, make_level_desc, qk_box, rad_params
+    from quokka_b200.device import DevMultiFab
+    from quokka_b200.problems import chop_domain
+
+    lib = capi.load()
+    n, box, ng, ncomp = 256, 128, 4, 10
+    prm = rad_params(c_light=1.0, c_hat=1.0, recon_order=3)
+    boxes = chop_domain(n, box)
+    dom = qk_box.make((0, 0, 0), (n - 1,) * 3)
+    dx = [1.0 / n] * 3
+    bc = [capi.QK_BC_INT_DIR] * (3 * ncomp)
+    desc, keep = make_level_desc(dom, (1, 1, 1), dx, ng, ncomp, boxes, [0] * len(boxes), 0, bc, bc)
+    lev = C.c_void_p()
+    check(lib.qk_level_create(C.byref(desc), C.byref(lev)))
+    host = []
+    for bx in boxes:
+        g = bx.grown(ng)
+        nz, ny, nx = g.shape()
+        z, y, x = np.meshgrid((np.arange(g.lo[2], g.hi[2] + 1) + 0.5) / n, (np.arange(g.lo[1], g.hi[1] + 1) + 0.5) / n,
+                              (np.arange(g.lo[0], g.hi[0] + 1) + 0.5) / n, indexing="ij", sparse=True)
+        a = np.ones((ncomp, nz, ny, nx))
+        E = 1.0e-3 + np.exp(-((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2) / (2 * 0.05 ** 2))
+        a[6] = E
+        a[7] = 0.9 * E
+        a[8] = 0.0
+        a[9] = 0.0
+        host.append(a)
+    U = [DevMultiFab(boxes, ncomp, ngrow=ng, host=host) for _ in range(3)]
+    dt = 0.3 * dx[0]
+
+    def step():
+        check(lib.qk_fill_boundary(lev, U[0].descs, 0, ncomp, None))
+        check(lib.qk_rad_advance_stage(lev, C.byref(prm), 1, U[0].descs, U[0].descs, U[1].descs, dt, None))
+        check(lib.qk_fill_boundary(lev, U[1].descs, 0, ncomp, None))
+        check(lib.qk_rad_advance_stage(lev, C.byref(prm), 2, U[0].descs, U[1].descs, U[2].descs, dt, None))
+        U[0], U[2] = U[2], U[0]
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    lib.qk_prof_enable(1)
+    l0 = lib.qk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.qk_launch_count() - l0
+    lib.qk_prof_enable(0)
+    buf = (capi.C.c_char * 8192)()
+    lib.qk_prof_report(buf, 8192)
+    prof = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
+    ncell = n ** 3
+    value = ncell * args.steps / (ms * 1e-3) / 1e6
+    peak, src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    st_ms = prof.get("rad_stage", (0, 0.0))[1] / (2 * args.steps)
+    ach = 64 * ncell / (st_ms * 1e-3) / 1e9 if st_ms > 0 else None
+    line = {"metric": "Mcell-updates/s (two-moment radiation transport substep, PPM + HLL, RK2)", "value": round(value, 2), "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "free-streaming Gaussian pulse 256^3 periodic, eight 128^3 boxes, 1 photon group, c_hat = c, cfl 0.3 (radiation rows of SURVEY 8a; "
+                                   "config C4's source terms are not part of this path)", "cells": ncell, "arith": "exact (bit-identical to the oracle)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_rad_stage", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": src, "unit": "GB/s",
+                         "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 64, "design_bytes_per_cell": 160,
+                         "avg_launch_ms": round(st_ms, 4)},
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+    if not args.no_extras:
+        # CPU baseline: the C oracle's transport substep (1 thread) on 48^3
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+
+        m = 48
+        bx = qk_box.make((0, 0, 0), (m - 1,) * 3)
+        d2, k2 = make_level_desc(bx, (1, 1, 1), [1.0 / m] * 3, ng, ncomp, [bx], [0], 0, bc, bc)
+        o = ol.oracle()
+        L = o.orc_level_create(C.byref(d2))
+        for which in (0, 1):
+            d = o.orc_level_state(L, which, 0)
+            v = np.ctypeslib.as_array(C.cast(d.p, C.POINTER(C.c_double)), shape=(ncomp, m + 8, m + 8, m + 8))
+            v[...] = 1.0
+            v[7:] = 0.1
+        t0 = time.time()
+        reps = 3
+        for _ in range(reps):
+            o.orc_level_swap(L)
+            o.orc_rad_advance_level(L, C.byref(prm), 0.3 / m)
+        el = time.time() - t0
+        o.orc_level_destroy(L)
+        line["cpu_baseline"] = {"value": round(m ** 3 * reps / el / 1e6, 4), "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"C oracle, 1 thread, {m}^3, {reps} substeps, {el:.1f} s"}
+    print(json.dumps(line))
+    lib.qk_level_destroy(lev)
+    return 0
+
+
+def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
     """dominant kernel class vs the measured HBM copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
-    Algorithmic bytes per cell per launch are documented in DESIGN.md section 4."""
+    Algorithmic and design bytes per cell are documented in DESIGN.md section 3."""
     peak, src = 6650.0, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -333,12 +446,17 @@ def roofline(prof, ncell_local, steps, ms_total):
     except Exception:
         pass
     # the unit is one cell of one direction sweep; ALGORITHMIC bytes = 96 (read 6 state variables, write 6).
-    # DESIGN bytes = what this implementation moves per unit (equals the ncu DRAM traffic within 3 %).
+    # DESIGN bytes = what this implementation moves per unit (equals the ncu DRAM traffic within a few %).
     ALG = 96
-    DESIGN = {"flux_function": 48 + 24 + 56, "sweep_x": 56 + 56 + 56, "sweep_y": 56 + 56 + 112, "sweep_z": 56 + 56 + 56 + 48 + 48}
-    # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at 256^3 per GPU (profiles/r01_ncu_sweeps_exact.csv;
-    # stage-1 / stage-2 launches averaged); None where no capture exists for the configuration being run
-    TRAFFIC = {"sweep_x": 2.894e9, "sweep_y": 4.003e9, "sweep_z": 4.742e9}
+    if arith == "exact":  # keeps 0.5*F(U0) on the faces between the RK stages
+        DESIGN = {"flux_function": 48 + 24 + 56, "sweep_x": 56 + 56 + 56, "sweep_y": 56 + 56 + 112, "sweep_z": 56 + 56 + 56 + 48 + 48}
+        # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at 256^3 per GPU, stage-1/stage-2 launches averaged
+        TRAFFIC = {"sweep_x": 2.894e9, "sweep_y": 4.003e9, "sweep_z": 4.742e9}  # profiles/r01_ncu_sweeps_exact.csv
+        fp64_per_cell, opmix = 740, "profiles/r01_ncu_opmix_exact.txt"
+    else:  # keeps R(U0) per cell instead
+        DESIGN = {"sweep_x": 56 + 56, "sweep_y": 56 + 112, "sweep_z": 56 + 56 + 48 + 48 + 48}
+        TRAFFIC = {"sweep_x": 1.919e9, "sweep_y": 3.028e9, "sweep_z": 4.573e9}  # profiles/r01_ncu_sweeps_relaxed.csv
+        fp64_per_cell, opmix = 490, "profiles/r01_ncu_opmix_relaxed.txt"
     cand = [(v[1], k) for k, v in prof.items() if k in DESIGN]
     if not cand:
         return None
@@ -348,14 +466,15 @@ def roofline(prof, ncell_local, steps, ms_total):
     passes = {"flux_function": 6, "sweep_x": 2, "sweep_y": 2, "sweep_z": 2}[name] * steps
     t = ms * 1e-3 / passes
     achieved = ALG * ncell_local / t / 1e9
-    # second roof: the FP64 pipe (64 lanes/SM/clk).  ~740 FP64-pipe thread instructions per cell-sweep (profiles/r01_ncu_opmix_exact.txt)
+    # second roof: the FP64 pipe (64 lanes/SM/clk at 1965 MHz)
     fp64_peak = 148 * 64 * 1.965e9
     return {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "traffic": TRAFFIC.get(name) if ncell_local == 256 ** 3 else None, "algorithmic_bytes_per_cell": ALG, "algorithmic_bytes_per_launch": ALG * ncell_local,
             "design_bytes_per_cell": DESIGN[name], "achieved_design_gbs": round(DESIGN[name] * ncell_local / t / 1e9, 1),
+            "frac_design": round(DESIGN[name] * ncell_local / t / 1e9 / peak, 4),
             "gcell_sweeps_per_s": round(ncell_local / t / 1e9, 3), "avg_launch_ms": round(ms / passes, 4), "launches": nl, "share_of_step": round(ms / ms_total, 4),
-            "fp64_roof": {"fp64_instr_per_cell": 740, "peak_instr_per_s": fp64_peak, "frac": round(740 * ncell_local / t / fp64_peak, 4),
-                          "note": "the exact op sequence is FP64-pipe bound, not HBM bound (DESIGN.md section 3)"}}
+            "fp64_roof": {"fp64_instr_per_cell": fp64_per_cell, "peak_instr_per_s": fp64_peak, "frac": round(fp64_per_cell * ncell_local / t / fp64_peak, 4),
+                          "note": f"FP64-pipe instructions per cell-sweep from {opmix}; the sweep is issue/FP64-pipe bound, not HBM bound (DESIGN.md section 3)"}}
 
 
 if __name__ == "__main__":
@@ -365,6 +484,9 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="relaxed", choices=["exact", "relaxed"], help="arithmetic mode of the fused sweeps (DESIGN.md section 3)")
+    ap.add_argument("--workload", default="hydro", choices=["hydro", "radiation"], help="hydro = the BASELINE.json metric (default); radiation = the transport sweep")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e and cpu_baseline legs (profiling runs)")
     a = ap.parse_args()
+    if a.workload == "radiation" and a.impl == "ours":
+        sys.exit(main_radiation(a))
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
