@@ -18,6 +18,10 @@
 #pragma once
 #include "qk_tma.cuh"
 
+#ifndef QK_MARCH_Y_BLOCKS
+#define QK_MARCH_Y_BLOCKS 4 // resident CTAs per SM of the relaxed y sweep: 5 (96 registers) was measured slower (spills): 2.08 vs 1.84 ms per step
+#endif
+
 // R0 (relaxed arithmetic only): instead of the three 0.5*F(U0) face arrays, stage 1 keeps its complete right-hand side
 // R(U0) per cell (in the z-face scratch array) and stage 2 forms 0.5*R(U0) + 0.5*R(U1): algebraically the same update
 // (the RK2 flux average is linear), 120 B/cell less traffic in each stage, but not the reference's rounding order.
@@ -37,7 +41,7 @@ template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 };
 
 template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
-__global__ void __launch_bounds__(128, 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
+__global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS : 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
 	constexpr bool R0 = (ARITH == 1);

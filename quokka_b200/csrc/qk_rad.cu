@@ -17,6 +17,7 @@
 // (tests/test_gpu_radiation.py).
 #include "qk_level.h"
 #include "qk_kernels.cuh"
+#include "qk_fast.cuh"
 
 #include <algorithm>
 
@@ -51,24 +52,31 @@ int check_rad(const qk_rad_params *p)
 	return qk_require_device();
 }
 
+// Quotients follow qk_fast.cuh: FAST = true forms every quotient over a shared denominator (the three direction cosines over
+// |f|, the three HLL coefficients over S_R - S_L) from one refined reciprocal with bit-identical results and raises `bad` when
+// an operand leaves the compiler's own fast-path domain; the caller then recomputes the face with FAST = false (plain `/`).
+
 // RadSystem::ComputeEddingtonFactor  :773-790 (Levermore 1984)
-__device__ __forceinline__ double rad_eddington_factor(double f_in)
+template <bool FAST> __device__ __forceinline__ double rad_eddington_factor(double f_in, unsigned &bad)
 {
 	const double f = clampd(f_in, 0., 1.);
 	const double f_fac = sqrt(4.0 - 3.0 * (f * f));
-	return (3.0 + 4.0 * (f * f)) / (5.0 + 2.0 * f_fac);
+	return div_d<FAST>(3.0 + 4.0 * (f * f), 5.0 + 2.0 * f_fac, bad);
 }
 
-// ComputeEddingtonTensor :873-916 + ComputeRadPressure<DIR> :918-983.  Only row DIR of the tensor is needed.
-template <int DIR> __device__ __forceinline__ void rad_pressure(double erad, double Fn, double fx, double fy, double fz, double *F, double &S)
+// ComputeEddingtonTensor :873-916 + ComputeRadPressure<DIR> :918-983.  Only row DIR of the tensor is needed; f = |(fx,fy,fz)| is
+// the value the caller has just formed with the same expression (:1036-1037 / :1077-1078 and :878).
+template <int DIR, bool FAST>
+__device__ __forceinline__ void rad_pressure(double erad, double Fn, double fx, double fy, double fz, double f, double *F, double &S, unsigned &bad)
 {
-	const double f = sqrt(fx * fx + fy * fy + fz * fz);
 	const double fv[3] = {fx, fy, fz};
 	double n[3];
+	const bool fpos = (f > 0.);
+	const QkRcp Rf = rcp_f<FAST>(fpos ? f : 1.0, bad);
 #pragma unroll
 	for (int ii = 0; ii < 3; ++ii)
-		n[ii] = (f > 0.) ? (fv[ii] / f) : 0.;
-	const double chi = rad_eddington_factor(f);
+		n[ii] = fpos ? div_r<FAST>(fv[ii], Rf, bad) : 0.;
+	const double chi = rad_eddington_factor<FAST>(f, bad);
 	const double Tdiag = (1.0 - chi) / 2.0;
 	const double Tf = (3.0 * chi - 1.0) / 2.0;
 	double T[3];
@@ -87,9 +95,9 @@ template <int DIR> __device__ __forceinline__ void rad_pressure(double erad, dou
 
 // HLL flux of one face of one group (ComputeFluxes<DIR> body :1028-1137, epsilon = 1).  L/R: reconstructed (E_r, fx, fy, fz);
 // consL/consR point at component radEnergy of the cells either side of the face (first-order fallback :1054-1079).
-template <int DIR>
-__device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
-					      double *F)
+template <int DIR, bool FAST>
+__device__ __forceinline__ void rad_face_flux_t(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
+						double *F, unsigned &bad)
 {
 	double erad_L = L[0], erad_R = R[0];
 	double fL[3] = {L[1], L[2], L[3]}, fR[3] = {R[1], R[2], R[3]};
@@ -115,9 +123,9 @@ __device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L
 		f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
 	}
 	double F_L[4], F_R[4], S_L, S_R;
-	rad_pressure<DIR>(erad_L, FL[DIR], fL[0], fL[1], fL[2], F_L, S_L);
+	rad_pressure<DIR, FAST>(erad_L, FL[DIR], fL[0], fL[1], fL[2], f_L, F_L, S_L, bad);
 	S_L *= -1.;
-	rad_pressure<DIR>(erad_R, FR[DIR], fR[0], fR[1], fR[2], F_R, S_R);
+	rad_pressure<DIR, FAST>(erad_R, FR[DIR], fR[0], fR[1], fR[2], f_R, F_R, S_R, bad);
 	F_L[0] *= c.chat_over_c;
 	F_R[0] *= c.chat_over_c;
 #pragma unroll
@@ -129,10 +137,20 @@ __device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L
 	S_R *= c.chat;
 	const double U_L[4] = {erad_L, FL[0], FL[1], FL[2]};
 	const double U_R[4] = {erad_R, FR[0], FR[1], FR[2]};
-	const double a = S_R / (S_R - S_L), b = S_L / (S_R - S_L), d = S_R * S_L / (S_R - S_L);
+	const QkRcp Rs = rcp_f<FAST>(S_R - S_L, bad);
+	const double a = div_r<FAST>(S_R, Rs, bad), b = div_r<FAST>(S_L, Rs, bad), d = div_r<FAST>(S_R * S_L, Rs, bad);
 #pragma unroll
 	for (int n = 0; n < 4; ++n)
 		F[n] = a * F_L[n] - b * F_R[n] + d * (U_R[n] - U_L[n]);
+}
+template <int DIR>
+__device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
+					      double *F)
+{
+	unsigned bad = 0;
+	rad_face_flux_t<DIR, true>(c, L, R, consL, consR, cns, F, bad);
+	if (bad)
+		rad_face_flux_t<DIR, false>(c, L, R, consL, consR, cns, F, bad);
 }
 
 // isStateValid :624-643 + amendRadState :645-665 on the NG groups of one cell
