@@ -25,6 +25,7 @@
 #include "AMReX_MultiFab.H"
 #include "AMReX_iMultiFab.H"
 
+#include "radiation/radiation_system.hpp" // RadSystem_Traits, RadSystem<problem_t> constants
 #include "hydro/hydro_system.hpp" // RiemannSolver, FluxDir, SlopeLimiter, EOS_Traits, HydroSystem_Traits, Physics_Traits
 #include "quokka_b200.h"
 
@@ -318,6 +319,93 @@ template <typename problem_t> class HydroSystemB200
 	}
 };
 
+// ---- radiation: RadSystem<problem_t>'s static functions take Array4s and a Box (one FAB at a time, as
+// QuokkaSimulation::fluxFunction<DIR> / advanceRadiation* call them, src/QuokkaSimulation.hpp:1791-1862, 1942-1986) ----------
+template <typename problem_t> inline auto make_rad_params() -> qk_rad_params
+{
+	qk_rad_params p{};
+	p.c_light = RadSystem<problem_t>::c_light_;
+	p.c_hat = RadSystem<problem_t>::c_hat_;
+	p.Erad_floor = RadSystem_Traits<problem_t>::Erad_floor;
+	p.ngroups = RadSystem<problem_t>::nGroups_;
+	p.nstart = RadSystem<problem_t>::nstartHyperbolic_;
+	p.reconstruction_order = 3; // radiationReconstructionOrder_, filled by the caller
+	p.integrator_order = 2;
+	return p;
+}
+
+template <typename problem_t> class RadSystemB200
+{
+      public:
+	using arrayconst_t = amrex::Array4<const amrex::Real> const;
+	using array_t = amrex::Array4<amrex::Real> const;
+
+	// RadSystem::ConservedToPrimitive(cons, primVar, indexRange)  src/radiation/radiation_system.hpp:589-614
+	static void ConservedToPrimitive(arrayconst_t &cons, array_t &primVar, amrex::Box const &indexRange)
+	{
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_array4 c = view(cons);
+		const qk_array4 q = view(primVar);
+		const qk_box bx = to_box(indexRange);
+		check(qk_rad_conserved_to_primitive(&prm, 1, &bx, &c, &q, 0, stream()), "RadSystem::ConservedToPrimitive");
+	}
+
+	// RadSystem::ComputeFluxes<DIR>(x1Flux, x1FluxDiffusive, left, right, x1FluxRange, consVar, dx, use_wavespeed_correction)  :985-1139
+	template <FluxDir DIR>
+	static void ComputeFluxes(array_t &x1Flux_in, array_t &x1FluxDiffusive_in, arrayconst_t &x1LeftState_in, arrayconst_t &x1RightState_in,
+				  amrex::Box const &indexRange, arrayconst_t &consVar_in, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> /*dx*/,
+				  bool const use_wavespeed_correction)
+	{
+		if (use_wavespeed_correction) {
+			amrex::Abort("libquokka_b200: the optical-depth wavespeed correction is not provided (radiation.use_wavespeed_correction = 0)");
+		}
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_array4 f = view(x1Flux_in);
+		const qk_array4 fd = view(x1FluxDiffusive_in);
+		const qk_array4 l = view(x1LeftState_in);
+		const qk_array4 r = view(x1RightState_in);
+		const qk_array4 c = view(consVar_in);
+		const qk_box bx = to_box(indexRange); // nodal in DIR -> enclosed cells; the library iterates over their faces
+		check(qk_rad_compute_fluxes(&prm, static_cast<int>(DIR), 1, &bx, &f, &fd, &l, &r, &c, stream()), "RadSystem::ComputeFluxes");
+	}
+
+	// RadSystem::PredictStep  :667-710
+	static void PredictStep(arrayconst_t &consVarOld, array_t &consVarNew, amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> fluxArray,
+				amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> /*fluxDiffusiveArray*/, double dt_in,
+				amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx_in, amrex::Box const &indexRange, int /*nvars*/)
+	{
+		static_assert(AMREX_SPACEDIM == 3, "libquokka_b200 operates on 3-D FABs");
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_array4 u0 = view(consVarOld);
+		const qk_array4 un = view(consVarNew);
+		const qk_array4 fx = view(fluxArray[0]);
+		const qk_array4 fy = view(fluxArray[1]);
+		const qk_array4 fz = view(fluxArray[2]);
+		const qk_box bx = to_box(indexRange);
+		const double dx[3] = {dx_in[0], dx_in[1], dx_in[2]};
+		check(qk_rad_predict_step(&prm, 1, &bx, &u0, &un, &fx, &fy, &fz, dt_in, dx, stream()), "RadSystem::PredictStep");
+	}
+
+	// RadSystem::AddFluxesRK2  :712-771
+	static void AddFluxesRK2(array_t &U_new, arrayconst_t &U0, arrayconst_t &U1, amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> fluxArrayOld,
+				 amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> fluxArray, amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> /*fluxDiffusiveArrayOld*/,
+				 amrex::GpuArray<arrayconst_t, AMREX_SPACEDIM> /*fluxDiffusiveArray*/, double dt_in,
+				 amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx_in, amrex::Box const &indexRange, int /*nvars*/)
+	{
+		static_assert(AMREX_SPACEDIM == 3, "libquokka_b200 operates on 3-D FABs");
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_array4 un = view(U_new);
+		const qk_array4 u0 = view(U0);
+		const qk_array4 u1 = view(U1);
+		const qk_array4 fo[3] = {view(fluxArrayOld[0]), view(fluxArrayOld[1]), view(fluxArrayOld[2])};
+		const qk_array4 fn[3] = {view(fluxArray[0]), view(fluxArray[1]), view(fluxArray[2])};
+		const qk_box bx = to_box(indexRange);
+		const double dx[3] = {dx_in[0], dx_in[1], dx_in[2]};
+		check(qk_rad_add_fluxes_rk2(&prm, 1, &bx, &un, &u0, &u1, &fo[0], &fo[1], &fo[2], &fn[0], &fn[1], &fn[2], dt_in, dx, stream()),
+		      "RadSystem::AddFluxesRK2");
+	}
+};
+
 // ---- stage-level drop-in -----------------------------------------------------------------------------------------
 // One qk_level per AMR level mirrors BoxArray + DistributionMapping + Geometry + BCRec; it is rebuilt when the grids
 // change (after regrid).  advanceStage replaces the body of one RK stage of advanceHydroAtLevel
@@ -380,6 +468,14 @@ class LevelB200
 		int64_t bad = 0;
 		check(qk_hydro_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStage");
 		return bad;
+	}
+	// one stage of the radiation transport substep (advanceRadiationForwardEuler / MidpointRK2 transport part), fused
+	void advanceRadiationStage(qk_rad_params const &prm, int stage, amrex::MultiFab const &U0, amrex::MultiFab const &Ustage, amrex::MultiFab &Uout, double dt)
+	{
+		MFView u0(U0);
+		MFView us(Ustage);
+		MFView uo(Uout);
+		check(qk_rad_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, stream()), "advanceRadiationStage");
 	}
 	[[nodiscard]] auto handle() const -> qk_level * { return lev_; }
 

@@ -62,3 +62,59 @@ auto stage_level(quokka::b200::LevelB200 &lev, amrex::MultiFab &U0, amrex::Multi
 	bad += lev.advanceStage(prm, 2, U0, U1, Unew, dt);
 	return bad;
 }
+
+// ---- radiation: the call sequence of QuokkaSimulation::fluxFunction<DIR> + advanceRadiation* on one FAB ----
+struct RadLike {
+};
+template <> struct quokka::EOS_Traits<RadLike> {
+	static constexpr double gamma = 5. / 3.;
+	static constexpr double mean_molecular_weight = C::m_u;
+	static constexpr double boltzmann_constant = C::k_B;
+};
+template <> struct Physics_Traits<RadLike> {
+	static constexpr bool is_hydro_enabled = true;
+	static constexpr int numMassScalars = 0;
+	static constexpr int numPassiveScalars = numMassScalars + 0;
+	static constexpr bool is_radiation_enabled = true;
+	static constexpr bool is_mhd_enabled = false;
+	static constexpr int nGroups = 1;
+};
+template <> struct RadSystem_Traits<RadLike> {
+	static constexpr double c_light = 1.0;
+	static constexpr double c_hat = 1.0;
+	static constexpr double radiation_constant = 1.0;
+	static constexpr double Erad_floor = 0.;
+	static constexpr int beta_order = 0;
+};
+
+template <typename Rad>
+void rad_box(amrex::FArrayBox &cons, amrex::FArrayBox &prim, amrex::FArrayBox &l, amrex::FArrayBox &r, std::array<amrex::FArrayBox, 3> &f,
+	     std::array<amrex::FArrayBox, 3> &fd, amrex::FArrayBox &unew, amrex::FArrayBox &u1, amrex::Box const &bx, double dt,
+	     amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx)
+{
+	Rad::ConservedToPrimitive(cons.const_array(), prim.array(), amrex::grow(bx, 4));
+	Rad::template ComputeFluxes<FluxDir::X1>(f[0].array(), fd[0].array(), l.const_array(), r.const_array(), amrex::surroundingNodes(bx, 0), cons.const_array(), dx,
+						 false);
+	Rad::template ComputeFluxes<FluxDir::X3>(f[2].array(), fd[2].array(), l.const_array(), r.const_array(), amrex::surroundingNodes(bx, 2), cons.const_array(), dx,
+						 false);
+	Rad::PredictStep(cons.const_array(), unew.array(), {f[0].const_array(), f[1].const_array(), f[2].const_array()},
+			 {fd[0].const_array(), fd[1].const_array(), fd[2].const_array()}, dt, dx, bx, 4);
+	Rad::AddFluxesRK2(unew.array(), cons.const_array(), u1.const_array(), {f[0].const_array(), f[1].const_array(), f[2].const_array()},
+			  {f[0].const_array(), f[1].const_array(), f[2].const_array()}, {fd[0].const_array(), fd[1].const_array(), fd[2].const_array()},
+			  {fd[0].const_array(), fd[1].const_array(), fd[2].const_array()}, dt, dx, bx, 4);
+}
+template void rad_box<RadSystem<RadLike>>(amrex::FArrayBox &, amrex::FArrayBox &, amrex::FArrayBox &, amrex::FArrayBox &, std::array<amrex::FArrayBox, 3> &,
+					  std::array<amrex::FArrayBox, 3> &, amrex::FArrayBox &, amrex::FArrayBox &, amrex::Box const &, double,
+					  amrex::GpuArray<amrex::Real, AMREX_SPACEDIM>);
+template void rad_box<quokka::b200::RadSystemB200<RadLike>>(amrex::FArrayBox &, amrex::FArrayBox &, amrex::FArrayBox &, amrex::FArrayBox &,
+							    std::array<amrex::FArrayBox, 3> &, std::array<amrex::FArrayBox, 3> &, amrex::FArrayBox &,
+							    amrex::FArrayBox &, amrex::Box const &, double, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM>);
+
+void rad_level(quokka::b200::LevelB200 &lev, amrex::MultiFab &U0, amrex::MultiFab &U1, amrex::MultiFab &Unew, double dt)
+{
+	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();
+	lev.fillBoundary(U0, 0, U0.nComp());
+	lev.advanceRadiationStage(prm, 1, U0, U0, U1, dt);
+	lev.fillBoundary(U1, 0, U1.nComp());
+	lev.advanceRadiationStage(prm, 2, U0, U1, Unew, dt);
+}

@@ -92,3 +92,18 @@ def test_compute_entries_refuse_without_a_device():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         capi.load(str(tmp_path / "libquokka_b200.so"))
+
+
+def test_bench_reference_arm_runs_the_reference_executable():
+    """bench.py --impl reference times the reference's own CPU build (oracle/_ref) and prints the contract's JSON line"""
+    import json
+    import sys
+
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "test_hydro3d_blast")):
+        pytest.skip("oracle/_ref not built")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "Mcell-updates/s"
