@@ -20,6 +20,7 @@
 #include "qk_fast.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace
 {
@@ -440,6 +441,201 @@ __global__ void __launch_bounds__(RTX *RTY *RTZ) k_rad_stage(RadConst c, const R
 			B.Uo.p[oo + n * B.Uo.ns] = cons[n];
 	}
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused stage, direction-split form (the default): one parabola per cell per direction, no shared memory, no block barriers
+//   k_rad_x   lane <-> cell x0-1+lane of a row tile of 30 cells: parabola of the own cell, left state and the next face's
+//             flux by warp shuffle; writes acc = FxU = (dt/dx)(F_i - F_{i+1})
+//   k_rad_m   y / z by MARCHING: lane <-> x (coalesced rows), each thread walks a 32-cell segment keeping a 5-row window of the
+//             primitives, the previous cell's right state and the previous face's flux in registers; y adds FyU to acc, the z
+//             instance forms (FxU + FyU) + FzU (the reference's association, :694-698 / :748-759) and carries the update
+// One photon group per launch (groups are independent in the transport step); with several groups the admissibility fix-up, which
+// looks at all groups of a cell (isStateValid :624-643), runs as k_rad_fix afterwards.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RSEG = 32;
+
+struct RadBox2 {
+	A4 U0, Us, Uo, prim, S0, acc;
+	int lo[3], hi[3];
+};
+
+template <int ORDER> __device__ __forceinline__ void rad_cell_parabola(double qm2, double qm1, double q0, double qp1, double qp2, double &am, double &ap)
+{
+	if (ORDER == 3)
+		recon_cell<3, 0>(qm2, qm1, q0, qp1, qp2, am, ap);
+	else if (ORDER == 2)
+		recon_cell<2, QK_MC>(qm2, qm1, q0, qp1, qp2, am, ap);
+	else
+		recon_cell<1, 0>(qm2, qm1, q0, qp1, qp2, am, ap);
+}
+
+__device__ __forceinline__ double rshfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double rshfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+template <int ORDER> __global__ void __launch_bounds__(128) k_rad_x(RadConst c, const RadBox2 *__restrict__ boxes, int g, double dtdx)
+{
+	const RadBox2 &B = boxes[blockIdx.z];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int row = blockIdx.y * 4 + warp;
+	if (row >= ny * nz)
+		return; // whole warp
+	const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+	const int x0 = B.lo[0] + blockIdx.x * 30;
+	if (x0 > B.hi[0])
+		return;
+	const int i = x0 - 1 + lane;
+	const int ic = (i <= B.hi[0] + 1) ? i : B.hi[0] + 1; // cells lo-1 .. hi+1 carry a parabola
+	const A4 &q = B.prim;
+	const double *qp = q.p + q.off(ic, j, k) + 4 * g * q.ns;
+	double am[4], ap[4], Ls[4];
+#pragma unroll
+	for (int n = 0; n < 4; ++n) {
+		const double *p = qp + n * q.ns;
+		rad_cell_parabola<ORDER>(p[-2], p[-1], p[0], p[1], p[2], am[n], ap[n]);
+		Ls[n] = rshfl_up1(ap[n]);
+	}
+	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
+	double F[4] = {0., 0., 0., 0.};
+	if (face_ok) {
+		const A4 &u = B.Us;
+		const double *cR = u.p + u.off(i, j, k) + (c.nstart + 4 * g) * u.ns;
+		rad_face_flux<0>(c, Ls, am, cR - 1, cR, u.ns, F);
+	}
+	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
+	const A4 &a = B.acc;
+	const int64_t oa = upd ? a.off(i, j, k) + 4 * g * a.ns : 0;
+#pragma unroll
+	for (int n = 0; n < 4; ++n) {
+		const double Fn = rshfl_dn1(F[n]);
+		if (upd)
+			a.p[oa + n * a.ns] = dtdx * (F[n] - Fn);
+	}
+}
+
+// STAGE / KEEP_S0 / FIX only matter when LAST
+template <int DIR, int ORDER, bool LAST, int STAGE, bool KEEP_S0, bool FIX>
+__global__ void __launch_bounds__(128, 4) k_rad_m(RadConst c, const RadBox2 *__restrict__ boxes, int nseg, int g, double dtd)
+{
+	constexpr int TD = (DIR == 1) ? 2 : 1;
+	const int box = blockIdx.z / nseg, seg = blockIdx.z - box * nseg;
+	const RadBox2 &B = boxes[box];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int i = B.lo[0] + blockIdx.x * 32 + lane;
+	const int t = B.lo[TD] + blockIdx.y * 4 + warp;
+	const int s0 = B.lo[DIR] + seg * RSEG;
+	if (i > B.hi[0] || t > B.hi[TD] || s0 > B.hi[DIR])
+		return;
+	const int s1 = min(s0 + RSEG, B.hi[DIR] + 1); // cells s0 .. s1-1 are updated, faces s0 .. s1 evaluated
+	const A4 &q = B.prim;
+	const int64_t sN = (DIR == 1) ? q.js : q.ks;
+	int idx[3];
+	idx[0] = i;
+	idx[TD] = t;
+	idx[DIR] = s0 - 1;
+	const double *qp = q.p + q.off(idx[0], idx[1], idx[2]) + 4 * g * q.ns;
+	const A4 &u = B.Us;
+	const int64_t suN = (DIR == 1) ? u.js : u.ks;
+	const double *cu = u.p + u.off(idx[0], idx[1], idx[2]) + (c.nstart + 4 * g) * u.ns;
+	const A4 &a = B.acc;
+	const int64_t saN = (DIR == 1) ? a.js : a.ks;
+	int64_t oa = a.off(idx[0], idx[1], idx[2]) + 4 * g * a.ns;
+	const int64_t s0N = (DIR == 1) ? B.S0.js : B.S0.ks, u0N = (DIR == 1) ? B.U0.js : B.U0.ks, uoN = (DIR == 1) ? B.Uo.js : B.Uo.ks;
+	int64_t os = B.S0.off(idx[0], idx[1], idx[2]) + 4 * g * B.S0.ns;
+	int64_t o0 = B.U0.off(idx[0], idx[1], idx[2]) + (c.nstart + 4 * g) * B.U0.ns;
+	int64_t oo = B.Uo.off(idx[0], idx[1], idx[2]) + (c.nstart + 4 * g) * B.Uo.ns;
+	// 5-row window of the four primitives around cell s0-1
+	double w[4][5];
+#pragma unroll
+	for (int n = 0; n < 4; ++n)
+#pragma unroll
+		for (int m = 0; m < 5; ++m)
+			w[n][m] = qp[n * q.ns + (m - 2) * sN];
+	double apL[4] = {0., 0., 0., 0.}, Fp[4] = {0., 0., 0., 0.};
+	for (int s = s0 - 1; s <= s1; ++s) {
+		double am[4], ap[4];
+#pragma unroll
+		for (int n = 0; n < 4; ++n)
+			rad_cell_parabola<ORDER>(w[n][0], w[n][1], w[n][2], w[n][3], w[n][4], am[n], ap[n]);
+		if (s >= s0) {
+			double F[4];
+			rad_face_flux<DIR>(c, apL, am, cu - suN, cu, u.ns, F);
+			if (s > s0) { // cell s-1: both faces known
+				const int64_t oac = oa - saN;
+				double cons[4];
+#pragma unroll
+				for (int n = 0; n < 4; ++n) {
+					const double d = dtd * (Fp[n] - F[n]);
+					const double sum = a.p[oac + n * a.ns] + d;
+					if (!LAST) {
+						a.p[oac + n * a.ns] = sum;
+					} else {
+						const double U_0 = B.U0.p[(o0 - u0N) + n * B.U0.ns];
+						if (STAGE == 1) {
+							cons[n] = U_0 + sum; // PredictStep :694-698
+							if (KEEP_S0)
+								B.S0.p[(os - s0N) + n * B.S0.ns] = sum;
+						} else { // AddFluxesRK2 :757-759
+							const double IMEX_a32 = 0.5;
+							const double U_1 = cu[-suN + n * u.ns];
+							const double div0 = B.S0.p[(os - s0N) + n * B.S0.ns];
+							cons[n] = (1.0 - IMEX_a32) * U_0 + IMEX_a32 * U_1 + ((0.5 - IMEX_a32) * div0) + (0.5 * sum);
+						}
+					}
+				}
+				if (LAST) {
+					if (FIX)
+						rad_validate<1>(c, 1, cons);
+#pragma unroll
+					for (int n = 0; n < 4; ++n)
+						B.Uo.p[(oo - uoN) + n * B.Uo.ns] = cons[n];
+				}
+			}
+#pragma unroll
+			for (int n = 0; n < 4; ++n)
+				Fp[n] = F[n];
+		}
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			apL[n] = ap[n];
+#pragma unroll
+			for (int m = 0; m < 4; ++m)
+				w[n][m] = w[n][m + 1];
+		}
+		qp += sN;
+		cu += suN;
+		oa += saN;
+		os += s0N;
+		o0 += u0N;
+		oo += uoN;
+		if (s < s1) { // next cell's +2 row
+#pragma unroll
+			for (int n = 0; n < 4; ++n)
+				w[n][4] = qp[n * q.ns + 2 * sN];
+		}
+	}
+}
+
+// isStateValid / amendRadState over all groups of a cell, in place (several photon groups only)
+__global__ void __launch_bounds__(256) k_rad_fix(RadConst c, const RadBox2 *__restrict__ boxes)
+{
+	const RadBox2 &B = boxes[blockIdx.y];
+	const int nx = B.hi[0] - B.lo[0] + 1, ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int64_t total = (int64_t)nx * ny * nz;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t jk = t / nx;
+		const int i = B.lo[0] + (int)(t - jk * nx);
+		const int k = B.lo[2] + (int)(jk / ny);
+		const int j = B.lo[1] + (int)(jk - (jk / ny) * ny);
+		const int64_t o = B.Uo.off(i, j, k) + c.nstart * B.Uo.ns;
+		double cons[4 * QK_MAX_GROUPS];
+		for (int n = 0; n < 4 * c.ng; ++n)
+			cons[n] = B.Uo.p[o + n * B.Uo.ns];
+		rad_validate<QK_MAX_GROUPS>(c, c.ng, cons);
+		for (int n = 0; n < 4 * c.ng; ++n)
+			B.Uo.p[o + n * B.Uo.ns] = cons[n];
+	}
+}
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -523,8 +719,9 @@ extern "C" int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const
 // ---- fused stage ------------------------------------------------------------------------------------------------
 struct RadState {
 	int nh = 0; // 4 * ngroups the scratch was built for
-	std::vector<qk_array4> prim, S0;
+	std::vector<qk_array4> prim, S0, acc;
 	RadBox *d_boxes = nullptr, *h_boxes = nullptr; // ring of 8 tables
+	RadBox2 *d_boxes2 = nullptr, *h_boxes2 = nullptr;
 	int ring = 0;
 	cudaEvent_t ev[8];
 	bool ev_used[8];
@@ -538,6 +735,10 @@ void qk_rad_free(qk_level *L)
 	RadState *R = L->rad;
 	if (R->d_boxes)
 		cudaFree(R->d_boxes);
+	if (R->d_boxes2)
+		cudaFree(R->d_boxes2);
+	if (R->h_boxes2)
+		cudaFreeHost(R->h_boxes2);
 	if (R->h_boxes) {
 		cudaFreeHost(R->h_boxes);
 		for (int i = 0; i < 8; ++i)
@@ -558,8 +759,11 @@ static int rad_setup(qk_level *L, int nh)
 	const int nb = (int)L->valid.size();
 	QK_TRY(L->alloc_fabs(R->prim, nh, 3, -1));
 	QK_TRY(L->alloc_fabs(R->S0, nh, 0, -1));
+	QK_TRY(L->alloc_fabs(R->acc, nh, 0, -1));
 	QK_CUDA(cudaMalloc(&R->d_boxes, sizeof(RadBox) * nb * 8));
 	QK_CUDA(cudaMallocHost(&R->h_boxes, sizeof(RadBox) * nb * 8));
+	QK_CUDA(cudaMalloc(&R->d_boxes2, sizeof(RadBox2) * nb * 8));
+	QK_CUDA(cudaMallocHost(&R->h_boxes2, sizeof(RadBox2) * nb * 8));
 	for (int i = 0; i < 8; ++i) {
 		QK_CUDA(cudaEventCreateWithFlags(&R->ev[i], cudaEventDisableTiming));
 		R->ev_used[i] = false;
@@ -607,6 +811,46 @@ static int dispatch_rad_order(int order, const RadConst &c, const RadBox *tab, i
 	return launch_rad_stage<1, NG>(c, tab, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
 }
 
+// direction-split launches of one stage for photon group g
+template <int ORDER>
+static int launch_rad_split(const RadConst &c, const RadBox2 *tab, int nb, const int maxn[3], int stage, bool keep, bool fix, int g, double dtdx, double dtdy,
+			    double dtdz, cudaStream_t s)
+{
+	{
+		dim3 grid((maxn[0] + 29) / 30, (maxn[1] * maxn[2] + 3) / 4, nb);
+		k_rad_x<ORDER><<<grid, 128, 0, s>>>(c, tab, g, dtdx);
+		QK_KERNEL_CHECK();
+	}
+	{
+		const int nseg = (maxn[1] + RSEG - 1) / RSEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[2] + 3) / 4, nb * nseg);
+		k_rad_m<1, ORDER, false, 1, false, false><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdy);
+		QK_KERNEL_CHECK();
+	}
+	{
+		const int nseg = (maxn[2] + RSEG - 1) / RSEG;
+		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
+		if (stage == 1 && keep) {
+			if (fix)
+				k_rad_m<2, ORDER, true, 1, true, true><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+			else
+				k_rad_m<2, ORDER, true, 1, true, false><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+		} else if (stage == 1) {
+			if (fix)
+				k_rad_m<2, ORDER, true, 1, false, true><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+			else
+				k_rad_m<2, ORDER, true, 1, false, false><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+		} else {
+			if (fix)
+				k_rad_m<2, ORDER, true, 2, false, true><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+			else
+				k_rad_m<2, ORDER, true, 2, false, false><<<grid, 128, 0, s>>>(c, tab, nseg, g, dtdz);
+		}
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
 extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout,
 				    double dt, void *stream)
 {
@@ -616,8 +860,9 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	if (!L->has_device)
 		return QK_ERR_NO_DEVICE;
 	const int ng = prm->ngroups;
-	if (ng != 1 && ng != 2 && ng != 4)
-		return QK_ERR_UNSUPPORTED; // instantiated group counts of the fused kernel
+	const bool tile_form = (getenv("QK_RAD_TILE") != nullptr); // the first-generation one-kernel form (kept for comparison)
+	if (tile_form && ng != 1 && ng != 2 && ng != 4)
+		return QK_ERR_UNSUPPORTED; // instantiated group counts of the tile kernel
 	if (L->nghost < 3 || prm->nstart + 4 * ng > L->ncomp)
 		return QK_ERR_BAD_ARG;
 	cudaStream_t s = S(stream);
@@ -634,8 +879,20 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	if (R->ev_used[slot])
 		QK_CUDA(cudaEventSynchronize(R->ev[slot]));
 	RadBox *hb = R->h_boxes + (size_t)slot * nb;
+	RadBox2 *hb2 = R->h_boxes2 + (size_t)slot * nb;
 	int maxn[3] = {1, 1, 1};
 	for (int b = 0; b < nb; ++b) {
+		RadBox2 &B2 = hb2[b];
+		B2.U0 = A4(U0[b]);
+		B2.Us = A4(Ustage[b]);
+		B2.Uo = A4(Uout[b]);
+		B2.prim = A4(R->prim[b]);
+		B2.S0 = A4(R->S0[b]);
+		B2.acc = A4(R->acc[b]);
+		for (int d = 0; d < 3; ++d) {
+			B2.lo[d] = L->valid[b].lo[d];
+			B2.hi[d] = L->valid[b].hi[d];
+		}
 		RadBox &B = hb[b];
 		B.U0 = A4(U0[b]);
 		B.Us = A4(Ustage[b]);
@@ -649,6 +906,8 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 		}
 	}
 	RadBox *db = R->d_boxes + (size_t)slot * nb;
+	RadBox2 *db2 = R->d_boxes2 + (size_t)slot * nb;
+	QK_CUDA(cudaMemcpyAsync(db2, hb2, sizeof(RadBox2) * nb, cudaMemcpyHostToDevice, s));
 	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(RadBox) * nb, cudaMemcpyHostToDevice, s));
 	QK_CUDA(cudaEventRecord(R->ev[slot], s));
 	R->ev_used[slot] = true;
@@ -662,15 +921,33 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	}
 	const bool keep = (stage == 1 && prm->integrator_order == 2);
 	const double dtdx = dt / L->dx[0], dtdy = dt / L->dx[1], dtdz = dt / L->dx[2];
-	int rc;
+	int rc = 0;
 	{
 		ProfScope p("rad_stage", s);
-		if (ng == 1)
-			rc = dispatch_rad_order<1>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
-		else if (ng == 2)
-			rc = dispatch_rad_order<2>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
-		else
-			rc = dispatch_rad_order<4>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+		if (tile_form) {
+			if (ng == 1)
+				rc = dispatch_rad_order<1>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+			else if (ng == 2)
+				rc = dispatch_rad_order<2>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+			else
+				rc = dispatch_rad_order<4>(prm->reconstruction_order, c, db, nb, maxn, stage, keep, dtdx, dtdy, dtdz, s);
+		} else {
+			const bool fix = (ng == 1); // one group: the admissibility fix-up is cell-local to the z sweep's epilogue
+			for (int g = 0; g < ng && rc == 0; ++g) {
+				if (prm->reconstruction_order == 3)
+					rc = launch_rad_split<3>(c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
+				else if (prm->reconstruction_order == 2)
+					rc = launch_rad_split<2>(c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
+				else
+					rc = launch_rad_split<1>(c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
+			}
+			if (rc == 0 && !fix) {
+				const int64_t cells = (int64_t)maxn[0] * maxn[1] * maxn[2];
+				dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+				k_rad_fix<<<grid, 256, 0, s>>>(c, db2);
+				QK_KERNEL_CHECK();
+			}
+		}
 	}
 	QK_TRY(rc);
 	R->s0_valid = (stage == 1 && keep);

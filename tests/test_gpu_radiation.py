@@ -20,7 +20,8 @@ NG = 4
 DX3 = (0.1, 0.07, 0.13)
 C_CGS = 2.99792458e10
 TRAITS = {0: dict(c_light=1.0, c_hat=1.0, Erad_floor=0.0), 1: dict(c_light=C_CGS, c_hat=C_CGS / 30.0, Erad_floor=1.0e-12),
-          2: dict(c_light=10.0, c_hat=2.5, Erad_floor=1.0e-9, ngroups=2, nstart=7)}
+          2: dict(c_light=10.0, c_hat=2.5, Erad_floor=1.0e-9, ngroups=2, nstart=7),
+          3: dict(c_light=3.0, c_hat=1.5, Erad_floor=1.0e-6, ngroups=3, nstart=6)}
 
 
 @pytest.fixture(scope="module")
@@ -236,6 +237,7 @@ CASES = {
     "donor_mixed": dict(ncell=(24, 16, 8), grid=8, periodic=(1, 0, 1), traits=0, order=1),
     "ppm_single_ragged": dict(ncell=(40, 12, 9), grid=64, periodic=(0, 1, 0), traits=1, order=3),
     "two_groups": dict(ncell=(32, 16, 16), grid=16, periodic=(1, 1, 0), traits=2, order=3),
+    "three_groups_plm": dict(ncell=(32, 16, 16), grid=16, periodic=(1, 0, 1), traits=3, order=2),
     "euler": dict(ncell=(16, 16, 16), grid=8, periodic=(1, 1, 1), traits=0, order=3, integrator=1),
 }
 
@@ -268,8 +270,10 @@ def test_rad_stage_argument_checks(lib):
     V = DevMultiFab(p.boxes, p.ncomp, ngrow=p.nghost)
     assert lib.qk_rad_advance_stage(lev, C.byref(prm), 1, U.descs, U.descs, U.descs, 1e-3, None) == capi.QK_ERR_BAD_ARG  # aliasing
     assert lib.qk_rad_advance_stage(lev, C.byref(prm), 2, U.descs, U.descs, V.descs, 1e-3, None) == capi.QK_ERR_BAD_ARG  # no stage 1 yet
-    bad = rad_params(ngroups=3)
+    bad = rad_params(ngroups=9)  # > QK_MAX_GROUPS
     assert lib.qk_rad_advance_stage(lev, C.byref(bad), 1, U.descs, U.descs, V.descs, 1e-3, None) == capi.QK_ERR_UNSUPPORTED
+    bad = rad_params(ngroups=2)  # does not fit the level's 10 components
+    assert lib.qk_rad_advance_stage(lev, C.byref(bad), 1, U.descs, U.descs, V.descs, 1e-3, None) == capi.QK_ERR_BAD_ARG
     lib.qk_level_destroy(lev)
 
 
