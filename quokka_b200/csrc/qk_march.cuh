@@ -154,11 +154,11 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 
 		// prologue: rows s0-3 .. s0 into slots 0 .. 3, transverse rows of cell s0-1
 		for (int sl = 0; sl < SM::NR; ++sl) {
-			if (lane == 0)
+			if (elect_one())
 				issue_prim(sl);
 			src_q += sN;
 		}
-		if (lane == 0)
+		if (elect_one())
 			issue_trans();
 		src_t += sN;
 		// rows s0-3 .. s0 -> unlimited interface value at the low face of cell s0-1
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 				ifl[n] = ppm_iface(PV(prim_s, n), PV(prim_s + SM::PR, n), PV(prim_s + 2 * SM::PR, n), PV(prim_s + 3 * SM::PR, n));
 		}
 		__syncwarp();
-		if (lane == 0)
+		if (elect_one())
 			issue_prim(0); // row s0+1 replaces row s0-3
 		src_q += sN;
 		unsigned aux_phase = 0;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 		for (int r = s0 - 1; r <= s1; ++r) {
 			__syncwarp(); // the aux slot is free again
 			const bool have_aux = aux_bytes(r) != 0;
-			if (lane == 0 && have_aux)
+			if (have_aux && elect_one())
 				issue_aux(r);
 			src_h += shN;
 			src_r += srN;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 				}
 			}
 			__syncwarp(); // row r-1 and the transverse rows have been consumed by every lane: refill them for step r+1
-			if (lane == 0) {
+			if (elect_one()) {
 				if (r + 3 <= s1 + 2)
 					issue_prim((k4 + 1) & 3);
 				if (r + 1 <= s1)
@@ -400,13 +400,13 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 				bulk_g2s(dst + SM::PRIM + SM::TRANS + n * 32, sh + n * h.ns, AB, bar);
 		}
 	};
-	if (lane == 0)
+	if (elect_one())
 		issue(0);
 	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
 	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
 	for (int m = 0; m < rows; ++m) {
 		__syncwarp();
-		if (lane == 0 && m + 1 < rows)
+		if (m + 1 < rows && elect_one())
 			issue(m + 1);
 		const double *sp = st0 + (m & 1) * SM::STAGE_DOUBLES;
 		mbar_wait(&bars[m & 1], (unsigned)(m >> 1) & 1u);

@@ -4,6 +4,20 @@
 #pragma once
 #include <stdint.h>
 
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0`, the predicate tells the compiler that exactly one lane
+// takes the branch, so the bulk copies inside it are issued from the uniform datapath without a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one()
+{
+	unsigned pred;
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "elect.sync _|p, 0xffffffff;\n"
+		     "selp.u32 %0, 1, 0, p;\n"
+		     "}\n"
+		     : "=r"(pred));
+	return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
