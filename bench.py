@@ -457,8 +457,8 @@ def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
         fp64_per_cell, opmix = 740, "profiles/r01_ncu_opmix_exact.txt"
     else:  # keeps R(U0) per cell instead
         DESIGN = {"sweep_x": 56 + 56, "sweep_y": 56 + 112, "sweep_z": 56 + 56 + 48 + 48 + 48}
-        TRAFFIC = {"sweep_x": 1.919e9, "sweep_y": 3.028e9, "sweep_z": 4.573e9}  # profiles/r01_ncu_sweeps_relaxed.csv
-        fp64_per_cell, opmix = 490, "profiles/r01_ncu_opmix_relaxed.txt"
+        TRAFFIC = {"sweep_x": 1.916e9, "sweep_y": 3.031e9, "sweep_z": 4.581e9}  # profiles/r01_ncu_sweeps_relaxed.csv
+        fp64_per_cell, opmix = 480, "profiles/r01_ncu_opmix_relaxed.txt"
     cand = [(v[1], k) for k, v in prof.items() if k in DESIGN]
     if not cand:
         return None
