@@ -378,9 +378,11 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 	}
 	__syncwarp();
 	constexpr unsigned PB = SM::PW * 8, TB = SM::TW * 8, AB = 32 * 8;
-	auto issue = [&](int m) { // stage row row0+m
-		const int row = row0 + m;
-		const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
+	// (j, k) of the row being staged / computed, advanced incrementally (one integer division per warp instead of two per row)
+	int jn = B.lo[1] + row0 % ny, kn = B.lo[2] + row0 / ny; // next row to stage
+	int j = jn, k = kn;					  // row being computed
+	auto issue = [&](int m) { // stage row row0+m = (jn, kn)
+		const int j = jn, k = kn;
 		double *dst = st0 + (m & 1) * SM::STAGE_DOUBLES;
 		uint64_t *bar = &bars[m & 1];
 		mbar_arrive_expect_tx(bar, (unsigned)(NV + 1) * PB + 4u * TB + ((STAGE == 2) ? (unsigned)(NV + 1) * AB : 0u));
@@ -402,16 +404,22 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 	};
 	if (elect_one())
 		issue(0);
+	if (++jn > B.hi[1]) {
+		jn = B.lo[1];
+		++kn;
+	}
 	const bool face_ok = (lane >= 1) && (i >= B.lo[0]) && (i <= B.hi[0] + 1);
 	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
 	for (int m = 0; m < rows; ++m) {
 		__syncwarp();
 		if (m + 1 < rows && elect_one())
 			issue(m + 1);
+		if (++jn > B.hi[1]) {
+			jn = B.lo[1];
+			++kn;
+		}
 		const double *sp = st0 + (m & 1) * SM::STAGE_DOUBLES;
 		mbar_wait(&bars[m & 1], (unsigned)(m >> 1) & 1u);
-		const int row = row0 + m;
-		const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
 		// PPM + flattening of the own cell (x0-1+lane sits at index lane+3 of a prim row)
 		const double chi = sp[NV * SM::PW + lane + 3], omchi = 1. - chi;
 		double am[NV], ap[NV], q0v1 = 0;
@@ -474,6 +482,10 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 		if (upd) {
 			const double dv = div_dx<ARITH>(c, 0, Vn - G[NV]);
 			r.p[orr + NV * r.ns] = dv;
+		}
+		if (++j > B.hi[1]) {
+			j = B.lo[1];
+			++k;
 		}
 	}
 }

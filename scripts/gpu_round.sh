@@ -15,3 +15,4 @@ cat $OUT/bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-extras > $OUT/ncu_launch.log 2>&1
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_march_t|k_sweep_xt' -s 6 -c 6 -o $OUT/prof_sweeps python bench.py --steps 2 --warmup 1 --no-extras > $OUT/ncu_full.log 2>&1
 ls -la $OUT
+timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; tail -2 $OUT/smoke.log
