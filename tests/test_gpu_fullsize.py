@@ -1,0 +1,67 @@
+"""Size-independent properties at BASELINE.json's full single-GPU size (configs[1]: Sedov 256^3 in eight 128^3 boxes), where the
+CPU oracle is too slow to compare against: conservation of mass and total energy to round-off (the reference's own pass
+criterion, test_hydro3d_blast.cpp:199-205), positivity, no retries, the blast's symmetry under permutation of the axes (the
+initial condition and the reflecting octant are symmetric; the direction sweeps are not applied in a symmetric order, so the
+symmetry holds to round-off, not bit for bit), and agreement of the two arithmetic modes within the stated tolerance."""
+import numpy as np
+import pytest
+
+from quokka_b200 import capi
+from quokka_b200.problems import SedovProblem
+
+pytestmark = pytest.mark.gpu
+N, BOX, STEPS = 256, 128, 20
+
+
+def run(arith):
+    from quokka_b200.simulation import HydroSimulation
+
+    prob = SedovProblem(N, BOX)
+    sim = HydroSimulation(prob, params=prob.params(arith=arith))
+    sim.setInitialConditions()
+    nd, _, _ = sim.evolve(STEPS)
+    assert nd == STEPS
+    out, t, retries, upd = sim.gather_global(), sim.time, sim.retries, sim.cellUpdates
+    sim.close()
+    return prob, out, t, retries, upd
+
+
+@pytest.fixture(scope="module")
+def exact_run():
+    return run(capi.QK_ARITH_EXACT)
+
+
+@pytest.fixture(scope="module")
+def relaxed_run():
+    return run(capi.QK_ARITH_FAST)
+
+
+@pytest.mark.parametrize("which", ["exact", "relaxed"])
+def test_sedov256_conservation_positivity_symmetry(which, exact_run, relaxed_run):
+    prob, U, t, retries, upd = exact_run if which == "exact" else relaxed_run
+    assert retries == 0 and upd == N ** 3 * STEPS and t > 0
+    vol = prob.dx[0] * prob.dx[1] * prob.dx[2]
+    E0 = sum(prob.initial_state(b, 0)[4].sum() for b in prob.boxes) * vol
+    M0 = prob.rho0 * N ** 3 * vol
+    assert abs(U[4].sum() * vol - E0) / E0 < 2e-13  # per-step round-off x 20 steps; the reference asks 2e-15 per its own norm
+    assert abs(U[0].sum() * vol - M0) / M0 < 2e-13
+    assert np.isfinite(U).all() and (U[0] > 0).all() and (U[4] > 0).all() and (U[5] > 0).all()
+    # the blast has left the corner cell and is still far from the far walls
+    assert U[0, 0, 0, 0] < prob.rho0 and np.abs(U[1]).max() > 0 and np.array_equal(U[0, -1, -1, :], np.full(N, prob.rho0))
+    # symmetry under x <-> y, y <-> z (array axes are (comp, z, y, x))
+    scale = [np.abs(U[c]).max() for c in range(6)]
+    def close(a, b, c):
+        return np.abs(a - b).max() <= 1e-11 * scale[c]
+    assert close(U[0], U[0].transpose(0, 2, 1), 0) and close(U[0], U[0].transpose(1, 0, 2), 0)
+    assert close(U[4], U[4].transpose(0, 2, 1), 4) and close(U[4], U[4].transpose(2, 1, 0), 4)
+    assert close(U[1], U[2].transpose(0, 2, 1), 1)  # px(x, y, z) = py(y, x, z)
+    assert close(U[2], U[3].transpose(1, 0, 2), 2)  # py(x, y, z) = pz(x, z, y)
+
+
+def test_sedov256_relaxed_matches_exact(exact_run, relaxed_run):
+    _, Ue, te, _, _ = exact_run
+    _, Ur, tr, _, _ = relaxed_run
+    assert abs(te - tr) <= 1e-13 * te
+    for c in range(6):
+        scale = np.abs(Ue[c]).max()
+        assert np.abs(Ur[c] - Ue[c]).max() / scale < 1e-12, c
