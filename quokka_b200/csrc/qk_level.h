@@ -134,7 +134,6 @@ void qk_fused_free(qk_level *L);
 void qk_rad_free(qk_level *L);
 void qk_fused_untaint(qk_level *L);
 int qk_fused_max_signal(qk_level *L, const qk_hydro_params *prm, const qk_array4 *state, double out[2], cudaStream_t s);
-bool qk_fused_take_signal(qk_level *L, const qk_array4 *state, double out[2]);
 
 // ---- communicator (qk_comm.cpp): NCCL resolved at run time with dlopen, so the library loads on machines
 // without NCCL and never conflicts with the copy a host application (or torch) already loaded ----

@@ -250,9 +250,9 @@ static int advance_hydro(qk_sim *s, std::vector<qk_array4> &Uold, double dt, int
 		return 0;
 	}
 	// isCflViolated (:992-1013)
-	// the final-stage epilogue of the fused path has already reduced both maxima of state_new; otherwise one pass does
+	// both maxima of state_new (isCflViolated's and the next computeTimestep's) in one pass
 	double both[2];
-	if (!qk_fused_take_signal(L, s->snew.data(), both)) {
+	{
 		int rc = qk_fused_max_signal(L, &s->prm, s->snew.data(), both, s->stream);
 		if (rc == QK_ERR_UNSUPPORTED)
 			rc = qk_hydro_max_signal_both(&s->prm, s->nb, L->valid.data(), s->snew.data(), both, s->stream);

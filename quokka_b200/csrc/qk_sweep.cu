@@ -35,10 +35,6 @@ struct FusedState {
 	cudaEvent_t ev[8];
 	bool ev_used[8];
 	bool tainted = false; // a previous stage left flagged cells in the state: stay on the faithful path
-	// signal speeds of the state the last final-stage epilogue wrote (local maxima), and the array they belong to
-	bool sig_valid = false;
-	const double *sig_of = nullptr;
-	double sig[2] = {0.0, 0.0};
 };
 
 void qk_fused_free(qk_level *L)
@@ -55,18 +51,6 @@ void qk_fused_free(qk_level *L)
 	}
 	delete F;
 	L->fused = nullptr;
-}
-
-// local signal-speed maxima reduced by the last final-stage epilogue, if they belong to `state` (and consume them)
-bool qk_fused_take_signal(qk_level *L, const qk_array4 *state, double out[2])
-{
-	FusedState *F = L->fused;
-	if (!F || !F->sig_valid || L->valid.empty() || F->sig_of != state[0].p)
-		return false;
-	out[0] = F->sig[0];
-	out[1] = F->sig[1];
-	F->sig_valid = false;
-	return true;
 }
 
 // one pass over the local boxes: out[0] = ComputeMaxSignalSpeed + norminf (simulation.hpp:709-710), out[1] = maxSignalSpeedLocal
@@ -195,10 +179,6 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	QK_CUDA(cudaEventRecord(F->ev[slot], s));
 	F->ev_used[slot] = true;
 	QK_CUDA(cudaMemsetAsync(L->d_counters, 0, 32, s));
-	F->sig_valid = false;
-	// (folding the dt / CFL reductions into the final-stage epilogue was measured: +0.40 ms per step at 256^3 from register
-	// pressure in the marching loop, against 0.12 ms for the one-pass k_signal kernel -- qk_fused_max_signal)
-	c.want_sig = 0;
 
 	const bool dual = (prm->integrator_order == 2);
 	int rc;
@@ -223,18 +203,6 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	} else {
 		if (ncells_bad)
 			*ncells_bad = 0;
-		if (c.want_sig && nb > 0) {
-			auto key2d = [](unsigned long long k) {
-				unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
-				double v;
-				memcpy(&v, &b, 8);
-				return v;
-			};
-			F->sig[0] = (L->h_counters[2] == 0ull) ? 0.0 : key2d(L->h_counters[2]);
-			F->sig[1] = (L->h_counters[3] == 0ull) ? -1.7976931348623157e308 : key2d(L->h_counters[3]);
-			F->sig_of = Uout[0].p;
-			F->sig_valid = true;
-		}
 	}
 	*handled = true;
 	return 0;
