@@ -1,5 +1,10 @@
 #!/bin/bash
-# quick check on one GPU: a test selection + the default bench line
-OUT=gpurun_out/${1:-quick}; mkdir -p $OUT
-timeout 900 python -m pytest tests/test_gpu_level.py -k "valid_only or sedov_matches" -m gpu -x -q > $OUT/pytest.log 2>&1; tail -4 $OUT/pytest.log
-timeout 300 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2>$OUT/bench.err; cat $OUT/bench.json | cut -c1-1600; tail -3 $OUT/bench.err
+# quick check on N GPUs: a test selection + the default bench line (usage under gpurun [--gpus N]: bash scripts/gpu_quick.sh <tag> [N])
+OUT=gpurun_out/${1:-quick}; N=${2:-1}; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_relaxed.py -k "flagged" tests/test_gpu_multirank.py -m gpu -x -q > $OUT/pytest.log 2>&1; tail -4 $OUT/pytest.log
+if [ "$N" -gt 1 ]; then
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 > $OUT/bench$N.json 2>$OUT/bench$N.err
+else
+  timeout 300 python bench.py --steps 10 --warmup 3 > $OUT/bench$N.json 2>$OUT/bench$N.err
+fi
+cut -c1-700 $OUT/bench$N.json; tail -2 $OUT/bench$N.err

@@ -115,3 +115,37 @@ def test_relaxed_sedov128_100_steps_vs_exact():
     err = rel_linf(got, ref)
     print("relaxed Sedov 128^3 x 100 steps, rel L_inf per component:", ["%.2e" % e for e in err])
     assert max(err) < TOL_100_STEPS, err
+
+
+def test_relaxed_flagged_stage_hands_over_to_the_exact_faithful_path(lib):
+    """large dt on a violent state: PredictStep flags cells in the relaxed fused stage too; the stage is then redone by the exact
+    faithful path (FOFC), so the result equals the oracle's bit for bit -- the relaxed arithmetic never decides a flux correction"""
+    p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic")
+    prm = p.params(arith=QK_ARITH_FAST)
+    prm.abort_on_fofc_failure = 0
+    st = p.states(seed=9, kind="shocked")
+    dt = 2.0e-3
+    lib.qk_prof_enable(1)
+    f1, f2, fb1, fb2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    counts = prof(lib)
+    lib.qk_prof_enable(0)
+    assert counts.get("flux_function", 0) > 0 and counts.get("replace_fluxes", 0) > 0, counts
+    prm_exact = p.params()
+    prm_exact.abort_on_fofc_failure = 0
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    bo1, bo2 = C.c_int64(), C.c_int64()
+    o.orc_advance_hydro_level(L, C.byref(prm_exact), dt, 1.0e9, C.byref(bo1), C.byref(bo2))
+    ng = p.nghost
+    if bo1.value > 0 and bo2.value > 0:  # both stages flagged in the exact run: both were redone by the exact path here as well
+        for b in range(len(p.boxes)):
+            ref = oracle_state(p, L, 0, b)
+            g, r = f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng]
+            assert ((g == r) | (np.isnan(g) & np.isnan(r))).all(), f"box {b}"
+    else:  # only stage 1 flagged: stage 2 ran relaxed on the exact stage-1 result
+        for b in range(len(p.boxes)):
+            ref = oracle_state(p, L, 0, b)
+            g, r = f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng]
+            scale = np.abs(r).reshape(p.ncomp, -1).max(axis=1)
+            assert (np.abs(g - r).reshape(p.ncomp, -1).max(axis=1) / scale < 1e-12).all(), f"box {b}"
+    o.orc_level_destroy(L)
