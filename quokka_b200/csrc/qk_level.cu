@@ -235,6 +235,7 @@ template <class T> static int upload(const std::vector<T> &h, T **d)
 int qk_exchange_plan::build(const qk_level &L, int ng, bool need_device)
 {
 	nghost = ng;
+	send_cells_all = recv_cells_all = 0;
 	std::vector<HostTag> all;
 	qk_plan_tags(L, ng, all);
 	local.clear();
@@ -273,6 +274,10 @@ int qk_exchange_plan::build(const qk_level &L, int ng, bool need_device)
 			}
 		}
 		pp.d_send = pp.d_recv = nullptr;
+		pp.send_off = send_cells_all;
+		pp.recv_off = recv_cells_all;
+		send_cells_all += pp.send_cells;
+		recv_cells_all += pp.recv_cells;
 		peers.push_back(pp);
 	}
 	bc.clear();
@@ -288,10 +293,25 @@ int qk_exchange_plan::build(const qk_level &L, int ng, bool need_device)
 	}
 	QK_CUDA((cudaError_t)upload(dl, &d_local));
 	n_local = (int)dl.size();
+	std::vector<DevTag> sa, ra;
 	for (PeerPlan &pp : peers) {
 		QK_CUDA((cudaError_t)upload(pp.send, &pp.d_send));
 		QK_CUDA((cudaError_t)upload(pp.recv, &pp.d_recv));
+		for (DevTag t : pp.send) {
+			t.off += pp.send_off;
+			max_send_tag = std::max(max_send_tag, t.ncells);
+			sa.push_back(t);
+		}
+		for (DevTag t : pp.recv) {
+			t.off += pp.recv_off;
+			max_recv_tag = std::max(max_recv_tag, t.ncells);
+			ra.push_back(t);
+		}
 	}
+	QK_CUDA((cudaError_t)upload(sa, &d_send_all));
+	QK_CUDA((cudaError_t)upload(ra, &d_recv_all));
+	n_send_all = (int)sa.size();
+	n_recv_all = (int)ra.size();
 	std::vector<DevBcTag> db;
 	for (const HostBcTag &t : bc) {
 		DevBcTag d;
@@ -313,6 +333,11 @@ void qk_exchange_plan::destroy()
 		cudaFree(d_local);
 	if (d_bc)
 		cudaFree(d_bc);
+	if (d_send_all)
+		cudaFree(d_send_all);
+	if (d_recv_all)
+		cudaFree(d_recv_all);
+	d_send_all = d_recv_all = nullptr;
 	for (PeerPlan &pp : peers) {
 		if (pp.d_send)
 			cudaFree(pp.d_send);
@@ -386,6 +411,16 @@ extern "C" void qk_level_destroy(qk_level *L)
 		cudaFree(L->d_counters);
 	if (L->h_counters)
 		cudaFreeHost(L->h_counters);
+	if (L->send_all.p)
+		cudaFree(L->send_all.p);
+	if (L->recv_all.p)
+		cudaFree(L->recv_all.p);
+	if (L->comm_stream)
+		cudaStreamDestroy(L->comm_stream);
+	if (L->ev_packed)
+		cudaEventDestroy(L->ev_packed);
+	if (L->ev_received)
+		cudaEventDestroy(L->ev_received);
 	for (auto &kv : L->msg_send)
 		cudaFree(kv.second.p);
 	for (auto &kv : L->msg_recv)
@@ -621,60 +656,59 @@ extern "C" int qk_fill_boundary(qk_level *L, const qk_array4 *state, int scomp, 
 int qk_level::fill_boundary_tab(const A4 *tab, int scomp, int nc, cudaStream_t s)
 {
 	ProfScope prof_("fill_boundary", s);
-	// pack + post the remote messages first so that NVLink traffic overlaps the local copies
+	// pack every peer's message with ONE launch, hand the grouped NCCL send/recv to the communication stream, run the same-rank
+	// copies on the caller's stream meanwhile (NVLink traffic overlaps them), then unpack everything with ONE launch
 	const bool remote = !plan.peers.empty();
 	if (remote) {
 		if (!comm)
 			return QK_ERR_BAD_ARG; // multi-rank level without qk_level_set_comm
-		for (const PeerPlan &pp : plan.peers) {
-			MsgBuf &sb = msg_send[pp.peer], &rb = msg_recv[pp.peer];
-			const size_t ns = (size_t)pp.send_cells * nc * sizeof(double), nr = (size_t)pp.recv_cells * nc * sizeof(double);
-			if (sb.bytes < ns) {
-				if (sb.p)
-					cudaFree(sb.p);
-				QK_CUDA(cudaMalloc(&sb.p, ns));
-				sb.bytes = ns;
-			}
-			if (rb.bytes < nr) {
-				if (rb.p)
-					cudaFree(rb.p);
-				QK_CUDA(cudaMalloc(&rb.p, nr));
-				rb.bytes = nr;
-			}
-			if (!pp.send.empty()) {
-				int64_t mx = 1;
-				for (const DevTag &t : pp.send)
-					mx = std::max(mx, t.ncells);
-				dim3 grid(tag_blocks(mx), (unsigned)pp.send.size());
-				k_tags<1><<<grid, 256, 0, s>>>(pp.d_send, tab, scomp, nc, (double *)sb.p);
-				QK_KERNEL_CHECK();
-			}
+		const size_t ns = (size_t)plan.send_cells_all * nc * sizeof(double), nr = (size_t)plan.recv_cells_all * nc * sizeof(double);
+		if (send_all.bytes < ns) {
+			if (send_all.p)
+				cudaFree(send_all.p);
+			QK_CUDA(cudaMalloc(&send_all.p, ns));
+			send_all.bytes = ns;
 		}
+		if (recv_all.bytes < nr) {
+			if (recv_all.p)
+				cudaFree(recv_all.p);
+			QK_CUDA(cudaMalloc(&recv_all.p, nr));
+			recv_all.bytes = nr;
+		}
+		if (!comm_stream) {
+			QK_CUDA(cudaStreamCreateWithFlags(&comm_stream, cudaStreamNonBlocking));
+			QK_CUDA(cudaEventCreateWithFlags(&ev_packed, cudaEventDisableTiming));
+			QK_CUDA(cudaEventCreateWithFlags(&ev_received, cudaEventDisableTiming));
+		}
+		if (plan.n_send_all > 0) {
+			dim3 grid(tag_blocks(plan.max_send_tag), (unsigned)plan.n_send_all);
+			k_tags<1><<<grid, 256, 0, s>>>(plan.d_send_all, tab, scomp, nc, (double *)send_all.p);
+			QK_KERNEL_CHECK();
+		}
+		QK_CUDA(cudaEventRecord(ev_packed, s));
+		QK_CUDA(cudaStreamWaitEvent(comm_stream, ev_packed, 0));
 		int rc = qk_comm_group_start(comm);
 		if (rc)
 			return rc;
 		for (const PeerPlan &pp : plan.peers) {
 			if (pp.recv_cells)
-				rc = rc ? rc : qk_comm_recv(comm, msg_recv[pp.peer].p, (size_t)pp.recv_cells * nc * sizeof(double), pp.peer, s);
+				rc = rc ? rc : qk_comm_recv(comm, (double *)recv_all.p + pp.recv_off * nc, (size_t)pp.recv_cells * nc * sizeof(double), pp.peer, comm_stream);
 			if (pp.send_cells)
-				rc = rc ? rc : qk_comm_send(comm, msg_send[pp.peer].p, (size_t)pp.send_cells * nc * sizeof(double), pp.peer, s);
+				rc = rc ? rc : qk_comm_send(comm, (double *)send_all.p + pp.send_off * nc, (size_t)pp.send_cells * nc * sizeof(double), pp.peer, comm_stream);
 		}
 		const int rc2 = qk_comm_group_end(comm);
 		if (rc || rc2)
 			return rc ? rc : rc2;
+		QK_CUDA(cudaEventRecord(ev_received, comm_stream));
 	}
 	int rc = fill_local(plan, tab, scomp, nc, s);
 	if (rc)
 		return rc;
 	if (remote) {
-		for (const PeerPlan &pp : plan.peers) {
-			if (pp.recv.empty())
-				continue;
-			int64_t mx = 1;
-			for (const DevTag &t : pp.recv)
-				mx = std::max(mx, t.ncells);
-			dim3 grid(tag_blocks(mx), (unsigned)pp.recv.size());
-			k_tags<2><<<grid, 256, 0, s>>>(pp.d_recv, tab, scomp, nc, (double *)msg_recv[pp.peer].p);
+		QK_CUDA(cudaStreamWaitEvent(s, ev_received, 0));
+		if (plan.n_recv_all > 0) {
+			dim3 grid(tag_blocks(plan.max_recv_tag), (unsigned)plan.n_recv_all);
+			k_tags<2><<<grid, 256, 0, s>>>(plan.d_recv_all, tab, scomp, nc, (double *)recv_all.p);
 			QK_KERNEL_CHECK();
 		}
 	}

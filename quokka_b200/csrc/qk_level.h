@@ -34,6 +34,7 @@ struct PeerPlan {
 	int peer;
 	std::vector<DevTag> send, recv;
 	int64_t send_cells, recv_cells; // per component
+	int64_t send_off, recv_off;	// cells (per component) before this peer's message in the level's combined send / recv buffers
 	DevTag *d_send, *d_recv;
 };
 
@@ -45,6 +46,10 @@ struct qk_exchange_plan {
 	std::vector<HostBcTag> bc;
 	DevTag *d_local = nullptr;
 	DevBcTag *d_bc = nullptr;
+	// all peers' pack / unpack tags in one table each (off = position in the combined buffer): one launch packs every message
+	DevTag *d_send_all = nullptr, *d_recv_all = nullptr;
+	int n_send_all = 0, n_recv_all = 0;
+	int64_t send_cells_all = 0, recv_cells_all = 0, max_send_tag = 1, max_recv_tag = 1;
 	int n_local = 0, n_bc = 0;
 	int64_t max_tag_cells = 1;
 	int build(const qk_level &L, int ng, bool need_device);
@@ -99,7 +104,10 @@ struct qk_level {
 	int32_t *d_bc_lo = nullptr, *d_bc_hi = nullptr;
 	DescRing ring;
 	qk_comm *comm = nullptr;
-	std::map<int, MsgBuf> msg_send, msg_recv;
+	std::map<int, MsgBuf> msg_send, msg_recv; // redoFlag exchange (rare)
+	MsgBuf send_all, recv_all;		   // combined ghost messages of the state exchange
+	cudaStream_t comm_stream = nullptr;	   // NCCL send/recv run here while the same-rank copies run on the caller's stream
+	cudaEvent_t ev_packed = nullptr, ev_received = nullptr;
 	unsigned long long *d_counters = nullptr, *h_counters = nullptr;
 
 	std::vector<void *> scratch_ptrs;
