@@ -139,3 +139,27 @@ def test_flagged_stage_is_redone_by_the_faithful_path(lib):
         ref = oracle_state(p, L, 0, b)
         exact(f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng], f"box {b}")
     o.orc_level_destroy(L)
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("arith", ["exact", "relaxed"])
+def test_lower_order_reconstruction_through_the_stage_entry(lib, order, arith):
+    """reconstructionOrder_ = 2 (PLM, minmod; config C4's hydro) and 1 (donor cell) through qk_hydro_advance_stage: the fused sweeps
+    are PPM-only (a run-time order switch inside the marching loop was measured to cost the PPM path 6-10 % in register pressure),
+    so these orders take the faithful per-operator path -- in either arithmetic mode -- and are bit-exact against the oracle"""
+    ncell, cuts, periodic, bc, ns, nms, reint, gamma = CASES["thin_boxes"]
+    p = RaggedProblem(ncell, cuts, periodic, bc, nscalars=ns, gamma=gamma)
+    prm = p.params(nmscalars=nms, reconstruct_eint=reint, recon_order=order, arith=capi.QK_ARITH_FAST if arith == "relaxed" else capi.QK_ARITH_EXACT)
+    st = p.states(seed=21, kind="shocked")
+    dt = 1.0e-4
+    f1, f2, fb1, fb2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    assert (fb1, fb2) == (0, 0)
+    prm_exact = p.params(nmscalars=nms, reconstruct_eint=reint, recon_order=order)
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    assert o.orc_advance_hydro_level(L, C.byref(prm_exact), dt, 1.0e9, None, None) == 1
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        ref = oracle_state(p, L, 0, b)[:, ng:-ng, ng:-ng, ng:-ng]
+        exact(f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref, f"order {order} box {b}")
+    o.orc_level_destroy(L)
