@@ -280,3 +280,16 @@ def test_sod_matches_reference_run(name):
     if "ref_l1_error" in g:
         e = sod_error_norm(state[:, 0, 0, :], g, prob)
         assert abs(e - float(g["ref_l1_error"])) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["sedov32_b16_s100", "sedov64_b32_s100", "sedov128_b64_s100"])
+def test_sedov_100_steps_digest_of_the_reference_run(name):
+    """BASELINE.json's "after 100 steps" point against the REFERENCE ITSELF at sizes whose dumps are too large to commit: the
+    SHA-256 of the library's state (exact arithmetic) equals the digest of the reference executable's (tests/golden/sedov_hashes.json)"""
+    from test_oracle_golden import load_hashes, state_digest
+
+    g = load_hashes()[name]
+    state, t, retries, upd, _ = run_gpu_sedov(g["ncell"], g["box"], g["nsteps"])
+    assert repr(float(t)) == g["time"] and retries == g["retries"]
+    assert [repr(float(state[c].sum())) for c in range(6)] == g["sums"]
+    assert state_digest(state) == g["sha256"]
