@@ -18,7 +18,7 @@ def free_port():
     return p
 
 
-@pytest.mark.parametrize("world,n,b,periodic", [(2, 32, 16, 0), (2, 32, 16, 1), (4, 32, 8, 1)])
+@pytest.mark.parametrize("world,n,b,periodic", [(2, 32, 16, 0), (2, 32, 16, 1), (4, 32, 8, 1), (8, 32, 8, 0)])
 def test_gloo_ghost_exchange(world, n, b, periodic):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1", "--master-port",
            str(free_port()), os.path.join(ROOT, "tests", "gloo_worker.py"), str(n), str(b), str(periodic)]
