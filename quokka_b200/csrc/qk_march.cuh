@@ -40,7 +40,7 @@ template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST>
+template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST, int ORDER = 3>
 __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS : 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 			mbar_wait(&bars[b], 0);
 		double apL[NV], ifl[NV], Gp[NV + 1];
 		double mVp = 0, mWp = 0, vNp = 0;
-		if (active) {
+		if (active && ORDER == 3) {
 #pragma unroll
 			for (int n = 0; n < NV; ++n)
 				ifl[n] = ppm_iface(PV(prim_s, n), PV(prim_s + SM::PR, n), PV(prim_s + 2 * SM::PR, n), PV(prim_s + 3 * SM::PR, n));
@@ -206,9 +206,13 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 					const double qm1 = PV(s_m1, n), q0 = PV(s_0, n), qp1 = PV(s_p1, n), qp2 = PV(s_p2, n);
 					if (n == 1 + DIR)
 						vN0 = q0;
-					const double ifh = ppm_iface(qm1, q0, qp1, qp2);
-					f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
-					ifl[n] = ifh;
+					if (ORDER == 3) {
+						const double ifh = ppm_iface(qm1, q0, qp1, qp2);
+						f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
+						ifl[n] = ifh;
+					} else {
+						f_plm_flat(qm1, q0, qp1, chi, omchi, am[n], ap[n]);
+					}
 				}
 			}
 			mbar_wait(&bars[4], tpar);
@@ -349,7 +353,7 @@ template <int NV, int STAGE> struct XSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3>
 __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
 {
 	constexpr int NV = 6 + NS;
@@ -429,7 +433,10 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 			const double qm2 = p[-2], qm1 = p[-1], q0 = p[0], qp1 = p[1], qp2 = p[2];
 			if (n == 1)
 				q0v1 = q0;
-			f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+			if (ORDER == 3)
+				f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+			else
+				f_plm_flat(qm1, q0, qp1, chi, omchi, am[n], ap[n]);
 		}
 		// transverse minima: V = y, W = z (cell x0-1+lane sits at index lane+1 of a transverse row)
 		const double *tr = sp + SM::PRIM;

@@ -26,6 +26,9 @@
 int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3], int stage,
 			   bool dual, bool tma, cudaStream_t s);
 
+int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3], int stage, bool dual,
+			       cudaStream_t s);
+
 struct FusedState {
 	int nv = 0; // 6 + nscalars the scratch was built for
 	std::vector<qk_array4> prim, chi3, rhs, hF[3];
@@ -135,7 +138,9 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	// configurations the fused kernels are instantiated for; anything else runs the faithful path
 	const int ns = prm->nscalars, nms = prm->nmscalars;
 	const bool inst = (ns == 0 && nms == 0) || (ns == 1 && nms == 0) || (ns == 3 && nms == 2);
-	if (prm->reconstruction_order != 3 || !inst || !prm->use_dual_energy || L->nghost < 4)
+	const int order = prm->reconstruction_order;
+	// PPM for every instantiated trait set; PLM (minmod) for the scalar-free, reconstruct_eint = false set (config C4's hydro)
+	if (!(order == 3 || (order == 2 && ns == 0 && !prm->reconstruct_eint)) || !inst || !prm->use_dual_energy || L->nghost < 4)
 		return 0;
 	if (L->fused && L->fused->tainted)
 		return 0;
@@ -182,7 +187,12 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 
 	const bool dual = (prm->integrator_order == 2);
 	int rc;
-	if (prm->arith == QK_ARITH_FAST && tma) // the relaxed kernels exist in the TMA-staged form only
+	if (order == 2 && !tma)
+		return 0; // the PLM kernels exist in the TMA-staged form only: the faithful path takes the stage (*handled stays false)
+	if (order == 2)
+		rc = (prm->arith == QK_ARITH_FAST) ? qk_sweep_stage_relaxed_plm(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s)
+						   : sweep_stage_dispatch_plm<0>(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s);
+	else if (prm->arith == QK_ARITH_FAST && tma) // the relaxed kernels exist in the TMA-staged form only
 		rc = qk_sweep_stage_relaxed(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
 	else
 		rc = sweep_stage_dispatch<0>(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);

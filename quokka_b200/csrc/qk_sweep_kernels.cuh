@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 			return r_;                                                                                                                   \
 	} while (0)
 
-template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL>
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3>
 static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], bool tma, cudaStream_t s)
 {
 	{
@@ -721,7 +721,7 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		constexpr int XSTAGE = (ARITH == 1) ? 1 : STAGE;
 		constexpr bool XDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL>;
+			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL, ORDER>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES));
@@ -729,7 +729,7 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 			}
 			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
 			kern<<<grid, 128, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES, s>>>(c, d_tab);
-		} else if constexpr (ARITH == 0) {
+		} else if constexpr (ARITH == 0 && ORDER == 3) {
 			dim3 grid(tiles_x, (rows + 3) / 4, nb);
 			k_sweep_x<ARITH, NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
 		} else {
@@ -744,14 +744,14 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		constexpr int YSTAGE = (ARITH == 1) ? 1 : STAGE;
 		constexpr bool YDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, YSTAGE, YDUAL, false>;
+			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, YSTAGE, YDUAL, false, ORDER>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
 			kern<<<grid, 128, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else if constexpr (ARITH == 0) {
+		} else if constexpr (ARITH == 0 && ORDER == 3) {
 			k_sweep_m<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();
@@ -761,14 +761,14 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		const int nseg = (maxn[2] + SEG - 1) / SEG;
 		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
 		if (tma) {
-			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true>;
+			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true, ORDER>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
 			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else if constexpr (ARITH == 0) {
+		} else if constexpr (ARITH == 0 && ORDER == 3) {
 			k_sweep_m<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();
@@ -776,15 +776,26 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 	return 0;
 }
 
-template <int ARITH, int NS, int NMS, bool REINT> static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma, cudaStream_t s)
+template <int ARITH, int NS, int NMS, bool REINT, int ORDER = 3>
+static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma,
+			  cudaStream_t s)
 {
 	if (stage == 1)
-		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true>(ng, d_counters, c, t, nb, maxn, tma, s) : launch_stage<ARITH, NS, NMS, REINT, 1, false>(ng, d_counters, c, t, nb, maxn, tma, s);
-	return launch_stage<ARITH, NS, NMS, REINT, 2, true>(ng, d_counters, c, t, nb, maxn, tma, s);
+		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s)
+			    : launch_stage<ARITH, NS, NMS, REINT, 1, false, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s);
+	return launch_stage<ARITH, NS, NMS, REINT, 2, true, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s);
 }
 
 
 // entry of one translation unit: all instantiated trait sets of one arithmetic mode
+// PLM (reconstructionOrder_ = 2) is instantiated for the trait set of config C4's hydro (no scalars, reconstruct_eint = false), TMA form only
+template <int ARITH>
+static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3], int stage,
+				    bool dual, cudaStream_t s)
+{
+	return dispatch_stage<ARITH, 0, 0, false, 2>(ng, d_counters, c, db, nb, maxn, stage, dual, true, s);
+}
+
 template <int ARITH>
 static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3],
 				int stage, bool dual, bool tma, cudaStream_t s)

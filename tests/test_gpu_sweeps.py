@@ -144,16 +144,21 @@ def test_flagged_stage_is_redone_by_the_faithful_path(lib):
 @pytest.mark.parametrize("order", [1, 2])
 @pytest.mark.parametrize("arith", ["exact", "relaxed"])
 def test_lower_order_reconstruction_through_the_stage_entry(lib, order, arith):
-    """reconstructionOrder_ = 2 (PLM, minmod; config C4's hydro) and 1 (donor cell) through qk_hydro_advance_stage: the fused sweeps
-    are PPM-only (a run-time order switch inside the marching loop was measured to cost the PPM path 6-10 % in register pressure),
-    so these orders take the faithful per-operator path -- in either arithmetic mode -- and are bit-exact against the oracle"""
+    """reconstructionOrder_ = 2 (PLM, minmod; config C4's hydro) runs through a compile-time PLM instantiation of the fused sweeps
+    (scalar-free, reconstruct_eint = false trait set): bit-exact against the oracle in the exact mode, within 2e-14 of max|U| per
+    component in the relaxed mode.  Order 1 (donor cell) takes the faithful per-operator path in either mode and is bit-exact."""
     ncell, cuts, periodic, bc, ns, nms, reint, gamma = CASES["thin_boxes"]
     p = RaggedProblem(ncell, cuts, periodic, bc, nscalars=ns, gamma=gamma)
     prm = p.params(nmscalars=nms, reconstruct_eint=reint, recon_order=order, arith=capi.QK_ARITH_FAST if arith == "relaxed" else capi.QK_ARITH_EXACT)
     st = p.states(seed=21, kind="shocked")
     dt = 1.0e-4
+    lib.qk_prof_enable(1)
     f1, f2, fb1, fb2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    counts = prof(lib)
+    lib.qk_prof_enable(0)
     assert (fb1, fb2) == (0, 0)
+    fused = counts.get("sweep_x", 0) == 2 and counts.get("flux_function", 0) == 0
+    assert fused == (order == 2), counts
     prm_exact = p.params(nmscalars=nms, reconstruct_eint=reint, recon_order=order)
     L, keep = oracle_level(p, st)
     o = ol.oracle()
@@ -161,5 +166,11 @@ def test_lower_order_reconstruction_through_the_stage_entry(lib, order, arith):
     ng = p.nghost
     for b in range(len(p.boxes)):
         ref = oracle_state(p, L, 0, b)[:, ng:-ng, ng:-ng, ng:-ng]
-        exact(f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref, f"order {order} box {b}")
+        got = f2[b][:, ng:-ng, ng:-ng, ng:-ng]
+        if arith == "exact" or order == 1:
+            exact(got, ref, f"order {order} box {b}")
+        else:
+            scale = np.abs(ref).reshape(p.ncomp, -1).max(axis=1)
+            assert (np.abs(got - ref).reshape(p.ncomp, -1).max(axis=1) / scale < 2e-14).all()
+            assert not np.array_equal(got, ref)
     o.orc_level_destroy(L)
