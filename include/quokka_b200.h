@@ -213,6 +213,41 @@ int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const qk_box *va
 			  const qk_array4 *fx_old, const qk_array4 *fy_old, const qk_array4 *fz_old, const qk_array4 *fx, const qk_array4 *fy,
 			  const qk_array4 *fz, double dt, const double dx[3], void *stream);
 
+/* ---- matter-radiation coupling source terms (single photon group): RadSystem<problem_t>::AddSourceTermsSingleGroup,
+ * src/radiation/source_terms_single_group.hpp:9-565, called twice per radiation substep through operatorSplitSourceTerms
+ * (src/QuokkaSimulation.hpp:1638,1656,1860-1885).  Run-time image of what the reference takes from RadSystem_Traits<problem_t>
+ * (radiation_constant, beta_order; src/radiation/radiation_system.hpp:73-82) and from the problem's opacity specialisations
+ * ComputePlanckOpacity / ComputeEnergyMeanOpacity / ComputeFluxMeanOpacity (:1141-1153; constants in
+ * src/problems/RadhydroShell/test_radhydro_shell.cpp:127-135).  The solver hyper-parameters are the reference's compile-time
+ * values (:34-44: include_work_term_in_source = true, enable_dE_constrain = true, force_rad_floor_in_iteration = false,
+ * add_line_cooling_to_radiation_in_jac = false; no dust model, zero net cooling and cosmic-ray heating, IMEX_a32 = 0.5). */
+enum { QK_OPACITY_CONSTANT = 0 };
+typedef struct qk_rad_source_params {
+	double radiation_constant; /* RadSystem_Traits::radiation_constant (a_rad) */
+	double kappa_P;		   /* ComputePlanckOpacity(rho, T)      [cm^2/g], constant */
+	double kappa_E;		   /* ComputeEnergyMeanOpacity(rho, T) */
+	double kappa_F;		   /* ComputeFluxMeanOpacity(rho, T) */
+	int32_t beta_order;	   /* RadSystem_Traits::beta_order: 0|1|2|3 */
+	int32_t opacity_model;	   /* QK_OPACITY_CONSTANT */
+} qk_rad_source_params;
+
+/* counters[0..3] = iteration_counter {cells solved, sum of Newton-Raphson iterations, max Newton-Raphson iterations, 0},
+ * counters[4..6] = iteration_failure_counter {Newton-Raphson not converged, dust temperature (always 0), outer work-term
+ * iteration not converged}   (src/QuokkaSimulation.hpp:1620-1625). */
+#define QK_RAD_SOURCE_NCOUNTERS 7
+/* RadSystem::AddSourceTermsSingleGroup(consVar, radEnergySource, indexRange, dt_radiation, stage, ., p_iteration_counter,
+ * p_iteration_failure_counter): updates gas momentum, gas energy, gas internal energy, E_r and F_r of `cons` in place on the
+ * valid boxes.  hydro supplies the EOS (gamma, mean molecular weight, k_B, small_temp/small_dens); gamma == 1 takes the
+ * reference's isothermal branch (flux update only).  rad_energy_source: one component per box (SetRadEnergySource,
+ * QuokkaSimulation.hpp:1866-1872) or NULL for zero.  counters: HOST array of QK_RAD_SOURCE_NCOUNTERS, accumulated into
+ * (the call then synchronises the stream), or NULL (fully asynchronous).  Arithmetic: the reference's operation order with
+ * contraction off; T^3, T^4 and lorentz^3, which the reference takes from std::pow, are formed in double-double and rounded
+ * once, so results agree with the CPU reference to the last bit except where libm's pow is itself not
+ * correctly rounded; the parity bar is 1e-13 relative. */
+int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_rad_params *prm, const qk_rad_source_params *src, int stage, int nboxes,
+			    const qk_box *valid, const qk_array4 *cons, const qk_array4 *rad_energy_source, double dt_radiation, int64_t *counters,
+			    void *stream);
+
 /* ---- level object: fused path + ghost fill -------------------------------------------------- */
 
 /* Description of the boxes of ONE AMR level owned by this rank (a MultiFab's local part) and of

@@ -954,6 +954,334 @@ void orc_rad_add_fluxes_rk2(const qk_rad_params *prm, const qk_array4 *unew, con
 }
 
 /* ================================================================================================
+ * Matter-radiation coupling, single photon group: RadSystem::AddSourceTermsSingleGroup
+ * src/radiation/source_terms_single_group.hpp:9-565 (hyper-parameters src/radiation/radiation_system.hpp:34-52:
+ * include_work_term_in_source = true, enable_dE_constrain = true, force_rad_floor_in_iteration = false,
+ * add_line_cooling_to_radiation_in_jac = false, IMEX_a32 = 0.5; no dust model (ISM_Traits default :85-89), zero
+ * DefineNetCoolingRate / DefineCosmicRayHeatingRate (:522-545)).
+ * ============================================================================================== */
+/* EOS::ComputeEintTempDerivative  src/hydro/EOS.hpp:200-240 */
+static double eos_eint_temp_derivative(const qk_hydro_params *prm, double rho, double Tgas)
+{
+	eos_state s = eos_new(prm);
+	s.rho = rho;
+	s.T = Tgas;
+	eos_call(prm, EOS_RT, &s);
+	return s.dedT * rho * prm->boltzmann_constant / C_k_B;
+}
+/* RadSystem::ComputeEintFromEgas / ComputeEgasFromEint  radiation_system.hpp:1289-1309 */
+static double rad_eint_from_egas(double rho, double px, double py, double pz, double Etot)
+{
+	const double p_sq = px * px + py * py + pz * pz;
+	const double Ekin = p_sq / (2.0 * rho);
+	return Etot - Ekin;
+}
+static double rad_egas_from_eint(double rho, double px, double py, double pz, double Eint)
+{
+	const double p_sq = px * px + py * py + pz * pz;
+	const double Ekin = p_sq / (2.0 * rho);
+	return Eint + Ekin;
+}
+/* RadSystem::ComputeEddingtonTensor  radiation_system.hpp:873-916 (all nine entries) */
+static void rad_eddington_tensor(double fx, double fy, double fz, double T[3][3])
+{
+	const double f = sqrt(fx * fx + fy * fy + fz * fz);
+	const double fvec[3] = {fx, fy, fz};
+	double n[3];
+	for (int ii = 0; ii < 3; ++ii)
+		n[ii] = (f > 0.) ? (fvec[ii] / f) : 0.;
+	const double chi = rad_eddington_factor(f);
+	const double Tdiag = (1.0 - chi) / 2.0;
+	const double Tf = (3.0 * chi - 1.0) / 2.0;
+	for (int ii = 0; ii < 3; ++ii)
+		for (int jj = 0; jj < 3; ++jj) {
+			const double delta_ij = (ii == jj) ? 1 : 0;
+			T[ii][jj] = Tdiag * delta_ij + Tf * (n[ii] * n[jj]);
+		}
+}
+/* RadSystem::Solve3x3matrix  radiation_system.hpp:560-580 */
+static void rad_solve3x3(double C00, double C01, double C02, double C10, double C11, double C12, double C20, double C21, double C22, double Y0,
+			 double Y1, double Y2, double X[3])
+{
+	const double E11 = C11 - C01 * C10 / C00;
+	const double E12 = C12 - C02 * C10 / C00;
+	const double E21 = C21 - C01 * C20 / C00;
+	const double E22 = C22 - C02 * C20 / C00;
+	const double Z1 = Y1 - Y0 * C10 / C00;
+	const double Z2 = Y2 - Y0 * C20 / C00;
+	const double X2 = (Z2 - Z1 * E21 / E11) / (E22 - E12 * E21 / E11);
+	const double X1 = (Z1 - E12 * X2) / E11;
+	const double X0 = (Y0 - C01 * X1 - C02 * X2) / C00;
+	X[0] = X0;
+	X[1] = X1;
+	X[2] = X2;
+}
+
+void orc_rad_add_source_terms(const qk_hydro_params *hp, const qk_rad_params *prm, const qk_rad_source_params *sp, const qk_array4 *cons,
+			      const qk_array4 *rad_energy_source, const qk_box *bx, double dt_radiation, int stage, int64_t *counters)
+{
+	const double IMEX_a32 = 0.5;
+	const int iE = prm->nstart, iFx = prm->nstart + 1, iFy = prm->nstart + 2, iFz = prm->nstart + 3;
+	const double gamma_ = hp->gamma;
+	const int beta_order_ = sp->beta_order;
+	const double Erad_floor_ = prm->Erad_floor / prm->ngroups; /* radiation_system.hpp:211 */
+	const double a_rad = sp->radiation_constant;
+	double dt = dt_radiation;
+	if (stage == 2) /* :17-19 */
+		dt = (1.0 - IMEX_a32) * dt_radiation;
+
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double c = prm->c_light;
+				const double chat = prm->c_hat;
+				/* :40-55 */
+				const double rho = A4(cons, i, j, k, RHO);
+				const double x1GasMom0 = A4(cons, i, j, k, MX);
+				const double x2GasMom0 = A4(cons, i, j, k, MY);
+				const double x3GasMom0 = A4(cons, i, j, k, MZ);
+				const double gasMtm0[3] = {x1GasMom0, x2GasMom0, x3GasMom0};
+				const double Egastot0 = A4(cons, i, j, k, EN);
+				const double Erad0 = A4(cons, i, j, k, iE);
+				const double Src = (rad_energy_source ? A4(rad_energy_source, i, j, k, 0) : 0.0) * dt * chat;
+
+				double Egas0 = NAN, Ekin0 = NAN, Etot0 = NAN, Egas_guess = NAN, T_gas = NAN, T_d = NAN;
+				double lorentz_factor = NAN, lorentz_factor_v = NAN, lorentz_factor_v_v = NAN;
+				double fourPiBoverC = NAN, Erad_guess = NAN, kappaP = NAN, kappaE = NAN, kappaF = NAN, kappaPoverE = NAN;
+				double work = 0.0, work_prev = 0.0;
+				double dMomentum[3] = {0., 0., 0.}, Frad_t1[3] = {0., 0., 0.};
+				const double cscale = c / chat;
+
+				if (gamma_ != 1.0) { /* :82-86 */
+					Egas0 = rad_eint_from_egas(rho, x1GasMom0, x2GasMom0, x3GasMom0, Egastot0);
+					Etot0 = Egas0 + cscale * (Erad0 + Src);
+				}
+				double gas_update_factor = 1.0;
+				if (stage == 1)
+					gas_update_factor = IMEX_a32;
+
+				const int max_ite = 5;
+				int ite = 0;
+				for (; ite < max_ite; ++ite) {
+					double R = NAN;
+					Erad_guess = Erad0;
+					if (gamma_ != 1.0) {
+						double tau0 = NAN, tau = NAN;
+						Egas_guess = Egas0;
+						Ekin0 = Egastot0 - Egas0;
+						const double betaSqr =
+						    (x1GasMom0 * x1GasMom0 + x2GasMom0 * x2GasMom0 + x3GasMom0 * x3GasMom0) / (rho * rho * c * c);
+						if (beta_order_ == 0 || beta_order_ == 1) { /* :115-131 */
+							lorentz_factor = 1.0;
+							lorentz_factor_v = 1.0;
+						} else if (beta_order_ == 2) {
+							lorentz_factor = 1.0 + 0.5 * betaSqr;
+							lorentz_factor_v = 1.0;
+							lorentz_factor_v_v = 1.0;
+						} else if (beta_order_ == 3) {
+							lorentz_factor = 1.0 + 0.5 * betaSqr;
+							lorentz_factor_v = 1.0 + 0.5 * betaSqr;
+							lorentz_factor_v_v = 1.0;
+						} else {
+							lorentz_factor = 1.0 / sqrt(1.0 - betaSqr);
+							lorentz_factor_v = lorentz_factor;
+							lorentz_factor_v_v = lorentz_factor;
+						}
+						double F_G = NAN, deltaEgas = NAN, deltaR = NAN, F_D = NAN;
+						const double resid_tol = 1.0e-11;
+						const int maxIter = 100;
+						int n = 0;
+						for (; n < maxIter; ++n) { /* Newton-Raphson :161-352 */
+							T_gas = eos_tgas_from_eint(hp, rho, Egas_guess);
+							T_d = T_gas; /* no dust model :166-167 */
+							/* ComputeThermalRadiationSingleGroup  radiation_system.hpp:471-479 */
+							fourPiBoverC = a_rad * pow(T_d, 4);
+							if (fourPiBoverC < Erad_floor_)
+								fourPiBoverC = Erad_floor_;
+							kappaP = sp->kappa_P;
+							kappaE = sp->kappa_E;
+							if (kappaE > 0.0)
+								kappaPoverE = kappaP / kappaE;
+							else
+								kappaPoverE = 1.0;
+							if (n == 0) { /* :192-215 */
+								kappaF = sp->kappa_F;
+								if (beta_order_ != 0) {
+									if (ite == 0) {
+										const double frad0 = A4(cons, i, j, k, iFx);
+										const double frad1 = A4(cons, i, j, k, iFy);
+										const double frad2 = A4(cons, i, j, k, iFz);
+										work = (x1GasMom0 * frad0 + x2GasMom0 * frad1 + x3GasMom0 * frad2) *
+										       (2.0 * kappaE - kappaF) * chat / (c * c) * lorentz_factor_v * dt;
+									}
+								}
+								tau0 = dt * rho * kappaP * chat * lorentz_factor;
+								tau = tau0;
+								R = (fourPiBoverC - Erad_guess / kappaPoverE) * tau0 + work;
+								tau0 = dmax(tau0, 1.0);
+							} else { /* :216-232 */
+								tau = dt * rho * kappaP * chat * lorentz_factor;
+								if (tau > 0.0)
+									Erad_guess = kappaPoverE * (fourPiBoverC - (R - work) / tau);
+							}
+							const double cooling = 0.0, cooling_derivative = 0.0;
+							const double CR_heating = 0.0 * dt;
+							F_G = Egas_guess - Egas0 + cscale * R + cooling * dt - CR_heating;
+							F_D = Erad_guess - Erad0 - (R + Src);
+							double F_D_abs = 0.0;
+							if (tau > 0.0)
+								F_D_abs = fabs(F_D);
+							else
+								F_D_abs = fabs(F_D + R);
+							if ((fabs(F_G) < resid_tol * Etot0) && (cscale * F_D_abs < resid_tol * Etot0))
+								break;
+							const double c_v = eos_eint_temp_derivative(hp, rho, T_gas);
+							/* ComputeThermalRadiationTempDerivativeSingleGroup  radiation_system.hpp:499-503 */
+							const double d_fourpiboverc_d_t = 4. * a_rad * pow(T_d, 3);
+							const double dEg_dT = kappaPoverE * d_fourpiboverc_d_t;
+							double J00, J01, J10, J11;
+							J00 = 1.0 + cooling_derivative * dt / c_v;
+							J01 = cscale;
+							J10 = 1.0 / c_v * dEg_dT - (1 / cscale) * cooling_derivative * dt;
+							if (tau <= 0.0)
+								J11 = -INFINITY;
+							else
+								J11 = -1.0 * kappaPoverE / tau - 1.0;
+							const double y0 = -F_G;
+							const double y1 = -1. * F_D;
+							const double det = J00 * J11 - J01 * J10;
+							deltaEgas = (J11 * y0 - J01 * y1) / det;
+							deltaR = (J00 * y1 - J10 * y0) / det;
+							/* enable_dE_constrain :330-342 */
+							const double T_rad = sqrt(sqrt(Erad_guess / a_rad));
+							if (deltaEgas / c_v > dmax(T_gas, T_rad)) {
+								Egas_guess = eos_eint_from_tgas(hp, rho, T_rad);
+							} else {
+								Egas_guess += deltaEgas;
+								R += deltaR;
+							}
+						}
+						if (counters) { /* :354-362 */
+							if (n >= maxIter)
+								counters[4] += 1;
+							counters[0] += 1;
+							counters[1] += n + 1;
+							if (counters[2] < n + 1)
+								counters[2] = n + 1;
+						}
+						{ /* !add_line_cooling_to_radiation_in_jac :367-373 */
+							const double cooling_tend = 0.0 * dt;
+							Erad_guess += (1 / cscale) * cooling_tend;
+						}
+						if (n > 0)
+							kappaF = sp->kappa_F;
+					} else { /* gamma == 1 :379-391 */
+						T_d = T_gas;
+						kappaF = sp->kappa_F;
+					}
+
+					/* 2. radiation flux update :396-490 */
+					double Frad_t0[3];
+					dMomentum[0] = dMomentum[1] = dMomentum[2] = 0.;
+					Frad_t0[0] = A4(cons, i, j, k, iFx);
+					Frad_t0[1] = A4(cons, i, j, k, iFy);
+					Frad_t0[2] = A4(cons, i, j, k, iFz);
+					if ((gamma_ != 1.0) && (beta_order_ != 0)) {
+						const double erad = Erad_guess;
+						const double gasVel[3] = {0., 0., 0.}; /* declared and never assigned in the reference (:407) */
+						double v_terms[3];
+						const double fx = Frad_t0[0] / (c * erad);
+						const double fy = Frad_t0[1] / (c * erad);
+						const double fz = Frad_t0[2] / (c * erad);
+						const double F_coeff = chat * rho * kappaF * dt * lorentz_factor;
+						double Tedd[3][3];
+						rad_eddington_tensor(fx, fy, fz, Tedd);
+						for (int n = 0; n < 3; ++n) {
+							double Planck_term = kappaP * fourPiBoverC * lorentz_factor_v;
+							if (kappaF != kappaE)
+								Planck_term += (kappaF - kappaE) * erad * pow(lorentz_factor_v, 3);
+							Planck_term *= chat * dt * gasMtm0[n];
+							double pressure_term = 0.0;
+							for (int z = 0; z < 3; ++z)
+								pressure_term += gasMtm0[z] * Tedd[n][z] * erad;
+							pressure_term *= chat * dt * kappaF * lorentz_factor_v;
+							v_terms[n] = Planck_term + pressure_term;
+						}
+						if (beta_order_ == 1 || kappaF == kappaE) {
+							for (int n = 0; n < 3; ++n) {
+								Frad_t1[n] = (Frad_t0[n] + v_terms[n]) / (1.0 + F_coeff);
+								dMomentum[n] += -(Frad_t1[n] - Frad_t0[n]) / (c * chat);
+							}
+						} else {
+							const double K0 = 2.0 * rho * chat * dt * (kappaF - kappaE) / c / c * pow(lorentz_factor_v_v, 3);
+							const double A00 = 1.0 + F_coeff + K0 * gasVel[0] * gasVel[0];
+							const double A01 = K0 * gasVel[0] * gasVel[1];
+							const double A02 = K0 * gasVel[0] * gasVel[2];
+							const double A10 = K0 * gasVel[1] * gasVel[0];
+							const double A11 = 1.0 + F_coeff + K0 * gasVel[1] * gasVel[1];
+							const double A12 = K0 * gasVel[1] * gasVel[2];
+							const double A20 = K0 * gasVel[2] * gasVel[0];
+							const double A21 = K0 * gasVel[2] * gasVel[1];
+							const double A22 = 1.0 + F_coeff + K0 * gasVel[2] * gasVel[2];
+							const double B0 = v_terms[0] + Frad_t0[0];
+							const double B1 = v_terms[1] + Frad_t0[1];
+							const double B2 = v_terms[2] + Frad_t0[2];
+							rad_solve3x3(A00, A01, A02, A10, A11, A12, A20, A21, A22, B0, B1, B2, Frad_t1);
+							for (int n = 0; n < 3; ++n)
+								dMomentum[n] += -(Frad_t1[n] - Frad_t0[n]) / (c * chat);
+						}
+					} else { /* :484-490 */
+						for (int n = 0; n < 3; ++n) {
+							Frad_t1[n] = Frad_t0[n] / (1.0 + rho * kappaF * chat * dt);
+							dMomentum[n] += -(Frad_t1[n] - Frad_t0[n]) / (c * chat);
+						}
+					}
+					const double x1GasMom1 = A4(cons, i, j, k, MX) + dMomentum[0];
+					const double x2GasMom1 = A4(cons, i, j, k, MY) + dMomentum[1];
+					const double x3GasMom1 = A4(cons, i, j, k, MZ) + dMomentum[2];
+
+					/* 3. work term :496-524 */
+					if ((gamma_ != 1.0) && (beta_order_ != 0)) {
+						const double Egastot1 = rad_egas_from_eint(rho, x1GasMom1, x2GasMom1, x3GasMom1, Egas_guess);
+						const double Ekin1 = Egastot1 - Egas_guess;
+						const double dEkin_work = Ekin1 - Ekin0;
+						Egas_guess -= dEkin_work;
+					}
+					if ((beta_order_ == 0) || (gamma_ == 1.0)) {
+						break;
+					} else { /* lagged work term :526-541 */
+						work_prev = work;
+						work = (x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat / (c * c) *
+						       lorentz_factor_v * (2.0 * kappaE - kappaF) * dt;
+						const double lag_tol = 1.0e-13;
+						if ((fabs(work) == 0.0) || (cscale * fabs(work - work_prev) < lag_tol * Etot0) ||
+						    (fabs(work - work_prev) <= lag_tol * R) || (fabs(work - work_prev) <= 1.0e-8 * fabs(work)))
+							break;
+					}
+				}
+				if (ite >= max_ite && counters) /* :544-547 */
+					counters[6] += 1;
+
+				/* 4b. store :549-564 */
+				const double x1GasMom1 = A4(cons, i, j, k, MX) + dMomentum[0] * gas_update_factor;
+				const double x2GasMom1 = A4(cons, i, j, k, MY) + dMomentum[1] * gas_update_factor;
+				const double x3GasMom1 = A4(cons, i, j, k, MZ) + dMomentum[2] * gas_update_factor;
+				A4(cons, i, j, k, MX) = x1GasMom1;
+				A4(cons, i, j, k, MY) = x2GasMom1;
+				A4(cons, i, j, k, MZ) = x3GasMom1;
+				if (gamma_ != 1.0) {
+					Egas_guess = Egas0 + (Egas_guess - Egas0) * gas_update_factor;
+					A4(cons, i, j, k, EI) = Egas_guess;
+					A4(cons, i, j, k, EN) = rad_egas_from_eint(rho, x1GasMom1, x2GasMom1, x3GasMom1, Egas_guess);
+					A4(cons, i, j, k, iE) = Erad_guess;
+				}
+				A4(cons, i, j, k, iFx) = Frad_t1[0];
+				A4(cons, i, j, k, iFy) = Frad_t1[1];
+				A4(cons, i, j, k, iFz) = Frad_t1[2];
+			}
+}
+
+/* ================================================================================================
  * Level driver (uniform single level, all boxes in this process)
  * ============================================================================================== */
 struct orc_level {

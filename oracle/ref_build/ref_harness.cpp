@@ -125,6 +125,62 @@ template <> struct RadSystem_Traits<R1> {
 	static constexpr int beta_order = 0;
 };
 
+// problem types for the matter-radiation source terms (RadSystem<P>::AddSourceTermsSingleGroup), one photon group:
+//   R2: RadhydroShell traits (src/problems/RadhydroShell/test_radhydro_shell.cpp:39-93,127-135): cgs, gamma = 5/3,
+//       mu = 2.2 m_H, c_hat = 860 * 2e5 cm/s, kappa_P = kappa_E = kappa_F = 20, beta_order = 1
+//   R3: dimensionless (k_B = 1, mu = 1, a_rad = 1, c = 10, c_hat = 5), kappa_P = 1, kappa_E = 1.5, kappa_F = 2, beta_order = 2
+//       (kappa_F != kappa_E: the 3x3 solve and the (kappa_F - kappa_E) Planck term)
+//   R4: as R3 with kappa_E = kappa_F = kappa_P = 3 and beta_order = 0 (no work term, no O(beta) flux terms)
+//   R5: as R3 with kappa_P = 0.5, kappa_E = kappa_F = 0.25, beta_order = 3, Erad_floor = 1e-6
+//   R6: gamma = 1 (isothermal branch: flux update only), c = c_hat = 1, kappa = 2
+#define QK_RS_TRAITS(NAME, GAMMA, MU, KB, CL, CH, AR, FLOOR, BETA)                                                                                   \
+	struct NAME {                                                                                                                                \
+	};                                                                                                                                           \
+	template <> struct quokka::EOS_Traits<NAME> {                                                                                                \
+		static constexpr double gamma = GAMMA;                                                                                               \
+		static constexpr double mean_molecular_weight = MU;                                                                                  \
+		static constexpr double boltzmann_constant = KB;                                                                                     \
+		static constexpr double cs_isothermal = 1.0;                                                                                         \
+	};                                                                                                                                           \
+	template <> struct Physics_Traits<NAME> {                                                                                                    \
+		static constexpr bool is_hydro_enabled = true;                                                                                       \
+		static constexpr int numMassScalars = 0;                                                                                             \
+		static constexpr int numPassiveScalars = numMassScalars + 0;                                                                         \
+		static constexpr bool is_radiation_enabled = true;                                                                                   \
+		static constexpr bool is_mhd_enabled = false;                                                                                        \
+		static constexpr int nGroups = 1;                                                                                                    \
+	};                                                                                                                                           \
+	template <> struct RadSystem_Traits<NAME> {                                                                                                  \
+		static constexpr double c_light = CL;                                                                                                \
+		static constexpr double c_hat = CH;                                                                                                  \
+		static constexpr double radiation_constant = AR;                                                                                     \
+		static constexpr double Erad_floor = FLOOR;                                                                                          \
+		static constexpr int beta_order = BETA;                                                                                              \
+	};
+#define QK_RS_OPACITY(NAME, KP, KE, KF)                                                                                                              \
+	template <> AMREX_GPU_HOST_DEVICE auto RadSystem<NAME>::ComputePlanckOpacity(const double /*rho*/, const double /*T*/) -> amrex::Real       \
+	{                                                                                                                                            \
+		return KP;                                                                                                                           \
+	}                                                                                                                                            \
+	template <> AMREX_GPU_HOST_DEVICE auto RadSystem<NAME>::ComputeEnergyMeanOpacity(const double /*rho*/, const double /*T*/) -> amrex::Real   \
+	{                                                                                                                                            \
+		return KE;                                                                                                                           \
+	}                                                                                                                                            \
+	template <> AMREX_GPU_HOST_DEVICE auto RadSystem<NAME>::ComputeFluxMeanOpacity(const double /*rho*/, const double /*T*/) -> amrex::Real     \
+	{                                                                                                                                            \
+		return KF;                                                                                                                           \
+	}
+QK_RS_TRAITS(R2, 5. / 3., 2.2 * C::m_u, C::k_B, c_light_cgs_, 860. * 2.0e5, radiation_constant_cgs_, 0., 1)
+QK_RS_TRAITS(R3, 5. / 3., 1.0, 1.0, 10.0, 5.0, 1.0, 0., 2)
+QK_RS_TRAITS(R4, 1.4, 1.0, 1.0, 10.0, 5.0, 1.0, 0., 0)
+QK_RS_TRAITS(R5, 5. / 3., 1.0, 1.0, 10.0, 5.0, 1.0, 1.0e-6, 3)
+QK_RS_TRAITS(R6, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0., 1)
+QK_RS_OPACITY(R2, 20.0, 20.0, 20.0)
+QK_RS_OPACITY(R3, 1.0, 1.5, 2.0)
+QK_RS_OPACITY(R4, 3.0, 3.0, 3.0)
+QK_RS_OPACITY(R5, 0.5, 0.25, 0.25)
+QK_RS_OPACITY(R6, 2.0, 2.0, 2.0)
+
 namespace
 {
 bool g_init = false;
@@ -446,6 +502,60 @@ void rad_update(int op, const qk_box *valid, const qk_array4 *unew, const qk_arr
 		return -1;                                                                                                                           \
 	}
 
+#define DISPATCH_RS(problem, CALL)                                                                                                                   \
+	switch (problem) {                                                                                                                           \
+	case 2: {                                                                                                                                    \
+		using P = R2;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 3: {                                                                                                                                    \
+		using P = R3;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 4: {                                                                                                                                    \
+		using P = R4;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 5: {                                                                                                                                    \
+		using P = R5;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 6: {                                                                                                                                    \
+		using P = R6;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	default:                                                                                                                                     \
+		return -1;                                                                                                                           \
+	}
+
+template <typename P>
+void rad_source_terms(const qk_box *valid, const qk_array4 *cons, const qk_array4 *src, double dt, int stage, int64_t *counters)
+{
+	set_eos<P>();
+	auto c = make_mf(valid, -1, RadSystem<P>::nvar_, 0);
+	auto e = make_mf(valid, -1, 1, 0);
+	copy_in(c, cons);
+	if (src != nullptr) {
+		copy_in(e, src);
+	} else {
+		e.setVal(0.);
+	}
+	int it[4] = {0, 0, 0, 0};
+	int fail[3] = {0, 0, 0};
+	auto arr = c.array(0);
+	RadSystem<P>::AddSourceTermsSingleGroup(arr, e.const_array(0), to_box(valid), dt, stage, 0.0, it, fail);
+	copy_out(c, cons);
+	if (counters != nullptr) {
+		counters[0] += it[0];
+		counters[1] += it[1];
+		counters[2] = std::max<int64_t>(counters[2], it[2]);
+		counters[3] += it[3];
+		for (int n = 0; n < 3; ++n) {
+			counters[4 + n] += fail[n];
+		}
+	}
+}
+
 #define DISPATCH_P(problem, CALL)                                                                                                                    \
 	switch (problem) {                                                                                                                           \
 	case 0: {                                                                                                                                    \
@@ -573,6 +683,39 @@ int ref_rad_update(int problem, int op, const qk_box *valid, const qk_array4 *un
 	const qk_array4 *fo[3] = {fxo, fyo, fzo};
 	const qk_array4 *fn[3] = {fx, fy, fz};
 	DISPATCH_R(problem, rad_update<P>(op, valid, unew, u0, u1, fo, fn, dt, dx3));
+	return 0;
+}
+
+// ---- matter-radiation source terms (problem = 2..6: R2..R6) ----
+int ref_rad_source_params(int problem, qk_hydro_params *hp, qk_rad_params *rp, qk_rad_source_params *sp)
+{
+	DISPATCH_RS(problem, {
+		std::memset(hp, 0, sizeof(*hp));
+		hp->gamma = quokka::EOS_Traits<P>::gamma;
+		hp->mean_molecular_weight = quokka::EOS_Traits<P>::mean_molecular_weight;
+		hp->boltzmann_constant = quokka::EOS_Traits<P>::boltzmann_constant;
+		hp->small_temp = 1e-10;
+		hp->small_dens = 1e-100;
+		rp->c_light = RadSystem<P>::c_light_;
+		rp->c_hat = RadSystem<P>::c_hat_;
+		rp->Erad_floor = RadSystem_Traits<P>::Erad_floor;
+		rp->ngroups = RadSystem<P>::nGroups_;
+		rp->nstart = RadSystem<P>::nstartHyperbolic_;
+		rp->reconstruction_order = 3;
+		rp->integrator_order = 2;
+		sp->radiation_constant = RadSystem<P>::radiation_constant_;
+		sp->kappa_P = RadSystem<P>::ComputePlanckOpacity(1.0, 1.0);
+		sp->kappa_E = RadSystem<P>::ComputeEnergyMeanOpacity(1.0, 1.0);
+		sp->kappa_F = RadSystem<P>::ComputeFluxMeanOpacity(1.0, 1.0);
+		sp->beta_order = RadSystem<P>::beta_order_;
+		sp->opacity_model = QK_OPACITY_CONSTANT;
+	});
+	return 0;
+}
+int ref_rad_add_source_terms(int problem, const qk_box *valid, const qk_array4 *cons, const qk_array4 *src, double dt, int stage, int64_t *counters)
+{
+	ensure_init();
+	DISPATCH_RS(problem, rad_source_terms<P>(valid, cons, src, dt, stage, counters));
 	return 0;
 }
 

@@ -106,6 +106,35 @@ def rad_params(c_light=1.0, c_hat=1.0, Erad_floor=0.0, ngroups=1, nstart=6, reco
     return p
 
 
+class qk_rad_source_params(C.Structure):
+    """run-time image of what RadSystem::AddSourceTermsSingleGroup takes from RadSystem_Traits<problem_t> and the problem's
+    opacity specialisations (src/radiation/source_terms_single_group.hpp:9-565, radiation_system.hpp:73-82,1141-1153)"""
+
+    _fields_ = [
+        ("radiation_constant", C.c_double),
+        ("kappa_P", C.c_double),
+        ("kappa_E", C.c_double),
+        ("kappa_F", C.c_double),
+        ("beta_order", C.c_int32),
+        ("opacity_model", C.c_int32),
+    ]
+
+
+QK_OPACITY_CONSTANT = 0
+QK_RAD_SOURCE_NCOUNTERS = 7
+
+
+def rad_source_params(radiation_constant=7.5657e-15, kappa_P=1.0, kappa_E=None, kappa_F=None, beta_order=1) -> qk_rad_source_params:
+    """kappa_E / kappa_F default to kappa_P as the reference's ComputeEnergyMeanOpacity / ComputeFluxMeanOpacity do (:1146-1154)."""
+    p = qk_rad_source_params()
+    p.radiation_constant = radiation_constant
+    p.kappa_P = kappa_P
+    p.kappa_E = kappa_P if kappa_E is None else kappa_E
+    p.kappa_F = kappa_P if kappa_F is None else kappa_F
+    p.beta_order, p.opacity_model = beta_order, QK_OPACITY_CONSTANT
+    return p
+
+
 K_B = 1.3806488e-16  # Microphysics constants/fundamental_constants.H:22
 M_U = 1.6605390666e-24  # :55
 
@@ -193,6 +222,7 @@ _D3 = C.POINTER(C.c_double)
 _RPRM = C.POINTER(qk_rad_params)
 _I64P = C.POINTER(C.c_int64)
 _VP = C.c_void_p
+_RSPRM = C.POINTER(qk_rad_source_params)
 
 # name -> (restype, argtypes): EVERY symbol include/quokka_b200.h declares
 SYMBOLS = {
@@ -221,6 +251,7 @@ SYMBOLS = {
     "qk_rad_compute_fluxes": (C.c_int, [_RPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _VP]),
     "qk_rad_predict_step": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
     "qk_rad_add_fluxes_rk2": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
+    "qk_rad_add_source_terms": (C.c_int, [_PRM, _RPRM, _RSPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_double, _I64P, _VP]),
     "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),
     "qk_level_create": (C.c_int, [C.POINTER(qk_level_desc), C.POINTER(_VP)]),
     "qk_level_destroy": (None, [_VP]),

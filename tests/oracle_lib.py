@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from quokka_b200.capi import (qk_array4, qk_box, qk_hydro_params, qk_iarray4, qk_level_desc, qk_rad_params)
+from quokka_b200.capi import (qk_array4, qk_box, qk_hydro_params, qk_iarray4, qk_level_desc, qk_rad_params, qk_rad_source_params)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
@@ -24,6 +24,7 @@ _BXP = C.POINTER(qk_box)
 _PRM = C.POINTER(qk_hydro_params)
 _D3 = C.POINTER(C.c_double)
 _RPRM = C.POINTER(qk_rad_params)
+_RSPRM = C.POINTER(qk_rad_source_params)
 _I64P = C.POINTER(C.c_int64)
 
 
@@ -75,6 +76,7 @@ def oracle() -> C.CDLL:
         "orc_rad_predict_step": (None, [_RPRM, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _BXP]),
         "orc_rad_add_fluxes_rk2": (None, [_RPRM, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _BXP]),
         "orc_rad_advance_level": (None, [C.c_void_p, _RPRM, C.c_double]),
+        "orc_rad_add_source_terms": (None, [_PRM, _RPRM, _RSPRM, _A4P, _A4P, _BXP, C.c_double, C.c_int, _I64P]),
         "orc_level_swap": (None, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
@@ -109,6 +111,8 @@ def ref() -> C.CDLL:
     lib.ref_rad_cons_to_prim.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_int]
     lib.ref_rad_compute_fluxes.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int]
     lib.ref_rad_update.argtypes = [C.c_int, C.c_int, _BXP] + [_A4P] * 9 + [C.c_double, _D3]
+    lib.ref_rad_source_params.argtypes = [C.c_int, _PRM, _RPRM, _RSPRM]
+    lib.ref_rad_add_source_terms.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_double, C.c_int, _I64P]
     _ref = lib
     return lib
 
@@ -215,4 +219,36 @@ def random_rad_cons(box: qk_box, prm, seed=777, kind="smooth", ncomp=None):
         a[s] = E
         for m_ in range(3):
             a[s + 1 + m_] = fmag * n[m_] * prm.c_light * np.abs(E)
+    return a
+
+
+def random_radhydro_cons(box: qk_box, hp, rp, sp, seed=4242, T0=1.0, rho0=1.0, vmax=1.0, fmax=0.9, spread=1.0):
+    """Seeded coupled gas + radiation states (one photon group) for the matter-radiation source terms: rho log-uniform over
+    2*spread decades around rho0, gas and radiation temperatures independently log-uniform over 2*spread decades around T0
+    (so cells heat and cool), |v| <= vmax, reduced flux |f| in [0, fmax] with random directions.  Eint from the gamma law
+    (c_v = k_B / (mu (gamma - 1))); for gamma == 1 the energies are arbitrary positive numbers."""
+    rng = np.random.default_rng(seed)
+    shp = box.shape()
+    rho = rho0 * 10.0 ** rng.uniform(-spread, spread, shp)
+    Tg = T0 * 10.0 ** rng.uniform(-spread, spread, shp)
+    Tr = T0 * 10.0 ** rng.uniform(-spread, spread, shp)
+    v = rng.uniform(-vmax, vmax, (3,) + shp)
+    if hp.gamma != 1.0:
+        eint = rho * hp.boltzmann_constant * Tg / (hp.mean_molecular_weight * (hp.gamma - 1.0))
+    else:
+        eint = rho * Tg
+    ke = 0.5 * rho * (v[0] ** 2 + v[1] ** 2 + v[2] ** 2)
+    E = sp.radiation_constant * Tr ** 4
+    fmag = rng.uniform(0.0, fmax, shp)
+    mu = rng.uniform(-1.0, 1.0, shp)
+    phi = rng.uniform(0.0, 2 * np.pi, shp)
+    n = np.stack([np.sqrt(1 - mu ** 2) * np.cos(phi), np.sqrt(1 - mu ** 2) * np.sin(phi), mu])
+    a = np.zeros((rp.nstart + 4,) + shp)
+    a[0] = rho
+    for m in range(3):
+        a[1 + m] = rho * v[m]
+        a[rp.nstart + 1 + m] = fmag * n[m] * rp.c_light * E
+    a[4] = eint + ke
+    a[5] = eint
+    a[rp.nstart] = E
     return a

@@ -46,6 +46,8 @@ def test_struct_layout_matches_the_header():
         "qk_hydro_params": [f for f, _ in capi.qk_hydro_params._fields_],
         "qk_level_desc": [f for f, _ in capi.qk_level_desc._fields_],
         "qk_copy_tag": [f for f, _ in capi.qk_copy_tag._fields_],
+        "qk_rad_params": [f for f, _ in capi.qk_rad_params._fields_],
+        "qk_rad_source_params": [f for f, _ in capi.qk_rad_source_params._fields_],
     }
     lines = ["#include <stdio.h>", "#include <stddef.h>", f'#include "{HEADER}"', "int main(void){"]
     for st, fl in fields.items():
@@ -80,6 +82,8 @@ def test_compute_entries_refuse_without_a_device():
     assert rc == capi.QK_ERR_NO_DEVICE
     m = C.c_double()
     assert lib.qk_hydro_max_signal_speed(C.byref(prm), 0, 1, C.byref(box), C.byref(a), C.byref(m), None) == capi.QK_ERR_NO_DEVICE
+    rp, sp = capi.rad_params(), capi.rad_source_params()
+    assert lib.qk_rad_add_source_terms(C.byref(prm), C.byref(rp), C.byref(sp), 1, 1, C.byref(box), C.byref(a), None, 1.0, None, None) == capi.QK_ERR_NO_DEVICE
     bad, rcp = C.c_int64(), C.c_int64()
     assert lib.qk_selftest_division(1, 0, 16, C.byref(bad), C.byref(rcp)) == capi.QK_ERR_NO_DEVICE
     with pytest.raises(RuntimeError):
