@@ -1,0 +1,177 @@
+// qk_rad_source.cu -- matter-radiation coupling source terms, single photon group: qk_rad_add_source_terms =
+// RadSystem<problem_t>::AddSourceTermsSingleGroup (src/radiation/source_terms_single_group.hpp:9-565) as called by
+// QuokkaSimulation::operatorSplitSourceTerms (src/QuokkaSimulation.hpp:1860-1885) twice per radiation substep (:1638,1656).
+//
+//   k_rad_source   one thread per cell, ALL boxes of the level in one launch (the reference launches box by box under MFIter,
+//                  :1631,1650): lane <-> x, so the ten component loads and nine component stores of a warp are contiguous
+//                  256-byte rows; the implicit solve (Newton-Raphson on (E_gas, R) inside the lagged work-term iteration) runs
+//                  entirely in registers (qk_rad_source.cuh).  Iteration counters are reduced per warp, then per CTA in shared
+//                  memory, and reach global memory as one atomic per CTA and counter.
+//
+// Cell-local and compute-bound (about sixteen IEEE divisions and two square roots per Newton-Raphson iteration, 5-20
+// iterations per cell): the roof is the FP64 pipe, not HBM; algorithmic traffic is 80 B read + 72 B written per cell
+// (+8 with an energy source array).  DESIGN.md section 3.
+#include "qk_common.cuh"
+#include "qk_rad_source.cuh"
+
+namespace
+{
+constexpr int SRC_TPB = 128;
+constexpr int SRC_MAXBOX = 24; // boxes per launch (kernel-parameter table, 24 * 152 B)
+
+struct SrcBox {
+	A4 cons, esrc; // esrc.p == nullptr: zero source
+	int lo[3], n[3];
+	int64_t total;
+};
+struct SrcTable {
+	SrcBox b[SRC_MAXBOX];
+};
+
+__global__ void __launch_bounds__(SRC_TPB) k_rad_source(const qk_rsrc::Const k, const SrcTable tab, const int nstart, int *__restrict__ counters)
+{
+	const SrcBox &B = tab.b[blockIdx.y];
+	const int64_t t = (int64_t)blockIdx.x * SRC_TPB + threadIdx.x;
+	const bool active = (t < B.total);
+	qk_rsrc::CellOut out;
+	out.solves = out.nr_iters = out.nr_max = out.fail_nr = out.fail_outer = 0;
+	if (active) {
+		const int64_t jk = t / B.n[0];
+		const int i = B.lo[0] + (int)(t - jk * B.n[0]);
+		const int kk = (int)(jk / B.n[1]);
+		const int j = B.lo[1] + (int)(jk - (int64_t)kk * B.n[1]);
+		const int kz = B.lo[2] + kk;
+		double *__restrict__ p = B.cons.p + B.cons.off(i, j, kz);
+		const int64_t ns = B.cons.ns;
+		double *__restrict__ pr = p + (int64_t)nstart * ns;
+		qk_rsrc::CellIn in;
+		in.rho = p[0];
+		in.mom[0] = p[ns];
+		in.mom[1] = p[2 * ns];
+		in.mom[2] = p[3 * ns];
+		in.Egastot = p[4 * ns];
+		in.Erad = pr[0];
+		in.F[0] = pr[ns];
+		in.F[1] = pr[2 * ns];
+		in.F[2] = pr[3 * ns];
+		in.src = (B.esrc.p != nullptr) ? B.esrc.p[B.esrc.off(i, j, kz)] : 0.0;
+		qk_rsrc::source_cell(k, in, out);
+		p[ns] = out.mom[0];
+		p[2 * ns] = out.mom[1];
+		p[3 * ns] = out.mom[2];
+		if (k.gamma != 1.0) { // :558-561
+			p[4 * ns] = out.Egastot;
+			p[5 * ns] = out.Eint;
+			pr[0] = out.Erad;
+		}
+		pr[ns] = out.F[0];
+		pr[2 * ns] = out.F[1];
+		pr[3 * ns] = out.F[2];
+	}
+	if (counters != nullptr) { // uniform across the grid
+		__shared__ int sh[5];
+		if (threadIdx.x < 5)
+			sh[threadIdx.x] = 0;
+		__syncthreads();
+		const unsigned full = 0xffffffffu;
+		const int s0 = __reduce_add_sync(full, out.solves);
+		const int s1 = __reduce_add_sync(full, out.nr_iters);
+		const int s2 = __reduce_max_sync(full, out.nr_max);
+		const int s3 = __reduce_add_sync(full, out.fail_nr);
+		const int s4 = __reduce_add_sync(full, out.fail_outer);
+		if ((threadIdx.x & 31) == 0) {
+			atomicAdd(&sh[0], s0);
+			atomicAdd(&sh[1], s1);
+			atomicMax(&sh[2], s2);
+			atomicAdd(&sh[3], s3);
+			atomicAdd(&sh[4], s4);
+		}
+		__syncthreads();
+		// counters[0..3] = iteration_counter, [4..6] = iteration_failure_counter (src/QuokkaSimulation.hpp:1620-1625)
+		if (threadIdx.x == 0 && sh[0] != 0) {
+			atomicAdd(&counters[0], sh[0]);
+			atomicAdd(&counters[1], sh[1]);
+			atomicMax(&counters[2], sh[2]);
+			if (sh[3])
+				atomicAdd(&counters[4], sh[3]);
+			if (sh[4])
+				atomicAdd(&counters[6], sh[4]);
+		}
+	}
+}
+
+int *g_dcount = nullptr; // 8 ints on the device
+int *g_hcount = nullptr; // pinned mirror
+} // namespace
+
+extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_rad_params *prm, const qk_rad_source_params *src, int stage, int nboxes,
+				       const qk_box *valid, const qk_array4 *cons, const qk_array4 *rad_energy_source, double dt_radiation,
+				       int64_t *counters, void *stream)
+{
+	if (!hydro || !prm || !src || (nboxes > 0 && (!valid || !cons)) || nboxes < 0 || (stage != 1 && stage != 2))
+		return QK_ERR_BAD_ARG;
+	// single group with user opacities = OpacityModel::single_group (radiation_system.hpp:63-64,216-222); multi-group
+	// (AddSourceTermsMultiGroup), the dust model and beta_order outside 0..3 (static_assert :113) are not built
+	if (prm->ngroups != 1 || src->opacity_model != QK_OPACITY_CONSTANT || src->beta_order < 0 || src->beta_order > 3 || prm->nstart < 6)
+		return QK_ERR_UNSUPPORTED;
+	{
+		const int r = qk_require_device();
+		if (r != 0)
+			return r;
+	}
+	cudaStream_t s = (cudaStream_t)stream;
+	const qk_rsrc::Const k = qk_rsrc::make_const(hydro, prm, src, dt_radiation, stage);
+	ProfScope prof_("rad_source_terms", s);
+	int *dcount = nullptr;
+	if (counters) {
+		if (!g_dcount) {
+			QK_CUDA(cudaMalloc(&g_dcount, 8 * sizeof(int)));
+			QK_CUDA(cudaMallocHost(&g_hcount, 8 * sizeof(int)));
+		}
+		dcount = g_dcount;
+		QK_CUDA(cudaMemsetAsync(dcount, 0, 8 * sizeof(int), s));
+	}
+	for (int b0 = 0; b0 < nboxes; b0 += SRC_MAXBOX) {
+		const int nb = (nboxes - b0 < SRC_MAXBOX) ? (nboxes - b0) : SRC_MAXBOX;
+		SrcTable tab;
+		int64_t most = 0;
+		for (int b = 0; b < nb; ++b) {
+			SrcBox &B = tab.b[b];
+			B.cons = A4(cons[b0 + b]);
+			if (cons[b0 + b].ncomp < prm->nstart + 4)
+				return QK_ERR_BAD_ARG;
+			if (rad_energy_source)
+				B.esrc = A4(rad_energy_source[b0 + b]);
+			else {
+				B.esrc = B.cons;
+				B.esrc.p = nullptr;
+			}
+			B.total = 1;
+			for (int d = 0; d < 3; ++d) {
+				B.lo[d] = valid[b0 + b].lo[d];
+				B.n[d] = valid[b0 + b].hi[d] - valid[b0 + b].lo[d] + 1;
+				if (B.n[d] < 0)
+					B.n[d] = 0;
+				B.total *= B.n[d];
+			}
+			if (B.total > most)
+				most = B.total;
+		}
+		if (most == 0)
+			continue;
+		const dim3 grid((unsigned)((most + SRC_TPB - 1) / SRC_TPB), (unsigned)nb);
+		k_rad_source<<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+		QK_KERNEL_CHECK();
+	}
+	if (counters) {
+		QK_CUDA(cudaMemcpyAsync(g_hcount, dcount, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+		QK_CUDA(cudaStreamSynchronize(s));
+		for (int n = 0; n < QK_RAD_SOURCE_NCOUNTERS; ++n) {
+			if (n == 2)
+				counters[2] = (counters[2] < g_hcount[2]) ? g_hcount[2] : counters[2];
+			else
+				counters[n] += g_hcount[n];
+		}
+	}
+	return 0;
+}

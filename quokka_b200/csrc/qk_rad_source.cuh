@@ -1,0 +1,393 @@
+// qk_rad_source.cuh -- one cell of the matter-radiation coupling source terms, single photon group:
+// RadSystem<problem_t>::AddSourceTermsSingleGroup, src/radiation/source_terms_single_group.hpp:9-565 (the lambda body :28-564),
+// with the reference's compile-time hyper-parameters (src/radiation/radiation_system.hpp:34-52: include_work_term_in_source,
+// enable_dE_constrain, !force_rad_floor_in_iteration, !add_line_cooling_to_radiation_in_jac, IMEX_a32 = 0.5), no dust model
+// (ISM_Traits default :85-89), zero DefineNetCoolingRate / DefineCosmicRayHeatingRate (:522-545) and constant opacities.
+//
+// Everything here is QK_HD (host + device) and free of array accesses so that tests/host_src/rad_source_host.cpp can run the
+// very same arithmetic on the CPU against the oracle (the product library only ever calls it from k_rad_source).
+//
+// Arithmetic: the reference's operation order, no FMA contraction (the library is built with --fmad=false; explicit fma()
+// calls below are deliberate).  The reference takes T^4, T^3 and lorentz^3 from std::pow; here they are formed in
+// double-double and rounded once (pow_dd<N>), i.e. correctly rounded except when the exact value lies within 2^-105 of a
+// rounding boundary.  libm's and CUDA's pow are not correctly rounded (0.52 / 2 ulp), so the CPU reference, the reference's
+// own CUDA build and this kernel may differ in the last bit of a thermal emission term; after the Newton-Raphson solve
+// (residual tolerance 1e-11 of the total energy, :158) the results agree to that tolerance.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/quokka_b200.h"
+
+#ifndef QK_HD
+#ifdef __CUDACC__
+#define QK_HD __host__ __device__ __forceinline__
+#else
+#define QK_HD static inline
+#endif
+#endif
+
+namespace qk_rsrc
+{
+// Microphysics constants/fundamental_constants.H:22,55
+constexpr double K_B = 1.3806488e-16;
+constexpr double M_U = 1.6605390666e-24;
+
+QK_HD double mn(double a, double b) { return (b < a) ? b : a; } // std::min(a, b)
+QK_HD double mx(double a, double b) { return (a < b) ? b : a; } // std::max(a, b)
+
+struct Const {
+	// RadSystem_Traits / problem opacities
+	double c, chat, cscale /* c / chat */, inv_cscale /* 1 / cscale */, cc /* c * c */, c_chat /* c * chat */;
+	double a_rad, floor_g /* Erad_floor / nGroups */;
+	double kP, kE, kF, kPoE /* kappaP / kappaE or 1 */, two_kE_m_kF /* 2 kappaE - kappaF */;
+	int beta_order;
+	// EOS_Traits + eos_init limits
+	double gamma, gm1, mu /* mean_molecular_weight / m_u */, mumn /* mu * m_u */, kB /* EOS_Traits::boltzmann_constant */;
+	double mindens, mintemp;
+	// per call
+	double dt /* stage 2: (1 - IMEX_a32) dt_radiation */, chat_dt /* chat * dt */, gas_update_factor;
+};
+
+struct CellIn {
+	double rho, mom[3], Egastot, Erad, F[3], src /* radEnergySource(i,j,k,0) */;
+};
+struct CellOut {
+	double mom[3], Egastot, Eint, Erad, F[3];
+	int solves, nr_iters, nr_max, fail_nr, fail_outer; // iteration_counter[0..2], iteration_failure_counter[0], [2]
+};
+
+// x^N (N = 3, 4) in double-double, rounded once
+QK_HD void two_prod(double a, double b, double &p, double &e)
+{
+	p = a * b;
+	e = fma(a, b, -p);
+}
+template <int N> QK_HD double pow_dd(double x)
+{
+	double h, l;
+	two_prod(x, x, h, l); // x^2 = h + l exactly
+	double p, e;
+	if (N == 4) { // (h + l)^2 = h^2 + 2 h l + l^2
+		two_prod(h, h, p, e);
+		e = fma(2.0 * h, l, e);
+		e = fma(l, l, e);
+	} else { // (h + l) x
+		two_prod(h, x, p, e);
+		e = fma(l, x, e);
+	}
+	const double s = p + e;
+	// non-finite or underflowing intermediates: fall back to the plain product (same value wherever it is finite and normal)
+	return (s == s && fabs(s) <= 1.79769313486231570815e308 && fabs(p) >= 1e-280) ? s : ((N == 4) ? (x * x) * (x * x) : (x * x) * x);
+}
+
+// ---- gamma-law EOS through Microphysics (interfaces/eos.H:395-435,141-205,69-79; EOS/gamma_law/actual_eos.H:47-294) as
+// called by EOS<problem_t>::ComputeTgasFromEint / ComputeEintFromTgas / ComputeEintTempDerivative (src/hydro/EOS.hpp:75-157,200-240)
+QK_HD double eos_clamp_rho(const Const &k, double rho) { return mn(1.e200, mx(k.mindens, rho)); }
+QK_HD double eos_clamp_T(const Const &k, double T) { return mn(1.e200, mx(k.mintemp, T)); }
+QK_HD double tgas_from_eint(const Const &k, double rho, double Eint)
+{
+	const double e = Eint / rho;
+	double T;
+	if (e < 1.e-200 || e > 1.e200)
+		T = k.mintemp; // eos_reset: T = clamp(0)
+	else
+		T = e * k.mu * M_U * k.gm1 / K_B; // actual_eos.H:128
+	return T * K_B / k.kB;
+}
+// e(rho, T) of eos_input_rt and the clamped temperature it was evaluated at
+QK_HD double eos_e_of_rT(const Const &k, double rho, double Tgas, double &T)
+{
+	const double r = eos_clamp_rho(k, rho);
+	T = eos_clamp_T(k, Tgas);
+	const double rhoinv = 1.0 / r;
+	const double pressure = r * T * K_B / k.mumn; // actual_eos.H:199
+	return pressure / k.gm1 * rhoinv;	       // :200
+}
+QK_HD double eint_from_tgas(const Const &k, double rho, double Tgas)
+{
+	double T;
+	const double e = eos_e_of_rT(k, rho, Tgas, T);
+	return e * rho * k.kB / K_B;
+}
+QK_HD double eint_temp_derivative(const Const &k, double rho, double Tgas)
+{
+	double T;
+	const double e = eos_e_of_rT(k, rho, Tgas, T);
+	const double dedT = e * (1.0 / T); // actual_eos.H:194,227
+	return dedT * rho * k.kB / K_B;
+}
+
+// RadSystem::ComputeEgasFromEint - Eint part (radiation_system.hpp:1289-1309): the kinetic energy p^2 / (2 rho)
+QK_HD double ekin_of(double rho, double px, double py, double pz)
+{
+	const double p_sq = px * px + py * py + pz * pz;
+	return p_sq / (2.0 * rho);
+}
+
+// RadSystem::ComputeEddingtonFactor :773-790 + ComputeEddingtonTensor :873-916
+QK_HD void eddington_tensor(double fx, double fy, double fz, double T[3][3])
+{
+	const double f = sqrt(fx * fx + fy * fy + fz * fz);
+	const double fvec[3] = {fx, fy, fz};
+	double n[3];
+	for (int ii = 0; ii < 3; ++ii)
+		n[ii] = (f > 0.) ? (fvec[ii] / f) : 0.;
+	const double fc = (f < 0.) ? 0. : (1. < f) ? 1. : f; // std::clamp(f, 0., 1.)
+	const double f_fac = sqrt(4.0 - 3.0 * (fc * fc));
+	const double chi = (3.0 + 4.0 * (fc * fc)) / (5.0 + 2.0 * f_fac);
+	const double Tdiag = (1.0 - chi) / 2.0;
+	const double Tf = (3.0 * chi - 1.0) / 2.0;
+	for (int ii = 0; ii < 3; ++ii)
+		for (int jj = 0; jj < 3; ++jj) {
+			const double delta_ij = (ii == jj) ? 1 : 0;
+			T[ii][jj] = Tdiag * delta_ij + Tf * (n[ii] * n[jj]);
+		}
+}
+
+// RadSystem::Solve3x3matrix :560-580
+QK_HD void solve3x3(double C00, double C01, double C02, double C10, double C11, double C12, double C20, double C21, double C22, double Y0, double Y1,
+		    double Y2, double X[3])
+{
+	const double E11 = C11 - C01 * C10 / C00;
+	const double E12 = C12 - C02 * C10 / C00;
+	const double E21 = C21 - C01 * C20 / C00;
+	const double E22 = C22 - C02 * C20 / C00;
+	const double Z1 = Y1 - Y0 * C10 / C00;
+	const double Z2 = Y2 - Y0 * C20 / C00;
+	const double X2 = (Z2 - Z1 * E21 / E11) / (E22 - E12 * E21 / E11);
+	const double X1 = (Z1 - E12 * X2) / E11;
+	const double X0 = (Y0 - C01 * X1 - C02 * X2) / C00;
+	X[0] = X0;
+	X[1] = X1;
+	X[2] = X2;
+}
+
+QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
+{
+	const double c = k.c, chat = k.chat, cscale = k.cscale, dt = k.dt;
+	const double rho = in.rho;
+	const double Egastot0 = in.Egastot, Erad0 = in.Erad;
+	const double Src = in.src * dt * chat; // :54
+	const bool gas = (k.gamma != 1.0);
+	const int beta_order = k.beta_order;
+	const double nan = NAN;
+
+	double Egas0 = nan, Ekin0 = nan, Etot0 = nan, Egas_guess = nan;
+	double lorentz_factor = nan, lorentz_factor_v = nan, lorentz_factor_v_v = nan;
+	double fourPiBoverC = nan, Erad_guess = nan;
+	const double kappaP = k.kP, kappaE = k.kE, kappaF = k.kF, kappaPoverE = k.kPoE;
+	double work = 0.0, work_prev = 0.0;
+	double dMomentum[3] = {0., 0., 0.}, Frad_t1[3] = {0., 0., 0.};
+	out.solves = out.nr_iters = out.nr_max = out.fail_nr = out.fail_outer = 0;
+
+	if (gas) { // :82-86
+		Egas0 = Egastot0 - ekin_of(rho, in.mom[0], in.mom[1], in.mom[2]);
+		Etot0 = Egas0 + cscale * (Erad0 + Src);
+		Ekin0 = Egastot0 - Egas0;
+		const double betaSqr = (in.mom[0] * in.mom[0] + in.mom[1] * in.mom[1] + in.mom[2] * in.mom[2]) / (rho * rho * c * c);
+		if (beta_order == 0 || beta_order == 1) { // :115-131
+			lorentz_factor = 1.0;
+			lorentz_factor_v = 1.0;
+		} else if (beta_order == 2) {
+			lorentz_factor = 1.0 + 0.5 * betaSqr;
+			lorentz_factor_v = 1.0;
+			lorentz_factor_v_v = 1.0;
+		} else { // beta_order == 3 (static_assert(beta_order_ <= 3) :113)
+			lorentz_factor = 1.0 + 0.5 * betaSqr;
+			lorentz_factor_v = 1.0 + 0.5 * betaSqr;
+			lorentz_factor_v_v = 1.0;
+		}
+	}
+	const double resid_limit = 1.0e-11 * Etot0; // resid_tol * Etot0 :158,254
+
+	const int max_ite = 5;
+	int ite = 0;
+	for (; ite < max_ite; ++ite) {
+		double R = nan;
+		Erad_guess = Erad0;
+		if (gas) {
+			double tau = nan;
+			Egas_guess = Egas0;
+			const int maxIter = 100;
+			int n = 0;
+			for (; n < maxIter; ++n) { // Newton-Raphson :161-352
+				const double T_gas = tgas_from_eint(k, rho, Egas_guess);
+				const double T_d = T_gas;
+				fourPiBoverC = k.a_rad * pow_dd<4>(T_d); // ComputeThermalRadiationSingleGroup :471-479
+				if (fourPiBoverC < k.floor_g)
+					fourPiBoverC = k.floor_g;
+				if (n == 0) { // :192-215
+					if (beta_order != 0 && ite == 0)
+						work = (in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat / k.cc *
+						       lorentz_factor_v * dt;
+					const double tau0 = dt * rho * kappaP * chat * lorentz_factor;
+					tau = tau0;
+					R = (fourPiBoverC - Erad_guess / kappaPoverE) * tau0 + work;
+				} else { // :216-232
+					tau = dt * rho * kappaP * chat * lorentz_factor;
+					if (tau > 0.0)
+						Erad_guess = kappaPoverE * (fourPiBoverC - (R - work) / tau);
+				}
+				// cooling = cooling_derivative = 0, CR_heating = 0 * dt: the terms are kept so that signed zeros and
+				// non-finite dt propagate as in the reference (:234-245)
+				const double cooling = 0.0, cooling_derivative = 0.0;
+				const double CR_heating = 0.0 * dt;
+				const double F_G = Egas_guess - Egas0 + cscale * R + cooling * dt - CR_heating;
+				const double F_D = Erad_guess - Erad0 - (R + Src);
+				const double F_D_abs = (tau > 0.0) ? fabs(F_D) : fabs(F_D + R);
+				if ((fabs(F_G) < resid_limit) && (cscale * F_D_abs < resid_limit))
+					break;
+				const double c_v = eint_temp_derivative(k, rho, T_gas);
+				const double d_fourpiboverc_d_t = 4. * k.a_rad * pow_dd<3>(T_d); // :499-503
+				const double dEg_dT = kappaPoverE * d_fourpiboverc_d_t;
+				const double J00 = 1.0 + cooling_derivative * dt / c_v;
+				const double J01 = cscale;
+				const double J10 = 1.0 / c_v * dEg_dT - k.inv_cscale * cooling_derivative * dt;
+				const double J11 = (tau <= 0.0) ? -INFINITY : (-1.0 * kappaPoverE / tau - 1.0);
+				const double y0 = -F_G;
+				const double y1 = -1. * F_D;
+				const double det = J00 * J11 - J01 * J10;
+				const double deltaEgas = (J11 * y0 - J01 * y1) / det;
+				const double deltaR = (J00 * y1 - J10 * y0) / det;
+				const double T_rad = sqrt(sqrt(Erad_guess / k.a_rad)); // enable_dE_constrain :330-342
+				if (deltaEgas / c_v > mx(T_gas, T_rad)) {
+					Egas_guess = eint_from_tgas(k, rho, T_rad);
+				} else {
+					Egas_guess += deltaEgas;
+					R += deltaR;
+				}
+			}
+			if (n >= maxIter) // :354-362
+				out.fail_nr += 1;
+			out.solves += 1;
+			out.nr_iters += n + 1;
+			out.nr_max = (out.nr_max < n + 1) ? (n + 1) : out.nr_max;
+			Erad_guess += k.inv_cscale * (0.0 * dt); // cooling_tend :367-373
+		}
+
+		// 2. radiation flux update :396-490
+		dMomentum[0] = dMomentum[1] = dMomentum[2] = 0.;
+		if (gas && (beta_order != 0)) {
+			const double erad = Erad_guess;
+			double v_terms[3];
+			const double fx = in.F[0] / (c * erad);
+			const double fy = in.F[1] / (c * erad);
+			const double fz = in.F[2] / (c * erad);
+			const double F_coeff = chat * rho * kappaF * dt * lorentz_factor;
+			double Tedd[3][3];
+			eddington_tensor(fx, fy, fz, Tedd);
+			const double lfv3 = (kappaF != kappaE) ? pow_dd<3>(lorentz_factor_v) : 0.;
+			for (int n = 0; n < 3; ++n) {
+				double Planck_term = kappaP * fourPiBoverC * lorentz_factor_v;
+				if (kappaF != kappaE)
+					Planck_term += (kappaF - kappaE) * erad * lfv3;
+				Planck_term *= k.chat_dt * in.mom[n];
+				double pressure_term = 0.0;
+				for (int z = 0; z < 3; ++z)
+					pressure_term += in.mom[z] * Tedd[n][z] * erad;
+				pressure_term *= k.chat_dt * kappaF * lorentz_factor_v;
+				v_terms[n] = Planck_term + pressure_term;
+			}
+			if (beta_order == 1 || kappaF == kappaE) {
+				for (int n = 0; n < 3; ++n) {
+					Frad_t1[n] = (in.F[n] + v_terms[n]) / (1.0 + F_coeff);
+					dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+				}
+			} else {
+				// gasVel is declared and never assigned in the reference (:407), so the K0 v_i v_j terms are K0 * 0 * 0; they
+				// are formed all the same (a non-finite K0 must poison the result as it does there)
+				const double gasVel[3] = {0., 0., 0.};
+				const double K0 = 2.0 * rho * chat * dt * (kappaF - kappaE) / c / c * pow_dd<3>(lorentz_factor_v_v);
+				const double A00 = 1.0 + F_coeff + K0 * gasVel[0] * gasVel[0];
+				const double A01 = K0 * gasVel[0] * gasVel[1];
+				const double A02 = K0 * gasVel[0] * gasVel[2];
+				const double A10 = K0 * gasVel[1] * gasVel[0];
+				const double A11 = 1.0 + F_coeff + K0 * gasVel[1] * gasVel[1];
+				const double A12 = K0 * gasVel[1] * gasVel[2];
+				const double A20 = K0 * gasVel[2] * gasVel[0];
+				const double A21 = K0 * gasVel[2] * gasVel[1];
+				const double A22 = 1.0 + F_coeff + K0 * gasVel[2] * gasVel[2];
+				solve3x3(A00, A01, A02, A10, A11, A12, A20, A21, A22, v_terms[0] + in.F[0], v_terms[1] + in.F[1], v_terms[2] + in.F[2],
+					 Frad_t1);
+				for (int n = 0; n < 3; ++n)
+					dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+			}
+		} else { // :484-490
+			for (int n = 0; n < 3; ++n) {
+				Frad_t1[n] = in.F[n] / (1.0 + rho * kappaF * chat * dt);
+				dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+			}
+		}
+		const double x1GasMom1 = in.mom[0] + dMomentum[0];
+		const double x2GasMom1 = in.mom[1] + dMomentum[1];
+		const double x3GasMom1 = in.mom[2] + dMomentum[2];
+
+		// 3. work term :496-541
+		if (!gas || beta_order == 0)
+			break;
+		{
+			const double Egastot1 = Egas_guess + ekin_of(rho, x1GasMom1, x2GasMom1, x3GasMom1);
+			const double Ekin1 = Egastot1 - Egas_guess;
+			const double dEkin_work = Ekin1 - Ekin0;
+			Egas_guess -= dEkin_work;
+		}
+		work_prev = work;
+		work = (x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat / k.cc * lorentz_factor_v * k.two_kE_m_kF * dt;
+		const double lag_tol = 1.0e-13;
+		const double dwork = fabs(work - work_prev);
+		if ((fabs(work) == 0.0) || (cscale * dwork < lag_tol * Etot0) || (dwork <= lag_tol * R) || (dwork <= 1.0e-8 * fabs(work)))
+			break;
+	}
+	if (ite >= max_ite) // :544-547
+		out.fail_outer = 1;
+
+	// 4b. store :549-564
+	for (int n = 0; n < 3; ++n) {
+		out.mom[n] = in.mom[n] + dMomentum[n] * k.gas_update_factor;
+		out.F[n] = Frad_t1[n];
+	}
+	if (gas) {
+		Egas_guess = Egas0 + (Egas_guess - Egas0) * k.gas_update_factor;
+		out.Eint = Egas_guess;
+		out.Egastot = Egas_guess + ekin_of(rho, out.mom[0], out.mom[1], out.mom[2]);
+		out.Erad = Erad_guess;
+	} else {
+		out.Eint = nan; // not written by the reference (:558-571); the caller skips these three
+		out.Egastot = nan;
+		out.Erad = nan;
+	}
+}
+
+// host: the per-call constants from the three parameter blocks (:13-19,88-91 for dt and gas_update_factor)
+static inline Const make_const(const qk_hydro_params *hp, const qk_rad_params *rp, const qk_rad_source_params *sp, double dt_radiation, int stage)
+{
+	const double IMEX_a32 = 0.5; // radiation_system.hpp:52
+	Const k;
+	k.c = rp->c_light;
+	k.chat = rp->c_hat;
+	k.cscale = k.c / k.chat;
+	k.inv_cscale = 1 / k.cscale;
+	k.cc = k.c * k.c;
+	k.c_chat = k.c * k.chat;
+	k.a_rad = sp->radiation_constant;
+	k.floor_g = rp->Erad_floor / rp->ngroups;
+	k.kP = sp->kappa_P;
+	k.kE = sp->kappa_E;
+	k.kF = sp->kappa_F;
+	k.kPoE = (k.kE > 0.0) ? (k.kP / k.kE) : 1.0; // :183-187
+	k.two_kE_m_kF = 2.0 * k.kE - k.kF;
+	k.beta_order = sp->beta_order;
+	k.gamma = hp->gamma;
+	k.gm1 = hp->gamma - 1.0;
+	k.mu = hp->mean_molecular_weight / M_U; // src/hydro/EOS.hpp:104
+	k.mumn = k.mu * M_U;
+	k.kB = hp->boltzmann_constant;
+	k.mindens = (1.e-200 < hp->small_dens) ? hp->small_dens : 1.e-200; // eos_init, interfaces/eos.H:40-44
+	k.mintemp = (1.e-200 < hp->small_temp) ? hp->small_temp : 1.e-200;
+	k.dt = (stage == 2) ? (1.0 - IMEX_a32) * dt_radiation : dt_radiation;
+	k.chat_dt = k.chat * k.dt;
+	k.gas_update_factor = (stage == 1) ? IMEX_a32 : 1.0;
+	return k;
+}
+} // namespace qk_rsrc
