@@ -12,12 +12,54 @@
 // iterations per cell): the roof is the FP64 pipe, not HBM; algorithmic traffic is 80 B read + 72 B written per cell
 // (+8 with an energy source array).  DESIGN.md section 3.
 #include "qk_common.cuh"
+#include "qk_div.cuh"
 #include "qk_rad_source.cuh"
+
+#include <stdlib.h>
 
 namespace
 {
 constexpr int SRC_TPB = 128;
 constexpr int SRC_MAXBOX = 24; // boxes per launch (kernel-parameter table, 24 * 152 B)
+
+// shared-reciprocal IEEE division (qk_div.cuh): the reciprocal of a denominator is refined once, every quotient over it is the
+// compiler's own three closing instructions; operands outside the compiler's fast-path domain take its `/`.  Bit-identical to
+// DivPlain (tests/test_zgpu_rad_source.py::test_shared_reciprocal_division_is_bit_identical, tests/test_gpu_division.py).
+struct DivShared {
+	typedef QkRcp R;
+	__device__ __forceinline__ static R rcp(double b) { return qk_rcp(b); }
+	__device__ __forceinline__ static double div(double a, const R &r) { return qk_div(a, r); }
+	// call-constant denominators: (b, refined 1/b) pairs in shared memory, filled once per CTA -- no registers are held for
+	// them across the Newton-Raphson loop; the host has checked that every b is finite and normal (else DivPlain runs)
+	struct CTab {
+		const double2 *sm;
+	};
+	__device__ __forceinline__ static double divc(double a, const CTab &t, int idx)
+	{
+		const double2 by = t.sm[idx];
+		QkRcp r;
+		r.b = by.x;
+		r.y = by.y;
+		r.ok = true;
+		return qk_div(a, r);
+	}
+};
+__device__ __forceinline__ void make_ctab(const qk_rsrc::Const &k, qk_rsrc::DivPlain::CTab &ct, double2 *) { qk_rsrc::const_denoms(k, ct.b); }
+__device__ __forceinline__ void make_ctab(const qk_rsrc::Const &k, DivShared::CTab &ct, double2 *sm)
+{
+	if (threadIdx.x < qk_rsrc::C_N) {
+		double b[qk_rsrc::C_N];
+		qk_rsrc::const_denoms(k, b);
+		double mine = b[0];
+#pragma unroll
+		for (int n = 1; n < qk_rsrc::C_N; ++n)
+			mine = (threadIdx.x == n) ? b[n] : mine;
+		const QkRcp r = qk_rcp(mine);
+		sm[threadIdx.x] = make_double2(r.b, r.y);
+	}
+	__syncthreads();
+	ct.sm = sm;
+}
 
 struct SrcBox {
 	A4 cons, esrc; // esrc.p == nullptr: zero source
@@ -28,18 +70,21 @@ struct SrcTable {
 	SrcBox b[SRC_MAXBOX];
 };
 
-__global__ void __launch_bounds__(SRC_TPB) k_rad_source(const qk_rsrc::Const k, const SrcTable tab, const int nstart, int *__restrict__ counters)
+template <class D, int MINB> __global__ void __launch_bounds__(SRC_TPB, MINB) k_rad_source(const qk_rsrc::Const k, const SrcTable tab, const int nstart, int *__restrict__ counters)
 {
 	const SrcBox &B = tab.b[blockIdx.y];
-	const int64_t t = (int64_t)blockIdx.x * SRC_TPB + threadIdx.x;
-	const bool active = (t < B.total);
+	const unsigned t = blockIdx.x * SRC_TPB + threadIdx.x; // the host refuses boxes of 2^31 cells or more
+	const bool active = (t < (unsigned)B.total);
 	qk_rsrc::CellOut out;
 	out.solves = out.nr_iters = out.nr_max = out.fail_nr = out.fail_outer = 0;
+	__shared__ double2 s_ct[qk_rsrc::C_N];
+	typename D::CTab ct;
+	make_ctab(k, ct, s_ct);
 	if (active) {
-		const int64_t jk = t / B.n[0];
-		const int i = B.lo[0] + (int)(t - jk * B.n[0]);
-		const int kk = (int)(jk / B.n[1]);
-		const int j = B.lo[1] + (int)(jk - (int64_t)kk * B.n[1]);
+		const unsigned jk = t / (unsigned)B.n[0];
+		const int i = B.lo[0] + (int)(t - jk * (unsigned)B.n[0]);
+		const int kk = (int)(jk / (unsigned)B.n[1]);
+		const int j = B.lo[1] + (int)(jk - (unsigned)kk * (unsigned)B.n[1]);
 		const int kz = B.lo[2] + kk;
 		double *__restrict__ p = B.cons.p + B.cons.off(i, j, kz);
 		const int64_t ns = B.cons.ns;
@@ -55,7 +100,7 @@ __global__ void __launch_bounds__(SRC_TPB) k_rad_source(const qk_rsrc::Const k, 
 		in.F[1] = pr[2 * ns];
 		in.F[2] = pr[3 * ns];
 		in.src = (B.esrc.p != nullptr) ? B.esrc.p[B.esrc.off(i, j, kz)] : 0.0;
-		qk_rsrc::source_cell(k, in, out);
+		qk_rsrc::source_cell<D>(k, ct, in, out);
 		p[ns] = out.mom[0];
 		p[2 * ns] = out.mom[1];
 		p[3 * ns] = out.mom[2];
@@ -122,6 +167,19 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 	cudaStream_t s = (cudaStream_t)stream;
 	const qk_rsrc::Const k = qk_rsrc::make_const(hydro, prm, src, dt_radiation, stage);
 	ProfScope prof_("rad_source_terms", s);
+	// QK_RADSRC_PLAIN_DIV=0: the shared-reciprocal instantiation (same bits; measured slower here)
+	const char *pd = getenv("QK_RADSRC_PLAIN_DIV");
+	bool plain_div = !(pd != nullptr && pd[0] == '0');
+	// QK_RADSRC_MINB: resident CTAs per SM the kernel is compiled for (register cap 168 / 128 / 96 / 80); tuning knob
+	const char *mb = getenv("QK_RADSRC_MINB");
+	const int minb = (mb != nullptr) ? atoi(mb) : 8;
+	{
+		double b[qk_rsrc::C_N];
+		qk_rsrc::const_denoms(k, b);
+		for (int n = 0; n < qk_rsrc::C_N; ++n)
+			if (!(fabs(b[n]) >= 2.3e-308 && fabs(b[n]) < 1.0e306)) // outside qk_rcp's fast-path domain
+				plain_div = true;
+	}
 	int *dcount = nullptr;
 	if (counters) {
 		if (!g_dcount) {
@@ -160,7 +218,27 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 		if (most == 0)
 			continue;
 		const dim3 grid((unsigned)((most + SRC_TPB - 1) / SRC_TPB), (unsigned)nb);
-		k_rad_source<<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+		if (most >= (int64_t(1) << 31))
+			return QK_ERR_UNSUPPORTED;
+#define QK_SRC_LAUNCH(DIV, MINB) k_rad_source<DIV, MINB><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount)
+		if (plain_div) {
+			switch (minb) {
+			case 3: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 3); break;
+			case 5: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 5); break;
+			case 4: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 4); break;
+			case 6: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 6); break;
+			case 7: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 7); break;
+			case 10: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 10); break;
+			default: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 8); break;
+			}
+		} else {
+			switch (minb) {
+			case 3: QK_SRC_LAUNCH(DivShared, 3); break;
+			case 5: QK_SRC_LAUNCH(DivShared, 5); break;
+			default: QK_SRC_LAUNCH(DivShared, 4); break;
+			}
+		}
+#undef QK_SRC_LAUNCH
 		QK_KERNEL_CHECK();
 	}
 	if (counters) {

@@ -22,8 +22,10 @@
 #ifndef QK_HD
 #ifdef __CUDACC__
 #define QK_HD __host__ __device__ __forceinline__
+#define QK_HDM __host__ __device__ __forceinline__ // for static member functions
 #else
 #define QK_HD static inline
+#define QK_HDM inline
 #endif
 #endif
 
@@ -81,58 +83,98 @@ template <int N> QK_HD double pow_dd(double x)
 	return (s == s && fabs(s) <= 1.79769313486231570815e308 && fabs(p) >= 1e-280) ? s : ((N == 4) ? (x * x) * (x * x) : (x * x) * x);
 }
 
+// ---- division policies.  Every `a / b` of the reference is IEEE division; D::div(a, D::rcp(b)) returns exactly that
+// quotient.  DivPlain is the literal form (host mirror, device fallback).  The device's DivShared (qk_rad_source.cu, built
+// on qk_div.cuh) refines the reciprocal of a denominator once with the compiler's own instruction sequence and reuses it for
+// every numerator over that denominator -- bit-identical, 3 FP64 instructions per quotient instead of 8 + MUFU.  Denominators
+// that are constant over a call (k_B, mu m_u, gamma - 1, a_rad, c c_hat, ...) or over a cell (rho, 2 rho, tau) get their
+// reciprocal once per thread, those of one Newton-Raphson iteration (c_v, det) once per iteration.
+enum { C_KB = 0, C_kB, C_mumn, C_gm1, C_arad, C_kPoE, C_cc, C_cchat, C_N }; // the call-constant denominators
+struct DivPlain {
+	struct R {
+		double b;
+	};
+	struct CTab {
+		double b[C_N];
+	};
+	QK_HDM static double divc(double a, const CTab &t, int idx) { return a / t.b[idx]; }
+	QK_HDM static R rcp(double b)
+	{
+		R r;
+		r.b = b;
+		return r;
+	}
+	QK_HDM static double div(double a, const R &r) { return a / r.b; }
+};
+
+template <class D> struct Recips { // per thread
+	typename D::R rho, rho2; // cell constants: rho, 2 rho
+	double r, rhoinv;	 // eos: clamped density and 1 / it
+};
+QK_HD void const_denoms(const Const &k, double b[C_N])
+{
+	b[C_KB] = K_B;
+	b[C_kB] = k.kB;
+	b[C_mumn] = k.mumn;
+	b[C_gm1] = k.gm1;
+	b[C_arad] = k.a_rad;
+	b[C_kPoE] = k.kPoE;
+	b[C_cc] = k.cc;
+	b[C_cchat] = k.c_chat;
+}
+
 // ---- gamma-law EOS through Microphysics (interfaces/eos.H:395-435,141-205,69-79; EOS/gamma_law/actual_eos.H:47-294) as
 // called by EOS<problem_t>::ComputeTgasFromEint / ComputeEintFromTgas / ComputeEintTempDerivative (src/hydro/EOS.hpp:75-157,200-240)
 QK_HD double eos_clamp_rho(const Const &k, double rho) { return mn(1.e200, mx(k.mindens, rho)); }
 QK_HD double eos_clamp_T(const Const &k, double T) { return mn(1.e200, mx(k.mintemp, T)); }
-QK_HD double tgas_from_eint(const Const &k, double rho, double Eint)
+template <class D> QK_HD double tgas_from_eint(const Const &k, const typename D::CTab &ct, const Recips<D> &q, double Eint)
 {
-	const double e = Eint / rho;
+	const double e = D::div(Eint, q.rho);
 	double T;
 	if (e < 1.e-200 || e > 1.e200)
 		T = k.mintemp; // eos_reset: T = clamp(0)
 	else
-		T = e * k.mu * M_U * k.gm1 / K_B; // actual_eos.H:128
-	return T * K_B / k.kB;
+		T = D::divc(e * k.mu * M_U * k.gm1, ct, C_KB); // actual_eos.H:128
+	return D::divc(T * K_B, ct, C_kB);
 }
 // e(rho, T) of eos_input_rt and the clamped temperature it was evaluated at
-QK_HD double eos_e_of_rT(const Const &k, double rho, double Tgas, double &T)
+template <class D> QK_HD double eos_e_of_rT(const Const &k, const typename D::CTab &ct, const Recips<D> &q, double Tgas, double &T)
 {
-	const double r = eos_clamp_rho(k, rho);
 	T = eos_clamp_T(k, Tgas);
-	const double rhoinv = 1.0 / r;
-	const double pressure = r * T * K_B / k.mumn; // actual_eos.H:199
-	return pressure / k.gm1 * rhoinv;	       // :200
+	const double pressure = D::divc(q.r * T * K_B, ct, C_mumn); // actual_eos.H:199
+	return D::divc(pressure, ct, C_gm1) * q.rhoinv;	       // :200
 }
-QK_HD double eint_from_tgas(const Const &k, double rho, double Tgas)
+template <class D> QK_HD double eint_from_tgas(const Const &k, const typename D::CTab &ct, const Recips<D> &q, double rho, double Tgas)
 {
 	double T;
-	const double e = eos_e_of_rT(k, rho, Tgas, T);
-	return e * rho * k.kB / K_B;
+	const double e = eos_e_of_rT<D>(k, ct, q, Tgas, T);
+	return D::divc(e * rho * k.kB, ct, C_KB);
 }
-QK_HD double eint_temp_derivative(const Const &k, double rho, double Tgas)
+template <class D> QK_HD double eint_temp_derivative(const Const &k, const typename D::CTab &ct, const Recips<D> &q, double rho, double Tgas)
 {
 	double T;
-	const double e = eos_e_of_rT(k, rho, Tgas, T);
+	const double e = eos_e_of_rT<D>(k, ct, q, Tgas, T);
 	const double dedT = e * (1.0 / T); // actual_eos.H:194,227
-	return dedT * rho * k.kB / K_B;
+	return D::divc(dedT * rho * k.kB, ct, C_KB);
 }
 
 // RadSystem::ComputeEgasFromEint - Eint part (radiation_system.hpp:1289-1309): the kinetic energy p^2 / (2 rho)
-QK_HD double ekin_of(double rho, double px, double py, double pz)
+template <class D> QK_HD double ekin_of(const Recips<D> &q, double px, double py, double pz)
 {
 	const double p_sq = px * px + py * py + pz * pz;
-	return p_sq / (2.0 * rho);
+	return D::div(p_sq, q.rho2);
 }
 
 // RadSystem::ComputeEddingtonFactor :773-790 + ComputeEddingtonTensor :873-916
-QK_HD void eddington_tensor(double fx, double fy, double fz, double T[3][3])
+template <class D> QK_HD void eddington_tensor(double fx, double fy, double fz, double T[3][3])
 {
 	const double f = sqrt(fx * fx + fy * fy + fz * fz);
 	const double fvec[3] = {fx, fy, fz};
 	double n[3];
+	const bool fpos = (f > 0.);
+	const typename D::R Rf = D::rcp(fpos ? f : 1.0);
 	for (int ii = 0; ii < 3; ++ii)
-		n[ii] = (f > 0.) ? (fvec[ii] / f) : 0.;
+		n[ii] = fpos ? D::div(fvec[ii], Rf) : 0.;
 	const double fc = (f < 0.) ? 0. : (1. < f) ? 1. : f; // std::clamp(f, 0., 1.)
 	const double f_fac = sqrt(4.0 - 3.0 * (fc * fc));
 	const double chi = (3.0 + 4.0 * (fc * fc)) / (5.0 + 2.0 * f_fac);
@@ -163,8 +205,9 @@ QK_HD void solve3x3(double C00, double C01, double C02, double C10, double C11, 
 	X[2] = X2;
 }
 
-QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
+template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab &ct, const CellIn &in, CellOut &out)
 {
+	typedef typename D::R Rc;
 	const double c = k.c, chat = k.chat, cscale = k.cscale, dt = k.dt;
 	const double rho = in.rho;
 	const double Egastot0 = in.Egastot, Erad0 = in.Erad;
@@ -172,6 +215,12 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 	const bool gas = (k.gamma != 1.0);
 	const int beta_order = k.beta_order;
 	const double nan = NAN;
+
+	Recips<D> q;
+	q.rho = D::rcp(rho);
+	q.rho2 = D::rcp(2.0 * rho);
+	q.r = eos_clamp_rho(k, rho);
+	q.rhoinv = (q.r == rho) ? D::div(1.0, q.rho) : (1.0 / q.r);
 
 	double Egas0 = nan, Ekin0 = nan, Etot0 = nan, Egas_guess = nan;
 	double lorentz_factor = nan, lorentz_factor_v = nan, lorentz_factor_v_v = nan;
@@ -182,24 +231,30 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 	out.solves = out.nr_iters = out.nr_max = out.fail_nr = out.fail_outer = 0;
 
 	if (gas) { // :82-86
-		Egas0 = Egastot0 - ekin_of(rho, in.mom[0], in.mom[1], in.mom[2]);
+		Egas0 = Egastot0 - ekin_of<D>(q, in.mom[0], in.mom[1], in.mom[2]);
 		Etot0 = Egas0 + cscale * (Erad0 + Src);
 		Ekin0 = Egastot0 - Egas0;
-		const double betaSqr = (in.mom[0] * in.mom[0] + in.mom[1] * in.mom[1] + in.mom[2] * in.mom[2]) / (rho * rho * c * c);
 		if (beta_order == 0 || beta_order == 1) { // :115-131
 			lorentz_factor = 1.0;
 			lorentz_factor_v = 1.0;
-		} else if (beta_order == 2) {
-			lorentz_factor = 1.0 + 0.5 * betaSqr;
-			lorentz_factor_v = 1.0;
-			lorentz_factor_v_v = 1.0;
-		} else { // beta_order == 3 (static_assert(beta_order_ <= 3) :113)
-			lorentz_factor = 1.0 + 0.5 * betaSqr;
-			lorentz_factor_v = 1.0 + 0.5 * betaSqr;
-			lorentz_factor_v_v = 1.0;
+		} else {
+			const double betaSqr = (in.mom[0] * in.mom[0] + in.mom[1] * in.mom[1] + in.mom[2] * in.mom[2]) / (rho * rho * c * c);
+			if (beta_order == 2) {
+				lorentz_factor = 1.0 + 0.5 * betaSqr;
+				lorentz_factor_v = 1.0;
+				lorentz_factor_v_v = 1.0;
+			} else { // beta_order == 3 (static_assert(beta_order_ <= 3) :113)
+				lorentz_factor = 1.0 + 0.5 * betaSqr;
+				lorentz_factor_v = 1.0 + 0.5 * betaSqr;
+				lorentz_factor_v_v = 1.0;
+			}
 		}
 	}
 	const double resid_limit = 1.0e-11 * Etot0; // resid_tol * Etot0 :158,254
+	// tau = dt rho kappaP chat lorentz_factor (:210,217) and J11 (:296-300) do not change within a cell
+	const double tau = dt * rho * kappaP * chat * lorentz_factor;
+	const Rc Rtau = D::rcp(tau);
+	const double J11 = (tau <= 0.0) ? -INFINITY : (D::div(-1.0 * kappaPoverE, Rtau) - 1.0);
 
 	const int max_ite = 5;
 	int ite = 0;
@@ -207,27 +262,22 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 		double R = nan;
 		Erad_guess = Erad0;
 		if (gas) {
-			double tau = nan;
 			Egas_guess = Egas0;
 			const int maxIter = 100;
 			int n = 0;
 			for (; n < maxIter; ++n) { // Newton-Raphson :161-352
-				const double T_gas = tgas_from_eint(k, rho, Egas_guess);
+				const double T_gas = tgas_from_eint<D>(k, ct, q, Egas_guess);
 				const double T_d = T_gas;
 				fourPiBoverC = k.a_rad * pow_dd<4>(T_d); // ComputeThermalRadiationSingleGroup :471-479
 				if (fourPiBoverC < k.floor_g)
 					fourPiBoverC = k.floor_g;
 				if (n == 0) { // :192-215
 					if (beta_order != 0 && ite == 0)
-						work = (in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat / k.cc *
+						work = D::divc((in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat, ct, C_cc) *
 						       lorentz_factor_v * dt;
-					const double tau0 = dt * rho * kappaP * chat * lorentz_factor;
-					tau = tau0;
-					R = (fourPiBoverC - Erad_guess / kappaPoverE) * tau0 + work;
-				} else { // :216-232
-					tau = dt * rho * kappaP * chat * lorentz_factor;
-					if (tau > 0.0)
-						Erad_guess = kappaPoverE * (fourPiBoverC - (R - work) / tau);
+					R = (fourPiBoverC - D::divc(Erad_guess, ct, C_kPoE)) * tau + work;
+				} else if (tau > 0.0) { // :216-232
+					Erad_guess = kappaPoverE * (fourPiBoverC - D::div(R - work, Rtau));
 				}
 				// cooling = cooling_derivative = 0, CR_heating = 0 * dt: the terms are kept so that signed zeros and
 				// non-finite dt propagate as in the reference (:234-245)
@@ -238,21 +288,33 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 				const double F_D_abs = (tau > 0.0) ? fabs(F_D) : fabs(F_D + R);
 				if ((fabs(F_G) < resid_limit) && (cscale * F_D_abs < resid_limit))
 					break;
-				const double c_v = eint_temp_derivative(k, rho, T_gas);
+				const double c_v = eint_temp_derivative<D>(k, ct, q, rho, T_gas);
+				const Rc Rcv = D::rcp(c_v);
 				const double d_fourpiboverc_d_t = 4. * k.a_rad * pow_dd<3>(T_d); // :499-503
 				const double dEg_dT = kappaPoverE * d_fourpiboverc_d_t;
-				const double J00 = 1.0 + cooling_derivative * dt / c_v;
+				// 0 * dt / c_v is +-0 for finite dt and finite non-zero c_v, so J00 is exactly 1; otherwise the quotient is formed
+				const double zdt = cooling_derivative * dt;
+				const double J00 = (zdt == 0.0 && c_v != 0.0 && fabs(c_v) <= 1.79769313486231570815e308) ? 1.0 : (1.0 + D::div(zdt, Rcv));
 				const double J01 = cscale;
-				const double J10 = 1.0 / c_v * dEg_dT - k.inv_cscale * cooling_derivative * dt;
-				const double J11 = (tau <= 0.0) ? -INFINITY : (-1.0 * kappaPoverE / tau - 1.0);
+				const double J10 = D::div(1.0, Rcv) * dEg_dT - k.inv_cscale * cooling_derivative * dt;
 				const double y0 = -F_G;
 				const double y1 = -1. * F_D;
 				const double det = J00 * J11 - J01 * J10;
-				const double deltaEgas = (J11 * y0 - J01 * y1) / det;
-				const double deltaR = (J00 * y1 - J10 * y0) / det;
-				const double T_rad = sqrt(sqrt(Erad_guess / k.a_rad)); // enable_dE_constrain :330-342
-				if (deltaEgas / c_v > mx(T_gas, T_rad)) {
-					Egas_guess = eint_from_tgas(k, rho, T_rad);
+				const Rc Rdet = D::rcp(det);
+				const double deltaEgas = D::div(J11 * y0 - J01 * y1, Rdet);
+				const double deltaR = D::div(J00 * y1 - J10 * y0, Rdet);
+				// enable_dE_constrain :330-342: deltaEgas / c_v > std::max(T_gas, T_rad), T_rad = (E_rad / a_rad)^(1/4).  The
+				// comparison is false whenever the quotient does not exceed T_gas (std::max(T_gas, NaN) is T_gas), so T_rad
+				// (a division and two square roots) is only formed for steps that jump by more than T_gas
+				const double dT = D::div(deltaEgas, Rcv);
+				double T_rad = 0.0;
+				bool jump = (dT > T_gas);
+				if (jump) {
+					T_rad = sqrt(sqrt(D::divc(Erad_guess, ct, C_arad)));
+					jump = (dT > mx(T_gas, T_rad));
+				}
+				if (jump) {
+					Egas_guess = eint_from_tgas<D>(k, ct, q, rho, T_rad);
 				} else {
 					Egas_guess += deltaEgas;
 					R += deltaR;
@@ -271,12 +333,13 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 		if (gas && (beta_order != 0)) {
 			const double erad = Erad_guess;
 			double v_terms[3];
-			const double fx = in.F[0] / (c * erad);
-			const double fy = in.F[1] / (c * erad);
-			const double fz = in.F[2] / (c * erad);
+			const Rc Rce = D::rcp(c * erad);
+			const double fx = D::div(in.F[0], Rce);
+			const double fy = D::div(in.F[1], Rce);
+			const double fz = D::div(in.F[2], Rce);
 			const double F_coeff = chat * rho * kappaF * dt * lorentz_factor;
 			double Tedd[3][3];
-			eddington_tensor(fx, fy, fz, Tedd);
+			eddington_tensor<D>(fx, fy, fz, Tedd);
 			const double lfv3 = (kappaF != kappaE) ? pow_dd<3>(lorentz_factor_v) : 0.;
 			for (int n = 0; n < 3; ++n) {
 				double Planck_term = kappaP * fourPiBoverC * lorentz_factor_v;
@@ -290,9 +353,10 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 				v_terms[n] = Planck_term + pressure_term;
 			}
 			if (beta_order == 1 || kappaF == kappaE) {
+				const Rc Rfc = D::rcp(1.0 + F_coeff);
 				for (int n = 0; n < 3; ++n) {
-					Frad_t1[n] = (in.F[n] + v_terms[n]) / (1.0 + F_coeff);
-					dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+					Frad_t1[n] = D::div(in.F[n] + v_terms[n], Rfc);
+					dMomentum[n] += D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
 				}
 			} else {
 				// gasVel is declared and never assigned in the reference (:407), so the K0 v_i v_j terms are K0 * 0 * 0; they
@@ -311,12 +375,13 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 				solve3x3(A00, A01, A02, A10, A11, A12, A20, A21, A22, v_terms[0] + in.F[0], v_terms[1] + in.F[1], v_terms[2] + in.F[2],
 					 Frad_t1);
 				for (int n = 0; n < 3; ++n)
-					dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+					dMomentum[n] += D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
 			}
 		} else { // :484-490
+			const Rc Rfc = D::rcp(1.0 + rho * kappaF * chat * dt);
 			for (int n = 0; n < 3; ++n) {
-				Frad_t1[n] = in.F[n] / (1.0 + rho * kappaF * chat * dt);
-				dMomentum[n] += -(Frad_t1[n] - in.F[n]) / k.c_chat;
+				Frad_t1[n] = D::div(in.F[n], Rfc);
+				dMomentum[n] += D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
 			}
 		}
 		const double x1GasMom1 = in.mom[0] + dMomentum[0];
@@ -327,13 +392,13 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 		if (!gas || beta_order == 0)
 			break;
 		{
-			const double Egastot1 = Egas_guess + ekin_of(rho, x1GasMom1, x2GasMom1, x3GasMom1);
+			const double Egastot1 = Egas_guess + ekin_of<D>(q, x1GasMom1, x2GasMom1, x3GasMom1);
 			const double Ekin1 = Egastot1 - Egas_guess;
 			const double dEkin_work = Ekin1 - Ekin0;
 			Egas_guess -= dEkin_work;
 		}
 		work_prev = work;
-		work = (x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat / k.cc * lorentz_factor_v * k.two_kE_m_kF * dt;
+		work = D::divc((x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat, ct, C_cc) * lorentz_factor_v * k.two_kE_m_kF * dt;
 		const double lag_tol = 1.0e-13;
 		const double dwork = fabs(work - work_prev);
 		if ((fabs(work) == 0.0) || (cscale * dwork < lag_tol * Etot0) || (dwork <= lag_tol * R) || (dwork <= 1.0e-8 * fabs(work)))
@@ -350,7 +415,7 @@ QK_HD void source_cell(const Const &k, const CellIn &in, CellOut &out)
 	if (gas) {
 		Egas_guess = Egas0 + (Egas_guess - Egas0) * k.gas_update_factor;
 		out.Eint = Egas_guess;
-		out.Egastot = Egas_guess + ekin_of(rho, out.mom[0], out.mom[1], out.mom[2]);
+		out.Egastot = Egas_guess + ekin_of<D>(q, out.mom[0], out.mom[1], out.mom[2]);
 		out.Erad = Erad_guess;
 	} else {
 		out.Eint = nan; // not written by the reference (:558-571); the caller skips these three

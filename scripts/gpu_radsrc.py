@@ -15,9 +15,12 @@ os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 import pytest
 import torch
 
-rc = pytest.main(["-q", "-x", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_zgpu_rad_source.py"),
-                  f"--junitxml={ROOT}/gpurun_out/radsrc_tests.xml"])
-open(os.path.join(ROOT, "gpurun_out", "radsrc_tests.log"), "w").write(f"pytest exit code {int(rc)}\n")
+TIME_ONLY = "--time-only" in sys.argv  # (for the ncu capture: no tests, one repetition)
+rc = -1
+if not TIME_ONLY:
+    rc = pytest.main(["-q", "-p", "no:cacheprovider", os.path.join(ROOT, "tests", "test_zgpu_rad_source.py"),
+                      f"--junitxml={ROOT}/gpurun_out/radsrc_tests.xml"])
+    open(os.path.join(ROOT, "gpurun_out", "radsrc_tests.log"), "w").write(f"pytest exit code {int(rc)}\n")
 
 from quokka_b200 import capi
 from quokka_b200.capi import check, qk_box
@@ -51,10 +54,19 @@ for f in U.fabs:
     init.append(f.t.clone())
 ncell = 8 * 128 ** 3
 res = {}
-for dt in gen["dts"]:
+VARIANTS = [("default", None, None)] if TIME_ONLY else [("default", None, None)] + [(f"{d}{m}", d, m) for d, m in
+                                                                                  [("plain", 4), ("plain", 5), ("plain", 6), ("plain", 7), ("plain", 8),
+                                                                                   ("plain", 10), ("shared", 5)]]
+for variant, div, minb in VARIANTS:
+  for dt in (gen["dts"][1:2] if (TIME_ONLY or div) else gen["dts"]):
+    os.environ.pop("QK_RADSRC_PLAIN_DIV", None)
+    os.environ.pop("QK_RADSRC_MINB", None)
+    if div:
+        os.environ["QK_RADSRC_PLAIN_DIV"] = "1" if div == "plain" else "0"
+        os.environ["QK_RADSRC_MINB"] = str(minb)
     times = []
     cnt = (C.c_int64 * 7)()
-    for rep in range(4):
+    for rep in range(2 if TIME_ONLY else 4):
         for f, t0 in zip(U.fabs, init):
             f.t.copy_(t0)
         torch.cuda.synchronize()
@@ -68,9 +80,10 @@ for dt in gen["dts"]:
         f.t.copy_(t0)
     check(lib.qk_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), 1, len(boxes), U.boxes_c, U.descs, None, dt, cnt, None))
     ms = min(times[1:])
-    res[str(dt)] = {"ms": ms, "Mcell_per_s": ncell / ms / 1e3, "GBps_algorithmic_152B": ncell * 152 / ms / 1e6,
+    res[f"{variant}:{dt}"] = {"ms": ms, "Mcell_per_s": ncell / ms / 1e3, "GBps_algorithmic_152B": ncell * 152 / ms / 1e6,
                     "newton_iters_per_cell": cnt[1] / ncell, "solves_per_cell": cnt[0] / ncell, "max_newton": cnt[2], "fail": [cnt[4], cnt[6]]}
 out = {"kernel": "k_rad_source", "workload": "8 x 128^3, RadhydroShell traits, stage 1", "pytest_rc": int(rc), "by_dt_radiation": res,
        "gpu": torch.cuda.get_device_name(0)}
-open(os.path.join(ROOT, "gpurun_out", "radsrc_timing.json"), "w").write(json.dumps(out, indent=1))
+if not TIME_ONLY:
+    open(os.path.join(ROOT, "gpurun_out", "radsrc_timing.json"), "w").write(json.dumps(out, indent=1))
 print(json.dumps(out))

@@ -14,6 +14,8 @@ extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_ra
 {
 	const qk_rsrc::Const k = qk_rsrc::make_const(hp, rp, sp, dt_radiation, stage);
 	const int ns = rp->nstart;
+	qk_rsrc::DivPlain::CTab ct;
+	qk_rsrc::const_denoms(k, ct.b);
 	for (int kk = bx->lo[2]; kk <= bx->hi[2]; ++kk)
 		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
 			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
@@ -27,7 +29,7 @@ extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_ra
 				in.Egastot = at(cons, i, j, kk, 4);
 				in.Erad = at(cons, i, j, kk, ns);
 				in.src = src ? at(src, i, j, kk, 0) : 0.0;
-				qk_rsrc::source_cell(k, in, out);
+				qk_rsrc::source_cell<qk_rsrc::DivPlain>(k, ct, in, out);
 				for (int m = 0; m < 3; ++m) {
 					at(cons, i, j, kk, 1 + m) = out.mom[m];
 					at(cons, i, j, kk, ns + 1 + m) = out.F[m];

@@ -99,6 +99,28 @@ def test_source_terms_vs_oracle(name, stage):
         assert min(fracs) >= 0.98, fracs
 
 
+@pytest.mark.parametrize("name", TRAITS)
+def test_every_instantiation_is_bit_identical(name, monkeypatch):
+    """the kernel exists with two division policies -- quotients over a common denominator from one refined reciprocal
+    (qk_div.cuh) and the compiler's `/` everywhere (QK_RADSRC_PLAIN_DIV=1) -- and several register caps (QK_RADSRC_MINB
+    resident CTAs per SM).  Same bits, same counters, whichever runs."""
+    hp, rp, sp, gen = trait_set(name)
+    for n, dt in enumerate(gen["dts"]):
+        states = make_states(hp, rp, sp, gen, BOXES, seed=500 + n)
+        monkeypatch.delenv("QK_RADSRC_PLAIN_DIV", raising=False)
+        monkeypatch.delenv("QK_RADSRC_MINB", raising=False)
+        a, ca = run_gpu(hp, rp, sp, BOXES, states, None, dt, 1 + n % 2)
+        for plain, minb in [("1", "3"), ("1", "4"), ("1", "5"), ("1", "6"), ("1", "7"), ("1", "10"), ("0", "3"), ("0", "4"), ("0", "5")]:
+            monkeypatch.setenv("QK_RADSRC_PLAIN_DIV", plain)
+            monkeypatch.setenv("QK_RADSRC_MINB", minb)
+            b, cb = run_gpu(hp, rp, sp, BOXES, states, None, dt, 1 + n % 2)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y, equal_nan=True), (plain, minb)
+            assert ca == cb
+        monkeypatch.delenv("QK_RADSRC_PLAIN_DIV", raising=False)
+        monkeypatch.delenv("QK_RADSRC_MINB", raising=False)
+
+
 def test_counters_are_optional_and_accumulate():
     hp, rp, sp, gen = trait_set("shell")
     states = make_states(hp, rp, sp, gen, BOXES[:1], seed=3)
