@@ -334,6 +334,21 @@ template <typename problem_t> inline auto make_rad_params() -> qk_rad_params
 	return p;
 }
 
+// constant-opacity problems only (the reference's default specialisations and RadhydroShell's,
+// src/radiation/radiation_system.hpp:1141-1153, src/problems/RadhydroShell/test_radhydro_shell.cpp:127-135): the opacity
+// functions are sampled once; a problem whose opacities depend on rho or T keeps the reference's kernel
+template <typename problem_t> inline auto make_rad_source_params() -> qk_rad_source_params
+{
+	qk_rad_source_params p{};
+	p.radiation_constant = RadSystem<problem_t>::radiation_constant_;
+	p.kappa_P = RadSystem<problem_t>::ComputePlanckOpacity(1.0, 1.0);
+	p.kappa_E = RadSystem<problem_t>::ComputeEnergyMeanOpacity(1.0, 1.0);
+	p.kappa_F = RadSystem<problem_t>::ComputeFluxMeanOpacity(1.0, 1.0);
+	p.beta_order = RadSystem<problem_t>::beta_order_;
+	p.opacity_model = QK_OPACITY_CONSTANT;
+	return p;
+}
+
 template <typename problem_t> class RadSystemB200
 {
       public:
@@ -403,6 +418,53 @@ template <typename problem_t> class RadSystemB200
 		const double dx[3] = {dx_in[0], dx_in[1], dx_in[2]};
 		check(qk_rad_add_fluxes_rk2(&prm, 1, &bx, &un, &u0, &u1, &fo[0], &fo[1], &fo[2], &fn[0], &fn[1], &fn[2], dt_in, dx, stream()),
 		      "RadSystem::AddFluxesRK2");
+	}
+
+	// RadSystem::AddSourceTermsSingleGroup(consVar, radEnergySource, indexRange, dt, stage, dustGasCoeff, p_iteration_counter,
+	// p_iteration_failure_counter)  src/radiation/source_terms_single_group.hpp:9-565, one FAB as operatorSplitSourceTerms calls it
+	// (src/QuokkaSimulation.hpp:1876).  The counters are HOST ints here (the reference passes device pointers it copies back,
+	// :1620-1625,1661); nullptr keeps the call asynchronous.
+	static void AddSourceTermsSingleGroup(array_t &consVar, arrayconst_t &radEnergySource, amrex::Box const &indexRange, amrex::Real dt, int stage,
+					      double /*dustGasCoeff*/, int *h_iteration_counter, int *h_iteration_failure_counter)
+	{
+		static_assert(!RadSystem<problem_t>::enable_dust_gas_thermal_coupling_model_, "libquokka_b200: the dust-gas coupling model is not provided");
+		const qk_hydro_params hp = make_params<problem_t>();
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_rad_source_params sp = make_rad_source_params<problem_t>();
+		const qk_array4 c = view(consVar);
+		const qk_array4 e = view(radEnergySource);
+		const qk_box bx = to_box(indexRange);
+		int64_t cnt[QK_RAD_SOURCE_NCOUNTERS] = {0, 0, 0, 0, 0, 0, 0};
+		const bool want = (h_iteration_counter != nullptr) || (h_iteration_failure_counter != nullptr);
+		check(qk_rad_add_source_terms(&hp, &prm, &sp, stage, 1, &bx, &c, &e, dt, want ? cnt : nullptr, stream()), "RadSystem::AddSourceTermsSingleGroup");
+		if (h_iteration_counter != nullptr) {
+			h_iteration_counter[0] += static_cast<int>(cnt[0]);
+			h_iteration_counter[1] += static_cast<int>(cnt[1]);
+			h_iteration_counter[2] = std::max(h_iteration_counter[2], static_cast<int>(cnt[2]));
+		}
+		if (h_iteration_failure_counter != nullptr) {
+			for (int n = 0; n < 3; ++n) {
+				h_iteration_failure_counter[n] += static_cast<int>(cnt[4 + n]);
+			}
+		}
+	}
+
+	// the same for the whole level in ONE launch: replaces both MFIter loops around operatorSplitSourceTerms
+	// (src/QuokkaSimulation.hpp:1631-1658); radEnergySource may be nullptr (SetRadEnergySource's default is zero, :582-587)
+	static void AddSourceTermsSingleGroup(amrex::MultiFab &state, amrex::MultiFab const *radEnergySource, amrex::Real dt, int stage, int64_t *counters)
+	{
+		const qk_hydro_params hp = make_params<problem_t>();
+		const qk_rad_params prm = make_rad_params<problem_t>();
+		const qk_rad_source_params sp = make_rad_source_params<problem_t>();
+		MFView s(state);
+		if (radEnergySource != nullptr) {
+			MFView e(*radEnergySource);
+			check(qk_rad_add_source_terms(&hp, &prm, &sp, stage, s.n(), s.valid.data(), s.arr.data(), e.arr.data(), dt, counters, stream()),
+			      "RadSystem::AddSourceTermsSingleGroup");
+		} else {
+			check(qk_rad_add_source_terms(&hp, &prm, &sp, stage, s.n(), s.valid.data(), s.arr.data(), nullptr, dt, counters, stream()),
+			      "RadSystem::AddSourceTermsSingleGroup");
+		}
 	}
 };
 

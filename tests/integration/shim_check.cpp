@@ -110,6 +110,20 @@ template void rad_box<quokka::b200::RadSystemB200<RadLike>>(amrex::FArrayBox &, 
 							    std::array<amrex::FArrayBox, 3> &, std::array<amrex::FArrayBox, 3> &, amrex::FArrayBox &,
 							    amrex::FArrayBox &, amrex::Box const &, double, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM>);
 
+// matter-radiation source terms: the reference's Array4 call (QuokkaSimulation.hpp:1876) and the level-wide form
+template <typename Rad> void rad_source_box(amrex::FArrayBox &cons, amrex::FArrayBox &esrc, amrex::Box const &bx, double dt, int *it, int *fail)
+{
+	Rad::AddSourceTermsSingleGroup(cons.array(), esrc.const_array(), bx, dt, 1, 0.0, it, fail);
+	Rad::AddSourceTermsSingleGroup(cons.array(), esrc.const_array(), bx, dt, 2, 0.0, it, fail);
+}
+template void rad_source_box<RadSystem<RadLike>>(amrex::FArrayBox &, amrex::FArrayBox &, amrex::Box const &, double, int *, int *);
+template void rad_source_box<quokka::b200::RadSystemB200<RadLike>>(amrex::FArrayBox &, amrex::FArrayBox &, amrex::Box const &, double, int *, int *);
+void rad_source_level(amrex::MultiFab &state, double dt, int64_t *counters)
+{
+	quokka::b200::RadSystemB200<RadLike>::AddSourceTermsSingleGroup(state, nullptr, dt, 1, counters);
+	quokka::b200::RadSystemB200<RadLike>::AddSourceTermsSingleGroup(state, nullptr, dt, 2, counters);
+}
+
 void rad_level(quokka::b200::LevelB200 &lev, amrex::MultiFab &U0, amrex::MultiFab &U1, amrex::MultiFab &Unew, double dt)
 {
 	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();
