@@ -1702,9 +1702,21 @@ int orc_advance_hydro_level(orc_level *L, const qk_hydro_params *prm, double dt,
 }
 
 /* AMRSimulation::computeTimestep, single level  src/simulation.hpp:703-818 */
+static double compute_timestep_floor(orc_level *L, const qk_hydro_params *prm, double cfl, double t_now, double stop_time, double signal_floor);
 double orc_compute_timestep(orc_level *L, const qk_hydro_params *prm, double cfl, double t_now, double stop_time)
 {
-	double smax = 0.0;
+	return compute_timestep_floor(L, prm, cfl, t_now, stop_time, 0.0);
+}
+/* radiation hydrodynamics: computeMaxSignalLocal (src/QuokkaSimulation.hpp:408-441) takes, per cell, std::max(c_hat / maxSubsteps_,
+ * hydro signal speed) (RadSystem::ComputeMaxSignalSpeed = c_hat, src/radiation/radiation_system.hpp:617-624) */
+double orc_compute_timestep_radhydro(orc_level *L, const qk_hydro_params *prm, const qk_rad_params *rp, int max_substeps, double cfl, double t_now,
+				     double stop_time)
+{
+	return compute_timestep_floor(L, prm, cfl, t_now, stop_time, rp->c_hat / (double)max_substeps);
+}
+static double compute_timestep_floor(orc_level *L, const qk_hydro_params *prm, double cfl, double t_now, double stop_time, double signal_floor)
+{
+	double smax = signal_floor;
 	for (int b = 0; b < L->nb; ++b) {
 		qk_array4 s = orc_level_state(L, 0, b);
 		smax = dmax(smax, orc_max_signal_speed(prm, 0, &s, &L->boxes[b]));
@@ -1803,15 +1815,11 @@ static void rad_fluxes_of_box(const qk_rad_params *prm, const qk_array4 *U, cons
 	free_a4(&prim);
 }
 
-void orc_rad_advance_level(orc_level *L, const qk_rad_params *prm, double dt)
+/* advanceRadiationForwardEuler :1791-1822 */
+static void rad_stage1_level(orc_level *L, const qk_rad_params *prm, double dt, qk_array4 *Uold, qk_array4 *Unew)
 {
 	const int nb = L->nb, ng = L->d.nghost, nc = L->d.ncomp;
 	const double *dx = L->d.dx;
-	qk_array4 *Uold = malloc(sizeof(qk_array4) * nb), *Unew = malloc(sizeof(qk_array4) * nb);
-	for (int b = 0; b < nb; ++b) {
-		Uold[b] = orc_level_state(L, 1, b);
-		Unew[b] = orc_level_state(L, 0, b);
-	}
 	orc_fill_boundary(L, Uold, 0, nc); /* :1798 */
 	for (int b = 0; b < nb; ++b) {
 		qk_array4 f[3];
@@ -1820,23 +1828,111 @@ void orc_rad_advance_level(orc_level *L, const qk_rad_params *prm, double dt)
 		for (int d = 0; d < 3; ++d)
 			free_a4(&f[d]);
 	}
-	if (prm->integrator_order == 2) {
-		orc_fill_boundary(L, Unew, 0, nc); /* :1831 */
-		/* stateInter and stateNew alias in the reference (:1840-1841): every box's fluxes are computed from the intermediate
-		 * state before that box is overwritten, and ghost cells of other boxes are not touched by the update */
-		for (int b = 0; b < nb; ++b) {
-			qk_array4 fo[3], f[3];
-			rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, fo);
-			rad_fluxes_of_box(prm, &Unew[b], L->boxes[b], ng, f);
-			orc_rad_add_fluxes_rk2(prm, &Unew[b], &Uold[b], &Unew[b], &fo[0], &fo[1], &fo[2], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
-			for (int d = 0; d < 3; ++d) {
-				free_a4(&fo[d]);
-				free_a4(&f[d]);
-			}
+}
+/* advanceRadiationMidpointRK2 :1824-1862 */
+static void rad_stage2_level(orc_level *L, const qk_rad_params *prm, double dt, qk_array4 *Uold, qk_array4 *Unew)
+{
+	const int nb = L->nb, ng = L->d.nghost, nc = L->d.ncomp;
+	const double *dx = L->d.dx;
+	orc_fill_boundary(L, Unew, 0, nc); /* :1831 */
+	/* stateInter and stateNew alias in the reference (:1840-1841): every box's fluxes are computed from the intermediate
+	 * state before that box is overwritten, and ghost cells of other boxes are not touched by the update */
+	for (int b = 0; b < nb; ++b) {
+		qk_array4 fo[3], f[3];
+		rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, fo);
+		rad_fluxes_of_box(prm, &Unew[b], L->boxes[b], ng, f);
+		orc_rad_add_fluxes_rk2(prm, &Unew[b], &Uold[b], &Unew[b], &fo[0], &fo[1], &fo[2], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
+		for (int d = 0; d < 3; ++d) {
+			free_a4(&fo[d]);
+			free_a4(&f[d]);
 		}
+	}
+}
+
+void orc_rad_advance_level(orc_level *L, const qk_rad_params *prm, double dt)
+{
+	const int nb = L->nb;
+	qk_array4 *Uold = malloc(sizeof(qk_array4) * nb), *Unew = malloc(sizeof(qk_array4) * nb);
+	for (int b = 0; b < nb; ++b) {
+		Uold[b] = orc_level_state(L, 1, b);
+		Unew[b] = orc_level_state(L, 0, b);
+	}
+	rad_stage1_level(L, prm, dt, Uold, Unew);
+	if (prm->integrator_order == 2)
+		rad_stage2_level(L, prm, dt, Uold, Unew);
+	free(Uold);
+	free(Unew);
+}
+
+/* computeNumberOfRadiationSubsteps  src/QuokkaSimulation.hpp:397-406 */
+int orc_rad_num_substeps(const orc_level *L, const qk_rad_params *prm, double rad_cfl, double dt_hydro)
+{
+	const double *dx = L->d.dx;
+	const double dx_min = dmin(dmin(dx[0], dx[1]), dx[2]);
+	const double dtrad_tmp = rad_cfl * (dx_min / prm->c_hat);
+	return (int)ceil(dt_hydro / dtrad_tmp);
+}
+
+/* subcycleRadiationAtLevel  src/QuokkaSimulation.hpp:1577-1700 (hydro enabled, no constant dt, no flux registers): nsub IMEX PD-ARS
+ * substeps, each = transport stage 1 (old -> new), source terms of stage 1 on new, transport stage 2, source terms of stage 2.
+ * esrc: radEnergySource per box (SetRadEnergySource is evaluated at time + dt but is time-independent for the problems used
+ * here) or NULL.  Returns nsub. */
+int orc_rad_subcycle_level(orc_level *L, const qk_hydro_params *hp, const qk_rad_params *prm, const qk_rad_source_params *sp, const qk_array4 *esrc,
+			   double dt_hydro, double rad_cfl, int64_t *counters)
+{
+	const int nb = L->nb, ns = prm->nstart, nh = 4 * prm->ngroups;
+	const int nsub = orc_rad_num_substeps(L, prm, rad_cfl, dt_hydro);
+	const double dt_radiation = dt_hydro / (double)nsub;
+	qk_array4 *Uold = malloc(sizeof(qk_array4) * nb), *Unew = malloc(sizeof(qk_array4) * nb);
+	for (int b = 0; b < nb; ++b) {
+		Uold[b] = orc_level_state(L, 1, b);
+		Unew[b] = orc_level_state(L, 0, b);
+	}
+	for (int i = 0; i < nsub; ++i) {
+		if (i > 0) /* swapRadiationState: MultiFab::Copy(old, new, nstart, nstart, ncompHyperbolic, 0)  :1570-1574,1604-1610 */
+			for (int b = 0; b < nb; ++b) {
+				const qk_box *vb = &L->boxes[b];
+				for (int n = ns; n < ns + nh; ++n)
+					for (int k = vb->lo[2]; k <= vb->hi[2]; ++k)
+						for (int j = vb->lo[1]; j <= vb->hi[1]; ++j)
+							for (int ii = vb->lo[0]; ii <= vb->hi[0]; ++ii)
+								A4(&Uold[b], ii, j, k, n) = A4(&Unew[b], ii, j, k, n);
+			}
+		rad_stage1_level(L, prm, dt_radiation, Uold, Unew);
+		for (int b = 0; b < nb; ++b) /* :1628-1641 */
+			orc_rad_add_source_terms(hp, prm, sp, &Unew[b], esrc ? &esrc[b] : NULL, &L->boxes[b], dt_radiation, 1, counters);
+		rad_stage2_level(L, prm, dt_radiation, Uold, Unew);
+		for (int b = 0; b < nb; ++b) /* :1649-1658 */
+			orc_rad_add_source_terms(hp, prm, sp, &Unew[b], esrc ? &esrc[b] : NULL, &L->boxes[b], dt_radiation, 2, counters);
 	}
 	free(Uold);
 	free(Unew);
+	return nsub;
+}
+
+/* Problem setup of config C4: RadSystem<ShellProblem>::SetRadEnergySource, src/problems/RadhydroShell/test_radhydro_shell.cpp:96-125
+ * (simulate_full_box = true): a Gaussian point-like source at the centre of the box.  Written in C with the same libm calls
+ * (std::pow(x, 2), std::exp) so that the array equals the reference's bit for bit.  out: one component on box bx. */
+void orc_shell_rad_energy_source(const qk_array4 *out, const qk_box *bx, const double dx[3], const double prob_lo[3], const double prob_hi[3])
+{
+	const double c = 2.99792458e10, Msun = 2.0e33, parsec_in_cm = 3.086e18;
+	const double specific_luminosity = 2000., GMC_mass = 1.0e6 * Msun, epsilon = 0.5;
+	const double L_star = (epsilon * GMC_mass) * specific_luminosity;
+	const double r_0 = 5.0 * parsec_in_cm, sigma_star = 0.3 * r_0;
+	const double x0 = prob_lo[0] + 0.5 * (prob_hi[0] - prob_lo[0]);
+	const double y0 = prob_lo[1] + 0.5 * (prob_hi[1] - prob_lo[1]);
+	const double z0 = prob_lo[2] + 0.5 * (prob_hi[2] - prob_lo[2]);
+	const double pi = 3.14159265358979323846; /* M_PI */
+	const double source_norm = (1.0 / c) * L_star / pow(2.0 * pi * sigma_star * sigma_star, 1.5);
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double x = prob_lo[0] + (i + 0.5) * dx[0];
+				const double y = prob_lo[1] + (j + 0.5) * dx[1];
+				const double z = prob_lo[2] + (k + 0.5) * dx[2];
+				const double r = sqrt(pow(x - x0, 2) + pow(y - y0, 2) + pow(z - z0, 2));
+				A4(out, i, j, k, 0) = source_norm * exp(-(r * r) / (2.0 * sigma_star * sigma_star));
+			}
 }
 
 /* swap state_new <-> state_old (the radiation subcycle copies new -> old, :1597-1600; a swap has the same effect for the

@@ -139,3 +139,62 @@ class SodProblem:
         v[4] = P / (self.gamma - 1.0) + 0.5 * rho * (0.0 * 0.0)
         v[5] = P / (self.gamma - 1.0)
         return a
+
+
+class ShellProblem:
+    """RadhydroShell (src/problems/RadhydroShell/test_radhydro_shell.cpp:34-93,127-135,396-431, tests/radhydro_shell*.in), config C4
+    of BASELINE.json on a uniform periodic level: gamma = 5/3, mu = 2.2 m_u, reduced speed of light 860 * 2e5 cm/s, constant opacity
+    20 cm^2/g, beta_order 1, PLM (minmod) hydro + PLM (MC) radiation, RK2, cfl 0.3 (hydro and radiation), density floor 1e-8 rho_0,
+    at most 10 radiation substeps per hydro step.  The initial condition (an interpolation table and libm pow calls) is taken
+    from the reference's own step-0 plotfile (tests/golden/shell*.npz), not re-derived."""
+
+    gamma = 5.0 / 3.0
+    cfl = 0.3
+    rad_cfl = 0.3  # radiationCflNumber_ (QuokkaSimulation.hpp:125)
+    max_substeps = 10  # maxSubsteps_ (:126)
+    ncomp = 10
+    nghost = 4
+    a_rad = 7.5646e-15
+    c_light = 2.99792458e10
+    c_hat = 860.0 * 2.0e5
+    kappa0 = 20.0
+    prob_hi = 3.086e19
+    r_0 = 5.0 * 3.086e18
+    rho_0 = ((1 - 0.5) * (1.0e6 * 2.0e33)) / ((4.0 / 3.0) * np.pi * r_0 * r_0 * r_0)
+    stop_time = 0.125 * (r_0 / 2.0e5)
+
+    def __init__(self, ncell, max_grid_size, initial=None):
+        from .capi import QK_BC_INT_DIR
+
+        self.ncell = [int(ncell)] * 3
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in self.ncell))
+        self.dx = [self.prob_hi / c for c in self.ncell]
+        self.boxes = chop_domain(self.ncell, max_grid_size)
+        self.periodic = (1, 1, 1)
+        self.bc_lo = [QK_BC_INT_DIR] * (3 * self.ncomp)
+        self.bc_hi = list(self.bc_lo)
+        self.initial = initial  # (10, nz, ny, nx) valid cells of the whole domain
+
+    def params(self, **kw):
+        from .capi import M_U, K_B
+
+        return hydro_params(gamma=self.gamma, reconstruct_eint=0, recon_order=2, density_floor=1.0e-8 * self.rho_0, mean_molecular_weight=2.2 * M_U,
+                            boltzmann_constant=K_B, **kw)
+
+    def rad_params(self):
+        from .capi import rad_params
+
+        return rad_params(c_light=self.c_light, c_hat=self.c_hat, Erad_floor=0.0, ngroups=1, nstart=6, recon_order=2, integrator_order=2)
+
+    def rad_source_params(self):
+        from .capi import rad_source_params
+
+        return rad_source_params(radiation_constant=self.a_rad, kappa_P=self.kappa0, beta_order=1)
+
+    def initial_state(self, box: qk_box, ng=None) -> np.ndarray:
+        ng = self.nghost if ng is None else ng
+        g = box.grown(ng)
+        nz, ny, nx = g.shape()
+        a = np.zeros((self.ncomp, nz, ny, nx))
+        a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng] = self.initial[:, box.lo[2]:box.hi[2] + 1, box.lo[1]:box.hi[1] + 1, box.lo[0]:box.hi[0] + 1]
+        return a

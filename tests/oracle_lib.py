@@ -77,6 +77,10 @@ def oracle() -> C.CDLL:
         "orc_rad_add_fluxes_rk2": (None, [_RPRM, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _BXP]),
         "orc_rad_advance_level": (None, [C.c_void_p, _RPRM, C.c_double]),
         "orc_rad_add_source_terms": (None, [_PRM, _RPRM, _RSPRM, _A4P, _A4P, _BXP, C.c_double, C.c_int, _I64P]),
+        "orc_rad_num_substeps": (C.c_int, [C.c_void_p, _RPRM, C.c_double, C.c_double]),
+        "orc_rad_subcycle_level": (C.c_int, [C.c_void_p, _PRM, _RPRM, _RSPRM, _A4P, C.c_double, C.c_double, _I64P]),
+        "orc_compute_timestep_radhydro": (C.c_double, [C.c_void_p, _PRM, _RPRM, C.c_int, C.c_double, C.c_double, C.c_double]),
+        "orc_shell_rad_energy_source": (None, [_A4P, _BXP, _D3, _D3, _D3]),
         "orc_level_swap": (None, [C.c_void_p]),
     }
     for name, (res, args) in sig.items():
