@@ -322,6 +322,25 @@ int qk_hydro_advance_stage(qk_level *lev, const qk_hydro_params *prm, int stage,
 int qk_rad_advance_stage(qk_level *lev, const qk_rad_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout,
 			 double dt, void *stream);
 
+/* QuokkaSimulation::subcycleRadiationAtLevel (src/QuokkaSimulation.hpp:1577-1700) for a uniform level, hydro enabled, no flux
+ * registers: nsub = computeNumberOfRadiationSubsteps (:397-406) = ceil(dt_hydro / (rad_cfl dx_min / c_hat)) IMEX PD-ARS substeps
+ * of dt_hydro / nsub, each
+ *     [i > 0: swapRadiationState, radiation components new -> old]                                  (:1570-1574,1604-1610)
+ *     ghost fill of U_old; transport stage 1 U_old -> U_new (advanceRadiationForwardEuler)          (:1791-1822)
+ *     source terms of stage 1 on U_new                                                              (:1628-1641)
+ *     ghost fill of U_new; transport stage 2 (advanceRadiationMidpointRK2)                          (:1824-1862)
+ *     source terms of stage 2 on U_new                                                              (:1649-1658)
+ * U_old = state_old_cc_ (pre-step state; its radiation components are overwritten from the second substep on, as in the
+ * reference), U_new = state_new_cc_ (hydro components already advanced; receives the result), U_tmp = a third MultiFab of the
+ * same shape owned by the caller: the fused transport stage may not write the array it reads its neighbours from, so stage 2
+ * goes U_new -> U_tmp and the four radiation components are copied back.  Only the radiation components' ghost cells are
+ * filled (the transport reads nothing else outside the valid boxes).  src may be NULL: transport only.
+ * rad_energy_source: one component per box or NULL.  counters as qk_rad_add_source_terms (accumulated over all substeps; the
+ * call synchronises when non-NULL).  nsub_out (may be NULL) receives nsub. */
+int qk_rad_subcycle(qk_level *lev, const qk_hydro_params *hydro, const qk_rad_params *prm, const qk_rad_source_params *src, const qk_array4 *U_old,
+		    const qk_array4 *U_new, const qk_array4 *U_tmp, const qk_array4 *rad_energy_source, double dt_hydro, double rad_cfl,
+		    int64_t *counters, int *nsub_out, void *stream);
+
 /* The same stage through the FAITHFUL path only: one kernel per reference operator, fluxes materialised as
  * MultiFabs exactly as QuokkaSimulation.hpp:1403-1490 does.  qk_hydro_advance_stage runs the fused sweep kernels
  * and falls back to this path when a cell is flagged (FOFC); both produce identical bits. */
@@ -374,6 +393,14 @@ void qk_sim_reset_clock(qk_sim *sim, double t, double dt_prev);
 int qk_sim_compute_timestep(qk_sim *sim, double stop_time, double *dt_out);
 /* one coarse step; *retries = number of dt-halving retries used, -1 if all 6 failed (the reference aborts there) */
 int qk_sim_step(qk_sim *sim, double dt, int *retries);
+/* Physics_Traits::is_radiation_enabled for this simulation: every qk_sim_step then runs subcycleRadiationAtLevel (qk_rad_subcycle)
+ * after the hydro advance (src/QuokkaSimulation.hpp:690-694) and qk_sim_compute_timestep takes std::max(c_hat / max_substeps,
+ * hydro signal speed) (computeMaxSignalLocal :408-441).  src == NULL: transport only.  rad_energy_source: one-component device
+ * FABs per local box (caller-owned, must outlive the simulation) or NULL.  The level must carry the radiation components. */
+int qk_sim_enable_radiation(qk_sim *sim, const qk_rad_params *rad, const qk_rad_source_params *src, const qk_array4 *rad_energy_source, double rad_cfl,
+			    int max_substeps);
+int qk_sim_last_rad_substeps(const qk_sim *sim);
+int64_t qk_sim_rad_cell_updates(const qk_sim *sim); /* radiationCellUpdates_, src/QuokkaSimulation.hpp:1697 */
 int qk_sim_evolve(qk_sim *sim, int max_steps, double stop_time, int *steps_done, double *elapsed_s, double *device_ms);
 
 #ifdef __cplusplus

@@ -252,6 +252,7 @@ SYMBOLS = {
     "qk_rad_predict_step": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
     "qk_rad_add_fluxes_rk2": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
     "qk_rad_add_source_terms": (C.c_int, [_PRM, _RPRM, _RSPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_double, _I64P, _VP]),
+    "qk_rad_subcycle": (C.c_int, [_VP, _PRM, _RPRM, _RSPRM, _A4P, _A4P, _A4P, _A4P, C.c_double, C.c_double, _I64P, C.POINTER(C.c_int), _VP]),
     "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),
     "qk_level_create": (C.c_int, [C.POINTER(qk_level_desc), C.POINTER(_VP)]),
     "qk_level_destroy": (None, [_VP]),
@@ -289,6 +290,9 @@ SYMBOLS = {
     "qk_sim_reset_clock": (None, [_VP, C.c_double, C.c_double]),
     "qk_sim_compute_timestep": (C.c_int, [_VP, C.c_double, _D3]),
     "qk_sim_step": (C.c_int, [_VP, C.c_double, C.POINTER(C.c_int)]),
+    "qk_sim_enable_radiation": (C.c_int, [_VP, _RPRM, _RSPRM, _A4P, C.c_double, C.c_int]),
+    "qk_sim_last_rad_substeps": (C.c_int, [_VP]),
+    "qk_sim_rad_cell_updates": (C.c_int64, [_VP]),
     "qk_sim_evolve": (C.c_int, [_VP, C.c_int, C.c_double, C.POINTER(C.c_int), _D3, _D3]),
 }
 

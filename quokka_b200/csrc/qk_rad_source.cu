@@ -11,10 +11,11 @@
 // Cell-local and compute-bound (about sixteen IEEE divisions and two square roots per Newton-Raphson iteration, 5-20
 // iterations per cell): the roof is the FP64 pipe, not HBM; algorithmic traffic is 80 B read + 72 B written per cell
 // (+8 with an energy source array).  DESIGN.md section 3.
-#include "qk_common.cuh"
+#include "qk_level.h"
 #include "qk_div.cuh"
 #include "qk_rad_source.cuh"
 
+#include <algorithm>
 #include <stdlib.h>
 
 namespace
@@ -145,6 +146,61 @@ template <class D, int MINB> __global__ void __launch_bounds__(SRC_TPB, MINB) k_
 	}
 }
 
+// radiation components of src -> dst on the valid boxes, all boxes in one launch (swapRadiationState; stage-2 result back)
+struct CopyBox {
+	A4 dst, src;
+	int lo[3], n[3];
+	unsigned total;
+};
+struct CopyTable {
+	CopyBox b[SRC_MAXBOX];
+};
+__global__ void __launch_bounds__(256) k_copy_comps(const CopyTable tab, const int c0, const int nc)
+{
+	const CopyBox &B = tab.b[blockIdx.y];
+	const unsigned t = blockIdx.x * 256u + threadIdx.x;
+	if (t >= B.total)
+		return;
+	const unsigned jk = t / (unsigned)B.n[0];
+	const int i = B.lo[0] + (int)(t - jk * (unsigned)B.n[0]);
+	const int kk = (int)(jk / (unsigned)B.n[1]);
+	const int j = B.lo[1] + (int)(jk - (unsigned)kk * (unsigned)B.n[1]);
+	const int k = B.lo[2] + kk;
+	const double *__restrict__ ps = B.src.p + B.src.off(i, j, k);
+	double *__restrict__ pd = B.dst.p + B.dst.off(i, j, k);
+	for (int n = c0; n < c0 + nc; ++n)
+		pd[n * B.dst.ns] = ps[n * B.src.ns];
+}
+int copy_comps(const qk_level *L, const qk_array4 *dst, const qk_array4 *src, int c0, int nc, cudaStream_t s)
+{
+	const int nboxes = (int)L->valid.size();
+	for (int b0 = 0; b0 < nboxes; b0 += SRC_MAXBOX) {
+		const int nb = (nboxes - b0 < SRC_MAXBOX) ? (nboxes - b0) : SRC_MAXBOX;
+		CopyTable tab;
+		unsigned most = 0;
+		for (int b = 0; b < nb; ++b) {
+			CopyBox &B = tab.b[b];
+			B.dst = A4(dst[b0 + b]);
+			B.src = A4(src[b0 + b]);
+			int64_t tot = 1;
+			for (int d = 0; d < 3; ++d) {
+				B.lo[d] = L->valid[b0 + b].lo[d];
+				B.n[d] = L->valid[b0 + b].hi[d] - L->valid[b0 + b].lo[d] + 1;
+				tot *= B.n[d];
+			}
+			if (tot >= (int64_t(1) << 31))
+				return QK_ERR_UNSUPPORTED;
+			B.total = (unsigned)tot;
+			most = (B.total > most) ? B.total : most;
+		}
+		if (most == 0)
+			continue;
+		k_copy_comps<<<dim3((most + 255u) / 256u, (unsigned)nb), 256, 0, s>>>(tab, c0, nc);
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+
 int *g_dcount = nullptr; // 8 ints on the device
 int *g_hcount = nullptr; // pinned mirror
 } // namespace
@@ -250,6 +306,48 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 			else
 				counters[n] += g_hcount[n];
 		}
+	}
+	return 0;
+}
+
+#define QK_TRY_(x)                                                                                                                                   \
+	do {                                                                                                                                         \
+		int r_ = (x);                                                                                                                        \
+		if (r_ != 0)                                                                                                                         \
+			return r_;                                                                                                                   \
+	} while (0)
+
+extern "C" int qk_rad_subcycle(qk_level *L, const qk_hydro_params *hydro, const qk_rad_params *prm, const qk_rad_source_params *src, const qk_array4 *U_old,
+			       const qk_array4 *U_new, const qk_array4 *U_tmp, const qk_array4 *rad_energy_source, double dt_hydro, double rad_cfl,
+			       int64_t *counters, int *nsub_out, void *stream)
+{
+	if (!L || !prm || !U_old || !U_new || !U_tmp || (src && !hydro) || !(dt_hydro > 0.0) || !(rad_cfl > 0.0))
+		return QK_ERR_BAD_ARG;
+	if (!L->has_device)
+		return QK_ERR_NO_DEVICE;
+	cudaStream_t s = (cudaStream_t)stream;
+	// computeNumberOfRadiationSubsteps  src/QuokkaSimulation.hpp:397-406
+	const double dx_min = std::min({L->dx[0], L->dx[1], L->dx[2]});
+	const double dtrad_tmp = rad_cfl * (dx_min / prm->c_hat);
+	const int nsub = (int)ceil(dt_hydro / dtrad_tmp);
+	if (nsub < 1)
+		return QK_ERR_BAD_ARG;
+	const double dt_radiation = dt_hydro / static_cast<double>(nsub);
+	if (nsub_out)
+		*nsub_out = nsub;
+	const int ns = prm->nstart, nh = 4 * prm->ngroups, nb = (int)L->valid.size();
+	for (int i = 0; i < nsub; ++i) {
+		if (i > 0)
+			QK_TRY_(copy_comps(L, U_old, U_new, ns, nh, s)); // swapRadiationState
+		QK_TRY_(qk_fill_boundary(L, U_old, ns, nh, stream));
+		QK_TRY_(qk_rad_advance_stage(L, prm, 1, U_old, U_old, U_new, dt_radiation, stream));
+		if (src)
+			QK_TRY_(qk_rad_add_source_terms(hydro, prm, src, 1, nb, L->valid.data(), U_new, rad_energy_source, dt_radiation, counters, stream));
+		QK_TRY_(qk_fill_boundary(L, U_new, ns, nh, stream));
+		QK_TRY_(qk_rad_advance_stage(L, prm, 2, U_old, U_new, U_tmp, dt_radiation, stream));
+		QK_TRY_(copy_comps(L, U_new, U_tmp, ns, nh, s));
+		if (src)
+			QK_TRY_(qk_rad_add_source_terms(hydro, prm, src, 2, nb, L->valid.data(), U_new, rad_energy_source, dt_radiation, counters, stream));
 	}
 	return 0;
 }

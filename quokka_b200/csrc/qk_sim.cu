@@ -33,6 +33,15 @@ struct qk_sim {
 	// advance (the next computeTimestep reads the same state); invalidated whenever state_new is changed from outside
 	bool sig_valid = false;
 	double sig_local = 0.0;
+	// radiation (is_radiation_enabled): subcycleRadiationAtLevel after the hydro advance, c_hat / maxSubsteps_ in the time step
+	bool rad_on = false, src_on = false;
+	qk_rad_params rprm;
+	qk_rad_source_params sprm;
+	std::vector<qk_array4> esrc; // radEnergySource per local box (caller-owned device memory) or empty
+	double rad_cfl = 0.3;	     // radiationCflNumber_  src/QuokkaSimulation.hpp:125
+	int max_substeps = 10;	     // maxSubsteps_  :126
+	int last_nsub = 0;
+	int64_t rad_cell_updates = 0; // radiationCellUpdates_
 };
 int qk_hydro_max_signal_both(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, double out[2], cudaStream_t s);
 
@@ -133,6 +142,32 @@ extern "C" void qk_sim_destroy(qk_sim *s)
 }
 
 extern "C" int qk_sim_nlocal(const qk_sim *s) { return s ? s->nb : 0; }
+
+// Physics_Traits::is_radiation_enabled for this simulation: every qk_sim_step then runs subcycleRadiationAtLevel after the hydro
+// advance (src/QuokkaSimulation.hpp:690-694) and computeTimestep takes std::max(c_hat / maxSubsteps_, hydro signal speed)
+// (computeMaxSignalLocal :408-441).  src == NULL: transport only.  esrc: one-component device FABs per local box, or NULL.
+extern "C" int qk_sim_enable_radiation(qk_sim *s, const qk_rad_params *rad, const qk_rad_source_params *src, const qk_array4 *esrc, double rad_cfl,
+				       int max_substeps)
+{
+	if (!s || !rad || !(rad_cfl > 0.0) || max_substeps < 1)
+		return QK_ERR_BAD_ARG;
+	if (rad->nstart + 4 * rad->ngroups > s->lev->ncomp)
+		return QK_ERR_BAD_ARG;
+	s->rprm = *rad;
+	s->src_on = (src != nullptr);
+	if (src)
+		s->sprm = *src;
+	s->esrc.clear();
+	if (esrc)
+		s->esrc.assign(esrc, esrc + s->nb);
+	s->rad_cfl = rad_cfl;
+	s->max_substeps = max_substeps;
+	s->rad_on = true;
+	s->sig_valid = false;
+	return 0;
+}
+extern "C" int qk_sim_last_rad_substeps(const qk_sim *s) { return s ? s->last_nsub : 0; }
+extern "C" int64_t qk_sim_rad_cell_updates(const qk_sim *s) { return s ? s->rad_cell_updates : 0; }
 extern "C" qk_level *qk_sim_level(qk_sim *s) { return s ? s->lev : nullptr; }
 extern "C" void *qk_sim_stream(qk_sim *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" double qk_sim_time(const qk_sim *s) { return s ? s->t : 0.0; }
@@ -207,6 +242,8 @@ extern "C" int qk_sim_compute_timestep(qk_sim *s, double stop_time, double *dt_o
 	else
 		QK_TRY(qk_hydro_max_signal_speed(&s->prm, 0, s->nb, s->lev->valid.data(), s->snew.data(), &smax, s->stream));
 	QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
+	if (s->rad_on) // std::max(maxSignalRadiation, maxSignalHydro) per cell  src/QuokkaSimulation.hpp:426-433
+		smax = dmaxh(s->rprm.c_hat / static_cast<double>(s->max_substeps), smax);
 	const double *dx = s->lev->dx;
 	const double dx_min = dminh(dminh(dx[0], dx[1]), dx[2]);
 	const double hydro_dt = s->cfl * (dx_min / smax);
@@ -307,6 +344,14 @@ extern "C" int qk_sim_step(qk_sim *s, double dt, int *retries_out)
 		*retries_out = result;
 	if (result < 0)
 		return 0; // the reference aborts here (:966-989); the caller sees retries = -1
+	if (s->rad_on) { // subcycleRadiationAtLevel :690-694; state_inter is free after the hydro advance and serves as U_tmp
+		int nsub = 0;
+		QK_TRY(qk_rad_subcycle(s->lev, &s->prm, &s->rprm, s->src_on ? &s->sprm : nullptr, s->sold.data(), s->snew.data(), s->sint.data(),
+				       s->esrc.empty() ? nullptr : s->esrc.data(), dt, s->rad_cfl, nullptr, &nsub, s->stream));
+		s->last_nsub = nsub;
+		s->rad_cell_updates += (int64_t)nsub * s->ncells_global; // radiationCellUpdates_ :1697
+		s->sig_valid = false;					 // the source terms changed the gas state
+	}
 	s->retries += result;
 	s->t += dt;
 	s->cell_updates += s->ncells_global; // cellUpdates_ += CountCells(lev)  simulation.hpp:1285

@@ -127,6 +127,18 @@ class HydroSimulation:
     def retries(self):
         return self.lib.qk_sim_retries(self.handle)
 
+    def enableRadiation(self, rad_params, source_params=None, rad_energy_source=None, rad_cfl=0.3, max_substeps=10):
+        """Physics_Traits::is_radiation_enabled: subcycleRadiationAtLevel after every hydro advance (QuokkaSimulation.hpp:690-694).
+        rad_energy_source: a DevMultiFab (one component, no ghost cells) over the local boxes, kept alive here."""
+        self._rad = (rad_params, source_params, rad_energy_source)
+        check(self.lib.qk_sim_enable_radiation(self.handle, C.byref(rad_params), C.byref(source_params) if source_params is not None else None,
+                                               rad_energy_source.descs if rad_energy_source is not None else None, rad_cfl, max_substeps),
+              "qk_sim_enable_radiation")
+
+    @property
+    def radiationSubsteps(self):
+        return self.lib.qk_sim_last_rad_substeps(self.handle)
+
     def computeTimestep(self, stop_time=None):
         dt = C.c_double()
         check(self.lib.qk_sim_compute_timestep(self.handle, self.problem.stop_time if stop_time is None else stop_time, C.byref(dt)),
