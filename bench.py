@@ -140,6 +140,32 @@ def run_reference_cpu(ncell, box, nsteps, threads):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def run_reference_shell_cpu(ncell, box, nsteps, threads):
+    """the reference's own RadhydroShell problem (oracle/_ref/test_radhydro_shell is hard-wired to 50 steps, so the same problem
+    file behind oracle/ref_build/shell_golden.cpp, which leaves the step count to the inputs) on the host cores; its
+    interpolation table travels as oracle/_ref/dust_shell_initial_conditions.txt.  Returns (Mupdates/s, elapsed s)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "shell_golden")
+    table = os.path.join(ROOT, "oracle", "_ref", "dust_shell_initial_conditions.txt")
+    tmp = tempfile.mkdtemp(prefix="qkref_")
+    try:
+        shutil.copy(table, os.path.join(tmp, "initial_conditions.txt"))
+        with open(os.path.join(tmp, "in"), "w") as f:
+            f.write("geometry.prob_lo = 0.0 0.0 0.0\ngeometry.prob_hi = 3.086e19 3.086e19 3.086e19\ngeometry.is_periodic = 1 1 1\namr.v = 0\n"
+                    "amr.max_level = 0\ndo_reflux = 0\ndo_subcycle = 0\nplotfile_interval = -1\ncheckpoint_interval = -1\n")
+            f.write(f"amr.n_cell = {ncell} {ncell} {ncell}\namr.max_grid_size = {box}\namr.blocking_factor = {box}\nmax_timesteps = {nsteps}\n")
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        out = subprocess.run([exe, "in"], cwd=tmp, env=env, capture_output=True, text=True).stdout
+        el = time.time() - t0
+        m = re.search(r"figure-of-merit:\s*([0-9.eE+-]+)\s*\S+/zone-update\s*\[([0-9.eE+-]+)\s*Mupdates/s\]", out)
+        me = re.search(r"elapsed time:\s*([0-9.eE+-]+)", out)
+        if not m:
+            raise RuntimeError("reference run printed no figure of merit:\n" + out[-2000:])
+        return float(m.group(2)), (float(me.group(1)) if me else el)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_oracle_port(ncell, box, nsteps):
     """fallback CPU baseline when oracle/_ref did not travel: the single-core C restatement (oracle/liboracle.so)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -438,6 +464,101 @@ def main_radiation(args):
     return 0
 
 
+def main_radhydro(args):
+    """python bench.py --workload radhydro: config C4's coarse step on one GPU -- hydro PLM(minmod)+HLLC RK2 advance, then
+    subcycleRadiationAtLevel: 10 IMEX substeps of (ghost fill, transport stage 1, matter-radiation source terms, ghost fill,
+    transport stage 2, source terms) -- RadhydroShell traits on 256^3 periodic in eight 128^3 boxes, through the C++ driver
+    (qk_sim_evolve).  The initial condition is SYNTHETIC: the reference's Gaussian shell density with an analytic radiation field
+    (its interpolation table lives in /root/reference and does not travel)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from quokka_b200 import capi
+    from quokka_b200.device import DevMultiFab
+    from quokka_b200.problems import ShellProblem
+    from quokka_b200.simulation import HydroSimulation
+
+    lib = capi.load()
+    n, box = 256, 128
+    P = ShellProblem
+    ax = (np.arange(n) + 0.5) * (P.prob_hi / n) - 0.5 * P.prob_hi
+    z, y, x = np.meshgrid(ax, ax, ax, indexing="ij", sparse=True)
+    r = np.sqrt(x * x + y * y + z * z)
+    sigma_sh = 0.3 * P.r_0 / (2.0 * np.sqrt(2.0 * np.log(2.0)))
+    M_shell = 0.5 * 1.0e6 * 2.0e33
+    rho = np.maximum(M_shell / (4.0 * np.pi * r * r * np.sqrt(2.0 * np.pi * sigma_sh * sigma_sh)) * np.exp(-(r - P.r_0) ** 2 / (2.0 * sigma_sh * sigma_sh)),
+                     1.0e-8 * P.rho_0)
+    T = 300.0 * (1.0 + (r / P.r_0) ** 2) ** -0.25  # K, gas and radiation in equilibrium
+    Er = P.a_rad * T ** 4
+    c_v = capi.K_B / ((2.2 * capi.M_U) * (P.gamma - 1.0))
+    init = np.zeros((10, n, n, n))
+    init[0] = rho
+    init[4] = rho * c_v * T
+    init[5] = init[4]
+    init[6] = Er
+    init[7] = init[8] = init[9] = 0.1 * P.c_light * Er / np.sqrt(3.0)
+    sigma_star = 0.3 * P.r_0
+    src = (1.0 / P.c_light) * (0.5 * 1.0e6 * 2.0e33 * 2000.0) / (2.0 * np.pi * sigma_star * sigma_star) ** 1.5 * np.exp(-(r * r) / (2.0 * sigma_star * sigma_star))
+    prob = ShellProblem(n, box, initial=init)
+    sim = HydroSimulation(prob)
+    esrc = DevMultiFab(prob.boxes, 1, ngrow=0,
+                       host=[np.ascontiguousarray(src[None, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]) for b in prob.boxes])
+    sim.enableRadiation(prob.rad_params(), prob.rad_source_params(), esrc, rad_cfl=prob.rad_cfl, max_substeps=prob.max_substeps)
+    sim.setInitialConditions()
+    del init, src
+    clocks = ClockSampler(0)
+    clocks.start()
+    nd, _, _ = sim.evolve(args.warmup)
+    assert nd == args.warmup
+    lib.qk_prof_enable(1)
+    l0 = lib.qk_launch_count()
+    nd, elapsed, ms = sim.evolve(args.steps)
+    launches = lib.qk_launch_count() - l0
+    lib.qk_prof_enable(0)
+    clk = clocks.stop()
+    assert nd == args.steps, (nd, args.steps)
+    buf = (capi.C.c_char * 8192)()
+    lib.qk_prof_report(buf, 8192)
+    prof = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
+    ncell = n ** 3
+    nsub = sim.radiationSubsteps
+    value = ncell * args.steps / (ms * 1e-3) / 1e6
+    peak, psrc = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, psrc = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    # dominant kernel class of the step: the source-term solve (2 launches per substep); 152 algorithmic bytes per cell
+    src_cnt, src_ms = prof.get("rad_source_terms", (0, 0.0))
+    per = src_ms / max(1, 2 * nsub * args.steps)
+    ach = 152 * ncell / (per * 1e-3) / 1e9 if per > 0 else None
+    st = sim.gather_global() if not args.no_extras else None
+    line = {"metric": "Mcell-updates/s (radiation hydrodynamics coarse step: hydro PLM+HLLC RK2 + 10 two-moment IMEX substeps with matter-radiation coupling)",
+            "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "RadhydroShell 256^3 periodic (configs[3] on one GPU), eight 128^3 boxes, 1 photon group, kappa = 20, beta_order 1, "
+                                   "PLM hydro + PLM radiation, cfl 0.3; state (1.6 GB) >> L2, no flush", "cells": ncell, "radiation_substeps_per_step": nsub,
+                       "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": "exact"},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "k_rad_source", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": psrc, "unit": "GB/s",
+                         "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 152, "avg_launch_ms": round(per, 4),
+                         "note": "FP64-pipe / latency bound implicit solve (DESIGN.md section 3); ncu: profiles/r01_ncu_radsrc.txt"},
+            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+    if not args.no_extras and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
+        cores = os.cpu_count() or 1
+        v, el = run_reference_shell_cpu(64, 32, 1, cores)
+        line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": f"reference RadhydroShell problem (OpenMP, {cores} threads), 64^3 in 32^3 boxes, 1 coarse step = 10 radiation substeps, {el:.1f} s"}
+    if st is not None:
+        line["sanity"] = {"finite": bool(np.isfinite(st).all()), "min_rho": float(st[0].min()), "min_Erad": float(st[6].min()),
+                          "sim_time": sim.time}
+    print(json.dumps(line))
+    sim.close()
+    return 0
+
+
 def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
     """dominant kernel class vs the measured HBM copy bandwidth (MEASURED_PEAKS.json, else the recipe's fallback).
     Algorithmic and design bytes per cell are documented in DESIGN.md section 3."""
@@ -486,9 +607,12 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arith", default="relaxed", choices=["exact", "relaxed"], help="arithmetic mode of the fused sweeps (DESIGN.md section 3)")
-    ap.add_argument("--workload", default="hydro", choices=["hydro", "radiation"], help="hydro = the BASELINE.json metric (default); radiation = the transport sweep")
+    ap.add_argument("--workload", default="hydro", choices=["hydro", "radiation", "radhydro"],
+                    help="hydro = the BASELINE.json metric (default); radiation = the transport sweep; radhydro = config C4's coarse step")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e and cpu_baseline legs (profiling runs)")
     a = ap.parse_args()
     if a.workload == "radiation" and a.impl == "ours":
         sys.exit(main_radiation(a))
+    if a.workload == "radhydro" and a.impl == "ours":
+        sys.exit(main_radhydro(a))
     sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))
