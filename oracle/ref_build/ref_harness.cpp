@@ -133,6 +133,7 @@ template <> struct RadSystem_Traits<R1> {
 //   R4: as R3 with kappa_E = kappa_F = kappa_P = 3 and beta_order = 0 (no work term, no O(beta) flux terms)
 //   R5: as R3 with kappa_P = 0.5, kappa_E = kappa_F = 0.25, beta_order = 3, Erad_floor = 1e-6
 //   R6: gamma = 1 (isothermal branch: flux update only), c = c_hat = 1, kappa = 2
+//   R7: as R3 with kappa_P = kappa_E = 0 (tau = 0: J11 = -inf, the F_D + R residual, kappaPoverE = 1), kappa_F = 0.3, beta_order 1
 #define QK_RS_TRAITS(NAME, GAMMA, MU, KB, CL, CH, AR, FLOOR, BETA)                                                                                   \
 	struct NAME {                                                                                                                                \
 	};                                                                                                                                           \
@@ -175,6 +176,8 @@ QK_RS_TRAITS(R3, 5. / 3., 1.0, 1.0, 10.0, 5.0, 1.0, 0., 2)
 QK_RS_TRAITS(R4, 1.4, 1.0, 1.0, 10.0, 5.0, 1.0, 0., 0)
 QK_RS_TRAITS(R5, 5. / 3., 1.0, 1.0, 10.0, 5.0, 1.0, 1.0e-6, 3)
 QK_RS_TRAITS(R6, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0., 1)
+QK_RS_TRAITS(R7, 5. / 3., 1.0, 1.0, 10.0, 5.0, 1.0, 0., 1)
+QK_RS_OPACITY(R7, 0.0, 0.0, 0.3)
 QK_RS_OPACITY(R2, 20.0, 20.0, 20.0)
 QK_RS_OPACITY(R3, 1.0, 1.5, 2.0)
 QK_RS_OPACITY(R4, 3.0, 3.0, 3.0)
@@ -522,6 +525,10 @@ void rad_update(int op, const qk_box *valid, const qk_array4 *unew, const qk_arr
 	} break;                                                                                                                                     \
 	case 6: {                                                                                                                                    \
 		using P = R6;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 7: {                                                                                                                                    \
+		using P = R7;                                                                                                                        \
 		CALL;                                                                                                                                \
 	} break;                                                                                                                                     \
 	default:                                                                                                                                     \

@@ -1,6 +1,6 @@
 """Pin the matter-radiation source terms of the C oracle (oracle/quokka_oracle.c: orc_rad_add_source_terms) against the
 REFERENCE's own RadSystem<problem_t>::AddSourceTermsSingleGroup (src/radiation/source_terms_single_group.hpp:9-565) compiled
-from /root/reference (oracle/_ref/libquokka_ref.so, problems R2..R6 of oracle/ref_build/ref_harness.cpp).  Both run on the
+from /root/reference (oracle/_ref/libquokka_ref.so, problems R2..R7 of oracle/ref_build/ref_harness.cpp).  Both run on the
 host with the same libm, so the bar is bit-exact, iteration counters included."""
 import ctypes as C
 
@@ -21,6 +21,7 @@ CASES = {
     4: dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[1e-3, 0.1, 10.0]),  # beta_order 0
     5: dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[1e-3, 0.1, 10.0]),  # beta_order 3, Erad_floor > 0
     6: dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[0.1]),  # gamma = 1
+    7: dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[1e-3, 0.1, 10.0]),  # kappa_P = kappa_E = 0: tau = 0 branches
 }
 
 

@@ -66,12 +66,18 @@ def trait_set(name):
         rp = capi.rad_params(c_light=1.0, c_hat=1.0, nstart=6)
         sp = capi.rad_source_params(radiation_constant=1.0, kappa_P=2.0, beta_order=1)
         gen = dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[0.1])
+    elif name == "kappa0":  # kappa_P = kappa_E = 0: tau = 0 (J11 = -inf, the F_D + R residual), only the flux is absorbed
+        hp = capi.hydro_params(gamma=5. / 3., mean_molecular_weight=1.0, boltzmann_constant=1.0)
+        rp = capi.rad_params(c_light=10.0, c_hat=5.0, nstart=6)
+        sp = capi.rad_source_params(radiation_constant=1.0, kappa_P=0.0, kappa_E=0.0, kappa_F=0.3, beta_order=1)
+        gen = dict(T0=1.0, rho0=1.0, vmax=1.0, dts=[1e-3, 0.1, 10.0])
     else:
         raise KeyError(name)
     return hp, rp, sp, gen
 
 
-TRAITS = ["shell", "kF_ne_kE", "beta0", "beta3_floor", "isothermal"]
+TRAITS = ["shell", "kF_ne_kE", "beta0", "beta3_floor", "isothermal"]  # also the GPU parity list (tests/test_zgpu_rad_source.py)
+HOST_TRAITS = TRAITS + ["kappa0"]
 
 
 def compare_with_oracle(got, want, st, rp, tol=1e-10):
@@ -94,7 +100,7 @@ def compare_with_oracle(got, want, st, rp, tol=1e-10):
     return same.mean()
 
 
-@pytest.mark.parametrize("name", TRAITS)
+@pytest.mark.parametrize("name", HOST_TRAITS)
 @pytest.mark.parametrize("stage", [1, 2])
 def test_kernel_arithmetic_on_host_matches_oracle(host, name, stage):
     hp, rp, sp, gen = trait_set(name)
