@@ -71,7 +71,7 @@ struct SrcTable {
 	SrcBox b[SRC_MAXBOX];
 };
 
-template <class D, int MINB> __global__ void __launch_bounds__(SRC_TPB, MINB) k_rad_source(const qk_rsrc::Const k, const SrcTable tab, const int nstart, int *__restrict__ counters)
+template <class D, int MINB, bool RELAXED> __global__ void __launch_bounds__(SRC_TPB, MINB) k_rad_source(const qk_rsrc::Const k, const SrcTable tab, const int nstart, int *__restrict__ counters)
 {
 	const SrcBox &B = tab.b[blockIdx.y];
 	const unsigned t = blockIdx.x * SRC_TPB + threadIdx.x; // the host refuses boxes of 2^31 cells or more
@@ -101,7 +101,7 @@ template <class D, int MINB> __global__ void __launch_bounds__(SRC_TPB, MINB) k_
 		in.F[1] = pr[2 * ns];
 		in.F[2] = pr[3 * ns];
 		in.src = (B.esrc.p != nullptr) ? B.esrc.p[B.esrc.off(i, j, kz)] : 0.0;
-		qk_rsrc::source_cell<D>(k, ct, in, out);
+		qk_rsrc::source_cell<D, RELAXED>(k, ct, in, out);
 		p[ns] = out.mom[0];
 		p[2 * ns] = out.mom[1];
 		p[3 * ns] = out.mom[2];
@@ -276,8 +276,13 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 		const dim3 grid((unsigned)((most + SRC_TPB - 1) / SRC_TPB), (unsigned)nb);
 		if (most >= (int64_t(1) << 31))
 			return QK_ERR_UNSUPPORTED;
-#define QK_SRC_LAUNCH(DIV, MINB) k_rad_source<DIV, MINB><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount)
-		if (plain_div) {
+#define QK_SRC_LAUNCH(DIV, MINB) k_rad_source<DIV, MINB, false><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount)
+		if (hydro->arith == QK_ARITH_FAST) { // relaxed arithmetic (qk_rad_source.cuh): closed-form EOS, reciprocal products
+			if (minb == 6)
+				k_rad_source<qk_rsrc::DivPlain, 6, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+			else
+				k_rad_source<qk_rsrc::DivPlain, 8, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+		} else if (plain_div) {
 			switch (minb) {
 			case 3: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 3); break;
 			case 5: QK_SRC_LAUNCH(qk_rsrc::DivPlain, 5); break;

@@ -13,6 +13,13 @@
 // rounding boundary.  libm's and CUDA's pow are not correctly rounded (0.52 / 2 ulp), so the CPU reference, the reference's
 // own CUDA build and this kernel may differ in the last bit of a thermal emission term; after the Newton-Raphson solve
 // (residual tolerance 1e-11 of the total energy, :158) the results agree to that tolerance.
+//
+// RELAXED = true (qk_hydro_params::arith == QK_ARITH_FAST) is the same algorithm -- same iteration, same branches, guards and
+// convergence tests -- with the gamma-law EOS in closed form (T = E_gas / (rho c_v'), c_v = rho c_v', c_v' = k_B / (mu m_u (gamma-1))
+// instead of the Microphysics round trip: no division where the exact form has eight), quotients over call or cell constants
+// as products with a reciprocal formed once, T^4 = (T^2)^2, and the identically-zero cooling terms dropped: one division per
+// Newton-Raphson iteration instead of thirteen.  Each operation differs from the exact form by O(1e-16); the converged state
+// agrees to the solver's own tolerance (1e-11 E_tot), inside the stated 1e-10 bar.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -49,6 +56,8 @@ struct Const {
 	double mindens, mintemp;
 	// per call
 	double dt /* stage 2: (1 - IMEX_a32) dt_radiation */, chat_dt /* chat * dt */, gas_update_factor;
+	// relaxed arithmetic (QK_ARITH_FAST): closed forms of the gamma-law EOS and reciprocals of the call constants
+	double cvc /* c_v / rho = k_B / (mu m_u (gamma - 1)) */, inv_cvc, inv_arad, inv_kPoE, inv_cc, inv_cchat, Tmin /* mintemp * K_B / k_B */;
 };
 
 struct CellIn {
@@ -205,7 +214,7 @@ QK_HD void solve3x3(double C00, double C01, double C02, double C10, double C11, 
 	X[2] = X2;
 }
 
-template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab &ct, const CellIn &in, CellOut &out)
+template <class D, bool RELAXED> QK_HD void source_cell(const Const &k, const typename D::CTab &ct, const CellIn &in, CellOut &out)
 {
 	typedef typename D::R Rc;
 	const double c = k.c, chat = k.chat, cscale = k.cscale, dt = k.dt;
@@ -221,6 +230,11 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 	q.rho2 = D::rcp(2.0 * rho);
 	q.r = eos_clamp_rho(k, rho);
 	q.rhoinv = (q.r == rho) ? D::div(1.0, q.rho) : (1.0 / q.r);
+	// relaxed-mode cell constants
+	const double inv_rho = RELAXED ? (1.0 / rho) : 0.0;
+	const double inv_2rho = 0.5 * inv_rho;
+	const double cv_cell = rho * k.cvc;	   // c_v
+	const double inv_cv = inv_rho * k.inv_cvc; // 1 / c_v
 
 	double Egas0 = nan, Ekin0 = nan, Etot0 = nan, Egas_guess = nan;
 	double lorentz_factor = nan, lorentz_factor_v = nan, lorentz_factor_v_v = nan;
@@ -231,7 +245,8 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 	out.solves = out.nr_iters = out.nr_max = out.fail_nr = out.fail_outer = 0;
 
 	if (gas) { // :82-86
-		Egas0 = Egastot0 - ekin_of<D>(q, in.mom[0], in.mom[1], in.mom[2]);
+		Egas0 = Egastot0 - (RELAXED ? (in.mom[0] * in.mom[0] + in.mom[1] * in.mom[1] + in.mom[2] * in.mom[2]) * inv_2rho
+				    : ekin_of<D>(q, in.mom[0], in.mom[1], in.mom[2]));
 		Etot0 = Egas0 + cscale * (Erad0 + Src);
 		Ekin0 = Egastot0 - Egas0;
 		if (beta_order == 0 || beta_order == 1) { // :115-131
@@ -254,7 +269,8 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 	// tau = dt rho kappaP chat lorentz_factor (:210,217) and J11 (:296-300) do not change within a cell
 	const double tau = dt * rho * kappaP * chat * lorentz_factor;
 	const Rc Rtau = D::rcp(tau);
-	const double J11 = (tau <= 0.0) ? -INFINITY : (D::div(-1.0 * kappaPoverE, Rtau) - 1.0);
+	const double inv_tau = (RELAXED && tau > 0.0) ? (1.0 / tau) : 0.0;
+	const double J11 = (tau <= 0.0) ? -INFINITY : (RELAXED ? (-kappaPoverE * inv_tau - 1.0) : (D::div(-1.0 * kappaPoverE, Rtau) - 1.0));
 
 	const int max_ite = 5;
 	int ite = 0;
@@ -266,55 +282,64 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 			const int maxIter = 100;
 			int n = 0;
 			for (; n < maxIter; ++n) { // Newton-Raphson :161-352
-				const double T_gas = tgas_from_eint<D>(k, ct, q, Egas_guess);
+				double T_gas;
+				if (RELAXED) {
+					const double e = Egas_guess * inv_rho;
+					T_gas = (e < 1.e-200 || e > 1.e200) ? k.Tmin : Egas_guess * inv_cv;
+				} else {
+					T_gas = tgas_from_eint<D>(k, ct, q, Egas_guess);
+				}
 				const double T_d = T_gas;
-				fourPiBoverC = k.a_rad * pow_dd<4>(T_d); // ComputeThermalRadiationSingleGroup :471-479
+				const double T2 = T_d * T_d;
+				fourPiBoverC = k.a_rad * (RELAXED ? (T2 * T2) : pow_dd<4>(T_d)); // ComputeThermalRadiationSingleGroup :471-479
 				if (fourPiBoverC < k.floor_g)
 					fourPiBoverC = k.floor_g;
 				if (n == 0) { // :192-215
 					if (beta_order != 0 && ite == 0)
-						work = D::divc((in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat, ct, C_cc) *
+						work = (RELAXED ? (in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat * k.inv_cc
+								: D::divc((in.mom[0] * in.F[0] + in.mom[1] * in.F[1] + in.mom[2] * in.F[2]) * k.two_kE_m_kF * chat, ct, C_cc)) *
 						       lorentz_factor_v * dt;
-					R = (fourPiBoverC - D::divc(Erad_guess, ct, C_kPoE)) * tau + work;
+					R = (fourPiBoverC - (RELAXED ? Erad_guess * k.inv_kPoE : D::divc(Erad_guess, ct, C_kPoE))) * tau + work;
 				} else if (tau > 0.0) { // :216-232
-					Erad_guess = kappaPoverE * (fourPiBoverC - D::div(R - work, Rtau));
+					Erad_guess = kappaPoverE * (fourPiBoverC - (RELAXED ? (R - work) * inv_tau : D::div(R - work, Rtau)));
 				}
 				// cooling = cooling_derivative = 0, CR_heating = 0 * dt: the terms are kept so that signed zeros and
 				// non-finite dt propagate as in the reference (:234-245)
 				const double cooling = 0.0, cooling_derivative = 0.0;
 				const double CR_heating = 0.0 * dt;
-				const double F_G = Egas_guess - Egas0 + cscale * R + cooling * dt - CR_heating;
+				const double F_G = RELAXED ? (Egas_guess - Egas0 + cscale * R) : (Egas_guess - Egas0 + cscale * R + cooling * dt - CR_heating);
 				const double F_D = Erad_guess - Erad0 - (R + Src);
 				const double F_D_abs = (tau > 0.0) ? fabs(F_D) : fabs(F_D + R);
 				if ((fabs(F_G) < resid_limit) && (cscale * F_D_abs < resid_limit))
 					break;
-				const double c_v = eint_temp_derivative<D>(k, ct, q, rho, T_gas);
+				const double c_v = RELAXED ? cv_cell : eint_temp_derivative<D>(k, ct, q, rho, T_gas);
 				const Rc Rcv = D::rcp(c_v);
-				const double d_fourpiboverc_d_t = 4. * k.a_rad * pow_dd<3>(T_d); // :499-503
+				const double d_fourpiboverc_d_t = 4. * k.a_rad * (RELAXED ? (T2 * T_d) : pow_dd<3>(T_d)); // :499-503
 				const double dEg_dT = kappaPoverE * d_fourpiboverc_d_t;
 				// 0 * dt / c_v is +-0 for finite dt and finite non-zero c_v, so J00 is exactly 1; otherwise the quotient is formed
 				const double zdt = cooling_derivative * dt;
-				const double J00 = (zdt == 0.0 && c_v != 0.0 && fabs(c_v) <= 1.79769313486231570815e308) ? 1.0 : (1.0 + D::div(zdt, Rcv));
+				const double J00 = (RELAXED || (zdt == 0.0 && c_v != 0.0 && fabs(c_v) <= 1.79769313486231570815e308)) ? 1.0 : (1.0 + D::div(zdt, Rcv));
 				const double J01 = cscale;
-				const double J10 = D::div(1.0, Rcv) * dEg_dT - k.inv_cscale * cooling_derivative * dt;
+				const double J10 = RELAXED ? (inv_cv * dEg_dT) : (D::div(1.0, Rcv) * dEg_dT - k.inv_cscale * cooling_derivative * dt);
 				const double y0 = -F_G;
 				const double y1 = -1. * F_D;
 				const double det = J00 * J11 - J01 * J10;
 				const Rc Rdet = D::rcp(det);
-				const double deltaEgas = D::div(J11 * y0 - J01 * y1, Rdet);
-				const double deltaR = D::div(J00 * y1 - J10 * y0, Rdet);
+				const double inv_det = RELAXED ? (1.0 / det) : 0.0;
+				const double deltaEgas = RELAXED ? ((J11 * y0 - J01 * y1) * inv_det) : D::div(J11 * y0 - J01 * y1, Rdet);
+				const double deltaR = RELAXED ? ((J00 * y1 - J10 * y0) * inv_det) : D::div(J00 * y1 - J10 * y0, Rdet);
 				// enable_dE_constrain :330-342: deltaEgas / c_v > std::max(T_gas, T_rad), T_rad = (E_rad / a_rad)^(1/4).  The
 				// comparison is false whenever the quotient does not exceed T_gas (std::max(T_gas, NaN) is T_gas), so T_rad
 				// (a division and two square roots) is only formed for steps that jump by more than T_gas
-				const double dT = D::div(deltaEgas, Rcv);
+				const double dT = RELAXED ? (deltaEgas * inv_cv) : D::div(deltaEgas, Rcv);
 				double T_rad = 0.0;
 				bool jump = (dT > T_gas);
 				if (jump) {
-					T_rad = sqrt(sqrt(D::divc(Erad_guess, ct, C_arad)));
+					T_rad = sqrt(sqrt(RELAXED ? (Erad_guess * k.inv_arad) : D::divc(Erad_guess, ct, C_arad)));
 					jump = (dT > mx(T_gas, T_rad));
 				}
 				if (jump) {
-					Egas_guess = eint_from_tgas<D>(k, ct, q, rho, T_rad);
+					Egas_guess = RELAXED ? (eos_clamp_T(k, T_rad) * cv_cell) : eint_from_tgas<D>(k, ct, q, rho, T_rad);
 				} else {
 					Egas_guess += deltaEgas;
 					R += deltaR;
@@ -325,7 +350,8 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 			out.solves += 1;
 			out.nr_iters += n + 1;
 			out.nr_max = (out.nr_max < n + 1) ? (n + 1) : out.nr_max;
-			Erad_guess += k.inv_cscale * (0.0 * dt); // cooling_tend :367-373
+			if (!RELAXED)
+				Erad_guess += k.inv_cscale * (0.0 * dt); // cooling_tend :367-373
 		}
 
 		// 2. radiation flux update :396-490
@@ -334,9 +360,10 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 			const double erad = Erad_guess;
 			double v_terms[3];
 			const Rc Rce = D::rcp(c * erad);
-			const double fx = D::div(in.F[0], Rce);
-			const double fy = D::div(in.F[1], Rce);
-			const double fz = D::div(in.F[2], Rce);
+			const double inv_ce = RELAXED ? (1.0 / (c * erad)) : 0.0;
+			const double fx = RELAXED ? (in.F[0] * inv_ce) : D::div(in.F[0], Rce);
+			const double fy = RELAXED ? (in.F[1] * inv_ce) : D::div(in.F[1], Rce);
+			const double fz = RELAXED ? (in.F[2] * inv_ce) : D::div(in.F[2], Rce);
 			const double F_coeff = chat * rho * kappaF * dt * lorentz_factor;
 			double Tedd[3][3];
 			eddington_tensor<D>(fx, fy, fz, Tedd);
@@ -354,9 +381,10 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 			}
 			if (beta_order == 1 || kappaF == kappaE) {
 				const Rc Rfc = D::rcp(1.0 + F_coeff);
+				const double inv_fc = RELAXED ? (1.0 / (1.0 + F_coeff)) : 0.0;
 				for (int n = 0; n < 3; ++n) {
-					Frad_t1[n] = D::div(in.F[n] + v_terms[n], Rfc);
-					dMomentum[n] += D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
+					Frad_t1[n] = RELAXED ? ((in.F[n] + v_terms[n]) * inv_fc) : D::div(in.F[n] + v_terms[n], Rfc);
+					dMomentum[n] += RELAXED ? (-(Frad_t1[n] - in.F[n]) * k.inv_cchat) : D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
 				}
 			} else {
 				// gasVel is declared and never assigned in the reference (:407), so the K0 v_i v_j terms are K0 * 0 * 0; they
@@ -379,9 +407,10 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 			}
 		} else { // :484-490
 			const Rc Rfc = D::rcp(1.0 + rho * kappaF * chat * dt);
+			const double inv_fc = RELAXED ? (1.0 / (1.0 + rho * kappaF * chat * dt)) : 0.0;
 			for (int n = 0; n < 3; ++n) {
-				Frad_t1[n] = D::div(in.F[n], Rfc);
-				dMomentum[n] += D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
+				Frad_t1[n] = RELAXED ? (in.F[n] * inv_fc) : D::div(in.F[n], Rfc);
+				dMomentum[n] += RELAXED ? (-(Frad_t1[n] - in.F[n]) * k.inv_cchat) : D::divc(-(Frad_t1[n] - in.F[n]), ct, C_cchat);
 			}
 		}
 		const double x1GasMom1 = in.mom[0] + dMomentum[0];
@@ -392,13 +421,16 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 		if (!gas || beta_order == 0)
 			break;
 		{
-			const double Egastot1 = Egas_guess + ekin_of<D>(q, x1GasMom1, x2GasMom1, x3GasMom1);
+			const double Egastot1 = Egas_guess + (RELAXED ? (x1GasMom1 * x1GasMom1 + x2GasMom1 * x2GasMom1 + x3GasMom1 * x3GasMom1) * inv_2rho
+								      : ekin_of<D>(q, x1GasMom1, x2GasMom1, x3GasMom1));
 			const double Ekin1 = Egastot1 - Egas_guess;
 			const double dEkin_work = Ekin1 - Ekin0;
 			Egas_guess -= dEkin_work;
 		}
 		work_prev = work;
-		work = D::divc((x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat, ct, C_cc) * lorentz_factor_v * k.two_kE_m_kF * dt;
+		work = (RELAXED ? (x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat * k.inv_cc
+				: D::divc((x1GasMom1 * Frad_t1[0] + x2GasMom1 * Frad_t1[1] + x3GasMom1 * Frad_t1[2]) * chat, ct, C_cc)) *
+		       lorentz_factor_v * k.two_kE_m_kF * dt;
 		const double lag_tol = 1.0e-13;
 		const double dwork = fabs(work - work_prev);
 		if ((fabs(work) == 0.0) || (cscale * dwork < lag_tol * Etot0) || (dwork <= lag_tol * R) || (dwork <= 1.0e-8 * fabs(work)))
@@ -415,7 +447,8 @@ template <class D> QK_HD void source_cell(const Const &k, const typename D::CTab
 	if (gas) {
 		Egas_guess = Egas0 + (Egas_guess - Egas0) * k.gas_update_factor;
 		out.Eint = Egas_guess;
-		out.Egastot = Egas_guess + ekin_of<D>(q, out.mom[0], out.mom[1], out.mom[2]);
+		out.Egastot = Egas_guess + (RELAXED ? (out.mom[0] * out.mom[0] + out.mom[1] * out.mom[1] + out.mom[2] * out.mom[2]) * inv_2rho
+						    : ekin_of<D>(q, out.mom[0], out.mom[1], out.mom[2]));
 		out.Erad = Erad_guess;
 	} else {
 		out.Eint = nan; // not written by the reference (:558-571); the caller skips these three
@@ -453,6 +486,13 @@ static inline Const make_const(const qk_hydro_params *hp, const qk_rad_params *r
 	k.dt = (stage == 2) ? (1.0 - IMEX_a32) * dt_radiation : dt_radiation;
 	k.chat_dt = k.chat * k.dt;
 	k.gas_update_factor = (stage == 1) ? IMEX_a32 : 1.0;
+	k.cvc = k.kB / (k.mumn * k.gm1);
+	k.inv_cvc = 1.0 / k.cvc;
+	k.inv_arad = 1.0 / k.a_rad;
+	k.inv_kPoE = 1.0 / k.kPoE;
+	k.inv_cc = 1.0 / k.cc;
+	k.inv_cchat = 1.0 / k.c_chat;
+	k.Tmin = k.mintemp * K_B / k.kB;
 	return k;
 }
 } // namespace qk_rsrc

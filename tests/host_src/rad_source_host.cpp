@@ -9,7 +9,8 @@ static inline double &at(const qk_array4 *a, int i, int j, int k, int n)
 	return a->p[(int64_t)(i - a->begin[0]) + (int64_t)(j - a->begin[1]) * a->jstride + (int64_t)(k - a->begin[2]) * a->kstride + n * a->nstride];
 }
 
-extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_rad_params *rp, const qk_rad_source_params *sp, const qk_array4 *cons,
+template <bool RELAXED>
+static void run_box(const qk_hydro_params *hp, const qk_rad_params *rp, const qk_rad_source_params *sp, const qk_array4 *cons,
 					  const qk_array4 *src, const qk_box *bx, double dt_radiation, int stage, int64_t *counters)
 {
 	const qk_rsrc::Const k = qk_rsrc::make_const(hp, rp, sp, dt_radiation, stage);
@@ -29,7 +30,7 @@ extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_ra
 				in.Egastot = at(cons, i, j, kk, 4);
 				in.Erad = at(cons, i, j, kk, ns);
 				in.src = src ? at(src, i, j, kk, 0) : 0.0;
-				qk_rsrc::source_cell<qk_rsrc::DivPlain>(k, ct, in, out);
+				qk_rsrc::source_cell<qk_rsrc::DivPlain, RELAXED>(k, ct, in, out);
 				for (int m = 0; m < 3; ++m) {
 					at(cons, i, j, kk, 1 + m) = out.mom[m];
 					at(cons, i, j, kk, ns + 1 + m) = out.F[m];
@@ -47,4 +48,13 @@ extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_ra
 					counters[6] += out.fail_outer;
 				}
 			}
+}
+
+extern "C" void host_rad_add_source_terms(const qk_hydro_params *hp, const qk_rad_params *rp, const qk_rad_source_params *sp, const qk_array4 *cons,
+					  const qk_array4 *src, const qk_box *bx, double dt_radiation, int stage, int64_t *counters)
+{
+	if (hp->arith == QK_ARITH_FAST)
+		run_box<true>(hp, rp, sp, cons, src, bx, dt_radiation, stage, counters);
+	else
+		run_box<false>(hp, rp, sp, cons, src, bx, dt_radiation, stage, counters);
 }

@@ -127,6 +127,32 @@ def test_kernel_arithmetic_on_host_matches_oracle(host, name, stage):
         assert min(fracs) >= 0.98, fracs
 
 
+@pytest.mark.parametrize("name", TRAITS)
+@pytest.mark.parametrize("stage", [1, 2])
+def test_relaxed_arithmetic_on_host_within_tolerance(host, name, stage):
+    """qk_hydro_params::arith == QK_ARITH_FAST: closed-form EOS and reciprocal products (one division per Newton-Raphson iteration
+    instead of thirteen).  Same algorithm, so the converged state agrees with the reference to the solver's own tolerance:
+    stated bar 1e-10 of the cell's energy / momentum scale (measured: <= 3e-12), iteration counts within 0.1 %."""
+    hp, rp, sp, gen = trait_set(name)
+    worst = 0.0
+    for n, dt in enumerate(gen["dts"]):
+        st = ol.random_radhydro_cons(VALID, hp, rp, sp, seed=31 * n + stage, T0=gen["T0"], rho0=gen["rho0"], vmax=gen["vmax"])
+        a, b = ol.HostFab(VALID, rp.nstart + 4), ol.HostFab(VALID, rp.nstart + 4)
+        a.a[...] = st
+        b.a[...] = st
+        ca = (C.c_int64 * QK_RAD_SOURCE_NCOUNTERS)()
+        cb = (C.c_int64 * QK_RAD_SOURCE_NCOUNTERS)()
+        with np.errstate(all="ignore"):
+            ol.oracle().orc_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), C.byref(a.desc()), None, C.byref(VALID), dt, stage, ca)
+        hp.arith = capi.QK_ARITH_FAST
+        host.host_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), C.byref(b.desc()), None, C.byref(VALID), dt, stage, cb)
+        hp.arith = capi.QK_ARITH_EXACT
+        if ca[4] == 0 and ca[6] == 0:  # cells that do not converge in the reference end on an arbitrary iterate
+            compare_with_oracle(b.a, a.a, st, rp, tol=1e-10)
+            assert abs(ca[1] - cb[1]) <= max(2, ca[1] // 1000), (list(ca), list(cb))
+            assert cb[4] == 0 and cb[6] == 0
+
+
 def test_pow_dd_is_correctly_rounded(host):
     """pow_dd<4>/<3> through the emission term: a_rad = 1, kappa huge so that E_rad -> T^4; instead of going through the solver,
     check the double-double product against Python's exact rational arithmetic on the host mirror below."""
