@@ -501,7 +501,10 @@ def main_radhydro(args):
     sigma_star = 0.3 * P.r_0
     src = (1.0 / P.c_light) * (0.5 * 1.0e6 * 2.0e33 * 2000.0) / (2.0 * np.pi * sigma_star * sigma_star) ** 1.5 * np.exp(-(r * r) / (2.0 * sigma_star * sigma_star))
     prob = ShellProblem(n, box, initial=init)
-    sim = HydroSimulation(prob)
+    # --arith relaxed (the parser's default) selects the relaxed fused PLM sweeps AND the relaxed source-term solve; the numbers in
+    # profiles/r01_bench_radhydro.json are --arith exact
+    arith = capi.QK_ARITH_FAST if args.arith == "relaxed" else capi.QK_ARITH_EXACT
+    sim = HydroSimulation(prob, params=prob.params(arith=arith))
     esrc = DevMultiFab(prob.boxes, 1, ngrow=0,
                        host=[np.ascontiguousarray(src[None, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]) for b in prob.boxes])
     sim.enableRadiation(prob.rad_params(), prob.rad_source_params(), esrc, rad_cfl=prob.rad_cfl, max_substeps=prob.max_substeps)
@@ -540,7 +543,7 @@ def main_radhydro(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "RadhydroShell 256^3 periodic (configs[3] on one GPU), eight 128^3 boxes, 1 photon group, kappa = 20, beta_order 1, "
                                    "PLM hydro + PLM radiation, cfl 0.3; state (1.6 GB) >> L2, no flush", "cells": ncell, "radiation_substeps_per_step": nsub,
-                       "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": "exact"},
+                       "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": args.arith},
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_rad_source", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": psrc, "unit": "GB/s",
                          "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 152, "avg_launch_ms": round(per, 4),
