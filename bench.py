@@ -193,6 +193,21 @@ def main_reference(args):
         return 0
     steps = args.steps + args.warmup
     cores = os.cpu_count() or 1
+    if getattr(args, "workload", "hydro") == "radhydro":  # config C4: the reference's own RadhydroShell problem on the host cores
+        if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/shell_golden not built (make -C oracle/ref_build shell_golden)"}))
+            return 0
+        nst = max(1, min(steps, 2))
+        v, el = run_reference_shell_cpu(64, 32, nst, cores)
+        txt = f"reference RadhydroShell problem (OpenMP, {cores} threads), 64^3 in 32^3 boxes, {nst} coarse steps of 10 radiation substeps, {el:.1f} s"
+        print(json.dumps({"impl": "reference", "metric": "Mcell-updates/s (radiation hydrodynamics coarse step: hydro PLM+HLLC RK2 + 10 two-moment IMEX "
+                          "substeps with matter-radiation coupling)", "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": round(el * 1e3 / nst, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "the reference's own initial condition",
+                          "config": {"workload": "RadhydroShell (configs[3]); bounded sample 64^3", "cells": 64 ** 3},
+                          "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference", "sample": txt},
+                          "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
     ncell = ncell_for(args.gpus)
     if os.path.exists(REF_EXE):
         # bounded sample of the workload: one 128^3 box-sized domain (the configs' building block) per "GPU"

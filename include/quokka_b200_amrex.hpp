@@ -539,6 +539,31 @@ class LevelB200
 		MFView uo(Uout);
 		check(qk_rad_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, stream()), "advanceRadiationStage");
 	}
+	// QuokkaSimulation::subcycleRadiationAtLevel (src/QuokkaSimulation.hpp:1577-1700) without flux registers: all substeps, transport
+	// stages, ghost fills and (single-group, constant-opacity) source terms inside the library.  U_tmp: a MultiFab shaped like the
+	// state (state_inter_cc_[lev] is free at this point).  Returns the number of substeps.
+	template <typename problem_t>
+	auto subcycleRadiation(qk_rad_params const &prm, amrex::MultiFab &state_old, amrex::MultiFab &state_new, amrex::MultiFab &U_tmp,
+			       amrex::MultiFab const *radEnergySource, double dt_lev_hydro, double radiationCflNumber, int64_t *counters) -> int
+	{
+		const qk_hydro_params hp = make_params<problem_t>();
+		const qk_rad_source_params sp = make_rad_source_params<problem_t>();
+		MFView uo(state_old);
+		MFView un(state_new);
+		MFView ut(U_tmp);
+		int nsub = 0;
+		if (radEnergySource != nullptr) {
+			MFView e(*radEnergySource);
+			check(qk_rad_subcycle(lev_, &hp, &prm, &sp, uo.arr.data(), un.arr.data(), ut.arr.data(), e.arr.data(), dt_lev_hydro, radiationCflNumber,
+					      counters, &nsub, stream()),
+			      "subcycleRadiation");
+		} else {
+			check(qk_rad_subcycle(lev_, &hp, &prm, &sp, uo.arr.data(), un.arr.data(), ut.arr.data(), nullptr, dt_lev_hydro, radiationCflNumber, counters,
+					      &nsub, stream()),
+			      "subcycleRadiation");
+		}
+		return nsub;
+	}
 	[[nodiscard]] auto handle() const -> qk_level * { return lev_; }
 
       private:

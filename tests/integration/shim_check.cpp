@@ -124,6 +124,12 @@ void rad_source_level(amrex::MultiFab &state, double dt, int64_t *counters)
 	quokka::b200::RadSystemB200<RadLike>::AddSourceTermsSingleGroup(state, nullptr, dt, 2, counters);
 }
 
+int rad_subcycle(quokka::b200::LevelB200 &lev, amrex::MultiFab &Uold, amrex::MultiFab &Unew, amrex::MultiFab &Utmp, double dt_hydro, int64_t *counters)
+{
+	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();
+	return lev.subcycleRadiation<RadLike>(prm, Uold, Unew, Utmp, nullptr, dt_hydro, 0.3, counters);
+}
+
 void rad_level(quokka::b200::LevelB200 &lev, amrex::MultiFab &U0, amrex::MultiFab &U1, amrex::MultiFab &Unew, double dt)
 {
 	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();
