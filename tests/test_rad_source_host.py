@@ -179,3 +179,39 @@ def test_pow_dd_is_correctly_rounded(host):
         # correctly rounded <=> |s - exact| <= half an ulp of s
         ulp = math.ulp(s)
         assert abs(Fraction(s) - exact) <= Fraction(ulp) / 2, x
+
+
+def _run_host(host, hp, rp, sp, st, dt, stage):
+    b = ol.HostFab(VALID, rp.nstart + 4)
+    b.a[...] = st
+    host.host_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), C.byref(b.desc()), None, C.byref(VALID), dt, stage, None)
+    return b.a
+
+
+def test_radiative_equilibrium_at_rest_is_a_fixed_point(host):
+    """known answer: gas at rest in equilibrium with an isotropic radiation field (a T^4 = E_r, F = 0, no source) is left alone --
+    the first residual test of the Newton-Raphson loop already passes"""
+    hp, rp, sp, gen = trait_set("shell")
+    st = ol.random_radhydro_cons(VALID, hp, rp, sp, seed=1, T0=gen["T0"], rho0=gen["rho0"], vmax=0.0, fmax=0.0)
+    T = st[5] * (hp.mean_molecular_weight * (hp.gamma - 1.0)) / (st[0] * hp.boltzmann_constant)
+    st[rp.nstart] = sp.radiation_constant * T ** 4
+    st[4] = st[5]
+    for stage in (1, 2):
+        out = _run_host(host, hp, rp, sp, st, gen["dts"][1], stage)
+        assert np.abs(out[5] / st[5] - 1).max() < 1e-10 and np.abs(out[rp.nstart] / st[rp.nstart] - 1).max() < 1e-10
+        assert np.array_equal(out[1:4], st[1:4]) and np.array_equal(out[rp.nstart + 1:], st[rp.nstart + 1:])
+
+
+def test_stage_1_applies_half_of_the_gas_update(host):
+    """known answer from the IMEX PD-ARS scheme (source_terms_single_group.hpp:13-19,88-91,549-557): stage 1 integrates over dt and
+    gives the gas IMEX_a32 = 1/2 of the exchange; stage 2 integrates over (1 - a32) dt and gives it all.  So stage 1 with dt and
+    stage 2 with 2 dt solve the same system: identical E_r and F_r, and exactly half the change of gas momentum and internal energy."""
+    hp, rp, sp, gen = trait_set("beta0")
+    st = ol.random_radhydro_cons(VALID, hp, rp, sp, seed=2, T0=gen["T0"], rho0=gen["rho0"], vmax=gen["vmax"])
+    a = _run_host(host, hp, rp, sp, st, 0.05, 1)
+    b = _run_host(host, hp, rp, sp, st, 0.10, 2)
+    ns = rp.nstart
+    assert np.array_equal(a[ns:], b[ns:])
+    for c in (1, 2, 3, 5):
+        da, db = a[c] - st[c], b[c] - st[c]
+        assert np.abs(da - 0.5 * db).max() <= 4e-16 * np.abs(st[c]).max() + 1e-15 * np.abs(db).max()
