@@ -243,7 +243,9 @@ typedef struct qk_rad_source_params {
  * (the call then synchronises the stream), or NULL (fully asynchronous).  Arithmetic: the reference's operation order with
  * contraction off; T^3, T^4 and lorentz^3, which the reference takes from std::pow, are formed in double-double and rounded
  * once, so results agree with the CPU reference to the last bit except where libm's pow is itself not
- * correctly rounded; the parity bar is 1e-13 relative. */
+ * correctly rounded; after the Newton-Raphson solve (residual tolerance 1e-11 E_tot) the stated parity bar is 1e-10 of the cell's
+ * energy / momentum scale (measured <= 1e-14).  hydro->arith == QK_ARITH_FAST selects the relaxed form (closed-form EOS, reciprocal
+ * products; <= 3e-12). */
 int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_rad_params *prm, const qk_rad_source_params *src, int stage, int nboxes,
 			    const qk_box *valid, const qk_array4 *cons, const qk_array4 *rad_energy_source, double dt_radiation, int64_t *counters,
 			    void *stream);
