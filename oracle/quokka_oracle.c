@@ -1282,6 +1282,143 @@ void orc_rad_add_source_terms(const qk_hydro_params *hp, const qk_rad_params *pr
 }
 
 /* ================================================================================================
+ * Coarse <-> fine transfer operators of the AMR ghost fill: the cell-centred interpolater Quokka selects with
+ * amr_interpolation_method = 1 (getAmrInterpolaterCellCentered, src/simulation.hpp:1389-1407) =
+ * amrex::mf_linear_slope_minmax_interp = MFCellConsLinMinmaxLimitInterp::interp (extern/amrex/Src/AmrCore/AMReX_MFInterpolater.cpp:
+ * 332-418) with mf_cell_cons_lin_interp_limit_minmax_llslope + mf_cell_cons_lin_interp (AMReX_MFInterp_3D_C.H:7-109,246-262) and
+ * mf_compute_slopes_{x,y,z} (AMReX_MFInterp_C.H:10-90); and amrex::average_down = amrex_avgdown (Base/AMReX_MultiFabUtil_3D_C.H:345-375).
+ * ============================================================================================== */
+static qk_array4 alloc_a4(qk_box b, int ncomp);
+static void free_a4(qk_array4 *a);
+static int coarsen_i(int i, int r) { return (i < 0) ? -((-i + r - 1) / r) : i / r; } /* amrex::coarsen(int, int): floor division */
+
+/* mf_compute_slopes_<dir>: centred slope, one-sided at a domain face whose BC is ext_dir or hoextrap */
+static double interp_slope(const qk_array4 *u, int i, int j, int k, int nu, int dir, const qk_box *domain, int bclo, int bchi)
+{
+	const int e[3] = {dir == 0, dir == 1, dir == 2};
+	const int idx[3] = {i, j, k};
+#define U_(o) A4(u, i + (o)*e[0], j + (o)*e[1], k + (o)*e[2], nu)
+	double dc = 0.5 * (U_(1) - U_(-1));
+	if (idx[dir] == domain->lo[dir] && (bclo == QK_BC_EXT_DIR || bclo == 4 /* hoextrap */)) {
+		if (idx[dir] + 2 < u->end[dir])
+			dc = -(16. / 15.) * U_(-1) + 0.5 * U_(0) + (2. / 3.) * U_(1) - 0.1 * U_(2);
+		else
+			dc = 0.25 * (U_(1) + 5. * U_(0) - 6. * U_(-1));
+	}
+	if (idx[dir] == domain->hi[dir] && (bchi == QK_BC_EXT_DIR || bchi == 4)) {
+		if (idx[dir] - 2 >= u->begin[dir])
+			dc = (16. / 15.) * U_(1) - 0.5 * U_(0) - (2. / 3.) * U_(-1) + 0.1 * U_(-2);
+		else
+			dc = -0.25 * (U_(-1) + 5. * U_(0) - 6. * U_(1));
+	}
+#undef U_
+	return dc;
+}
+
+/* slopes of all ncomp components of coarse cell (i,j,k): slope has 3*ncomp components (x block, y block, z block) */
+static void interp_limited_slopes(const qk_array4 *slope, const qk_array4 *u, int i, int j, int k, int scomp, int ncomp, const qk_box *domain,
+				  const int ratio[3], const int32_t *bc_lo, const int32_t *bc_hi)
+{
+	double sf[3] = {1.0, 1.0, 1.0};
+	for (int ns = 0; ns < ncomp; ++ns) {
+		const int nu = ns + scomp;
+		double sl[3] = {0., 0., 0.}, dcv[3] = {0., 0., 0.};
+		for (int d = 0; d < 3; ++d) {
+			const int e0 = (d == 0), e1 = (d == 1), e2 = (d == 2);
+			if (ratio[d] > 1) {
+				dcv[d] = interp_slope(u, i, j, k, nu, d, domain, bc_lo[3 * ns + d], bc_hi[3 * ns + d]);
+				const double df = 2.0 * (A4(u, i + e0, j + e1, k + e2, nu) - A4(u, i, j, k, nu));
+				const double db = 2.0 * (A4(u, i, j, k, nu) - A4(u, i - e0, j - e1, k - e2, nu));
+				double sd = (df * db >= 0.0) ? dmin(fabs(df), fabs(db)) : 0.;
+				sd = copysign(1., dcv[d]) * dmin(sd, fabs(dcv[d]));
+				sl[d] = sd;
+				A4(slope, i, j, k, ns + d * ncomp) = dcv[d]; /* unlimited slope */
+			} else {
+				A4(slope, i, j, k, ns + d * ncomp) = 0.0;
+			}
+		}
+		/* :62-87 no new extrema in this component */
+		double alpha = 1.0;
+		if (sl[0] != 0.0 || sl[1] != 0.0 || sl[2] != 0.0) {
+			const double dumax = fabs(sl[0]) * (double)(ratio[0] - 1) / (double)(2 * ratio[0]) +
+					     fabs(sl[1]) * (double)(ratio[1] - 1) / (double)(2 * ratio[1]) +
+					     fabs(sl[2]) * (double)(ratio[2] - 1) / (double)(2 * ratio[2]);
+			const double uc = A4(u, i, j, k, nu);
+			double umax = uc, umin = uc;
+			const int il = ratio[0] > 1, jl = ratio[1] > 1, kl = ratio[2] > 1;
+			for (int ko = -kl; ko <= kl; ++ko)
+				for (int jo = -jl; jo <= jl; ++jo)
+					for (int io = -il; io <= il; ++io) {
+						umin = dmin(umin, A4(u, i + io, j + jo, k + ko, nu));
+						umax = dmax(umax, A4(u, i + io, j + jo, k + ko, nu));
+					}
+			if (dumax * alpha > (umax - uc))
+				alpha = (umax - uc) / dumax;
+			if (dumax * alpha > (uc - umin))
+				alpha = (uc - umin) / dumax;
+		}
+		for (int d = 0; d < 3; ++d) {
+			sl[d] *= alpha;
+			if (dcv[d] != 0.0) /* :90-98 */
+				sf[d] = dmin(sf[d], sl[d] / dcv[d]);
+		}
+	}
+	for (int ns = 0; ns < ncomp; ++ns) /* :102-106: one limiter per direction for ALL components (preserves linear combinations) */
+		for (int d = 0; d < 3; ++d)
+			A4(slope, i, j, k, ns + d * ncomp) *= sf[d];
+}
+
+/* MFCellConsLinMinmaxLimitInterp::interp on one box pair.  crse covers CoarseBox(fine_region) = coarsen(fine_region) grown by 1;
+ * the fine cells of fine_region that lie inside dest_domain are written.  bc_lo / bc_hi: [3 * comp + dim] for comps ccomp.. */
+void orc_interp_cons_lin_minmax(const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *fine_region,
+				const qk_box *dest_domain, const qk_box *cdomain, const int ratio[3], const int32_t *bc_lo, const int32_t *bc_hi)
+{
+	qk_box cb; /* crse box shrunk by 1 where ratio > 1 (:391) */
+	for (int d = 0; d < 3; ++d) {
+		const int m1 = (ratio[d] > 1) ? 1 : 0;
+		cb.lo[d] = crse->begin[d] + m1;
+		cb.hi[d] = crse->end[d] - 1 - m1;
+	}
+	qk_array4 slope = alloc_a4(cb, 3 * ncomp);
+	for (int k = cb.lo[2]; k <= cb.hi[2]; ++k)
+		for (int j = cb.lo[1]; j <= cb.hi[1]; ++j)
+			for (int i = cb.lo[0]; i <= cb.hi[0]; ++i)
+				interp_limited_slopes(&slope, crse, i, j, k, ccomp, ncomp, cdomain, ratio, bc_lo, bc_hi);
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = fine_region->lo[2]; k <= fine_region->hi[2]; ++k)
+			for (int j = fine_region->lo[1]; j <= fine_region->hi[1]; ++j)
+				for (int i = fine_region->lo[0]; i <= fine_region->hi[0]; ++i) {
+					if (i < dest_domain->lo[0] || i > dest_domain->hi[0] || j < dest_domain->lo[1] || j > dest_domain->hi[1] ||
+					    k < dest_domain->lo[2] || k > dest_domain->hi[2])
+						continue;
+					const int ic = coarsen_i(i, ratio[0]), jc = coarsen_i(j, ratio[1]), kc = coarsen_i(k, ratio[2]);
+					const double xoff = ((double)(i - ic * ratio[0]) + 0.5) / (double)ratio[0] - 0.5;
+					const double yoff = ((double)(j - jc * ratio[1]) + 0.5) / (double)ratio[1] - 0.5;
+					const double zoff = ((double)(k - kc * ratio[2]) + 0.5) / (double)ratio[2] - 0.5;
+					A4(fine, i, j, k, fcomp + n) = A4(crse, ic, jc, kc, ccomp + n) + xoff * A4(&slope, ic, jc, kc, n) +
+								       yoff * A4(&slope, ic, jc, kc, n + ncomp) + zoff * A4(&slope, ic, jc, kc, n + ncomp * 2);
+				}
+	free_a4(&slope);
+}
+
+/* amrex_avgdown: crse(i,j,k) = volfrac * sum of the ratio^3 fine cells, summed x fastest */
+void orc_average_down(const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *cbx, const int ratio[3])
+{
+	const double volfrac = 1.0 / (double)(ratio[0] * ratio[1] * ratio[2]);
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = cbx->lo[2]; k <= cbx->hi[2]; ++k)
+			for (int j = cbx->lo[1]; j <= cbx->hi[1]; ++j)
+				for (int i = cbx->lo[0]; i <= cbx->hi[0]; ++i) {
+					double c = 0;
+					for (int kr = 0; kr < ratio[2]; ++kr)
+						for (int jr = 0; jr < ratio[1]; ++jr)
+							for (int ir = 0; ir < ratio[0]; ++ir)
+								c += A4(fine, i * ratio[0] + ir, j * ratio[1] + jr, k * ratio[2] + kr, n + fcomp);
+					A4(crse, i, j, k, n + ccomp) = volfrac * c;
+				}
+}
+
+/* ================================================================================================
  * Level driver (uniform single level, all boxes in this process)
  * ============================================================================================== */
 struct orc_level {

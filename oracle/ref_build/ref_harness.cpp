@@ -18,6 +18,8 @@
 #include "AMReX_MultiFab.H"
 #include "AMReX_ParmParse.H"
 #include "AMReX_iMultiFab.H"
+#include "AMReX_MFInterpolater.H"
+#include "AMReX_MultiFabUtil.H"
 
 #include "hydro/hydro_system.hpp"
 #include "hyperbolic_system.hpp"
@@ -723,6 +725,51 @@ int ref_rad_add_source_terms(int problem, const qk_box *valid, const qk_array4 *
 {
 	ensure_init();
 	DISPATCH_RS(problem, rad_source_terms<P>(valid, cons, src, dt, stage, counters));
+	return 0;
+}
+
+// ---- AMR transfer operators: AMReX's own code (the interpolater Quokka selects, src/simulation.hpp:1389-1407) ----
+// crse: FAB on CoarseBox(fine_region); fine: FAB containing fine_region; bc_lo/bc_hi: [3 * comp + dim]
+int ref_interp_cons_lin_minmax(const qk_array4 *crse, const qk_array4 *fine, int ncomp, const qk_box *fine_region, const qk_box *dest_domain,
+			       const qk_box *cdomain, const int *ratio, const int32_t *bc_lo, const int32_t *bc_hi)
+{
+	ensure_init();
+	const amrex::IntVect rr(ratio[0], ratio[1], ratio[2]);
+	const amrex::Box fbx = to_box(fine_region);
+	const amrex::Box cbx = amrex::mf_linear_slope_minmax_interp.CoarseBox(fbx, rr);
+	qk_box cb{{cbx.smallEnd(0), cbx.smallEnd(1), cbx.smallEnd(2)}, {cbx.bigEnd(0), cbx.bigEnd(1), cbx.bigEnd(2)}};
+	auto cmf = make_mf(&cb, -1, ncomp, 0);
+	auto fmf = make_mf(fine_region, -1, ncomp, 0);
+	copy_in(cmf, crse);
+	copy_in(fmf, fine);
+	amrex::Vector<amrex::BCRec> bcs(ncomp);
+	for (int n = 0; n < ncomp; ++n) {
+		for (int d = 0; d < 3; ++d) {
+			bcs[n].setLo(d, bc_lo[3 * n + d]);
+			bcs[n].setHi(d, bc_hi[3 * n + d]);
+		}
+	}
+	amrex::RealBox rb({0., 0., 0.}, {1., 1., 1.});
+	amrex::Geometry cgeom(to_box(cdomain), rb, 0, {0, 0, 0});
+	amrex::Geometry fgeom(amrex::refine(to_box(cdomain), rr), rb, 0, {0, 0, 0});
+	amrex::mf_linear_slope_minmax_interp.interp(cmf, 0, fmf, 0, ncomp, amrex::IntVect(0), cgeom, fgeom, to_box(dest_domain), rr, bcs, 0);
+	copy_out(fmf, fine);
+	return 0;
+}
+int ref_average_down(const qk_array4 *crse, const qk_array4 *fine, int ncomp, const qk_box *cbx, const int *ratio)
+{
+	ensure_init();
+	const amrex::IntVect rr(ratio[0], ratio[1], ratio[2]);
+	qk_box fb;
+	for (int d = 0; d < 3; ++d) {
+		fb.lo[d] = cbx->lo[d] * ratio[d];
+		fb.hi[d] = (cbx->hi[d] + 1) * ratio[d] - 1;
+	}
+	auto cmf = make_mf(cbx, -1, ncomp, 0);
+	auto fmf = make_mf(&fb, -1, ncomp, 0);
+	copy_in(fmf, fine);
+	amrex::average_down(fmf, cmf, 0, ncomp, rr);
+	copy_out(cmf, crse);
 	return 0;
 }
 
