@@ -250,6 +250,25 @@ int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_rad_params *p
 			    const qk_box *valid, const qk_array4 *cons, const qk_array4 *rad_energy_source, double dt_radiation, int64_t *counters,
 			    void *stream);
 
+/* ---- coarse <-> fine transfer operators of the AMR ghost fill -------------------------------------------------
+ * amrex::mf_linear_slope_minmax_interp, the cell-centred interpolater Quokka selects with amr_interpolation_method = 1
+ * (getAmrInterpolaterCellCentered, src/simulation.hpp:1389-1407; MFCellConsLinMinmaxLimitInterp::interp,
+ * extern/amrex/Src/AmrCore/AMReX_MFInterpolater.cpp:332-418 with AMReX_MFInterp_3D_C.H:7-109,246-262 and AMReX_MFInterp_C.H:10-90):
+ * conservative linear interpolation whose slopes are limited so that no component gets a new extremum, with ONE limiter per
+ * direction for all ncomp components (linear combinations of the components are preserved).  Per box pair p: crse[p] must
+ * cover CoarseBox(fine_region[p]) = coarsen(fine_region[p]) grown by one cell in every refined direction (ghost cells of the
+ * coarse data already filled); the cells of fine_region[p] that lie inside dest_domain are written, components
+ * fcomp .. fcomp + ncomp - 1 from ccomp .. ccomp + ncomp - 1 (ncomp <= 16).  cdomain: the coarse level's domain; bc_lo / bc_hi:
+ * amrex::BCType per [3 * comp + dim] (one-sided slopes at ext_dir / hoextrap walls).  One launch for all pairs (16 per launch);
+ * no slope MultiFab.  Bit-identical to AMReX. */
+int qk_amr_interp_cons_lin_minmax(int npatch, const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *fine_region,
+				  const qk_box *dest_domain, const qk_box *cdomain, const int ratio[3], const int32_t *bc_lo, const int32_t *bc_hi,
+				  void *stream);
+/* amrex::average_down(S_fine, S_crse, scomp, ncomp, ratio) (extern/amrex/Src/Base/AMReX_MultiFabUtil_3D_C.H:345-375; AverageDownTo,
+ * src/simulation.hpp:1309-1343): crse(i,j,k) = mean of its ratio^3 fine cells on the coarse boxes cbx[p]. */
+int qk_amr_average_down(int npatch, const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *cbx, const int ratio[3],
+			void *stream);
+
 /* ---- level object: fused path + ghost fill -------------------------------------------------- */
 
 /* Description of the boxes of ONE AMR level owned by this rank (a MultiFab's local part) and of

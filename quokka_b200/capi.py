@@ -252,6 +252,9 @@ SYMBOLS = {
     "qk_rad_predict_step": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
     "qk_rad_add_fluxes_rk2": (C.c_int, [_RPRM, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_double, _D3, _VP]),
     "qk_rad_add_source_terms": (C.c_int, [_PRM, _RPRM, _RSPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_double, _I64P, _VP]),
+    "qk_amr_interp_cons_lin_minmax": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int32), _VP]),
+    "qk_amr_average_down": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, C.POINTER(C.c_int), _VP]),
     "qk_rad_subcycle": (C.c_int, [_VP, _PRM, _RPRM, _RSPRM, _A4P, _A4P, _A4P, _A4P, C.c_double, C.c_double, _I64P, C.POINTER(C.c_int), _VP]),
     "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),
     "qk_level_create": (C.c_int, [C.POINTER(qk_level_desc), C.POINTER(_VP)]),

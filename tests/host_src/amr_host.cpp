@@ -1,0 +1,47 @@
+// tests/host_src/amr_host.cpp -- TEST INFRASTRUCTURE.  Compiles the product's per-coarse-cell AMR transfer arithmetic
+// (quokka_b200/csrc/qk_amr.cuh, the bodies of k_amr_interp / k_amr_avgdown) for the HOST and runs it over one box pair so that it
+// can be compared with the oracle without a GPU (tests/test_amr_host.py).  Never linked into libquokka_b200.so.
+#include "../../quokka_b200/csrc/qk_amr.cuh"
+
+extern "C" void host_amr_interp(const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *fine_region,
+				const qk_box *dest_domain, const qk_box *cdomain, const int *ratio, const int32_t *bc_lo, const int32_t *bc_hi)
+{
+	qk_amr::InterpParams P;
+	qk_amr::Box region;
+	for (int d = 0; d < 3; ++d) {
+		P.cdomain.lo[d] = cdomain->lo[d];
+		P.cdomain.hi[d] = cdomain->hi[d];
+		P.dest.lo[d] = dest_domain->lo[d];
+		P.dest.hi[d] = dest_domain->hi[d];
+		P.ratio[d] = ratio[d];
+		region.lo[d] = fine_region->lo[d];
+		region.hi[d] = fine_region->hi[d];
+	}
+	P.ccomp = ccomp;
+	P.fcomp = fcomp;
+	P.ncomp = ncomp;
+	for (int n = 0; n < 3 * ncomp; ++n) {
+		P.bc_lo[n] = bc_lo[n];
+		P.bc_hi[n] = bc_hi[n];
+	}
+	const qk_amr::V4 c = qk_amr::view(*crse), f = qk_amr::view(*fine);
+	int clo[3], chi[3];
+	for (int d = 0; d < 3; ++d) {
+		clo[d] = qk_amr::coarsen(region.lo[d], ratio[d]);
+		chi[d] = qk_amr::coarsen(region.hi[d], ratio[d]);
+	}
+	for (int k = clo[2]; k <= chi[2]; ++k)
+		for (int j = clo[1]; j <= chi[1]; ++j)
+			for (int i = clo[0]; i <= chi[0]; ++i)
+				qk_amr::interp_coarse_cell(c, f, i, j, k, region, P);
+}
+
+extern "C" void host_amr_average_down(const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *cbx, const int *ratio)
+{
+	const qk_amr::V4 c = qk_amr::view(*crse), f = qk_amr::view(*fine);
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = cbx->lo[2]; k <= cbx->hi[2]; ++k)
+			for (int j = cbx->lo[1]; j <= cbx->hi[1]; ++j)
+				for (int i = cbx->lo[0]; i <= cbx->hi[0]; ++i)
+					qk_amr::at(c, i, j, k, n + ccomp) = qk_amr::avgdown_cell(f, i, j, k, n + fcomp, ratio);
+}

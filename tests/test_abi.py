@@ -84,6 +84,13 @@ def test_compute_entries_refuse_without_a_device():
     assert lib.qk_hydro_max_signal_speed(C.byref(prm), 0, 1, C.byref(box), C.byref(a), C.byref(m), None) == capi.QK_ERR_NO_DEVICE
     rp, sp = capi.rad_params(), capi.rad_source_params()
     assert lib.qk_rad_add_source_terms(C.byref(prm), C.byref(rp), C.byref(sp), 1, 1, C.byref(box), C.byref(a), None, 1.0, None, None) == capi.QK_ERR_NO_DEVICE
+    r3 = (C.c_int * 3)(2, 2, 2)
+    bcs = (C.c_int32 * 18)()
+    assert lib.qk_amr_average_down(1, C.byref(a), 0, C.byref(a), 0, 1, C.byref(box), r3, None) == capi.QK_ERR_NO_DEVICE
+    assert lib.qk_amr_interp_cons_lin_minmax(1, C.byref(a), 0, C.byref(a), 0, 6, C.byref(box), C.byref(box), C.byref(box), r3, bcs, bcs,
+                                             None) == capi.QK_ERR_NO_DEVICE
+    assert lib.qk_amr_interp_cons_lin_minmax(1, C.byref(a), 0, C.byref(a), 0, 17, C.byref(box), C.byref(box), C.byref(box), r3, bcs, bcs,
+                                             None) == capi.QK_ERR_UNSUPPORTED  # more than QK_AMR_MAXCOMP components
     bad, rcp = C.c_int64(), C.c_int64()
     assert lib.qk_selftest_division(1, 0, 16, C.byref(bad), C.byref(rcp)) == capi.QK_ERR_NO_DEVICE
     with pytest.raises(RuntimeError):
