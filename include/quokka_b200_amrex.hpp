@@ -22,7 +22,9 @@
 #include "AMReX_BCRec.H"
 #include "AMReX_Geometry.H"
 #include "AMReX_GpuDevice.H"
+#include "AMReX_MFInterpolater.H"
 #include "AMReX_MultiFab.H"
+#include "AMReX_MultiFabUtil.H"
 #include "AMReX_iMultiFab.H"
 
 #include "radiation/radiation_system.hpp" // RadSystem_Traits, RadSystem<problem_t> constants
@@ -571,5 +573,59 @@ class LevelB200
 	std::vector<qk_box> boxes_;
 	std::vector<int32_t> owner_, bc_lo_, bc_hi_;
 };
+
+// ---- AMR transfer operators --------------------------------------------------------------------------------
+// AMReX's own plugin interface for coarse->fine interpolation is the virtual class amrex::MFInterpolater; Quokka hands an
+// instance to FillPatcher / FillPatchTwoLevels / InterpFromCoarseLevel through getAmrInterpolaterCellCentered()
+// (src/simulation.hpp:1389-1407).  MFInterpB200 is a drop-in for amrex::mf_linear_slope_minmax_interp (amr_interpolation_method
+// = 1): return &quokka::b200::mf_interp_b200 there.  One launch for all local FABs; no slope MultiFab.
+class MFInterpB200 final : public amrex::MFInterpolater
+{
+      public:
+	auto CoarseBox(amrex::Box const &fine, int ratio) -> amrex::Box override { return amrex::mf_linear_slope_minmax_interp.CoarseBox(fine, ratio); }
+	auto CoarseBox(amrex::Box const &fine, amrex::IntVect const &ratio) -> amrex::Box override
+	{
+		return amrex::mf_linear_slope_minmax_interp.CoarseBox(fine, ratio);
+	}
+	void interp(amrex::MultiFab const &crsemf, int ccomp, amrex::MultiFab &finemf, int fcomp, int nc, amrex::IntVect const &ng, amrex::Geometry const &cgeom,
+		    amrex::Geometry const & /*fgeom*/, amrex::Box const &dest_domain, amrex::IntVect const &ratio, amrex::Vector<amrex::BCRec> const &bcs,
+		    int bcomp) override
+	{
+		static_assert(AMREX_SPACEDIM == 3, "libquokka_b200 operates on 3-D FABs");
+		std::vector<qk_array4> c;
+		std::vector<qk_array4> f;
+		std::vector<qk_box> region;
+		for (amrex::MFIter mfi(finemf); mfi.isValid(); ++mfi) {
+			c.push_back(view(crsemf.const_array(mfi)));
+			f.push_back(view(finemf.const_array(mfi)));
+			region.push_back(to_box(amrex::grow(mfi.validbox(), ng)));
+		}
+		std::vector<int32_t> lo(3 * static_cast<std::size_t>(nc));
+		std::vector<int32_t> hi(3 * static_cast<std::size_t>(nc));
+		for (int n = 0; n < nc; ++n) {
+			for (int d = 0; d < 3; ++d) {
+				lo[3 * n + d] = bcs[bcomp + n].lo(d);
+				hi[3 * n + d] = bcs[bcomp + n].hi(d);
+			}
+		}
+		const qk_box dest = to_box(dest_domain);
+		const qk_box cdom = to_box(cgeom.Domain());
+		const int rr[3] = {ratio[0], ratio[1], ratio[2]};
+		check(qk_amr_interp_cons_lin_minmax(static_cast<int>(c.size()), c.data(), ccomp, f.data(), fcomp, nc, region.data(), &dest, &cdom, rr, lo.data(),
+						    hi.data(), stream()),
+		      "MFInterpB200::interp");
+	}
+};
+inline MFInterpB200 mf_interp_b200; // NOLINT(cppcoreguidelines-avoid-non-const-global-variables): mirrors amrex::mf_linear_slope_minmax_interp
+
+// amrex::average_down(S_fine, S_crse, scomp, ncomp, ratio) for fine and coarse MultiFabs with matching (coarsened) BoxArrays, as
+// AverageDownTo builds them (src/simulation.hpp:1309-1343 averages into a coarsened copy and ParallelCopies it).
+inline void average_down_b200(amrex::MultiFab const &S_fine, amrex::MultiFab &S_crse_on_fine_layout, int scomp, int ncomp, amrex::IntVect const &ratio)
+{
+	MFView f(S_fine);
+	MFView c(S_crse_on_fine_layout);
+	const int rr[3] = {ratio[0], ratio[1], ratio[2]};
+	check(qk_amr_average_down(c.n(), c.arr.data(), scomp, f.arr.data(), scomp, ncomp, c.valid.data(), rr, stream()), "average_down_b200");
+}
 
 } // namespace quokka::b200

@@ -124,6 +124,10 @@ void rad_source_level(amrex::MultiFab &state, double dt, int64_t *counters)
 	quokka::b200::RadSystemB200<RadLike>::AddSourceTermsSingleGroup(state, nullptr, dt, 2, counters);
 }
 
+// AMR: the interpolater is an amrex::MFInterpolater, i.e. it can be handed to AMReX wherever mf_linear_slope_minmax_interp is
+amrex::MFInterpolater *amr_mapper(bool ours) { return ours ? static_cast<amrex::MFInterpolater *>(&quokka::b200::mf_interp_b200) : &amrex::mf_linear_slope_minmax_interp; }
+void amr_average_down(amrex::MultiFab const &fine, amrex::MultiFab &crse, amrex::IntVect const &ratio) { quokka::b200::average_down_b200(fine, crse, 0, 6, ratio); }
+
 int rad_subcycle(quokka::b200::LevelB200 &lev, amrex::MultiFab &Uold, amrex::MultiFab &Unew, amrex::MultiFab &Utmp, double dt_hydro, int64_t *counters)
 {
 	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();
