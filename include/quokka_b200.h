@@ -269,6 +269,12 @@ int qk_amr_interp_cons_lin_minmax(int npatch, const qk_array4 *crse, int ccomp, 
 int qk_amr_average_down(int npatch, const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *cbx, const int ratio[3],
 			void *stream);
 
+/* QuokkaSimulation::PreInterpState / PostInterpState (src/QuokkaSimulation.hpp:804-841), the hooks FillPatcher runs on the coarse data
+ * before and on the fine data after the interpolation: gas total energy (component 4) -> specific internal energy (E - KE) / rho,
+ * and back E = rho e + KE, on the cells of bx[b] of state[b].  One launch for all boxes. */
+int qk_amr_pre_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream);
+int qk_amr_post_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream);
+
 /* ---- level object: fused path + ghost fill -------------------------------------------------- */
 
 /* Description of the boxes of ONE AMR level owned by this rank (a MultiFab's local part) and of

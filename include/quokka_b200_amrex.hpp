@@ -618,6 +618,19 @@ class MFInterpB200 final : public amrex::MFInterpolater
 };
 inline MFInterpB200 mf_interp_b200; // NOLINT(cppcoreguidelines-avoid-non-const-global-variables): mirrors amrex::mf_linear_slope_minmax_interp
 
+// QuokkaSimulation::PreInterpState / PostInterpState (src/QuokkaSimulation.hpp:804-841) with the hooks' own signature, so that they can
+// be passed to fillBoundaryConditions / FillPatchWithData in their place (:798,1076): one launch for all FABs of mf
+inline void PreInterpStateB200(amrex::MultiFab &mf, int /*scomp*/, int /*ncomp*/)
+{
+	MFView s(mf);
+	check(qk_amr_pre_interp_state(s.n(), s.valid.data(), s.arr.data(), stream()), "PreInterpState");
+}
+inline void PostInterpStateB200(amrex::MultiFab &mf, int /*scomp*/, int /*ncomp*/)
+{
+	MFView s(mf);
+	check(qk_amr_post_interp_state(s.n(), s.valid.data(), s.arr.data(), stream()), "PostInterpState");
+}
+
 // amrex::average_down(S_fine, S_crse, scomp, ncomp, ratio) for fine and coarse MultiFabs with matching (coarsened) BoxArrays, as
 // AverageDownTo builds them (src/simulation.hpp:1309-1343 averages into a coarsened copy and ParallelCopies it).
 inline void average_down_b200(amrex::MultiFab const &S_fine, amrex::MultiFab &S_crse_on_fine_layout, int scomp, int ncomp, amrex::IntVect const &ratio)

@@ -1401,6 +1401,32 @@ void orc_interp_cons_lin_minmax(const qk_array4 *crse, int ccomp, const qk_array
 	free_a4(&slope);
 }
 
+/* QuokkaSimulation::PreInterpState / PostInterpState  src/QuokkaSimulation.hpp:804-841: the hooks FillPatcher runs on the coarse data
+ * before, and on the fine data after, the interpolation: gas total energy <-> specific internal energy */
+void orc_pre_interp_state(const qk_array4 *c, const qk_box *bx)
+{
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(c, i, j, k, RHO), px = A4(c, i, j, k, MX), py = A4(c, i, j, k, MY), pz = A4(c, i, j, k, MZ);
+				const double Etot = A4(c, i, j, k, EN);
+				const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+				A4(c, i, j, k, EN) = (Etot - kinetic_energy) / rho;
+			}
+}
+void orc_post_interp_state(const qk_array4 *c, const qk_box *bx)
+{
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(c, i, j, k, RHO), px = A4(c, i, j, k, MX), py = A4(c, i, j, k, MY), pz = A4(c, i, j, k, MZ);
+				const double e = A4(c, i, j, k, EN);
+				const double Eint = rho * e;
+				const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+				A4(c, i, j, k, EN) = Eint + kinetic_energy;
+			}
+}
+
 /* amrex_avgdown: crse(i,j,k) = volfrac * sum of the ratio^3 fine cells, summed x fastest */
 void orc_average_down(const qk_array4 *crse, int ccomp, const qk_array4 *fine, int fcomp, int ncomp, const qk_box *cbx, const int ratio[3])
 {

@@ -24,6 +24,7 @@
 #include "hydro/hydro_system.hpp"
 #include "hyperbolic_system.hpp"
 #include "radiation/radiation_system.hpp"
+#include "QuokkaSimulation.hpp" // only QuokkaSimulation<P>::PreInterpState / PostInterpState (static members) are instantiated
 
 #include "../../include/quokka_b200.h"
 
@@ -770,6 +771,21 @@ int ref_average_down(const qk_array4 *crse, const qk_array4 *fine, int ncomp, co
 	copy_in(fmf, fine);
 	amrex::average_down(fmf, cmf, 0, ncomp, rr);
 	copy_out(cmf, crse);
+	return 0;
+}
+
+// ---- QuokkaSimulation<P>::PreInterpState / PostInterpState (src/QuokkaSimulation.hpp:804-841), problem 0 (P0) ----
+int ref_pre_post_interp_state(int post, const qk_box *bx, const qk_array4 *state)
+{
+	ensure_init();
+	auto mf = make_mf(bx, -1, 6, 0);
+	copy_in(mf, state);
+	if (post != 0) {
+		QuokkaSimulation<P0>::PostInterpState(mf, 0, 6);
+	} else {
+		QuokkaSimulation<P0>::PreInterpState(mf, 0, 6);
+	}
+	copy_out(mf, state);
 	return 0;
 }
 

@@ -254,6 +254,8 @@ SYMBOLS = {
     "qk_rad_add_source_terms": (C.c_int, [_PRM, _RPRM, _RSPRM, C.c_int, C.c_int, _BXP, _A4P, _A4P, C.c_double, _I64P, _VP]),
     "qk_amr_interp_cons_lin_minmax": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32),
                                                 C.POINTER(C.c_int32), _VP]),
+    "qk_amr_pre_interp_state": (C.c_int, [C.c_int, _BXP, _A4P, _VP]),
+    "qk_amr_post_interp_state": (C.c_int, [C.c_int, _BXP, _A4P, _VP]),
     "qk_amr_average_down": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, C.POINTER(C.c_int), _VP]),
     "qk_rad_subcycle": (C.c_int, [_VP, _PRM, _RPRM, _RSPRM, _A4P, _A4P, _A4P, _A4P, C.c_double, C.c_double, _I64P, C.POINTER(C.c_int), _VP]),
     "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),

@@ -65,6 +65,19 @@ __global__ void __launch_bounds__(AMR_TPB) k_amr_avgdown(const AvgTable tab, con
 		qk_amr::at(T.crse, i, j, k, n + P.ccomp) = qk_amr::avgdown_cell(T.fine, i, j, k, n + P.fcomp, P.ratio);
 }
 
+template <bool POST> __global__ void __launch_bounds__(256) k_amr_prepost(const AvgTable tab)
+{
+	const AvgPatch &T = tab.p[blockIdx.y]; // only .crse, .lo, .n, .total are used
+	const unsigned t = blockIdx.x * 256u + threadIdx.x;
+	if (t >= T.total)
+		return;
+	const unsigned jk = t / (unsigned)T.n[0];
+	const int i = T.lo[0] + (int)(t - jk * (unsigned)T.n[0]);
+	const int kk = (int)(jk / (unsigned)T.n[1]);
+	const int j = T.lo[1] + (int)(jk - (unsigned)kk * (unsigned)T.n[1]);
+	qk_amr::prepost_cell<POST>(T.crse, i, j, T.lo[2] + kk);
+}
+
 bool contains(const qk_array4 &a, const int lo[3], const int hi[3])
 {
 	for (int d = 0; d < 3; ++d)
@@ -203,3 +216,55 @@ extern "C" int qk_amr_average_down(int npatch, const qk_array4 *crse, int ccomp,
 	}
 	return 0;
 }
+
+static int prepost(bool post, int nboxes, const qk_box *bx, const qk_array4 *state, void *stream)
+{
+	if (nboxes < 0 || (nboxes > 0 && (!bx || !state)))
+		return QK_ERR_BAD_ARG;
+	{
+		const int r = qk_require_device();
+		if (r != 0)
+			return r;
+	}
+	cudaStream_t s = (cudaStream_t)stream;
+	ProfScope prof_(post ? "amr_post_interp" : "amr_pre_interp", s);
+	for (int p0 = 0; p0 < nboxes; p0 += AMR_MAXPATCH) {
+		const int np = (nboxes - p0 < AMR_MAXPATCH) ? (nboxes - p0) : AMR_MAXPATCH;
+		AvgTable tab;
+		unsigned most = 0;
+		for (int p = 0; p < np; ++p) {
+			AvgPatch &T = tab.p[p];
+			const qk_array4 &c = state[p0 + p];
+			const qk_box &b = bx[p0 + p];
+			if (c.ncomp < 5)
+				return QK_ERR_BAD_ARG;
+			T.crse = qk_amr::view(c);
+			T.fine = T.crse;
+			int64_t tot = 1;
+			for (int d = 0; d < 3; ++d) {
+				T.lo[d] = b.lo[d];
+				T.n[d] = b.hi[d] - b.lo[d] + 1;
+				if (T.n[d] < 0)
+					T.n[d] = 0;
+				tot *= T.n[d];
+			}
+			if (tot > 0 && !contains(c, b.lo, b.hi))
+				return QK_ERR_BAD_ARG;
+			if (tot >= (int64_t(1) << 31))
+				return QK_ERR_UNSUPPORTED;
+			T.total = (unsigned)tot;
+			most = (T.total > most) ? T.total : most;
+		}
+		if (most == 0)
+			continue;
+		const dim3 grid((most + 255u) / 256u, (unsigned)np);
+		if (post)
+			k_amr_prepost<true><<<grid, 256, 0, s>>>(tab);
+		else
+			k_amr_prepost<false><<<grid, 256, 0, s>>>(tab);
+		QK_KERNEL_CHECK();
+	}
+	return 0;
+}
+extern "C" int qk_amr_pre_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream) { return prepost(false, nboxes, bx, state, stream); }
+extern "C" int qk_amr_post_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream) { return prepost(true, nboxes, bx, state, stream); }

@@ -166,6 +166,21 @@ QK_AHD void interp_coarse_cell(const V4 &crse, const V4 &fine, int ic, int jc, i
 	}
 }
 
+// QuokkaSimulation::PreInterpState / PostInterpState  src/QuokkaSimulation.hpp:804-841 for one cell: gas total energy (component 4)
+// <-> specific internal energy, the variable the reference interpolates instead of E
+template <bool POST> QK_AHD void prepost_cell(const V4 &c, int i, int j, int k)
+{
+	const double rho = at(c, i, j, k, 0), px = at(c, i, j, k, 1), py = at(c, i, j, k, 2), pz = at(c, i, j, k, 3);
+	const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);
+	double &E = at(c, i, j, k, 4);
+	if (POST) {
+		const double Eint = rho * E;
+		E = Eint + kinetic_energy;
+	} else {
+		E = (E - kinetic_energy) / rho;
+	}
+}
+
 // amrex_avgdown for one coarse cell and component
 QK_AHD double avgdown_cell(const V4 &fine, int i, int j, int k, int n, const int ratio[3])
 {

@@ -45,3 +45,16 @@ extern "C" void host_amr_average_down(const qk_array4 *crse, int ccomp, const qk
 				for (int i = cbx->lo[0]; i <= cbx->hi[0]; ++i)
 					qk_amr::at(c, i, j, k, n + ccomp) = qk_amr::avgdown_cell(f, i, j, k, n + fcomp, ratio);
 }
+
+extern "C" void host_amr_prepost(int post, const qk_array4 *state, const qk_box *bx)
+{
+	const qk_amr::V4 c = qk_amr::view(*state);
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				if (post)
+					qk_amr::prepost_cell<true>(c, i, j, k);
+				else
+					qk_amr::prepost_cell<false>(c, i, j, k);
+			}
+}

@@ -128,6 +128,14 @@ void rad_source_level(amrex::MultiFab &state, double dt, int64_t *counters)
 amrex::MFInterpolater *amr_mapper(bool ours) { return ours ? static_cast<amrex::MFInterpolater *>(&quokka::b200::mf_interp_b200) : &amrex::mf_linear_slope_minmax_interp; }
 void amr_average_down(amrex::MultiFab const &fine, amrex::MultiFab &crse, amrex::IntVect const &ratio) { quokka::b200::average_down_b200(fine, crse, 0, 6, ratio); }
 
+void amr_hooks(amrex::MultiFab &mf)
+{
+	void (*pre)(amrex::MultiFab &, int, int) = &quokka::b200::PreInterpStateB200; // the type of QuokkaSimulation<P>::PreInterpState
+	void (*post)(amrex::MultiFab &, int, int) = &quokka::b200::PostInterpStateB200;
+	pre(mf, 0, 6);
+	post(mf, 0, 6);
+}
+
 int rad_subcycle(quokka::b200::LevelB200 &lev, amrex::MultiFab &Uold, amrex::MultiFab &Unew, amrex::MultiFab &Utmp, double dt_hydro, int64_t *counters)
 {
 	qk_rad_params prm = quokka::b200::make_rad_params<RadLike>();

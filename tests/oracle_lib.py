@@ -83,6 +83,8 @@ def oracle() -> C.CDLL:
         "orc_shell_rad_energy_source": (None, [_A4P, _BXP, _D3, _D3, _D3]),
         "orc_interp_cons_lin_minmax": (None, [_A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32),
                                               C.POINTER(C.c_int32)]),
+        "orc_pre_interp_state": (None, [_A4P, _BXP]),
+        "orc_post_interp_state": (None, [_A4P, _BXP]),
         "orc_average_down": (None, [_A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, C.POINTER(C.c_int)]),
         "orc_level_swap": (None, [C.c_void_p]),
     }
@@ -119,6 +121,7 @@ def ref() -> C.CDLL:
     lib.ref_rad_compute_fluxes.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int]
     lib.ref_rad_update.argtypes = [C.c_int, C.c_int, _BXP] + [_A4P] * 9 + [C.c_double, _D3]
     lib.ref_interp_cons_lin_minmax.argtypes = [_A4P, _A4P, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.ref_pre_post_interp_state.argtypes = [C.c_int, _BXP, _A4P]
     lib.ref_average_down.argtypes = [_A4P, _A4P, C.c_int, _BXP, C.POINTER(C.c_int)]
     lib.ref_rad_source_params.argtypes = [C.c_int, _PRM, _RPRM, _RSPRM]
     lib.ref_rad_add_source_terms.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_double, C.c_int, _I64P]

@@ -29,6 +29,7 @@ def host():
     P = C.POINTER
     lib.host_amr_interp.argtypes = [P(capi.qk_array4), C.c_int, P(capi.qk_array4), C.c_int, C.c_int, P(qk_box), P(qk_box), P(qk_box), P(C.c_int),
                                     P(C.c_int32), P(C.c_int32)]
+    lib.host_amr_prepost.argtypes = [C.c_int, P(capi.qk_array4), P(qk_box)]
     lib.host_amr_average_down.argtypes = [P(capi.qk_array4), C.c_int, P(capi.qk_array4), C.c_int, C.c_int, P(qk_box), P(C.c_int)]
     return lib
 
@@ -81,3 +82,30 @@ def test_avgdown_kernel_arithmetic_bit_exact(host, ratio):
     host.host_amr_average_down(C.byref(b.desc()), 1, C.byref(fine.desc()), 1, 3, C.byref(cbx), r)
     assert np.array_equal(a.a, b.a)
     assert (b.a[0] == 3.0).all() and not (b.a[1:, 1:-1, 1:-1, 1:-1] == 3.0).any()
+
+
+def prepost_state(seed=8):
+    bx = qk_box.make((3, -2, 5), (18, 9, 12))
+    f = ol.HostFab(bx.grown(2), 10, fill=1.0)
+    rng = np.random.default_rng(seed)
+    f.a[0] = rng.uniform(0.1, 10.0, f.a[0].shape)
+    f.a[1:4] = rng.uniform(-3.0, 3.0, f.a[1:4].shape) * f.a[0]
+    f.a[4] = rng.uniform(0.1, 10.0, f.a[0].shape) + 0.5 * (f.a[1:4] ** 2).sum(0) / f.a[0]
+    return bx, f
+
+
+@pytest.mark.parametrize("post", [0, 1])
+def test_prepost_kernel_arithmetic_bit_exact(host, post):
+    bx, a = prepost_state()
+    _, b = prepost_state()
+    (ol.oracle().orc_post_interp_state if post else ol.oracle().orc_pre_interp_state)(C.byref(a.desc()), C.byref(bx))
+    host.host_amr_prepost(post, C.byref(b.desc()), C.byref(bx))
+    assert np.array_equal(a.a, b.a)
+
+
+def test_pre_then_post_restores_the_energy(host):
+    bx, a = prepost_state()
+    before = a.a.copy()
+    host.host_amr_prepost(0, C.byref(a.desc()), C.byref(bx))
+    host.host_amr_prepost(1, C.byref(a.desc()), C.byref(bx))
+    assert np.abs(a.a[4] / before[4] - 1).max() < 1e-14 and np.array_equal(np.delete(a.a, 4, 0), np.delete(before, 4, 0))

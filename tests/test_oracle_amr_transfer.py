@@ -86,3 +86,23 @@ def test_average_down_bit_exact(ratio):
     ol.oracle().orc_average_down(C.byref(a.desc()), 0, C.byref(fine.desc()), 0, ncomp, C.byref(cbx), r)
     assert ol.ref().ref_average_down(C.byref(b.desc()), C.byref(fine.desc()), ncomp, C.byref(cbx), r) == 0
     exact(a.a, b.a)
+
+
+@pytest.mark.parametrize("post", [0, 1])
+def test_pre_post_interp_state_bit_exact(post):
+    """QuokkaSimulation<P0>::PreInterpState / PostInterpState (src/QuokkaSimulation.hpp:804-841) called as static members"""
+    bx = qk_box.make((3, -2, 5), (18, 9, 12))
+    a, b = ol.HostFab(bx, 6), ol.HostFab(bx, 6)
+    rng = np.random.default_rng(8)
+    a.a[0] = rng.uniform(0.1, 10.0, a.a[0].shape)
+    a.a[1:4] = rng.uniform(-3.0, 3.0, a.a[1:4].shape) * a.a[0]
+    a.a[4] = rng.uniform(0.1, 10.0, a.a[0].shape) + 0.5 * (a.a[1:4] ** 2).sum(0) / a.a[0]
+    a.a[5] = rng.uniform(0.1, 10.0, a.a[0].shape)
+    if post:
+        a.a[4] = rng.uniform(0.1, 10.0, a.a[0].shape)  # a specific internal energy
+    b.a[...] = a.a
+    before = a.a.copy()
+    (ol.oracle().orc_post_interp_state if post else ol.oracle().orc_pre_interp_state)(C.byref(a.desc()), C.byref(bx))
+    assert ol.ref().ref_pre_post_interp_state(post, C.byref(bx), C.byref(b.desc())) == 0
+    exact(a.a, b.a)
+    assert np.array_equal(a.a[[0, 1, 2, 3, 5]], before[[0, 1, 2, 3, 5]]) and not np.array_equal(a.a[4], before[4])

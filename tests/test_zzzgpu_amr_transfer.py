@@ -10,7 +10,7 @@ import pytest
 import oracle_lib as ol
 from quokka_b200 import capi
 from quokka_b200.capi import check, qk_array4, qk_box
-from test_amr_host import interp_inputs
+from test_amr_host import interp_inputs, prepost_state
 from test_oracle_amr_transfer import CASES
 
 pytestmark = pytest.mark.gpu
@@ -116,3 +116,15 @@ def test_interp_then_average_down_is_conservative_at_full_size():
     assert float((back.t - inner).abs().max()) <= 1e-14 * 10.0
     assert bool(torch.equal(df.t[0], df.t[5]))
     assert float(df.t.min()) >= float(dc.t.min()) - 1e-13 and float(df.t.max()) <= float(dc.t.max()) + 1e-13  # rounding of uc + offsets only
+
+
+@pytest.mark.parametrize("post", [0, 1])
+def test_pre_post_interp_state_vs_oracle(post):
+    lib = capi.load()
+    bx, want = prepost_state()
+    _, start = prepost_state()
+    (ol.oracle().orc_post_interp_state if post else ol.oracle().orc_pre_interp_state)(C.byref(want.desc()), C.byref(bx))
+    d = dev(start)
+    fn = lib.qk_amr_post_interp_state if post else lib.qk_amr_pre_interp_state
+    check(fn(1, (qk_box * 1)(bx), (qk_array4 * 1)(d.desc()), None))
+    assert np.array_equal(d.numpy(), want.a)
