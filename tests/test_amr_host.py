@@ -109,3 +109,26 @@ def test_pre_then_post_restores_the_energy(host):
     host.host_amr_prepost(0, C.byref(a.desc()), C.byref(bx))
     host.host_amr_prepost(1, C.byref(a.desc()), C.byref(bx))
     assert np.abs(a.a[4] / before[4] - 1).max() < 1e-14 and np.array_equal(np.delete(a.a, 4, 0), np.delete(before, 4, 0))
+
+
+def test_interp_regions_that_cut_coarse_cells(host):
+    """fine regions with odd bounds (a coarse cell contributes only some of its children), random sizes down to one cell, ratio 2 and 4"""
+    rng = np.random.default_rng(12)
+    ncomp = 5
+    for trial in range(40):
+        ratio = (2, 2, 2) if trial % 2 == 0 else (4, 4, 4)
+        o = [int(x) for x in rng.integers(-9, 30, 3)]
+        n = [int(x) for x in rng.integers(1, 11, 3)]
+        region = qk_box.make(tuple(o), tuple(o[d] + n[d] - 1 for d in range(3)))
+        cb = qk_box.make(tuple(region.lo[d] // ratio[d] - 1 for d in range(3)), tuple(region.hi[d] // ratio[d] + 1 for d in range(3)))
+        cdomain = qk_box.make((-8, -8, -8), (23, 23, 23))
+        dest = qk_box.make((-8 * ratio[0],) * 3, (24 * ratio[0] - 1,) * 3)
+        c = ol.HostFab(cb, ncomp)
+        c.a[...] = rng.uniform(0.1, 10.0, c.a.shape)
+        a, b = ol.HostFab(region.grown(1), ncomp, fill=-1.0), ol.HostFab(region.grown(1), ncomp, fill=-1.0)
+        r = (C.c_int * 3)(*ratio)
+        bc = (C.c_int32 * (3 * ncomp))()
+        ol.oracle().orc_interp_cons_lin_minmax(C.byref(c.desc()), 0, C.byref(a.desc()), 0, ncomp, C.byref(region), C.byref(dest), C.byref(cdomain), r, bc, bc)
+        host.host_amr_interp(C.byref(c.desc()), 0, C.byref(b.desc()), 0, ncomp, C.byref(region), C.byref(dest), C.byref(cdomain), r, bc, bc)
+        assert np.array_equal(a.a, b.a), (trial, o, n, ratio)
+        assert not (b.a[:, 1:-1, 1:-1, 1:-1] == -1.0).any()

@@ -106,3 +106,25 @@ def test_pre_post_interp_state_bit_exact(post):
     assert ol.ref().ref_pre_post_interp_state(post, C.byref(bx), C.byref(b.desc())) == 0
     exact(a.a, b.a)
     assert np.array_equal(a.a[[0, 1, 2, 3, 5]], before[[0, 1, 2, 3, 5]]) and not np.array_equal(a.a[4], before[4])
+
+
+def test_interpolater_random_regions_bit_exact():
+    """fine regions with odd bounds and negative indices, down to one cell, ratio 2 and 4, against AMReX"""
+    rng = np.random.default_rng(12)
+    ncomp = 5
+    for trial in range(30):
+        ratio = (2, 2, 2) if trial % 2 == 0 else (4, 4, 4)
+        o = [int(x) for x in rng.integers(-9, 30, 3)]
+        n = [int(x) for x in rng.integers(1, 11, 3)]
+        region = qk_box.make(tuple(o), tuple(o[d] + n[d] - 1 for d in range(3)))
+        cb = coarse_box(region, ratio)
+        cdomain = qk_box.make((-8, -8, -8), (23, 23, 23))
+        dest = qk_box.make((-8 * ratio[0],) * 3, (24 * ratio[0] - 1,) * 3)
+        c = ol.HostFab(cb, ncomp)
+        c.a[...] = rng.uniform(0.1, 10.0, c.a.shape)
+        a, b = ol.HostFab(region, ncomp, fill=-1.0), ol.HostFab(region, ncomp, fill=-1.0)
+        r = (C.c_int * 3)(*ratio)
+        bc = (C.c_int32 * (3 * ncomp))()
+        ol.oracle().orc_interp_cons_lin_minmax(C.byref(c.desc()), 0, C.byref(a.desc()), 0, ncomp, C.byref(region), C.byref(dest), C.byref(cdomain), r, bc, bc)
+        assert ol.ref().ref_interp_cons_lin_minmax(C.byref(c.desc()), C.byref(b.desc()), ncomp, C.byref(region), C.byref(dest), C.byref(cdomain), r, bc, bc) == 0
+        exact(a.a, b.a)
