@@ -8,9 +8,12 @@
 //                  entirely in registers (qk_rad_source.cuh).  Iteration counters are reduced per warp, then per CTA in shared
 //                  memory, and reach global memory as one atomic per CTA and counter.
 //
-// Cell-local and compute-bound (about sixteen IEEE divisions and two square roots per Newton-Raphson iteration, 5-20
-// iterations per cell): the roof is the FP64 pipe, not HBM; algorithmic traffic is 80 B read + 72 B written per cell
-// (+8 with an energy source array).  DESIGN.md section 3.
+// Cell-local and compute-bound (thirteen IEEE divisions per Newton-Raphson iteration in the exact arithmetic mode, one in the
+// relaxed mode; 5-20 iterations per cell): the roof is the FP64 pipe, not HBM; algorithmic traffic is 80 B read + 72 B written
+// per cell (+8 with an energy source array).  The kernel is instantiated per register cap: measured on B200, 64 registers
+// (8 CTAs of 128 threads per SM) is the optimum -- the solve is one dependent chain per thread and needs warps to hide it.
+// qk_rad_subcycle (below) is subcycleRadiationAtLevel: transport stages, source terms, ghost fills and component copies.
+// DESIGN.md section 3.
 #include "qk_level.h"
 #include "qk_div.cuh"
 #include "qk_rad_source.cuh"
@@ -21,7 +24,7 @@
 namespace
 {
 constexpr int SRC_TPB = 128;
-constexpr int SRC_MAXBOX = 24; // boxes per launch (kernel-parameter table, 24 * 152 B)
+constexpr int SRC_MAXBOX = 24; // boxes per launch (kernel-parameter table, 24 * 128 B)
 
 // shared-reciprocal IEEE division (qk_div.cuh): the reciprocal of a denominator is refined once, every quotient over it is the
 // compiler's own three closing instructions; operands outside the compiler's fast-path domain take its `/`.  Bit-identical to
