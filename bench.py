@@ -249,7 +249,7 @@ def main_ours(args):
     from quokka_b200.simulation import Communicator, HydroSimulation
 
     lib = capi.load()
-    ncell = ncell_for(world)
+    ncell = [args.ncell] * 3 if getattr(args, "ncell", 0) else ncell_for(world)
     prob = SedovProblem(ncell, 128)
     comm = None
     if world > 1:
@@ -627,6 +627,8 @@ if __name__ == "__main__":
     ap.add_argument("--arith", default="relaxed", choices=["exact", "relaxed"], help="arithmetic mode of the fused sweeps (DESIGN.md section 3)")
     ap.add_argument("--workload", default="hydro", choices=["hydro", "radiation", "radhydro"],
                     help="hydro = the BASELINE.json metric (default); radiation = the transport sweep; radhydro = config C4's coarse step")
+    ap.add_argument("--ncell", type=int, default=0, help="override the grid: N^3 cells in 128^3 boxes over all ranks (e.g. 512 on one GPU, BASELINE.json's "
+                    "north-star size: use with --no-extras, the e2e leg would pin 7.7 GB of host memory)")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e and cpu_baseline legs (profiling runs)")
     a = ap.parse_args()
     if a.workload == "radiation" and a.impl == "ours":
