@@ -4,7 +4,8 @@
  1. the GPU parity tests that have not run on a GPU yet (tests/test_zzzgpu_amr_transfer.py) and the newest verified ones;
  2. CUDA-event timings of k_rad_source in the exact and the relaxed arithmetic mode (8 x 128^3, RadhydroShell traits);
  3. CUDA-event timings of the AMR transfer kernels (128^3 coarse -> 256^3 fine, 6 components) with their HBM fractions;
- 4. bench.py --workload radhydro in both arithmetic modes (run as subprocesses)."""
+ 4. bench.py --workload radhydro in both arithmetic modes (run as subprocesses);
+ 5. bench.py --ncell 512 (Sedov 512^3 on one GPU, BASELINE.json's north-star size) in both arithmetic modes."""
 import ctypes as C
 import json
 import os
@@ -118,5 +119,13 @@ for mode in ("exact", "relaxed"):
         res[f"bench_radhydro_{mode}"] = json.loads(p.stdout.strip().splitlines()[-1])
     except Exception:
         res[f"bench_radhydro_{mode}"] = {"error": (p.stdout + p.stderr)[-1500:]}
+# ---- 5. the north-star size on one GPU: Sedov 512^3 (64 boxes of 128^3), both arithmetic modes ------------------------------
+for mode in ("relaxed", "exact"):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--ncell", "512", "--arith", mode, "--steps", "5", "--warmup", "3", "--no-extras"],
+                       capture_output=True, text=True)
+    try:
+        res[f"bench_sedov512_{mode}"] = json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception:
+        res[f"bench_sedov512_{mode}"] = {"error": (p.stdout + p.stderr)[-1500:]}
 json.dump(res, open(os.path.join(OUT, "next_measurements.json"), "w"), indent=1)
 print(json.dumps({k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items() if kk in ("ms", "frac_hbm", "value", "ms_per_step", "error")}) for k, v in res.items()}, indent=1))
