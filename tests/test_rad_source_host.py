@@ -215,3 +215,29 @@ def test_stage_1_applies_half_of_the_gas_update(host):
     for c in (1, 2, 3, 5):
         da, db = a[c] - st[c], b[c] - st[c]
         assert np.abs(da - 0.5 * db).max() <= 4e-16 * np.abs(st[c]).max() + 1e-15 * np.abs(db).max()
+
+
+def test_wide_dynamic_range_inputs(host):
+    """edge cases the reference's tests exercise through their problems: six decades of density and temperature contrast, gas at rest,
+    vanishing and nearly beamed radiation flux, fast gas; iteration counters (incl. the failure counters) must be identical and the
+    values within the bar wherever the reference's iteration converges"""
+    for name in ["shell", "kF_ne_kE", "beta0", "beta3_floor"]:
+        hp, rp, sp, gen = trait_set(name)
+        for trial in range(6):
+            st = ol.random_radhydro_cons(VALID, hp, rp, sp, seed=1000 + trial, T0=gen["T0"], rho0=gen["rho0"], vmax=gen["vmax"] * [1, 0, 0.01, 1, 3, 1][trial],
+                                         spread=[0.5, 1.5, 2.5, 3.0, 1.0, 2.0][trial], fmax=[0.9, 0.0, 0.99, 0.5, 0.9, 0.1][trial])
+            if trial == 3:
+                st[1:4] = 0
+            for dt in gen["dts"]:
+                a, b = ol.HostFab(VALID, 10), ol.HostFab(VALID, 10)
+                a.a[...] = st
+                b.a[...] = st
+                ca = (C.c_int64 * QK_RAD_SOURCE_NCOUNTERS)()
+                cb = (C.c_int64 * QK_RAD_SOURCE_NCOUNTERS)()
+                with np.errstate(all="ignore"):
+                    ol.oracle().orc_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), C.byref(a.desc()), None, C.byref(VALID), dt, 1 + trial % 2, ca)
+                host.host_rad_add_source_terms(C.byref(hp), C.byref(rp), C.byref(sp), C.byref(b.desc()), None, C.byref(VALID), dt, 1 + trial % 2, cb)
+                assert list(ca) == list(cb), (name, trial, dt)
+                assert np.array_equal(np.isnan(a.a), np.isnan(b.a))
+                if ca[4] == 0 and ca[6] == 0:
+                    compare_with_oracle(b.a, a.a, st, rp)
