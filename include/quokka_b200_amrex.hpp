@@ -533,6 +533,27 @@ class LevelB200
 		check(qk_hydro_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStage");
 		return bad;
 	}
+	// the same stage through the materialised-flux path, for levels with flux registers: afterwards stageFluxes(d) are the
+	// face fluxes the reference hands to incrementFluxRegisters (src/QuokkaSimulation.hpp:1195-1198: stage 1 after the FOFC
+	// replacement; :1280-1283: stage 2's own F(U1))
+	auto advanceStageWithFluxes(qk_hydro_params const &prm, int stage, amrex::MultiFab const &U0, amrex::MultiFab const &Ustage, amrex::MultiFab &Uout,
+				    double dt) -> int64_t
+	{
+		MFView u0(U0);
+		MFView us(Ustage);
+		MFView uo(Uout);
+		int64_t bad = 0;
+		check(qk_hydro_advance_stage_faithful(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStageWithFluxes");
+		return bad;
+	}
+	// descriptors of the last stage's face-flux arrays in direction d, one per local box in MFIter order (nodal in d, 6 + nscalars
+	// components, contiguous Fortran order: an alias amrex::FArrayBox(surroundingNodes(validbox, d), ncomp, p) views them)
+	[[nodiscard]] auto stageFluxes(int d) const -> std::vector<qk_array4>
+	{
+		std::vector<qk_array4> out(static_cast<std::size_t>(qk_level_nlocal(lev_)));
+		check(qk_level_stage_fluxes(lev_, d, out.data()), "stageFluxes");
+		return out;
+	}
 	// one stage of the radiation transport substep (advanceRadiationForwardEuler / MidpointRK2 transport part), fused
 	void advanceRadiationStage(qk_rad_params const &prm, int stage, amrex::MultiFab const &U0, amrex::MultiFab const &Ustage, amrex::MultiFab &Uout, double dt)
 	{
@@ -564,6 +585,19 @@ class LevelB200
 					      &nsub, stream()),
 			      "subcycleRadiation");
 		}
+		return nsub;
+	}
+	// the same with the parameter blocks filled by the caller (arithmetic mode, floors, reconstruction order)
+	auto subcycleRadiation(qk_hydro_params const &hp, qk_rad_params const &prm, qk_rad_source_params const &sp, amrex::MultiFab &state_old,
+			       amrex::MultiFab &state_new, amrex::MultiFab &U_tmp, double dt_lev_hydro, double radiationCflNumber, int64_t *counters) -> int
+	{
+		MFView uo(state_old);
+		MFView un(state_new);
+		MFView ut(U_tmp);
+		int nsub = 0;
+		check(qk_rad_subcycle(lev_, &hp, &prm, &sp, uo.arr.data(), un.arr.data(), ut.arr.data(), nullptr, dt_lev_hydro, radiationCflNumber, counters, &nsub,
+				      stream()),
+		      "subcycleRadiation");
 		return nsub;
 	}
 	[[nodiscard]] auto handle() const -> qk_level * { return lev_; }

@@ -1054,6 +1054,15 @@ extern "C" int qk_hydro_advance_stage_faithful(qk_level *L, const qk_hydro_param
 	return L->faithful_stage(prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream));
 }
 
+extern "C" int qk_level_stage_fluxes(const qk_level *L, int dir, qk_array4 *out)
+{
+	if (!L || !out || dir < 0 || dir > 2 || L->scr.nv == 0)
+		return QK_ERR_BAD_ARG;
+	for (size_t b = 0; b < L->valid.size(); ++b)
+		out[b] = L->scr.flx[dir][b];
+	return 0;
+}
+
 // The production entry point.  Until a level has a fused plan (qk_sweep.cu) it is the faithful path.
 int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
 		   int64_t *ncells_bad, cudaStream_t s, bool *handled);
