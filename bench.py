@@ -31,7 +31,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mcell-updates/s (Sedov 3D PPM+HLLC)"
 UNIT = "Mcell-updates/s"
-REF_EXE = os.path.join(ROOT, "oracle", "_ref", "test_hydro3d_blast")
+# the reference's own CPU executable: the -O3 -march=x86-64-v3 build when present (oracle/ref_build/Makefile OPT=...), else the -O2 one the golden
+# vectors were made with (both -ffp-contract=off; same bits)
+REF_EXE = next((p for p in (os.path.join(ROOT, "oracle", "_ref", "o3", "test_hydro3d_blast"), os.path.join(ROOT, "oracle", "_ref", "test_hydro3d_blast"))
+                if os.path.exists(p)), os.path.join(ROOT, "oracle", "_ref", "test_hydro3d_blast"))
+REF_OPT = "-O3 -march=x86-64-v3" if os.sep + "o3" + os.sep in REF_EXE else "-O2"
 
 REF_INPUT = """
 geometry.prob_lo     =  0.0  0.0  0.0
@@ -60,18 +64,23 @@ def ncell_for(ngpus):
     return n
 
 
-def make_config(world, ncell, arith="exact"):
-    which = "configs[1]" if world == 1 else "configs[2]" if world == 8 else "weak-scaled configs[1]"
-    return {"workload": f"Sedov blast {ncell[0]}x{ncell[1]}x{ncell[2]} uniform ({which}), 128^3 boxes (8 per GPU), PPM+HLLC RK2, gamma=1.4, "
-                        "reflecting BCs, cfl 0.3",
+def make_config(world, ncell):
+    """identical for both arms (the driver compares them); the arithmetic mode of our arm is the top-level key `arith`"""
+    which = "configs[1]" if (world == 1 and ncell[0] == 256) else "configs[2]" if ncell[0] * ncell[1] * ncell[2] == 512 ** 3 else "weak-scaled configs[1]"
+    return {"workload": f"Sedov blast {ncell[0]}x{ncell[1]}x{ncell[2]} uniform ({which}), 128^3 boxes, PPM+HLLC RK2, gamma=1.4, reflecting BCs, cfl 0.3",
             "cells": ncell[0] * ncell[1] * ncell[2], "l2": "state per GPU (0.8 GB) >> 126 MB L2, no flush needed",
-            "arith": ("exact (IEEE order, no FMA contraction; bit-identical to the reference)" if arith == "exact" else
-                      "relaxed (closed-form gamma-law EOS, ~1-ulp reciprocals, FMA; rel L_inf vs reference < 1e-12 after 100 steps, tests/test_gpu_relaxed.py)"),
             "parallelism": f"dp{world} (boxes over ranks, NCCL ghost exchange)" if world > 1 else "1 GPU"}
+
+
+ARITH_TEXT = {"exact": "exact (IEEE order, no FMA contraction; bit-identical to the reference's CPU build)",
+              "relaxed": "relaxed (closed-form gamma-law EOS, ~1-ulp reciprocals, FMA; rel L_inf vs reference < 1e-12 after 100 steps, tests/test_gpu_relaxed.py)"}
 
 
 # ---- clocks --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi -lms 20 in the background (the recipe's clocks line).  Started BEFORE the problem is set up -- nvidia-smi needs ~1 s to
+    deliver its first row, longer than a K-step timed region -- and every row is time-stamped on arrival, so that stop() can report the
+    median over the window [t_load_start, t_load_end] in which this process kept the GPU busy with the benchmark's own kernels."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
@@ -90,11 +99,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def count(self, t0):
+        return sum(1 for t, _ in self.rows if t >= t0)
+
+    def stop(self, t0=None, t1=None):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -102,7 +114,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -115,7 +129,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "warm-up + timed region + identical untimed steps until >= 10 samples"}
 
 
 # ---- the reference's own CPU implementation ---------------------------------------------------------------------
@@ -182,7 +197,8 @@ def cpu_baseline(steps):
     if os.path.exists(REF_EXE):
         v, el = run_reference_cpu([128, 128, 128], 64, steps, cores)
         return {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
-                "sample": f"reference executable (OpenMP, {cores} threads), Sedov 128^3 in 64^3 boxes, {steps} steps, {el:.1f} s"}
+                "sample": f"BOUNDED SAMPLE of the workload: reference executable ({REF_OPT}, OpenMP, {cores} threads), Sedov 128^3 in 64^3 boxes, {steps} steps, "
+                          f"{el:.1f} s (the full 256^3 configuration is what `bench.py --impl reference` runs)"}
     v, el = run_oracle_port(48, 48, steps)
     return {"value": round(v, 4), "unit": UNIT, "cores": 1, "kind": "port", "sample": f"C oracle, 1 thread, Sedov 48^3, {steps} steps, {el:.1f} s"}
 
@@ -210,11 +226,15 @@ def main_reference(args):
         return 0
     ncell = ncell_for(args.gpus)
     if os.path.exists(REF_EXE):
-        # bounded sample of the workload: one 128^3 box-sized domain (the configs' building block) per "GPU"
-        sample = [c // 2 for c in ncell]
-        v, el = run_reference_cpu(sample, 64, steps, cores)
-        kind, sample_txt = "reference", f"reference executable (OpenMP, {cores} threads), Sedov {sample[0]}x{sample[1]}x{sample[2]} in 64^3 boxes, {steps} steps, {el:.1f} s"
-        ms = el * 1e3 / steps
+        # the REAL configuration of our arm (same grid, same 128^3 boxes).  Bounded in wall time, not in problem size: the step count is
+        # cut so that the run stays near 150 s on the box's cores (a 256^3 step takes ~4.5 s on 16 cores); Mcell-updates/s is a rate.
+        cells = ncell[0] * ncell[1] * ncell[2]
+        nrun = max(2, min(steps, int(150.0 * 0.23e6 * cores / cells)))
+        v, el = run_reference_cpu(ncell, 128, nrun, cores)
+        kind = "reference"
+        sample_txt = (f"reference executable ({REF_OPT} -ffp-contract=off, OpenMP, {cores} threads), the full configuration: Sedov {ncell[0]}x{ncell[1]}x{ncell[2]} in "
+                      f"128^3 boxes, {nrun} of the {steps} requested steps, {el:.1f} s")
+        ms = el * 1e3 / nrun
     else:
         v, el = run_oracle_port(48, 48, steps)
         cores, kind, sample_txt = 1, "port", f"C oracle, 1 thread, Sedov 48^3, {steps} steps, {el:.1f} s"
@@ -229,6 +249,116 @@ def main_reference(args):
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------
+def read_prof(lib, capi):
+    buf = (capi.C.c_char * 8192)()
+    lib.qk_prof_report(buf, 8192)
+    prof = {}
+    for ln in buf.value.decode().splitlines():
+        nm, cnt, ms = ln.split()
+        prof[nm] = (int(cnt), float(ms))
+    return prof
+
+
+def sweep_fracs(prof, ncell_local, steps):
+    """per direction sweep: average launch ms and fraction of the measured HBM copy bandwidth at SURVEY 8(d)'s 96 B per cell-sweep"""
+    peak, _ = hbm_peak()
+    out = {}
+    for k in ("sweep_x", "sweep_y", "sweep_z"):
+        if k in prof:
+            ms = prof[k][1] / (2 * steps)
+            out[k] = {"avg_launch_ms": round(ms, 4), "achieved_gbs": round(96 * ncell_local / (ms * 1e-3) / 1e9, 1),
+                      "frac": round(96 * ncell_local / (ms * 1e-3) / 1e9 / peak, 4)}
+    return out
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def gpu_reference_record(steps):
+    """the reference's own CUDA build (oracle/_ref/cuda, made from /root/reference by oracle/ref_build/Makefile.cuda) on this GPU: the stock
+    executable, and the same problem file with advanceHydroAtLevel routed through libquokka_b200, both timed by the
+    reference's own figure-of-merit line (src/simulation.hpp:972-977) on configs[1] with plotfiles off"""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import gpu_refcuda as g
+
+    if not (os.path.exists(os.path.join(g.CUDA, "test_hydro3d_blast_cuda.xz")) or os.path.exists(os.path.join(g.CUDA, "test_hydro3d_blast_cuda"))):
+        return {"unavailable": "oracle/_ref/cuda not built (make -f Makefile.cuda -C oracle/ref_build stock patched pack)"}
+    inputs = g.SEDOV.format(v=0, n=256, maxlev=0, grid=128, bf=128, amr=0, steps=steps, plot=-1)
+    base = tempfile.mkdtemp(prefix="qk_gpuref_")
+    arena = ["amrex.the_arena_init_size=40000000000"]
+    rec = {"workload": f"Sedov 256^3, 128^3 boxes, {steps} steps from t = 0, plotfile_interval = -1; the reference's own FOM line (wall clock of evolve())",
+           "build": "nvcc 12.9 -gencode arch=compute_100,code=sm_100 --fmad=false -maxrregcount=255, AMReX 24.09 CUDA, no MPI"}
+    try:
+        r = g.run("test_hydro3d_blast_cuda", inputs, arena, os.path.join(base, "stock", "run"))
+        rec["stock_cuda"] = {"value": r.get("fom_Mupdates_s"), "unit": UNIT}
+        for mode in ("exact", "relaxed"):
+            r = g.run("test_hydro3d_blast_b200", inputs, arena + ["b200.enabled=1", f"b200.arith={mode}"], os.path.join(base, mode, "run"))
+            rec[f"through_libquokka_b200_{mode}"] = {"value": r.get("fom_Mupdates_s"), "unit": UNIT}
+            if rec["stock_cuda"]["value"] and r.get("fom_Mupdates_s"):
+                rec[f"through_libquokka_b200_{mode}"]["ratio_vs_stock_cuda"] = round(r["fom_Mupdates_s"] / rec["stock_cuda"]["value"], 3)
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+    return rec
+
+
+def nrank_parity(torch, dist, world, rank, comm, capi):
+    """N-rank parity inside the scaling run: 5 exact-mode steps of Sedov on a (64^3 x N) domain in 32^3 boxes across the N ranks, and the
+    same problem on rank 0 alone; SHA-256 of the assembled global state must agree (bit-exact, exact arithmetic)."""
+    import hashlib
+
+    import numpy as np
+
+    from quokka_b200.problems import SedovProblem
+    from quokka_b200.simulation import HydroSimulation
+
+    ncell = [c // 4 for c in ncell_for(world)]
+    prob = SedovProblem(ncell, 32)
+    prm = prob.params(arith=capi.QK_ARITH_EXACT)
+    nsteps = 5
+
+    def run(nranks, r, cm):
+        sim = HydroSimulation(prob, nranks=nranks, rank=r, comm=cm, params=prm)
+        sim.setInitialConditions()
+        nd, _, _ = sim.evolve(nsteps)
+        st = sim.state_valid()
+        t = sim.time
+        ids = list(sim.local_ids)
+        sim.close()
+        return nd, t, ids, st
+
+    nd, t, ids, st = run(world, rank, comm)
+    mine = torch.from_numpy(np.stack([st[i] for i in ids])).cuda()
+    allt = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device="cuda")
+    dist.all_gather_into_tensor(allt, mine)
+    idt = torch.tensor(ids, dtype=torch.int64, device="cuda")
+    allid = torch.empty((world, len(ids)), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(allid, idt)
+    rec = None
+    if rank == 0:
+        def assemble(pieces):
+            out = np.zeros((6,) + tuple(reversed(ncell)))
+            for gid, a in pieces.items():
+                bx = prob.boxes[gid]
+                out[:, bx.lo[2]:bx.hi[2] + 1, bx.lo[1]:bx.hi[1] + 1, bx.lo[0]:bx.hi[0] + 1] = a
+            return out
+        allt_h, allid_h = allt.cpu().numpy(), allid.cpu().numpy()
+        pieces = {int(allid_h[r][b]): allt_h[r][b] for r in range(world) for b in range(allid_h.shape[1])}
+        g_n = assemble(pieces)
+        nd1, t1, ids1, st1 = run(1, 0, None)
+        g_1 = assemble(st1)
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        rec = {"what": f"Sedov {ncell[0]}x{ncell[1]}x{ncell[2]} in 32^3 boxes, {nsteps} exact-arithmetic steps: {world} ranks vs rank 0 alone",
+               "sha_nrank": sha(g_n), "sha_1rank": sha(g_1), "equal": bool(sha(g_n) == sha(g_1)), "time_equal": bool(t == t1),
+               "max_abs_diff": float(np.abs(g_n - g_1).max())}
+    dist.barrier()
+    return rec
+
+
 def main_ours(args):
     import torch
 
@@ -238,6 +368,9 @@ def main_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (libquokka_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # nvidia-smi needs ~1 s for its first row: start it before the problem is built
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -276,12 +409,8 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # clocks are sampled (nvidia-smi -lms 20) from the start of the warm-up to the end of the timed region: the timed region
-    # alone (K steps of ~9 ms) is shorter than nvidia-smi's start-up, and the warm-up runs the same kernels
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     # warm-up (also builds the scratch pools)
+    t_load0 = time.perf_counter()
     sim.evolve(args.warmup)
     barrier()
     lib.qk_prof_enable(1)
@@ -291,24 +420,36 @@ def main_ours(args):
     barrier()
     launches = lib.qk_launch_count() - l0
     lib.qk_prof_enable(0)
-    clk = clocks.stop() if rank == 0 else None
     assert nd == args.steps, (nd, args.steps)
     ms_total = max_over_ranks(dev_ms)
     value = ncells_total * args.steps / (ms_total * 1e-3) / 1e6
+    prof = read_prof(lib, capi)
+    # clocks under load: the timed region (K steps of ~8 ms) is shorter than nvidia-smi's sampling can resolve, so the same kernels keep
+    # running, untimed, until the sampler has >= 10 rows inside the load window (at most 4 s)
+    clk = None
+    extra_steps = 0
+    while True:
+        enough = (clocks.count(t_load0) >= 10) if rank == 0 else True
+        if dist is not None:
+            flag = torch.tensor([1 if enough else 0], device="cuda")
+            dist.broadcast(flag, src=0)
+            enough = bool(flag.item())
+        if enough or time.perf_counter() - t_load0 > 4.0 + 1e-3 * ms_total or args.no_extras:
+            break
+        sim.evolve(args.steps)
+        extra_steps += args.steps
+    barrier()
+    if rank == 0:
+        clk = clocks.stop(t_load0, time.perf_counter())
+        clk["untimed_steps_for_sampling"] = extra_steps
 
-    # per-kernel-class device time (CUDA events on the sim's stream inside the timed region)
-    buf = (capi.C.c_char * 8192)()
-    lib.qk_prof_report(buf, 8192)
-    prof = {}
-    for ln in buf.value.decode().splitlines():
-        nm, cnt, ms = ln.split()
-        prof[nm] = (int(cnt), float(ms))
     ncell_local = sum(b.ncells() for b in sim.local_boxes)
     roof = roofline(prof, ncell_local, args.steps, ms_total, args.arith)
 
     if args.no_extras:  # profiling runs (ncu): kernels only
         if rank == 0:
             print(json.dumps({"value": round(value, 2), "ms_per_step": round(ms_total / args.steps, 4), "gpu_launches": int(launches), "roofline": roof,
+                              "sweeps": sweep_fracs(prof, ncell_local, args.steps),
                               "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}))
         sim.close()
         return 0
@@ -327,38 +468,98 @@ def main_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = ncells_total * e2e_steps / e2e_s / 1e6
     hb = sim.h2d_bytes()
-
-    # the same workload with the bit-exact arithmetic mode, for the record (short: 5 steps after 2 warm-up steps)
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+    # the same workload with the bit-exact arithmetic mode, for the record (short: 5 steps after the warm-up)
     other = None
     if args.arith == "relaxed":
         sim2 = HydroSimulation(prob, nranks=world, rank=rank, comm=comm, params=prob.params(arith=capi.QK_ARITH_EXACT))
         sim2.setInitialConditions()
         sim2.evolve(args.warmup)
         barrier()
+        lib.qk_prof_enable(1)
         nd2, _, ms2 = sim2.evolve(5)
         barrier()
+        lib.qk_prof_enable(0)
         ms2 = max_over_ranks(ms2)
-        other = {"arith": "exact (bit-identical to the reference)", "value": round(ncells_total * nd2 / (ms2 * 1e-3) / 1e6, 2), "ms_per_step": round(ms2 / nd2, 4)}
+        other = {"arith": ARITH_TEXT["exact"], "value": round(ncells_total * nd2 / (ms2 * 1e-3) / 1e6, 2), "ms_per_step": round(ms2 / nd2, 4),
+                 "sweeps": sweep_fracs(read_prof(lib, capi), ncell_local, nd2)}
         sim2.close()
+        del sim2
+        torch.cuda.empty_cache()
+
+    parity = None
+    if world > 1:
+        try:
+            parity = nrank_parity(torch, dist, world, rank, comm, capi)
+        except Exception as e:  # never lose the scaling line
+            parity = {"error": repr(e)}
+
+    # ---- sub-records of the N = 1 line: the north-star size on one GPU, config C4, the reference's own CUDA build on this GPU -------------
+    north = radhydro = gpu_ref = None
+    if world == 1 and not getattr(args, "ncell", 0) and not args.no_subrecords:
+        try:
+            free, _ = torch.cuda.mem_get_info()
+            if free > 90e9:
+                p512 = SedovProblem([512] * 3, 128)
+                s5 = HydroSimulation(p512, params=p512.params(arith=capi.QK_ARITH_FAST if args.arith == "relaxed" else capi.QK_ARITH_EXACT))
+                s5.setInitialConditions()
+                s5.evolve(2)
+                torch.cuda.synchronize()
+                lib.qk_prof_enable(1)
+                n5, _, ms5 = s5.evolve(4)
+                lib.qk_prof_enable(0)
+                pr5 = read_prof(lib, capi)
+                north = {"workload": "Sedov blast 512^3 uniform on ONE GPU (configs[2]'s grid, tests/blast_unigrid_512.in; BASELINE.json's north-star size), 64 boxes of 128^3",
+                         "arith": args.arith, "steps": n5, "warmup": 2, "value": round(512 ** 3 * n5 / (ms5 * 1e-3) / 1e6, 2), "unit": UNIT,
+                         "ms_per_step": round(ms5 / n5, 3), "sweeps": sweep_fracs(pr5, 512 ** 3, n5),
+                         "kernel_ms_per_step": {k: round(v[1] / n5, 3) for k, v in sorted(pr5.items(), key=lambda kv: -kv[1][1])},
+                         "target": "north_star: >= 0.70 of the HBM roofline on the x sweep at 96 B/cell"}
+                s5.close()
+                del s5
+                torch.cuda.empty_cache()
+            else:
+                north = {"skipped": f"only {free / 1e9:.0f} GB of device memory free"}
+        except Exception as e:
+            north = {"error": repr(e)}
+        try:
+            radhydro = radhydro_record(args.arith, 2, 1, extras=False)
+            radhydro = {k: radhydro[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "gpu_launches", "roofline",
+                                                 "kernel_ms_per_step")}
+        except Exception as e:
+            radhydro = {"error": repr(e)}
+        try:
+            gpu_ref = gpu_reference_record(args.steps + args.warmup)
+        except Exception as e:
+            gpu_ref = {"error": repr(e)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": make_config(world, ncell, args.arith),
+                "config": make_config(world, ncell), "arith": ARITH_TEXT[args.arith],
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": hb, "steps": e2e_steps,
                         "note": "host-buffer plugin call: pinned state upload + step + state download per step"},
-                "roofline": roof, "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+                "roofline": roof, "sweeps": sweep_fracs(prof, ncell_local, args.steps),
+                "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
         if other:
             line["exact_arith"] = other
+        if parity is not None:
+            line["parity"] = parity
+        if north is not None:
+            line["north_star_512"] = north
+        if radhydro is not None:
+            line["radhydro"] = radhydro
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
         if world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline(3)
             except Exception as e:  # never lose the GPU line to a CPU-side problem
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
         print(json.dumps(line))
-    sim.close()
     if comm:
         comm.close()
     if dist is not None:
@@ -479,7 +680,7 @@ def main_radiation(args):
     return 0
 
 
-def main_radhydro(args):
+def radhydro_record(arith_name, steps, warmup, extras=True):
     """python bench.py --workload radhydro: config C4's coarse step on one GPU -- hydro PLM(minmod)+HLLC RK2 advance, then
     subcycleRadiationAtLevel: 10 IMEX substeps of (ghost fill, transport stage 1, matter-radiation source terms, ghost fill,
     transport stage 2, source terms) -- RadhydroShell traits on 256^3 periodic in eight 128^3 boxes, through the C++ driver
@@ -518,7 +719,7 @@ def main_radhydro(args):
     prob = ShellProblem(n, box, initial=init)
     # --arith relaxed (the parser's default) selects the relaxed fused PLM sweeps AND the relaxed source-term solve; the numbers in
     # profiles/r01_bench_radhydro.json are --arith exact
-    arith = capi.QK_ARITH_FAST if args.arith == "relaxed" else capi.QK_ARITH_EXACT
+    arith = capi.QK_ARITH_FAST if arith_name == "relaxed" else capi.QK_ARITH_EXACT
     sim = HydroSimulation(prob, params=prob.params(arith=arith))
     esrc = DevMultiFab(prob.boxes, 1, ngrow=0,
                        host=[np.ascontiguousarray(src[None, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]) for b in prob.boxes])
@@ -527,21 +728,21 @@ def main_radhydro(args):
     del init, src
     clocks = ClockSampler(0)
     clocks.start()
-    nd, _, _ = sim.evolve(args.warmup)
-    assert nd == args.warmup
+    nd, _, _ = sim.evolve(warmup)
+    assert nd == warmup
     lib.qk_prof_enable(1)
     l0 = lib.qk_launch_count()
-    nd, elapsed, ms = sim.evolve(args.steps)
+    nd, elapsed, ms = sim.evolve(steps)
     launches = lib.qk_launch_count() - l0
     lib.qk_prof_enable(0)
     clk = clocks.stop()
-    assert nd == args.steps, (nd, args.steps)
+    assert nd == steps, (nd, steps)
     buf = (capi.C.c_char * 8192)()
     lib.qk_prof_report(buf, 8192)
     prof = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
     ncell = n ** 3
     nsub = sim.radiationSubsteps
-    value = ncell * args.steps / (ms * 1e-3) / 1e6
+    value = ncell * steps / (ms * 1e-3) / 1e6
     peak, psrc = 6650.0, "fallback"
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -550,21 +751,21 @@ def main_radhydro(args):
         pass
     # dominant kernel class of the step: the source-term solve (2 launches per substep); 152 algorithmic bytes per cell
     src_cnt, src_ms = prof.get("rad_source_terms", (0, 0.0))
-    per = src_ms / max(1, 2 * nsub * args.steps)
+    per = src_ms / max(1, 2 * nsub * steps)
     ach = 152 * ncell / (per * 1e-3) / 1e9 if per > 0 else None
-    st = sim.gather_global() if not args.no_extras else None
+    st = sim.gather_global() if extras else None
     line = {"metric": "Mcell-updates/s (radiation hydrodynamics coarse step: hydro PLM+HLLC RK2 + 10 two-moment IMEX substeps with matter-radiation coupling)",
-            "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+            "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "RadhydroShell 256^3 periodic (configs[3] on one GPU), eight 128^3 boxes, 1 photon group, kappa = 20, beta_order 1, "
                                    "PLM hydro + PLM radiation, cfl 0.3; state (1.6 GB) >> L2, no flush", "cells": ncell, "radiation_substeps_per_step": nsub,
-                       "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": args.arith},
+                       "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": arith_name},
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_rad_source", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": psrc, "unit": "GB/s",
                          "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 152, "avg_launch_ms": round(per, 4),
                          "note": "FP64-pipe / latency bound implicit solve (DESIGN.md section 3); ncu: profiles/r01_ncu_radsrc.txt"},
-            "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
-    if not args.no_extras and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
+            "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+    if extras and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
         cores = os.cpu_count() or 1
         v, el = run_reference_shell_cpu(64, 32, 1, cores)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
@@ -572,8 +773,16 @@ def main_radhydro(args):
     if st is not None:
         line["sanity"] = {"finite": bool(np.isfinite(st).all()), "min_rho": float(st[0].min()), "min_Erad": float(st[6].min()),
                           "sim_time": sim.time}
-    print(json.dumps(line))
     sim.close()
+    del sim, esrc
+    import torch
+
+    torch.cuda.empty_cache()
+    return line
+
+
+def main_radhydro(args):
+    print(json.dumps(radhydro_record(args.arith, args.steps, args.warmup, extras=not args.no_extras)))
     return 0
 
 
@@ -591,13 +800,25 @@ def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
     ALG = 96
     if arith == "exact":  # keeps 0.5*F(U0) on the faces between the RK stages
         DESIGN = {"flux_function": 48 + 24 + 56, "sweep_x": 56 + 56 + 56, "sweep_y": 56 + 56 + 112, "sweep_z": 56 + 56 + 56 + 48 + 48}
-        # ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch at 256^3 per GPU, stage-1/stage-2 launches averaged
-        TRAFFIC = {"sweep_x": 2.894e9, "sweep_y": 4.003e9, "sweep_z": 4.742e9}  # profiles/r01_ncu_sweeps_exact.csv
         fp64_per_cell, opmix = 740, "profiles/r01_ncu_opmix_exact.txt"
     else:  # keeps R(U0) per cell instead
         DESIGN = {"sweep_x": 56 + 56, "sweep_y": 56 + 112, "sweep_z": 56 + 56 + 48 + 48 + 48}
-        TRAFFIC = {"sweep_x": 1.916e9, "sweep_y": 3.031e9, "sweep_z": 4.581e9}  # profiles/r01_ncu_sweeps_relaxed.csv
         fp64_per_cell, opmix = 480, "profiles/r01_ncu_opmix_relaxed.txt"
+    # measured DRAM traffic per launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, stage-1/stage-2 launches averaged) from the
+    # committed capture profiles/ncu_traffic.json -- reported only while the kernel sources are the ones that were profiled
+    TRAFFIC, traffic_note = {}, "profiles/ncu_traffic.json missing"
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from make_ncu_traffic import sources_sha
+
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("sources_sha256") == sources_sha() and arith in tj:
+            TRAFFIC, traffic_note = tj[arith]["bytes_per_launch"], tj[arith]["from"]
+        else:
+            traffic_note = "stale: the kernel sources changed since profiles/ncu_traffic.json was captured"
+    except Exception as e:
+        traffic_note = f"unavailable: {e}"
     cand = [(v[1], k) for k, v in prof.items() if k in DESIGN]
     if not cand:
         return None
@@ -610,7 +831,7 @@ def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
     # second roof: the FP64 pipe (64 lanes/SM/clk at 1965 MHz)
     fp64_peak = 148 * 64 * 1.965e9
     return {"bound": "hbm", "kernel": name, "achieved": round(achieved, 1), "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": TRAFFIC.get(name) if ncell_local == 256 ** 3 else None, "algorithmic_bytes_per_cell": ALG, "algorithmic_bytes_per_launch": ALG * ncell_local,
+            "traffic": TRAFFIC.get(name) if ncell_local == 256 ** 3 else None, "traffic_source": traffic_note, "algorithmic_bytes_per_cell": ALG, "algorithmic_bytes_per_launch": ALG * ncell_local,
             "design_bytes_per_cell": DESIGN[name], "achieved_design_gbs": round(DESIGN[name] * ncell_local / t / 1e9, 1),
             "frac_design": round(DESIGN[name] * ncell_local / t / 1e9 / peak, 4),
             "gcell_sweeps_per_s": round(ncell_local / t / 1e9, 3), "avg_launch_ms": round(ms / passes, 4), "launches": nl, "share_of_step": round(ms / ms_total, 4),
@@ -630,6 +851,7 @@ if __name__ == "__main__":
     ap.add_argument("--ncell", type=int, default=0, help="override the grid: N^3 cells in 128^3 boxes over all ranks (e.g. 512 on one GPU, BASELINE.json's "
                     "north-star size: use with --no-extras, the e2e leg would pin 7.7 GB of host memory)")
     ap.add_argument("--no-extras", action="store_true", help="skip the e2e and cpu_baseline legs (profiling runs)")
+    ap.add_argument("--no-subrecords", action="store_true", help="N = 1 only: skip the north_star_512 / radhydro / gpu_reference sub-records")
     a = ap.parse_args()
     if a.workload == "radiation" and a.impl == "ours":
         sys.exit(main_radiation(a))

@@ -34,7 +34,17 @@ extern "C" {
 #define QK_MAX_SCALARS 8
 #define QK_MAX_GROUPS 8
 
-enum { QK_OK = 0, QK_ERR_NO_DEVICE = -1, QK_ERR_BAD_ARG = -2, QK_ERR_UNSUPPORTED = -3, QK_ERR_NOMEM = -4 };
+enum {
+	QK_OK = 0,
+	QK_ERR_NO_DEVICE = -1,
+	QK_ERR_BAD_ARG = -2,
+	QK_ERR_UNSUPPORTED = -3,
+	QK_ERR_NOMEM = -4,
+	/* the implicit matter-radiation solve did not converge in some cell (the reference aborts: "Newton-Raphson iteration for
+	 * matter-radiation coupling failed to converge!", src/QuokkaSimulation.hpp:1700-1711) or the radiation subcycle needs more
+	 * than maxSubsteps_ + 1 substeps (AMREX_ALWAYS_ASSERT, :1597) */
+	QK_ERR_NOT_CONVERGED = -5
+};
 
 /* flux direction: FluxDir::{X1,X2,X3}, src/util/ArrayView_3d.hpp:18 */
 enum { QK_X1 = 0, QK_X2 = 1, QK_X3 = 2 };
@@ -274,6 +284,41 @@ int qk_amr_average_down(int npatch, const qk_array4 *crse, int ccomp, const qk_a
  * and back E = rho e + KE, on the cells of bx[b] of state[b].  One launch for all boxes. */
 int qk_amr_pre_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream);
 int qk_amr_post_interp_state(int nboxes, const qk_box *bx, const qk_array4 *state, void *stream);
+
+/* Time interpolation of the coarse data of the fine-level ghost fill: amrex::FillPatcher::fill (extern/amrex/Src/AmrCore/AMReX_FillPatcher.H:
+ * 340-387; the same expression in FillPatchSingleLevel, AMReX_FillPatchUtil_I.H:140-175), which AMRSimulation::fillBoundaryConditions
+ * reaches through FillPatchWithData (src/simulation.hpp:1789-1858) with the old and new coarse states that GetData returns (:1860-1905).
+ * With teps = |t1 - t0| * 1e-3:  time within teps of t0 -> copy of src0 (returns 0); within teps of t1 -> copy of src1 (returns 1); else
+ *     dst(i,j,k,dcomp+n) = alpha * src0(i,j,k,scomp+n) + beta * src1(i,j,k,scomp+n),  alpha = (t1-time)/(t1-t0), beta = (time-t0)/(t1-t0)
+ * (two roundings of the products and one of the sum, no contraction; returns 2) on region[p] of each patch.  src1 may be NULL when only one
+ * coarse time level exists (copy of src0).  *which (may be NULL) receives the branch taken.  One launch for all patches. */
+int qk_amr_time_interp(int npatch, const qk_array4 *dst, int dcomp, const qk_array4 *src0, const qk_array4 *src1, int scomp, int ncomp,
+		       const qk_box *region, double t0, double t1, double time, int *which, void *stream);
+
+/* ---- regrid support ------------------------------------------------------------------------------------------------------
+ * amrex::TagBox is BaseFab<char>: the tag arrays have the layout of qk_array4 with 1-byte elements; TagBox::CLEAR = 0, TagBox::BUF = 1, TagBox::SET = 2
+ * (extern/amrex/Src/AmrCore/AMReX_TagBox.H:33). */
+#define QK_TAG_SET 2
+typedef struct qk_carray4 {
+	char *p;
+	int64_t jstride, kstride, nstride;
+	int32_t begin[3], end[3];
+	int32_t ncomp;
+} qk_carray4;
+/* QuokkaSimulation<SedovProblem>::ErrorEst (src/problems/HydroBlast3D/test_hydro3d_blast.cpp:118-151): with P = HydroSystem::ComputePressure
+ * of the conserved state (needs one filled ghost cell), tag(i,j,k) = SET where
+ *     max over x,y,z of max(|P(+1) - P|, |P - P(-1)|) / P > eta_threshold   and   P > P_min.
+ * Cells that do not satisfy the criterion are left untouched (the reference never clears).  *ntagged (may be NULL: asynchronous) receives
+ * the number of cells this call set. */
+int qk_tag_pressure_gradient(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, const qk_carray4 *tags,
+			     double eta_threshold, double P_min, int64_t *ntagged, void *stream);
+/* QuokkaSimulation<ShocktubeProblem>::ErrorEst (src/problems/HydroShocktube/test_hydro_shocktube.cpp:146-171): component `comp`,
+ *     sqrt(del^2) / q > eta_threshold and q >= q_min,   del = (q(i+1,j,k) - q(i-1,j,k)) / (2.0 * dx)        (x direction only) */
+int qk_tag_gradient_x(int nboxes, const qk_box *valid, const qk_array4 *state, int comp, const qk_carray4 *tags, double dx, double eta_threshold,
+		      double q_min, int64_t *ntagged, void *stream);
+/* QuokkaSimulation::FixupState (src/QuokkaSimulation.hpp:761-770), called after reflux / average-down (src/simulation.hpp:1311): EnforceLimits
+ * followed by SyncDualEnergy on the valid cells, one launch each for all boxes. */
+int qk_hydro_fixup_state(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *state, void *stream);
 
 /* ---- level object: fused path + ghost fill -------------------------------------------------- */
 

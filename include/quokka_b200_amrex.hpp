@@ -589,14 +589,19 @@ class LevelB200
 	}
 	// the same with the parameter blocks filled by the caller (arithmetic mode, floors, reconstruction order)
 	auto subcycleRadiation(qk_hydro_params const &hp, qk_rad_params const &prm, qk_rad_source_params const &sp, amrex::MultiFab &state_old,
-			       amrex::MultiFab &state_new, amrex::MultiFab &U_tmp, double dt_lev_hydro, double radiationCflNumber, int64_t *counters) -> int
+			       amrex::MultiFab &state_new, amrex::MultiFab &U_tmp, amrex::MultiFab const *radEnergySource, double dt_lev_hydro,
+			       double radiationCflNumber, int64_t *counters) -> int
 	{
 		MFView uo(state_old);
 		MFView un(state_new);
 		MFView ut(U_tmp);
+		std::vector<qk_array4> src;
+		if (radEnergySource != nullptr) {
+			src = MFView(*radEnergySource).arr;
+		}
 		int nsub = 0;
-		check(qk_rad_subcycle(lev_, &hp, &prm, &sp, uo.arr.data(), un.arr.data(), ut.arr.data(), nullptr, dt_lev_hydro, radiationCflNumber, counters, &nsub,
-				      stream()),
+		check(qk_rad_subcycle(lev_, &hp, &prm, &sp, uo.arr.data(), un.arr.data(), ut.arr.data(), src.empty() ? nullptr : src.data(), dt_lev_hydro,
+				      radiationCflNumber, counters, &nsub, stream()),
 		      "subcycleRadiation");
 		return nsub;
 	}

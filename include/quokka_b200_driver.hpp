@@ -11,6 +11,7 @@
 //   b200.enabled = 1|0      (0: the stock path, same executable)
 //   b200.arith   = exact|relaxed
 //   b200.fill    = 1|0      (1: level-0 ghost fill by qk_fill_boundary when no ext_dir BC is present; 0: always AMReX's)
+//   b200.radiation = 1|0 (0: radiation subcycle stays the reference's; needed when SetRadEnergySource depends on time)
 //   b200.fused_amr = 1|0    (1: levels with flux registers use the fused sweeps + captured face fluxes when available)
 //
 // Written for this repository; it names the reference's members because that is the boundary.
@@ -39,6 +40,7 @@ struct DriverState {
 	int arith = QK_ARITH_EXACT;
 	int lib_fill = 1;
 	int fused_amr = 1;
+	int radiation = 1;
 	int64_t stages_fused = 0, stages_faithful = 0, rad_subcycles = 0;
 
 	void parse()
@@ -54,6 +56,7 @@ struct DriverState {
 		arith = (a == "relaxed" || a == "fast") ? QK_ARITH_FAST : QK_ARITH_EXACT;
 		pp.query("fill", lib_fill);
 		pp.query("fused_amr", fused_amr);
+		pp.query("radiation", radiation);
 		amrex::Print() << "[b200] libquokka_b200 driver: enabled = " << enabled << ", arith = " << (arith == QK_ARITH_FAST ? "relaxed" : "exact")
 			       << ", fill = " << lib_fill << "\n";
 	}
@@ -214,7 +217,7 @@ auto QuokkaSimulation<problem_t>::advanceHydroAtLevelB200(amrex::MultiFab &state
 // QuokkaSimulation::subcycleRadiationAtLevel (src/QuokkaSimulation.hpp:1577-1720) for a level without flux registers: substep
 // count, swapRadiationState, both transport stages, both source-term solves and the ghost fills inside qk_rad_subcycle; the
 // reference's assertions and its three convergence aborts are kept.
-template <typename problem_t> void QuokkaSimulation<problem_t>::subcycleRadiationAtLevelB200(int lev, amrex::Real /*time*/, amrex::Real dt_lev_hydro)
+template <typename problem_t> void QuokkaSimulation<problem_t>::subcycleRadiationAtLevelB200(int lev, amrex::Real time, amrex::Real dt_lev_hydro)
 {
 	BL_PROFILE("QuokkaSimulation::subcycleRadiationAtLevelB200()");
 	namespace b2 = quokka::b200;
@@ -229,8 +232,25 @@ template <typename problem_t> void QuokkaSimulation<problem_t>::subcycleRadiatio
 		rp.integrator_order = 2;
 		const qk_rad_source_params sp = b2::make_rad_source_params<problem_t>();
 		amrex::MultiFab U_tmp(grids[lev], dmap[lev], Physics_Indices<problem_t>::nvarTotal_cc, nghost_cc_);
+		// operatorSplitSourceTerms (:1860-1885) evaluates RadSystem::SetRadEnergySource box by box before every solve, at time_subcycle +
+		// dt_radiation.  Here it is evaluated ONCE per coarse step (at the first substep's time) into a one-component MultiFab that all
+		// substeps read: exact for time-independent sources (RadhydroShell's Gaussian star, the reference's default of zero); a problem
+		// whose source depends on time keeps the stock path (b200.radiation = 0).
+		amrex::MultiFab radEnergySource(grids[lev], dmap[lev], 1, 0);
+		radEnergySource.setVal(0.);
+		{
+			const int nsub_expected = computeNumberOfRadiationSubsteps(lev, dt_lev_hydro);
+			const amrex::Real dt_radiation = dt_lev_hydro / static_cast<double>(nsub_expected);
+			auto const &dx = geom[lev].CellSizeArray();
+			auto const &prob_lo = geom[lev].ProbLoArray();
+			auto const &prob_hi = geom[lev].ProbHiArray();
+			for (amrex::MFIter iter(radEnergySource); iter.isValid(); ++iter) {
+				RadSystem<problem_t>::SetRadEnergySource(radEnergySource.array(iter), iter.validbox(), dx, prob_lo, prob_hi, time + dt_radiation);
+			}
+		}
 		int64_t counters[QK_RAD_SOURCE_NCOUNTERS] = {};
-		const int nsubSteps = L.subcycleRadiation(hp, rp, sp, state_old_cc_[lev], state_new_cc_[lev], U_tmp, dt_lev_hydro, radiationCflNumber_, counters);
+		const int nsubSteps =
+		    L.subcycleRadiation(hp, rp, sp, state_old_cc_[lev], state_new_cc_[lev], U_tmp, &radEnergySource, dt_lev_hydro, radiationCflNumber_, counters);
 		if (Verbose() != 0) {
 			amrex::Print() << "\tRadiation substeps: " << nsubSteps << "\tdt: " << dt_lev_hydro / nsubSteps << "\n";
 		}

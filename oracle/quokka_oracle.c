@@ -2106,3 +2106,78 @@ void orc_level_swap(orc_level *L)
 	L->snew = L->sold;
 	L->sold = t;
 }
+
+/* ---- time interpolation, regrid tagging, FixupState ------------------------------------------------------- */
+/* amrex::FillPatcher::fill  extern/amrex/Src/AmrCore/AMReX_FillPatcher.H:340-387 */
+int orc_time_interp(const qk_array4 *dst, int dcomp, const qk_array4 *src0, const qk_array4 *src1, int scomp, int ncomp, const qk_box *region, double t0,
+		    double t1, double time)
+{
+	int idata = 0;
+	if (src1) {
+		const double teps = fabs(t1 - t0) * 1.e-3;
+		if (time > t0 - teps && time < t0 + teps)
+			idata = 0;
+		else if (time > t1 - teps && time < t1 + teps)
+			idata = 1;
+		else
+			idata = 2;
+	}
+	const double alpha = (idata == 2) ? (t1 - time) / (t1 - t0) : 0.0;
+	const double beta = (idata == 2) ? (time - t0) / (t1 - t0) : 0.0;
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = region->lo[2]; k <= region->hi[2]; ++k)
+			for (int j = region->lo[1]; j <= region->hi[1]; ++j)
+				for (int i = region->lo[0]; i <= region->hi[0]; ++i) {
+					if (idata == 0)
+						A4(dst, i, j, k, dcomp + n) = A4(src0, i, j, k, scomp + n);
+					else if (idata == 1)
+						A4(dst, i, j, k, dcomp + n) = A4(src1, i, j, k, scomp + n);
+					else
+						A4(dst, i, j, k, dcomp + n) = alpha * A4(src0, i, j, k, scomp + n) + beta * A4(src1, i, j, k, scomp + n);
+				}
+	return idata;
+}
+
+static double max2(double a, double b) { return (a < b) ? b : a; } /* std::max */
+
+/* QuokkaSimulation<SedovProblem>::ErrorEst  src/problems/HydroBlast3D/test_hydro3d_blast.cpp:118-151 */
+void orc_tag_pressure_gradient(const qk_hydro_params *prm, const qk_array4 *cons, char *tags, const qk_box *bx, double eta_threshold, double P_min)
+{
+	const int nx = bx->hi[0] - bx->lo[0] + 1, ny = bx->hi[1] - bx->lo[1] + 1;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double P = cons_pressure(prm, cons, i, j, k);
+				const double P_xplus = cons_pressure(prm, cons, i + 1, j, k), P_xminus = cons_pressure(prm, cons, i - 1, j, k);
+				const double P_yplus = cons_pressure(prm, cons, i, j + 1, k), P_yminus = cons_pressure(prm, cons, i, j - 1, k);
+				const double P_zplus = cons_pressure(prm, cons, i, j, k + 1), P_zminus = cons_pressure(prm, cons, i, j, k - 1);
+				const double del_x = max2(fabs(P_xplus - P), fabs(P - P_xminus));
+				const double del_y = max2(fabs(P_yplus - P), fabs(P - P_yminus));
+				const double del_z = max2(fabs(P_zplus - P), fabs(P - P_zminus));
+				const double gradient_indicator = max2(max2(del_x, del_y), del_z) / P;
+				if ((gradient_indicator > eta_threshold) && (P > P_min))
+					tags[(i - bx->lo[0]) + (int64_t)nx * ((j - bx->lo[1]) + (int64_t)ny * (k - bx->lo[2]))] = 2; /* TagBox::SET */
+			}
+}
+
+/* QuokkaSimulation<ShocktubeProblem>::ErrorEst  src/problems/HydroShocktube/test_hydro_shocktube.cpp:146-171 */
+void orc_tag_gradient_x(const qk_array4 *state, int comp, char *tags, const qk_box *bx, double dx, double eta_threshold, double q_min)
+{
+	const int nx = bx->hi[0] - bx->lo[0] + 1, ny = bx->hi[1] - bx->lo[1] + 1;
+	for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
+				const double rho = A4(state, i, j, k, comp);
+				const double del_x = (A4(state, i + 1, j, k, comp) - A4(state, i - 1, j, k, comp)) / (2.0 * dx);
+				const double gradient_indicator = sqrt(del_x * del_x) / rho;
+				if (gradient_indicator > eta_threshold && rho >= q_min)
+					tags[(i - bx->lo[0]) + (int64_t)nx * ((j - bx->lo[1]) + (int64_t)ny * (k - bx->lo[2]))] = 2; /* TagBox::SET */
+			}
+}
+
+/* QuokkaSimulation::FixupState  src/QuokkaSimulation.hpp:761-770 */
+void orc_fixup_state(const qk_hydro_params *prm, const qk_array4 *state, const qk_box *bx)
+{
+	orc_enforce_limits(prm, state, bx);
+	orc_sync_dual_energy(prm, state, bx);
+}

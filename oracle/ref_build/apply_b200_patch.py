@@ -37,7 +37,7 @@ HYDRO_HOOK = """\tif (b200_.on() && do_tracers == 0) {
 \t\treturn advanceHydroAtLevelB200(state_old_cc_tmp, fr_as_crse, fr_as_fine, lev, time, dt_lev);
 \t}
 """
-RAD_HOOK = """\tif (b200_.on() && fr_as_crse == nullptr && fr_as_fine == nullptr && Physics_Traits<problem_t>::is_hydro_enabled && !(constantDt_ > 0.) &&
+RAD_HOOK = """\tif (b200_.on() && b200_.radiation != 0 && fr_as_crse == nullptr && fr_as_fine == nullptr && Physics_Traits<problem_t>::is_hydro_enabled && !(constantDt_ > 0.) &&
 \t    Physics_Traits<problem_t>::nGroups == 1 && b200CanFill(lev)) {
 \t\tsubcycleRadiationAtLevelB200(lev, time, dt_lev_hydro);
 \t\treturn;

@@ -20,6 +20,8 @@
 #include "AMReX_iMultiFab.H"
 #include "AMReX_MFInterpolater.H"
 #include "AMReX_MultiFabUtil.H"
+#include "AMReX_FillPatchUtil.H"
+#include "AMReX_PhysBCFunct.H"
 
 #include "hydro/hydro_system.hpp"
 #include "hyperbolic_system.hpp"
@@ -771,6 +773,24 @@ int ref_average_down(const qk_array4 *crse, const qk_array4 *fine, int ncomp, co
 	copy_in(fmf, fine);
 	amrex::average_down(fmf, cmf, 0, ncomp, rr);
 	copy_out(cmf, crse);
+	return 0;
+}
+
+// ---- time interpolation between two states: amrex::FillPatchSingleLevel (AMReX_FillPatchUtil_I.H:140-175), the same
+// alpha * old + beta * new expression FillPatcher::fill applies to the coarse data (AMReX_FillPatcher.H:372-383) ----
+int ref_time_interp(const qk_box *bx, const qk_array4 *dst, const qk_array4 *src0, const qk_array4 *src1, int ncomp, double t0, double t1, double time)
+{
+	ensure_init();
+	auto d = make_mf(bx, -1, ncomp, 0);
+	auto s0 = make_mf(bx, -1, ncomp, 0);
+	auto s1 = make_mf(bx, -1, ncomp, 0);
+	copy_in(s0, src0);
+	copy_in(s1, src1);
+	amrex::RealBox rb({0., 0., 0.}, {1., 1., 1.});
+	amrex::Geometry geom(to_box(bx), rb, 0, {0, 0, 0});
+	amrex::PhysBCFunctNoOp bc;
+	amrex::FillPatchSingleLevel(d, time, amrex::Vector<amrex::MultiFab *>{&s0, &s1}, amrex::Vector<amrex::Real>{t0, t1}, 0, 0, ncomp, geom, bc, 0);
+	copy_out(d, dst);
 	return 0;
 }
 

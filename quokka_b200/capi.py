@@ -214,7 +214,14 @@ def make_level_desc(domain: qk_box, periodic, dx, nghost, ncomp, boxes, owner, m
     return d, (barr, oarr, lo, hi)
 
 
+class qk_carray4(C.Structure):
+    """amrex::Array4<char> (TagBox)"""
+    _fields_ = [("p", C.c_void_p), ("jstride", C.c_int64), ("kstride", C.c_int64), ("nstride", C.c_int64), ("begin", C.c_int32 * 3), ("end", C.c_int32 * 3),
+                ("ncomp", C.c_int32)]
+
+
 _A4P = C.POINTER(qk_array4)
+_CA4P = C.POINTER(qk_carray4)
 _IA4P = C.POINTER(qk_iarray4)
 _BXP = C.POINTER(qk_box)
 _PRM = C.POINTER(qk_hydro_params)
@@ -257,6 +264,10 @@ SYMBOLS = {
     "qk_amr_pre_interp_state": (C.c_int, [C.c_int, _BXP, _A4P, _VP]),
     "qk_amr_post_interp_state": (C.c_int, [C.c_int, _BXP, _A4P, _VP]),
     "qk_amr_average_down": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, C.POINTER(C.c_int), _VP]),
+    "qk_amr_time_interp": (C.c_int, [C.c_int, _A4P, C.c_int, _A4P, _A4P, C.c_int, C.c_int, _BXP, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int), _VP]),
+    "qk_tag_pressure_gradient": (C.c_int, [_PRM, C.c_int, _BXP, _A4P, _CA4P, C.c_double, C.c_double, _I64P, _VP]),
+    "qk_tag_gradient_x": (C.c_int, [C.c_int, _BXP, _A4P, C.c_int, _CA4P, C.c_double, C.c_double, C.c_double, _I64P, _VP]),
+    "qk_hydro_fixup_state": (C.c_int, [_PRM, C.c_int, _BXP, _A4P, _VP]),
     "qk_rad_subcycle": (C.c_int, [_VP, _PRM, _RPRM, _RSPRM, _A4P, _A4P, _A4P, _A4P, C.c_double, C.c_double, _I64P, C.POINTER(C.c_int), _VP]),
     "qk_rad_advance_stage": (C.c_int, [_VP, _RPRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _VP]),
     "qk_level_create": (C.c_int, [C.POINTER(qk_level_desc), C.POINTER(_VP)]),

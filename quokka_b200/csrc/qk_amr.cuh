@@ -192,4 +192,54 @@ QK_AHD double avgdown_cell(const V4 &fine, int i, int j, int k, int n, const int
 				c += at(fine, i * ratio[0] + ir, j * ratio[1] + jr, k * ratio[2] + kr, n);
 	return volfrac * c;
 }
+
+// ---- time interpolation between two coarse states: amrex::FillPatcher::fill, AMReX_FillPatcher.H:340-387 ------------------------------
+// which: 0 copy of src0, 1 copy of src1, 2 alpha * src0 + beta * src1 (products rounded separately, then the sum: no contraction)
+QK_AHD int time_interp_branch(double t0, double t1, double time, bool have1)
+{
+	if (!have1)
+		return 0;
+	const double teps = fabs(t1 - t0) * 1.e-3;
+	if (time > t0 - teps && time < t0 + teps)
+		return 0;
+	if (time > t1 - teps && time < t1 + teps)
+		return 1;
+	return 2;
+}
+QK_AHD double time_interp_value(int which, double alpha, double beta, double a0, double a1)
+{
+	if (which == 0)
+		return a0;
+	if (which == 1)
+		return a1;
+#ifdef __CUDA_ARCH__
+	return __dadd_rn(__dmul_rn(alpha, a0), __dmul_rn(beta, a1));
+#else
+	return alpha * a0 + beta * a1; // host builds use -ffp-contract=off
+#endif
+}
+
+// ---- regrid tagging ------------------------------------------------------------------------------------------------------------------
+// QuokkaSimulation<SedovProblem>::ErrorEst, src/problems/HydroBlast3D/test_hydro3d_blast.cpp:118-151; P[0] = centre, then x+, x-, y+, y-, z+, z-
+QK_AHD bool tag_pressure_gradient(const double P[7], double eta_threshold, double P_min)
+{
+	const double del_x = mx(fabs(P[1] - P[0]), fabs(P[0] - P[2]));
+	const double del_y = mx(fabs(P[3] - P[0]), fabs(P[0] - P[4]));
+	const double del_z = mx(fabs(P[5] - P[0]), fabs(P[0] - P[6]));
+	// std::max({a, b, c}): the first of the largest
+	double m = del_x;
+	if (m < del_y)
+		m = del_y;
+	if (m < del_z)
+		m = del_z;
+	const double gradient_indicator = m / P[0];
+	return (gradient_indicator > eta_threshold) && (P[0] > P_min);
+}
+// QuokkaSimulation<ShocktubeProblem>::ErrorEst, src/problems/HydroShocktube/test_hydro_shocktube.cpp:146-171
+QK_AHD bool tag_gradient_x(double qm, double q0, double qp, double dx, double eta_threshold, double q_min)
+{
+	const double del_x = (qp - qm) / (2.0 * dx);
+	const double gradient_indicator = sqrt(del_x * del_x) / q0;
+	return (gradient_indicator > eta_threshold) && (q0 >= q_min);
+}
 } // namespace qk_amr

@@ -32,9 +32,12 @@ void qk_plan_tags(const qk_level &L, int ng, std::vector<HostTag> &out)
 	const int nb = (int)L.boxes.size();
 	const qk_box dom = L.domain;
 	int smin[3], smax[3];
+	// amrex::Periodicity::shiftIntVect(nghost): a periodic direction shorter than the ghost width (one-cell-thick quasi-1-D / 2-D
+	// domains) needs ceil(ng / length) images on either side, not one
 	for (int d = 0; d < 3; ++d) {
-		smin[d] = L.periodic[d] ? -1 : 0;
-		smax[d] = L.periodic[d] ? 1 : 0;
+		const int nimg = L.periodic[d] ? (ng + blen(dom, d) - 1) / blen(dom, d) : 0;
+		smin[d] = -std::max(nimg, L.periodic[d] ? 1 : 0);
+		smax[d] = -smin[d];
 	}
 	for (int b = 0; b < nb; ++b) {
 		const qk_box g = bgrow(L.boxes[b], ng);

@@ -117,6 +117,8 @@ extern "C" const char *qk_error_string(int code)
 		return "unsupported configuration (isothermal EOS, K_visc != 0, > QK_MAX_SCALARS scalars, MHD)";
 	case QK_ERR_NOMEM:
 		return "out of device memory";
+	case QK_ERR_NOT_CONVERGED:
+		return "matter-radiation coupling failed to converge, or the radiation subcycle exceeds maxSubsteps + 1";
 	default:
 		return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown";
 	}

@@ -40,6 +40,7 @@ struct qk_sim {
 	std::vector<qk_array4> esrc; // radEnergySource per local box (caller-owned device memory) or empty
 	double rad_cfl = 0.3;	     // radiationCflNumber_  src/QuokkaSimulation.hpp:125
 	int max_substeps = 10;	     // maxSubsteps_  :126
+	int64_t rad_failures = 0;    // nf_coupling + nf_dust + nf_outer over the run (:1692-1699)
 	int last_nsub = 0;
 	int64_t rad_cell_updates = 0; // radiationCellUpdates_
 };
@@ -346,9 +347,20 @@ extern "C" int qk_sim_step(qk_sim *s, double dt, int *retries_out)
 		return 0; // the reference aborts here (:966-989); the caller sees retries = -1
 	if (s->rad_on) { // subcycleRadiationAtLevel :690-694; state_inter is free after the hydro advance and serves as U_tmp
 		int nsub = 0;
+		// the reference reads its failure counters after every substep and aborts (:1692-1711); here they are accumulated over the
+		// subcycle and read once per coarse step (one stream synchronisation)
+		int64_t counters[QK_RAD_SOURCE_NCOUNTERS] = {};
 		QK_TRY(qk_rad_subcycle(s->lev, &s->prm, &s->rprm, s->src_on ? &s->sprm : nullptr, s->sold.data(), s->snew.data(), s->sint.data(),
-				       s->esrc.empty() ? nullptr : s->esrc.data(), dt, s->rad_cfl, nullptr, &nsub, s->stream));
+				       s->esrc.empty() ? nullptr : s->esrc.data(), dt, s->rad_cfl, s->src_on ? counters : nullptr, &nsub, s->stream));
 		s->last_nsub = nsub;
+		int64_t nfail = counters[4] + counters[5] + counters[6];
+		QK_TRY(s->lev->global_sum(&nfail, s->stream));
+		s->rad_failures += nfail;
+		if (nfail > 0 || nsub > s->max_substeps + 1) { // AMREX_ALWAYS_ASSERT(nsubSteps <= maxSubsteps_ + 1) :1597
+			if (retries_out)
+				*retries_out = -1;
+			return QK_ERR_NOT_CONVERGED;
+		}
 		s->rad_cell_updates += (int64_t)nsub * s->ncells_global; // radiationCellUpdates_ :1697
 		s->sig_valid = false;					 // the source terms changed the gas state
 	}

@@ -58,3 +58,19 @@ extern "C" void host_amr_prepost(int post, const qk_array4 *state, const qk_box 
 					qk_amr::prepost_cell<false>(c, i, j, k);
 			}
 }
+
+// time interpolation and regrid tagging: the per-cell functions of k_amr_time_interp / k_tag
+extern "C" int host_time_interp(const qk_array4 *dst, const qk_array4 *s0, const qk_array4 *s1, int ncomp, const qk_box *bx, double t0, double t1, double time)
+{
+	const qk_amr::V4 d = qk_amr::view(*dst), a = qk_amr::view(*s0), b = qk_amr::view(*s1);
+	const int which = qk_amr::time_interp_branch(t0, t1, time, true);
+	const double alpha = (which == 2) ? (t1 - time) / (t1 - t0) : 0.0, beta = (which == 2) ? (time - t0) / (t1 - t0) : 0.0;
+	for (int n = 0; n < ncomp; ++n)
+		for (int k = bx->lo[2]; k <= bx->hi[2]; ++k)
+			for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
+				for (int i = bx->lo[0]; i <= bx->hi[0]; ++i)
+					qk_amr::at(d, i, j, k, n) = qk_amr::time_interp_value(which, alpha, beta, qk_amr::at(a, i, j, k, n), qk_amr::at(b, i, j, k, n));
+	return which;
+}
+extern "C" int host_tag_pressure(const double *P7, double eta, double pmin) { return qk_amr::tag_pressure_gradient(P7, eta, pmin) ? 1 : 0; }
+extern "C" int host_tag_gradient_x(double qm, double q0, double qp, double dx, double eta, double qmin) { return qk_amr::tag_gradient_x(qm, q0, qp, dx, eta, qmin) ? 1 : 0; }

@@ -87,6 +87,10 @@ def oracle() -> C.CDLL:
         "orc_post_interp_state": (None, [_A4P, _BXP]),
         "orc_average_down": (None, [_A4P, C.c_int, _A4P, C.c_int, C.c_int, _BXP, C.POINTER(C.c_int)]),
         "orc_level_swap": (None, [C.c_void_p]),
+        "orc_time_interp": (C.c_int, [_A4P, C.c_int, _A4P, _A4P, C.c_int, C.c_int, _BXP, C.c_double, C.c_double, C.c_double]),
+        "orc_tag_pressure_gradient": (None, [_PRM, _A4P, C.c_char_p, _BXP, C.c_double, C.c_double]),
+        "orc_tag_gradient_x": (None, [_A4P, C.c_int, C.c_char_p, _BXP, C.c_double, C.c_double, C.c_double]),
+        "orc_fixup_state": (None, [_PRM, _A4P, _BXP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -123,6 +127,8 @@ def ref() -> C.CDLL:
     lib.ref_interp_cons_lin_minmax.argtypes = [_A4P, _A4P, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.ref_pre_post_interp_state.argtypes = [C.c_int, _BXP, _A4P]
     lib.ref_average_down.argtypes = [_A4P, _A4P, C.c_int, _BXP, C.POINTER(C.c_int)]
+    if hasattr(lib, "ref_time_interp"):
+        lib.ref_time_interp.argtypes = [_BXP, _A4P, _A4P, _A4P, C.c_int, C.c_double, C.c_double, C.c_double]
     lib.ref_rad_source_params.argtypes = [C.c_int, _PRM, _RPRM, _RSPRM]
     lib.ref_rad_add_source_terms.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_double, C.c_int, _I64P]
     _ref = lib

@@ -64,3 +64,14 @@ def test_distribute_is_balanced_and_compact(nranks):
             mine = [boxes[i] for i, o in enumerate(owner) if o == r]
             for d in range(3):
                 assert max(b.hi[d] for b in mine) - min(b.lo[d] for b in mine) + 1 == 256
+
+
+@pytest.mark.parametrize("ncell,box", [((32, 1, 1), 16), ((16, 2, 3), 8), ((16, 16, 1), 8)])
+def test_periodic_direction_thinner_than_the_ghost_width(ncell, box):
+    # one-cell-thick quasi-1-D / 2-D domains: amrex::Periodicity::shiftIntVect(nghost) enumerates ceil(nghost / length) images on
+    # either side, so all four ghost layers of a 1-cell periodic direction are copies of that one cell (qk_plan_tags)
+    p = Prob(ncell, box, (1, 1, 1))
+    L = HostLevel(p, [0] * len(p.boxes), 0)
+    L.fill_local()
+    L.check_ghosts()
+    L.close()
