@@ -583,7 +583,8 @@ def main_radiation(args):
 
     lib = capi.load()
     n, box, ng, ncomp = 256, 128, 4, 10
-    prm = rad_params(c_light=1.0, c_hat=1.0, recon_order=3)
+    order = int(os.environ.get("QK_BENCH_RAD_ORDER", "3"))  # 3 = PPM (default), 2 = PLM(MC) as config C4 uses
+    prm = rad_params(c_light=1.0, c_hat=1.0, recon_order=order, arith=capi.QK_ARITH_FAST if args.arith == "relaxed" else capi.QK_ARITH_EXACT)
     boxes = chop_domain(n, box)
     dom = qk_box.make((0, 0, 0), (n - 1,) * 3)
     dx = [1.0 / n] * 3
@@ -645,7 +646,7 @@ def main_radiation(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "free-streaming Gaussian pulse 256^3 periodic, eight 128^3 boxes, 1 photon group, c_hat = c, cfl 0.3 (radiation rows of SURVEY 8a; "
-                                   "config C4's source terms are not part of this path)", "cells": ncell, "arith": "exact (bit-identical to the oracle)"},
+                                   "config C4's source terms are not part of this path)", "cells": ncell, "reconstruction_order": order, "arith": ARITH_TEXT[args.arith]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_rad_stage", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": src, "unit": "GB/s",
                          "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 64, "design_bytes_per_cell": 160,

@@ -203,6 +203,9 @@ typedef struct qk_rad_params {
 	int32_t nstart;		      /* nstartHyperbolic_ = radFirstIndex = 6 + numPassiveScalars */
 	int32_t reconstruction_order; /* radiationReconstructionOrder_: 1 donor cell | 2 PLM(MC) | 3 PPM (QuokkaSimulation.hpp:1942-1957) */
 	int32_t integrator_order;     /* 1 forward Euler | 2 RK2 (IMEX PD-ARS transport part, IMEX_a32 = 0.5, :52) */
+	int32_t arith;		      /* QK_ARITH_EXACT (0, the default of a zero-initialised struct): bit-identical to the oracle; QK_ARITH_FAST: relaxed
+				       * transport sweeps.  qk_rad_subcycle overrides it with hydro->arith. */
+	int32_t reserved_;
 } qk_rad_params;
 
 /* RadSystem::ConservedToPrimitive(cons, primVar, ghostRange)  radiation_system.hpp:589-614.  prim has 4*ngroups components

@@ -18,175 +18,15 @@
 #include "qk_level.h"
 #include "qk_kernels.cuh"
 #include "qk_fast.cuh"
+#include "qk_tma.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
 
+#include "qk_rad_kernels.cuh"
+
 namespace
 {
-struct RadConst {
-	double c, chat;
-	double chat_over_c, chat_times_c; // c_hat_/c_light_ and c_hat_*c_light_ as the reference forms them (:1087-1093)
-	double floor_g;			   // Erad_floor_ = Erad_floor / nGroups (:211)
-	int ng, nstart;
-};
-
-RadConst make_rad_const(const qk_rad_params *p)
-{
-	RadConst c;
-	c.c = p->c_light;
-	c.chat = p->c_hat;
-	c.chat_over_c = p->c_hat / p->c_light;
-	c.chat_times_c = p->c_hat * p->c_light;
-	c.floor_g = p->Erad_floor / p->ngroups;
-	c.ng = p->ngroups;
-	c.nstart = p->nstart;
-	return c;
-}
-
-int check_rad(const qk_rad_params *p)
-{
-	if (!p)
-		return QK_ERR_BAD_ARG;
-	if (p->ngroups < 1 || p->ngroups > QK_MAX_GROUPS || p->nstart < 0 || p->reconstruction_order < 1 || p->reconstruction_order > 3)
-		return QK_ERR_UNSUPPORTED;
-	return qk_require_device();
-}
-
-// Quotients follow qk_fast.cuh: FAST = true forms every quotient over a shared denominator (the three direction cosines over
-// |f|, the three HLL coefficients over S_R - S_L) from one refined reciprocal with bit-identical results and raises `bad` when
-// an operand leaves the compiler's own fast-path domain; the caller then recomputes the face with FAST = false (plain `/`).
-
-// RadSystem::ComputeEddingtonFactor  :773-790 (Levermore 1984)
-template <bool FAST> __device__ __forceinline__ double rad_eddington_factor(double f_in, unsigned &bad)
-{
-	const double f = clampd(f_in, 0., 1.);
-	const double f_fac = sqrt(4.0 - 3.0 * (f * f));
-	return div_d<FAST>(3.0 + 4.0 * (f * f), 5.0 + 2.0 * f_fac, bad);
-}
-
-// ComputeEddingtonTensor :873-916 + ComputeRadPressure<DIR> :918-983.  Only row DIR of the tensor is needed; f = |(fx,fy,fz)| is
-// the value the caller has just formed with the same expression (:1036-1037 / :1077-1078 and :878).
-template <int DIR, bool FAST>
-__device__ __forceinline__ void rad_pressure(double erad, double Fn, double fx, double fy, double fz, double f, double *F, double &S, unsigned &bad)
-{
-	const double fv[3] = {fx, fy, fz};
-	double n[3];
-	const bool fpos = (f > 0.);
-	const QkRcp Rf = rcp_f<FAST>(fpos ? f : 1.0, bad);
-#pragma unroll
-	for (int ii = 0; ii < 3; ++ii)
-		n[ii] = fpos ? div_r<FAST>(fv[ii], Rf, bad) : 0.;
-	const double chi = rad_eddington_factor<FAST>(f, bad);
-	const double Tdiag = (1.0 - chi) / 2.0;
-	const double Tf = (3.0 * chi - 1.0) / 2.0;
-	double T[3];
-#pragma unroll
-	for (int jj = 0; jj < 3; ++jj) {
-		const double delta_ij = (DIR == jj) ? 1 : 0;
-		T[jj] = Tdiag * delta_ij + Tf * (n[DIR] * n[jj]);
-	}
-	F[0] = Fn;
-	F[1] = T[0] * erad;
-	F[2] = T[1] * erad;
-	F[3] = T[2] * erad;
-	const double sq = sqrt(T[DIR]);
-	S = (0.1 < sq) ? sq : 0.1; // std::max(0.1, std::sqrt(Tnormal)) :980
-}
-
-// HLL flux of one face of one group (ComputeFluxes<DIR> body :1028-1137, epsilon = 1).  L/R: reconstructed (E_r, fx, fy, fz);
-// consL/consR point at component radEnergy of the cells either side of the face (first-order fallback :1054-1079).
-template <int DIR, bool FAST>
-__device__ __forceinline__ void rad_face_flux_t(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
-						double *F, unsigned &bad)
-{
-	double erad_L = L[0], erad_R = R[0];
-	double fL[3] = {L[1], L[2], L[3]}, fR[3] = {R[1], R[2], R[3]};
-	double f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
-	double f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
-	double FL[3], FR[3];
-#pragma unroll
-	for (int m = 0; m < 3; ++m) {
-		FL[m] = fL[m] * (c.c * erad_L);
-		FR[m] = fR[m] * (c.c * erad_R);
-	}
-	if ((erad_L <= 0.) || (erad_R <= 0.) || (f_L >= 1.) || (f_R >= 1.)) {
-		erad_L = consL[0];
-		erad_R = consR[0];
-#pragma unroll
-		for (int m = 0; m < 3; ++m) {
-			FL[m] = consL[(1 + m) * cns];
-			FR[m] = consR[(1 + m) * cns];
-			fL[m] = FL[m] / (c.c * erad_L);
-			fR[m] = FR[m] / (c.c * erad_R);
-		}
-		f_L = sqrt(fL[0] * fL[0] + fL[1] * fL[1] + fL[2] * fL[2]);
-		f_R = sqrt(fR[0] * fR[0] + fR[1] * fR[1] + fR[2] * fR[2]);
-	}
-	double F_L[4], F_R[4], S_L, S_R;
-	rad_pressure<DIR, FAST>(erad_L, FL[DIR], fL[0], fL[1], fL[2], f_L, F_L, S_L, bad);
-	S_L *= -1.;
-	rad_pressure<DIR, FAST>(erad_R, FR[DIR], fR[0], fR[1], fR[2], f_R, F_R, S_R, bad);
-	F_L[0] *= c.chat_over_c;
-	F_R[0] *= c.chat_over_c;
-#pragma unroll
-	for (int n = 1; n < 4; ++n) {
-		F_L[n] *= c.chat_times_c;
-		F_R[n] *= c.chat_times_c;
-	}
-	S_L *= c.chat;
-	S_R *= c.chat;
-	const double U_L[4] = {erad_L, FL[0], FL[1], FL[2]};
-	const double U_R[4] = {erad_R, FR[0], FR[1], FR[2]};
-	const QkRcp Rs = rcp_f<FAST>(S_R - S_L, bad);
-	const double a = div_r<FAST>(S_R, Rs, bad), b = div_r<FAST>(S_L, Rs, bad), d = div_r<FAST>(S_R * S_L, Rs, bad);
-#pragma unroll
-	for (int n = 0; n < 4; ++n)
-		F[n] = a * F_L[n] - b * F_R[n] + d * (U_R[n] - U_L[n]);
-}
-template <int DIR>
-__device__ __forceinline__ void rad_face_flux(const RadConst &c, const double *L, const double *R, const double *consL, const double *consR, int64_t cns,
-					      double *F)
-{
-	unsigned bad = 0;
-	rad_face_flux_t<DIR, true>(c, L, R, consL, consR, cns, F, bad);
-	if (bad)
-		rad_face_flux_t<DIR, false>(c, L, R, consL, consR, cns, F, bad);
-}
-
-// isStateValid :624-643 + amendRadState :645-665 on the NG groups of one cell
-template <int NGMAX> __device__ __forceinline__ void rad_validate(const RadConst &c, int ng, double *cons)
-{
-	bool valid = true;
-#pragma unroll
-	for (int g = 0; g < NGMAX; ++g) {
-		if (g < ng) {
-			const double E_r = cons[4 * g], Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
-			const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
-			const double f = Fnorm / (c.c * E_r);
-			valid = (valid && (E_r > 0.) && (f <= 1.));
-		}
-	}
-	if (valid)
-		return;
-#pragma unroll
-	for (int g = 0; g < NGMAX; ++g) {
-		if (g < ng) {
-			double E_r = cons[4 * g];
-			if (E_r < c.floor_g) {
-				E_r = c.floor_g;
-				cons[4 * g] = c.floor_g;
-			}
-			const double Fx = cons[4 * g + 1], Fy = cons[4 * g + 2], Fz = cons[4 * g + 3];
-			if (Fx * Fx + Fy * Fy + Fz * Fz > c.c * c.c * E_r * E_r) {
-				const double Fnorm = sqrt(Fx * Fx + Fy * Fy + Fz * Fz);
-				cons[4 * g + 1] = Fx / Fnorm * c.c * E_r;
-				cons[4 * g + 2] = Fy / Fnorm * c.c * E_r;
-				cons[4 * g + 3] = Fz / Fnorm * c.c * E_r;
-			}
-		}
-	}
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // per-operator kernels
@@ -452,26 +292,6 @@ __global__ void __launch_bounds__(RTX *RTY *RTZ) k_rad_stage(RadConst c, const R
 // One photon group per launch (groups are independent in the transport step); with several groups the admissibility fix-up, which
 // looks at all groups of a cell (isStateValid :624-643), runs as k_rad_fix afterwards.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int RSEG = 32;
-
-struct RadBox2 {
-	A4 U0, Us, Uo, prim, S0, acc;
-	int lo[3], hi[3];
-};
-
-template <int ORDER> __device__ __forceinline__ void rad_cell_parabola(double qm2, double qm1, double q0, double qp1, double qp2, double &am, double &ap)
-{
-	if (ORDER == 3)
-		recon_cell<3, 0>(qm2, qm1, q0, qp1, qp2, am, ap);
-	else if (ORDER == 2)
-		recon_cell<2, QK_MC>(qm2, qm1, q0, qp1, qp2, am, ap);
-	else
-		recon_cell<1, 0>(qm2, qm1, q0, qp1, qp2, am, ap);
-}
-
-__device__ __forceinline__ double rshfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
-__device__ __forceinline__ double rshfl_dn1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
 template <int ORDER> __global__ void __launch_bounds__(128) k_rad_x(RadConst c, const RadBox2 *__restrict__ boxes, int g, double dtdx)
 {
 	const RadBox2 &B = boxes[blockIdx.z];
@@ -716,6 +536,10 @@ extern "C" int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const
 	return 0;
 }
 
+// qk_rad_relaxed.cu: the TMA-staged sweeps instantiated with relaxed arithmetic (compiled with FMA contraction)
+int qk_rad_stage_relaxed(int order, const void *rad_const, const void *boxes, int nb, const int maxn[3], int stage, bool keep, bool fix, int g, double dtdx,
+			 double dtdy, double dtdz, cudaStream_t s);
+
 // ---- fused stage ------------------------------------------------------------------------------------------------
 struct RadState {
 	int nh = 0; // 4 * ngroups the scratch was built for
@@ -870,7 +694,7 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	RadState *R = L->rad;
 	const int nb = (int)L->valid.size();
 	if (stage == 2 && !R->s0_valid)
-		return QK_ERR_BAD_ARG; // stage 2 needs the stage-1 flux divergence of the same step
+		return QK_ERR_BAD_ARG; // stage 2 needs the stage-1 flux divergence of the same step (the relaxed sweeps drop the term but keep the protocol)
 	for (int b = 0; b < nb; ++b)
 		if (Uout[b].p == Ustage[b].p || Uout[b].p == U0[b].p)
 			return QK_ERR_BAD_ARG; // a tile reads its neighbours' cells of Ustage / U0 while other tiles write Uout
@@ -889,6 +713,7 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 		B2.prim = A4(R->prim[b]);
 		B2.S0 = A4(R->S0[b]);
 		B2.acc = A4(R->acc[b]);
+		B2.us_xend = Ustage[b].end[0];
 		for (int d = 0; d < 3; ++d) {
 			B2.lo[d] = L->valid[b].lo[d];
 			B2.hi[d] = L->valid[b].hi[d];
@@ -912,7 +737,20 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	QK_CUDA(cudaEventRecord(R->ev[slot], s));
 	R->ev_used[slot] = true;
 	const RadConst c = make_rad_const(prm);
-	{
+	// The TMA-staged sweeps (qk_rad_kernels.cuh) bulk-copy rows of the caller's state and of the level's scratch: every row must start on a
+	// 16-byte boundary (even pitches, even ghost offset) and the x sweep reads four ghost cells.  Anything else takes the first-generation
+	// direction-split kernels below (global loads; exact arithmetic only).
+	bool tma = !tile_form && (getenv("QK_RAD_V1") == nullptr) && (L->nghost >= 4);
+	auto rows16 = [](const qk_array4 &a, int lo0) {
+		return ((uintptr_t)a.p % 16 == 0) && (a.jstride % 2 == 0) && (a.kstride % 2 == 0) && (a.nstride % 2 == 0) && ((lo0 - a.begin[0]) % 2 == 0);
+	};
+	for (int b = 0; b < nb && tma; ++b) {
+		const int lo0 = L->valid[b].lo[0];
+		tma = rows16(U0[b], lo0) && rows16(Ustage[b], lo0) && rows16(R->acc[b], lo0) && rows16(R->S0[b], lo0) && (lo0 - 4 >= Ustage[b].begin[0]) &&
+		      (L->valid[b].lo[1] - 3 >= Ustage[b].begin[1]) && (L->valid[b].lo[2] - 3 >= Ustage[b].begin[2]);
+	}
+	const bool relaxed = (prm->arith == QK_ARITH_FAST) && tma; // the relaxed arithmetic exists in the TMA-staged form only
+	if (!tma) {
 		ProfScope p("rad_prim", s);
 		const int64_t cells = (int64_t)(maxn[0] + 6) * (maxn[1] + 6) * (maxn[2] + 6);
 		dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
@@ -922,7 +760,19 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	const bool keep = (stage == 1 && prm->integrator_order == 2);
 	const double dtdx = dt / L->dx[0], dtdy = dt / L->dx[1], dtdz = dt / L->dx[2];
 	int rc = 0;
-	{
+	if (tma) {
+		ProfScope p("rad_stage", s);
+		const bool fix = (ng == 1);
+		for (int g = 0; g < ng && rc == 0; ++g)
+			rc = relaxed ? qk_rad_stage_relaxed(prm->reconstruction_order, &c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s)
+				     : dispatch_rad_tma<0>(prm->reconstruction_order, c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
+		if (rc == 0 && !fix) {
+			const int64_t cells = (int64_t)maxn[0] * maxn[1] * maxn[2];
+			dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);
+			k_rad_fix<<<grid, 256, 0, s>>>(c, db2);
+			QK_KERNEL_CHECK();
+		}
+	} else {
 		ProfScope p("rad_stage", s);
 		if (tile_form) {
 			if (ng == 1)

@@ -344,6 +344,11 @@ extern "C" int qk_rad_subcycle(qk_level *L, const qk_hydro_params *hydro, const 
 	if (nsub_out)
 		*nsub_out = nsub;
 	const int ns = prm->nstart, nh = 4 * prm->ngroups, nb = (int)L->valid.size();
+	// one arithmetic mode for the whole subcycle: the hydro block's (relaxed transport sweeps with relaxed source terms)
+	qk_rad_params rp = *prm;
+	if (hydro)
+		rp.arith = hydro->arith;
+	prm = &rp;
 	for (int i = 0; i < nsub; ++i) {
 		if (i > 0)
 			QK_TRY_(copy_comps(L, U_old, U_new, ns, nh, s)); // swapRadiationState

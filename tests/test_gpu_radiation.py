@@ -258,6 +258,82 @@ def test_fused_rad_stage_pair(lib, case, kind):
         exact(got[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], st[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], "hydro components untouched")
 
 
+@pytest.mark.parametrize("case", ["ppm_periodic", "plm_reflect", "two_groups"])
+def test_first_generation_sweeps_stay_bit_exact(lib, case, monkeypatch):
+    """QK_RAD_V1 forces the direction-split kernels without TMA staging (the path unaligned boxes take): same bits as the oracle"""
+    monkeypatch.setenv("QK_RAD_V1", "1")
+    cfg = CASES[case]
+    prm = rad_params(recon_order=cfg["order"], integrator_order=cfg.get("integrator", 2), **TRAITS[cfg["traits"]])
+    p = RadProblem(cfg["ncell"], cfg["grid"], cfg["periodic"], prm)
+    st = p.states("beam")
+    dt = 0.3 * min(p.dx) / prm.c_hat
+    got = gpu_rad_steps(lib, p, st, dt, 2)
+    want = oracle_rad_steps(p, st, dt, 2)
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        exact(got[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], want[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], f"{case} box {b}")
+
+
+RELAXED_TOL = 1e-12  # stated bar of the relaxed transport sweeps: L-inf of a component over that component's maximum, 3 substeps
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_relaxed_rad_stage_pair_within_tolerance(lib, case):
+    """qk_rad_params::arith = QK_ARITH_FAST (FMA contraction, ~1-ulp reciprocals and square roots, f^2 form of the closure): three substeps of
+    smooth admissible fields stay within RELAXED_TOL of the oracle.  ("beam" fields sit ON the |f| = 1 admissibility threshold, where a
+    one-ulp change flips the first-order fallback: that regime is covered by the properties test below.)"""
+    cfg = CASES[case]
+    tr = dict(TRAITS[cfg["traits"]])
+    prm = rad_params(recon_order=cfg["order"], integrator_order=cfg.get("integrator", 2), arith=capi.QK_ARITH_FAST, **tr)
+    prm_exact = rad_params(recon_order=cfg["order"], integrator_order=cfg.get("integrator", 2), **tr)
+    p = RadProblem(cfg["ncell"], cfg["grid"], cfg["periodic"], prm)
+    st = p.states("smooth")
+    dt = 0.3 * min(p.dx) / prm.c_hat
+    got = gpu_rad_steps(lib, p, st, dt, 3)
+    p.prm = prm_exact
+    want = oracle_rad_steps(p, st, dt, 3)
+    ng = p.nghost
+    worst = 0.0
+    for n in range(prm.nstart, p.ncomp):
+        scale = max(np.abs(w[n, ng:-ng, ng:-ng, ng:-ng]).max() for w in want)
+        g0 = (n - prm.nstart) // 4 * 4 + prm.nstart  # fluxes are measured against c * E_r of their group
+        if n != g0:
+            scale = max(scale, prm.c_light * max(np.abs(w[g0, ng:-ng, ng:-ng, ng:-ng]).max() for w in want))
+        err = max(np.abs(g[n, ng:-ng, ng:-ng, ng:-ng] - w[n, ng:-ng, ng:-ng, ng:-ng]).max() for g, w in zip(got, want))
+        worst = max(worst, err / scale)
+    print(f"relaxed radiation sweeps, {case}: worst L-inf / scale after 3 substeps = {worst:.3e}")
+    assert worst < RELAXED_TOL
+    for b in range(len(p.boxes)):
+        exact(got[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], st[b][:prm.nstart, ng:-ng, ng:-ng, ng:-ng], "hydro components untouched")
+
+
+@pytest.mark.parametrize("case", ["plm_reflect", "ppm_single_ragged"])
+def test_relaxed_rad_beam_properties(lib, case):
+    """relaxed sweeps on fields with inadmissible states (E_r <= 0, |f| > 1, |f| = 1 - 1e-12: first-order fallback, amendRadState with a
+    non-zero floor): the result is finite and admissible wherever the oracle's is, and all but a small fraction of the values agree with
+    the oracle to 1e-10 of the group's energy scale (a one-ulp change may flip a threshold decision; such flips stay local)"""
+    cfg = CASES[case]
+    tr = TRAITS[cfg["traits"]]
+    prm = rad_params(recon_order=cfg["order"], arith=capi.QK_ARITH_FAST, **tr)
+    p = RadProblem(cfg["ncell"], cfg["grid"], cfg["periodic"], prm)
+    st = p.states("beam")
+    dt = 0.3 * min(p.dx) / prm.c_hat
+    got = gpu_rad_steps(lib, p, st, dt, 3)
+    p.prm = rad_params(recon_order=cfg["order"], **tr)
+    want = oracle_rad_steps(p, st, dt, 3)
+    ng = p.nghost
+    nbad = ntot = 0
+    for g, w in zip(got, want):
+        v, r = g[prm.nstart:, ng:-ng, ng:-ng, ng:-ng], w[prm.nstart:, ng:-ng, ng:-ng, ng:-ng]
+        assert np.isfinite(r).all() and np.isfinite(v).all()
+        assert (v[0] > 0).all() and (np.sqrt(v[1] ** 2 + v[2] ** 2 + v[3] ** 2) <= prm.c_light * v[0] * (1 + 1e-14)).all()
+        scale = np.array([1.0, prm.c_light, prm.c_light, prm.c_light])[:, None, None, None] * np.abs(r[0]).max()
+        nbad += int((np.abs(v - r) > 1e-10 * scale).sum())
+        ntot += v.size
+    print(f"relaxed radiation sweeps, beam fields, {case}: {nbad} of {ntot} values beyond 1e-10")
+    assert nbad <= 0.01 * ntot
+
+
 def test_rad_stage_argument_checks(lib):
     prm = rad_params()
     p = RadProblem((16, 16, 16), 16, (1, 1, 1), prm)
