@@ -681,7 +681,7 @@ def main_radiation(args):
     return 0
 
 
-def radhydro_record(arith_name, steps, warmup, extras=True):
+def radhydro_record(arith_name, steps, warmup, extras=True, dist_ok=False, ncell_override=0):
     """python bench.py --workload radhydro: config C4's coarse step on one GPU -- hydro PLM(minmod)+HLLC RK2 advance, then
     subcycleRadiationAtLevel: 10 IMEX substeps of (ghost fill, transport stage 1, matter-radiation source terms, ghost fill,
     transport stage 2, source terms) -- RadhydroShell traits on 256^3 periodic in eight 128^3 boxes, through the C++ driver
@@ -697,51 +697,98 @@ def radhydro_record(arith_name, steps, warmup, extras=True):
     from quokka_b200.simulation import HydroSimulation
 
     lib = capi.load()
-    n, box = 256, 128
+    world = int(os.environ.get("WORLD_SIZE", "1")) if dist_ok else 1
+    rank = int(os.environ.get("RANK", "0")) if dist_ok else 0
+    # N = 1: config C4's grid on one GPU (256^3 in eight 128^3 boxes).  N > 1: weak scaling with 256^3 cells per GPU unless --ncell fixes the grid
+    # (--ncell 256 --gpus 8 is configs[3] literally: one 128^3 box per GPU)
+    nc3 = [ncell_override] * 3 if ncell_override else ncell_for(world)
+    box = 128
     P = ShellProblem
-    ax = (np.arange(n) + 0.5) * (P.prob_hi / n) - 0.5 * P.prob_hi
-    z, y, x = np.meshgrid(ax, ax, ax, indexing="ij", sparse=True)
-    r = np.sqrt(x * x + y * y + z * z)
-    sigma_sh = 0.3 * P.r_0 / (2.0 * np.sqrt(2.0 * np.log(2.0)))
-    M_shell = 0.5 * 1.0e6 * 2.0e33
-    rho = np.maximum(M_shell / (4.0 * np.pi * r * r * np.sqrt(2.0 * np.pi * sigma_sh * sigma_sh)) * np.exp(-(r - P.r_0) ** 2 / (2.0 * sigma_sh * sigma_sh)),
-                     1.0e-8 * P.rho_0)
-    T = 300.0 * (1.0 + (r / P.r_0) ** 2) ** -0.25  # K, gas and radiation in equilibrium
-    Er = P.a_rad * T ** 4
-    c_v = capi.K_B / ((2.2 * capi.M_U) * (P.gamma - 1.0))
-    init = np.zeros((10, n, n, n))
-    init[0] = rho
-    init[4] = rho * c_v * T
-    init[5] = init[4]
-    init[6] = Er
-    init[7] = init[8] = init[9] = 0.1 * P.c_light * Er / np.sqrt(3.0)
-    sigma_star = 0.3 * P.r_0
-    src = (1.0 / P.c_light) * (0.5 * 1.0e6 * 2.0e33 * 2000.0) / (2.0 * np.pi * sigma_star * sigma_star) ** 1.5 * np.exp(-(r * r) / (2.0 * sigma_star * sigma_star))
-    prob = ShellProblem(n, box, initial=init)
-    # --arith relaxed (the parser's default) selects the relaxed fused PLM sweeps AND the relaxed source-term solve; the numbers in
-    # profiles/r01_bench_radhydro.json are --arith exact
+    h = P.prob_hi / min(nc3)  # cubic cells; the periodic domain grows with the rank count (weak scaling at the 256^3 problem's cell size)
+
+    class SyntheticShell(ShellProblem):
+        """the reference's Gaussian shell density with an analytic radiation field, evaluated box by box (nothing of size n^3 on the host)"""
+
+        def fields(self, bx, ng):
+            g = bx.grown(ng)
+            ax = [((np.arange(g.lo[d], g.hi[d] + 1) % nc3[d]) + 0.5) * h - 0.5 * h * nc3[d] for d in range(3)]
+            z, y, x = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij", sparse=True)
+            return np.sqrt(x * x + y * y + z * z)
+
+        def initial_state(self, bx, ng=None):
+            ng = self.nghost if ng is None else ng
+            r = self.fields(bx, ng)
+            sigma_sh = 0.3 * P.r_0 / (2.0 * np.sqrt(2.0 * np.log(2.0)))
+            M_shell = 0.5 * 1.0e6 * 2.0e33
+            rho = np.maximum(M_shell / (4.0 * np.pi * r * r * np.sqrt(2.0 * np.pi * sigma_sh * sigma_sh)) * np.exp(-(r - P.r_0) ** 2 / (2.0 * sigma_sh * sigma_sh)),
+                             1.0e-8 * P.rho_0)
+            T = 300.0 * (1.0 + (r / P.r_0) ** 2) ** -0.25  # K, gas and radiation in equilibrium
+            Er = P.a_rad * T ** 4
+            c_v = capi.K_B / ((2.2 * capi.M_U) * (P.gamma - 1.0))
+            a = np.zeros((10,) + r.shape)
+            a[0] = rho
+            a[4] = rho * c_v * T
+            a[5] = a[4]
+            a[6] = Er
+            a[7] = a[8] = a[9] = 0.1 * P.c_light * Er / np.sqrt(3.0)
+            return a
+
+        def source(self, bx):
+            r = self.fields(bx, 0)
+            sigma_star = 0.3 * P.r_0
+            return np.ascontiguousarray(((1.0 / P.c_light) * (0.5 * 1.0e6 * 2.0e33 * 2000.0) / (2.0 * np.pi * sigma_star * sigma_star) ** 1.5
+                                         * np.exp(-(r * r) / (2.0 * sigma_star * sigma_star)))[None])
+
+    prob = SyntheticShell(nc3, box)
+    prob.dx = [h] * 3
+    # --arith relaxed (the parser's default) selects the relaxed fused PLM sweeps, the relaxed transport sweeps AND the relaxed source-term solve
     arith = capi.QK_ARITH_FAST if arith_name == "relaxed" else capi.QK_ARITH_EXACT
-    sim = HydroSimulation(prob, params=prob.params(arith=arith))
-    esrc = DevMultiFab(prob.boxes, 1, ngrow=0,
-                       host=[np.ascontiguousarray(src[None, b.lo[2]:b.hi[2] + 1, b.lo[1]:b.hi[1] + 1, b.lo[0]:b.hi[0] + 1]) for b in prob.boxes])
+    comm = dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        from quokka_b200.simulation import Communicator
+
+        def bcast(b):
+            obj = [b]
+            dist.broadcast_object_list(obj, src=0)
+            return obj[0]
+        comm = Communicator(rank, world, bcast)
+    sim = HydroSimulation(prob, nranks=world, rank=rank, comm=comm, params=prob.params(arith=arith))
+    esrc = DevMultiFab(sim.local_boxes, 1, ngrow=0, host=[prob.source(b) for b in sim.local_boxes])
     sim.enableRadiation(prob.rad_params(), prob.rad_source_params(), esrc, rad_cfl=prob.rad_cfl, max_substeps=prob.max_substeps)
     sim.setInitialConditions()
-    del init, src
-    clocks = ClockSampler(0)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")) if dist_ok else 0)
     clocks.start()
     nd, _, _ = sim.evolve(warmup)
     assert nd == warmup
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
     lib.qk_prof_enable(1)
     l0 = lib.qk_launch_count()
     nd, elapsed, ms = sim.evolve(steps)
     launches = lib.qk_launch_count() - l0
     lib.qk_prof_enable(0)
+    if dist is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = max_over_ranks(ms)
     clk = clocks.stop()
     assert nd == steps, (nd, steps)
     buf = (capi.C.c_char * 8192)()
     lib.qk_prof_report(buf, 8192)
     prof = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
-    ncell = n ** 3
+    ncell = nc3[0] * nc3[1] * nc3[2]
     nsub = sim.radiationSubsteps
     value = ncell * steps / (ms * 1e-3) / 1e6
     peak, psrc = 6650.0, "fallback"
@@ -754,19 +801,21 @@ def radhydro_record(arith_name, steps, warmup, extras=True):
     src_cnt, src_ms = prof.get("rad_source_terms", (0, 0.0))
     per = src_ms / max(1, 2 * nsub * steps)
     ach = 152 * ncell / (per * 1e-3) / 1e9 if per > 0 else None
-    st = sim.gather_global() if extras else None
+    ncell_local = sum(b.ncells() for b in sim.local_boxes)
+    ach = 152 * ncell_local / (per * 1e-3) / 1e9 if per > 0 else None
+    st = sim.gather_global() if (extras and world == 1) else None
     line = {"metric": "Mcell-updates/s (radiation hydrodynamics coarse step: hydro PLM+HLLC RK2 + 10 two-moment IMEX substeps with matter-radiation coupling)",
-            "value": round(value, 2), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4),
+            "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "RadhydroShell 256^3 periodic (configs[3] on one GPU), eight 128^3 boxes, 1 photon group, kappa = 20, beta_order 1, "
-                                   "PLM hydro + PLM radiation, cfl 0.3; state (1.6 GB) >> L2, no flush", "cells": ncell, "radiation_substeps_per_step": nsub,
+            "config": {"workload": f"RadhydroShell {nc3[0]}x{nc3[1]}x{nc3[2]} periodic (configs[3]'s problem; {world} GPU(s)), {len(prob.boxes)} boxes of 128^3, 1 photon group, kappa = 20, "
+                                   "beta_order 1, PLM hydro + PLM radiation, cfl 0.3; state per GPU (>= 0.2 GB) >> L2, no flush", "cells": ncell, "radiation_substeps_per_step": nsub,
                        "radiation_Mcell_updates_per_s": round(value * nsub, 1), "arith": arith_name},
             "gpu_launches": int(launches), "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "k_rad_source", "achieved": round(ach, 1) if ach else None, "peak": peak, "peak_source": psrc, "unit": "GB/s",
                          "frac": round(ach / peak, 4) if ach else None, "traffic": None, "algorithmic_bytes_per_cell": 152, "avg_launch_ms": round(per, 4),
                          "note": "FP64-pipe / latency bound implicit solve (DESIGN.md section 3); ncu: profiles/r01_ncu_radsrc.txt"},
             "kernel_ms_per_step": {k: round(v[1] / steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
-    if extras and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
+    if extras and world == 1 and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "shell_golden")):
         cores = os.cpu_count() or 1
         v, el = run_reference_shell_cpu(64, 32, 1, cores)
         line["cpu_baseline"] = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "reference",
@@ -776,6 +825,8 @@ def radhydro_record(arith_name, steps, warmup, extras=True):
                           "sim_time": sim.time}
     sim.close()
     del sim, esrc
+    if comm:
+        comm.close()
     import torch
 
     torch.cuda.empty_cache()
@@ -783,7 +834,21 @@ def radhydro_record(arith_name, steps, warmup, extras=True):
 
 
 def main_radhydro(args):
-    print(json.dumps(radhydro_record(args.arith, args.steps, args.warmup, extras=not args.no_extras)))
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = radhydro_record(args.arith, args.steps, args.warmup, extras=not args.no_extras, dist_ok=True, ncell_override=getattr(args, "ncell", 0))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

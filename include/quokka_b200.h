@@ -422,12 +422,21 @@ int qk_rad_subcycle(qk_level *lev, const qk_hydro_params *hydro, const qk_rad_pa
 int qk_hydro_advance_stage_faithful(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
 				    const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
 
-/* Face fluxes of the LAST faithful stage in direction dir (0|1|2), one descriptor per local box (qk_level_nlocal, MFIter order):
+/* The stage for a level with FLUX REGISTERS (AMR with do_reflux; src/QuokkaSimulation.hpp:1195-1198,1280-1283): the fused sweeps of
+ * qk_hydro_advance_stage, which additionally store the stage's own face fluxes -- F(U0) in stage 1, F(U1) in stage 2 -- for
+ * incrementFluxRegisters (src/simulation.hpp:1345-1387).  Same state bits as qk_hydro_advance_stage.  A stage the fused kernels cannot
+ * take (rows that cannot be bulk-copied, an uninstantiated trait set) or that flags a cell (FOFC) runs on the faithful path; either way
+ * qk_level_stage_fluxes returns the stage's flux arrays afterwards. */
+int qk_hydro_advance_stage_keep_fluxes(qk_level *lev, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
+				       const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream);
+
+/* Face fluxes of the LAST stage that kept them (qk_hydro_advance_stage_keep_fluxes or qk_hydro_advance_stage_faithful) in direction dir (0|1|2),
+ * one descriptor per local box (qk_level_nlocal, MFIter order):
  * nodal in dir, 6 + nscalars components, no padding.  These are the `fluxArrays` QuokkaSimulation::advanceHydroAtLevel hands to
  * incrementFluxRegisters (src/QuokkaSimulation.hpp:1195-1198,1280-1283 -> src/simulation.hpp:1345-1387, YAFluxRegister::CrseAdd /
  * FineAdd): after stage 1 the stage's fluxes with the first-order replacements of FOFC applied, after stage 2 F(U1) as evaluated
  * (the reference passes the uncorrected stage-2 array there; the corrected average lives in flux_rk2).  The pointers stay valid
- * until the level is destroyed; the contents until the next stage.  QK_ERR_BAD_ARG before the first faithful stage. */
+ * until the level is destroyed; the contents until the next stage.  QK_ERR_BAD_ARG before the first flux-keeping stage. */
 int qk_level_stage_fluxes(const qk_level *lev, int dir, qk_array4 *out);
 
 /* bytes of device scratch currently held by the level */

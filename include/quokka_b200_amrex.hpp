@@ -533,7 +533,8 @@ class LevelB200
 		check(qk_hydro_advance_stage(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStage");
 		return bad;
 	}
-	// the same stage through the materialised-flux path, for levels with flux registers: afterwards stageFluxes(d) are the
+	// the same stage for levels with flux registers (fused sweeps that also store the stage's face fluxes; the one-kernel-per-operator
+	// path only when the fused kernels cannot take the stage or a cell is flagged): afterwards stageFluxes(d) are the
 	// face fluxes the reference hands to incrementFluxRegisters (src/QuokkaSimulation.hpp:1195-1198: stage 1 after the FOFC
 	// replacement; :1280-1283: stage 2's own F(U1))
 	auto advanceStageWithFluxes(qk_hydro_params const &prm, int stage, amrex::MultiFab const &U0, amrex::MultiFab const &Ustage, amrex::MultiFab &Uout,
@@ -543,7 +544,7 @@ class LevelB200
 		MFView us(Ustage);
 		MFView uo(Uout);
 		int64_t bad = 0;
-		check(qk_hydro_advance_stage_faithful(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStageWithFluxes");
+		check(qk_hydro_advance_stage_keep_fluxes(lev_, &prm, stage, u0.arr.data(), us.arr.data(), uo.arr.data(), dt, &bad, stream()), "advanceStageWithFluxes");
 		return bad;
 	}
 	// descriptors of the last stage's face-flux arrays in direction d, one per local box in MFIter order (nodal in d, 6 + nscalars

@@ -285,6 +285,7 @@ SYMBOLS = {
     "qk_fill_physical_bc": (C.c_int, [_VP, _A4P, C.c_int, C.c_int, _VP]),
     "qk_hydro_advance_stage": (C.c_int, [_VP, _PRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _I64P, _VP]),
     "qk_hydro_advance_stage_faithful": (C.c_int, [_VP, _PRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _I64P, _VP]),
+    "qk_hydro_advance_stage_keep_fluxes": (C.c_int, [_VP, _PRM, C.c_int, _A4P, _A4P, _A4P, C.c_double, _I64P, _VP]),
     "qk_level_stage_fluxes": (C.c_int, [_VP, C.c_int, _A4P]),
     "qk_level_scratch_bytes": (C.c_int64, [_VP]),
     "qk_comm_unique_id": (C.c_int, [_VP]),

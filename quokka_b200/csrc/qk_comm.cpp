@@ -152,6 +152,16 @@ extern "C" int qk_comm_allreduce_sum_i64(qk_comm *c, int64_t *v, cudaStream_t s)
 	return 0;
 }
 
+// in-place all-reduce of `count` unsigned 64-bit values that already live in DEVICE memory (sum, or max when is_max): no staging copies and no
+// host synchronisation -- the caller reads the result with the D2H copy it makes anyway (cell counters of a stage; the order-preserving keys
+// of the signal-speed maxima)
+extern "C" int qk_comm_allreduce_dev_u64(qk_comm *c, unsigned long long *d_vals, int count, int is_max, cudaStream_t s)
+{
+	if (!c || c->nranks == 1)
+		return 0;
+	return nc(g_nccl.AllReduce(d_vals, d_vals, (size_t)count, ncclUint64, is_max ? ncclMax : ncclSum, c->comm, s));
+}
+
 extern "C" int qk_comm_allreduce_max_f64(qk_comm *c, double *v, cudaStream_t s)
 {
 	if (!c || c->nranks == 1)

@@ -1057,9 +1057,18 @@ extern "C" int qk_hydro_advance_stage_faithful(qk_level *L, const qk_hydro_param
 	return L->faithful_stage(prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream));
 }
 
+const std::vector<qk_array4> *qk_fused_kept_fluxes(const qk_level *L, int dir);
+
 extern "C" int qk_level_stage_fluxes(const qk_level *L, int dir, qk_array4 *out)
 {
-	if (!L || !out || dir < 0 || dir > 2 || L->scr.nv == 0)
+	if (!L || !out || dir < 0 || dir > 2)
+		return QK_ERR_BAD_ARG;
+	if (const std::vector<qk_array4> *kept = qk_fused_kept_fluxes(L, dir)) { // the last stage ran on the fused flux-keeping path
+		for (size_t b = 0; b < L->valid.size(); ++b)
+			out[b] = (*kept)[b];
+		return 0;
+	}
+	if (L->scr.nv == 0)
 		return QK_ERR_BAD_ARG;
 	for (size_t b = 0; b < L->valid.size(); ++b)
 		out[b] = L->scr.flx[dir][b];
@@ -1068,16 +1077,33 @@ extern "C" int qk_level_stage_fluxes(const qk_level *L, int dir, qk_array4 *out)
 
 // The production entry point.  Until a level has a fused plan (qk_sweep.cu) it is the faithful path.
 int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
-		   int64_t *ncells_bad, cudaStream_t s, bool *handled);
+		   int64_t *ncells_bad, cudaStream_t s, bool *handled, bool keepf);
+
+static int advance_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
+			 int64_t *ncells_bad, void *stream, bool keepf);
 
 extern "C" int qk_hydro_advance_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
 				      const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream)
+{
+	return advance_stage(L, prm, stage, U0, Ustage, Uout, dt, ncells_bad, stream, false);
+}
+
+// The stage for a level with flux registers: the fused sweeps also store the stage's face fluxes (qk_sweep_keepf.cu); a stage the fused
+// kernels cannot take, or one that flags a cell, runs on the faithful path, whose flux arrays qk_level_stage_fluxes then returns.
+extern "C" int qk_hydro_advance_stage_keep_fluxes(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage,
+						  const qk_array4 *Uout, double dt, int64_t *ncells_bad, void *stream)
+{
+	return advance_stage(L, prm, stage, U0, Ustage, Uout, dt, ncells_bad, stream, true);
+}
+
+static int advance_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
+			 int64_t *ncells_bad, void *stream, bool keepf)
 {
 	QK_NEED_DEV(L);
 	if (!prm || (stage != 1 && stage != 2) || !U0 || !Ustage || !Uout)
 		return QK_ERR_BAD_ARG;
 	bool handled = false;
-	QK_TRY(qk_fused_stage(L, prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream), &handled));
+	QK_TRY(qk_fused_stage(L, prm, stage, U0, Ustage, Uout, dt, ncells_bad, S(stream), &handled, keepf));
 	if (handled)
 		return 0;
 	int64_t bad = 0;

@@ -152,4 +152,5 @@ int qk_comm_send(qk_comm *c, const void *buf, size_t bytes, int peer, cudaStream
 int qk_comm_recv(qk_comm *c, void *buf, size_t bytes, int peer, cudaStream_t s);
 int qk_comm_allreduce_sum_i64(qk_comm *c, int64_t *v, cudaStream_t s);
 int qk_comm_allreduce_max_f64(qk_comm *c, double *v, cudaStream_t s);
+int qk_comm_allreduce_dev_u64(qk_comm *c, unsigned long long *d_vals, int count, int is_max, cudaStream_t s);
 }

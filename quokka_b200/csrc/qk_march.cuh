@@ -40,7 +40,7 @@ template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST, int ORDER = 3>
+template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST, int ORDER = 3, bool KEEPF = false>
 __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS : 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 		int64_t o_h = h.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_r = rh.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_o = uo.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
+		const A4 &fk = B.fo[DIR];
+		const int64_t sfN = (DIR == 1) ? fk.js : fk.ks;
+		int64_t o_f = KEEPF ? fk.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1) : 0; // face r of the kept-flux array
 		// k4: slot of row r+2 (the newest row a step reads), par4 its phase parity; rows r+1, r, r-1 sit in the slots before it
 		int k4 = 0;
 		unsigned par4 = 1, tpar = 0;
@@ -251,6 +254,11 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 					for (int n = 0; n < NV; ++n)
 						G[n] = F[n];
 					G[NV] = vf;
+					if (KEEPF) { // the stage's own flux of face r, for the flux registers
+#pragma unroll
+						for (int n = 0; n < NV; ++n)
+							fk.p[o_f + n * fk.ns] = F[n];
+					}
 				}
 				if (have_aux) {
 					mbar_wait(&bars[5], aux_phase);
@@ -318,6 +326,8 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 			o_h += shN;
 			o_r += srN;
 			o_o += soN;
+			if (KEEPF)
+				o_f += sfN;
 			// rotate the ring
 			k4 = (k4 + 1) & 3;
 			if (k4 == 0)
@@ -353,7 +363,7 @@ template <int NV, int STAGE> struct XSmem {
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
-template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3>
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
 __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
 {
 	constexpr int NV = 6 + NS;
@@ -455,6 +465,13 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 		if (face_ok) {
 			double F[NV], vf;
 			hllc_face<ARITH, 0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
+			if (KEEPF && (lane <= 30 || i == B.hi[0] + 1)) { // the stage's own flux of face i, for the flux registers
+				const A4 &fk = B.fo[0];
+				const int64_t of = fk.off(i, j, k);
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					fk.p[of + n * fk.ns] = F[n];
+			}
 			if (STAGE == 1) {
 #pragma unroll
 				for (int n = 0; n < NV; ++n)

@@ -31,6 +31,7 @@ struct qk_sim {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// local ComputeMaxSignalSpeed maximum of state_new, computed in the same pass as isCflViolated's at the end of the last
 	// advance (the next computeTimestep reads the same state); invalidated whenever state_new is changed from outside
+	bool sig_is_global = false; // sig_local is already the maximum over all ranks
 	bool sig_valid = false;
 	double sig_local = 0.0;
 	// radiation (is_radiation_enabled): subcycleRadiationAtLevel after the hydro advance, c_hat / maxSubsteps_ in the time step
@@ -242,7 +243,8 @@ extern "C" int qk_sim_compute_timestep(qk_sim *s, double stop_time, double *dt_o
 		smax = s->sig_local;
 	else
 		QK_TRY(qk_hydro_max_signal_speed(&s->prm, 0, s->nb, s->lev->valid.data(), s->snew.data(), &smax, s->stream));
-	QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
+	if (!(s->sig_valid && s->sig_is_global)) // the one-pass kernel of the previous step has already reduced its maximum over the ranks on the device
+		QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
 	if (s->rad_on) // std::max(maxSignalRadiation, maxSignalHydro) per cell  src/QuokkaSimulation.hpp:426-433
 		smax = dmaxh(s->rprm.c_hat / static_cast<double>(s->max_substeps), smax);
 	const double *dx = s->lev->dx;
@@ -291,15 +293,19 @@ static int advance_hydro(qk_sim *s, std::vector<qk_array4> &Uold, double dt, int
 	// both maxima of state_new (isCflViolated's and the next computeTimestep's) in one pass
 	double both[2];
 	{
-		int rc = qk_fused_max_signal(L, &s->prm, s->snew.data(), both, s->stream);
-		if (rc == QK_ERR_UNSUPPORTED)
+		int rc = qk_fused_max_signal(L, &s->prm, s->snew.data(), both, s->stream); // both maxima come back reduced over all ranks
+		s->sig_is_global = true;
+		if (rc == QK_ERR_UNSUPPORTED) { // decided by the constants: the same on every rank
 			rc = qk_hydro_max_signal_both(&s->prm, s->nb, L->valid.data(), s->snew.data(), both, s->stream);
+			s->sig_is_global = false;
+		}
 		QK_TRY(rc);
 	}
 	s->sig_local = both[0];
 	s->sig_valid = true;
 	double smax = both[1];
-	QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
+	if (!s->sig_is_global)
+		QK_TRY(qk_comm_allreduce_max_f64(s->comm, &smax, s->stream));
 	const double dx_min = dminh(dminh(L->dx[0], L->dx[1]), L->dx[2]);
 	const double dt_cfl = s->cfl * (dx_min / smax);
 	if (dt > 1.1 * dt_cfl)

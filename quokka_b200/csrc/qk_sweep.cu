@@ -28,16 +28,25 @@ int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_cou
 
 int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3], int stage, bool dual,
 			       cudaStream_t s);
+// qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu: the TMA-staged kernels instantiated with KEEPF = true (they also store the stage's own face
+// fluxes into SweepBox::fo for incrementFluxRegisters); arith selects the translation unit, order 2 = the PLM instantiation
+int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3],
+			 int stage, bool dual, cudaStream_t s);
+int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb,
+				 const int maxn[3], int stage, bool dual, cudaStream_t s);
 
 struct FusedState {
 	int nv = 0; // 6 + nscalars the scratch was built for
 	std::vector<qk_array4> prim, chi3, rhs, hF[3];
+	std::vector<qk_array4> fo[3]; // kept face fluxes of the last stage (tight rows; allocated on the first flux-keeping stage)
+	bool fo_valid = false;	      // the last stage of this level ran fused with KEEPF and was not redone: fo[] are its fluxes
 	SweepBox *d_boxes = nullptr;
 	SweepBox *h_boxes = nullptr; // pinned staging, one table per in-flight stage (ring of 8)
 	int ring = 0;
 	cudaEvent_t ev[8];
 	bool ev_used[8];
 	bool tainted = false; // a previous stage left flagged cells in the state: stay on the faithful path
+	int tma_agreed = -1;  // N ranks: -1 not negotiated yet, else min over ranks of "my rows can be bulk-copied" (the kernel family is a collective choice)
 };
 
 void qk_fused_free(qk_level *L)
@@ -57,7 +66,7 @@ void qk_fused_free(qk_level *L)
 }
 
 // one pass over the local boxes: out[0] = ComputeMaxSignalSpeed + norminf (simulation.hpp:709-710), out[1] = maxSignalSpeedLocal
-// (isCflViolated); returns QK_ERR_UNSUPPORTED when the constants leave the shared-reciprocal domain (caller uses qk_ops.cu's kernels)
+// (isCflViolated), both already reduced over all ranks of the level's communicator; returns QK_ERR_UNSUPPORTED when the constants leave the shared-reciprocal domain (caller uses qk_ops.cu's kernels)
 int qk_fused_max_signal(qk_level *L, const qk_hydro_params *prm, const qk_array4 *state, double out[2], cudaStream_t s)
 {
 	FastConst c;
@@ -85,6 +94,9 @@ int qk_fused_max_signal(qk_level *L, const qk_hydro_params *prm, const qk_array4
 			QK_KERNEL_CHECK();
 		}
 	}
+	// N ranks: the two maxima are order-preserving 64-bit keys, so the global maxima are one in-place device all-reduce (no extra host round trip)
+	if (L->comm && L->nranks > 1)
+		QK_TRY(qk_comm_allreduce_dev_u64(L->comm, L->d_counters + 4, 2, 1, s));
 	QK_CUDA(cudaMemcpyAsync(L->h_counters + 4, L->d_counters + 4, 16, cudaMemcpyDeviceToHost, s));
 	QK_CUDA(cudaStreamSynchronize(s));
 	auto key2d = [](unsigned long long k) {
@@ -131,10 +143,18 @@ static int fused_setup(qk_level *L, int nv)
 	return 0;
 }
 
+// face-flux arrays of the last stage if it ran on the fused flux-keeping path (else nullptr: the faithful path's scr.flx hold them)
+const std::vector<qk_array4> *qk_fused_kept_fluxes(const qk_level *L, int dir)
+{
+	return (L->fused && L->fused->fo_valid) ? &L->fused->fo[dir] : nullptr;
+}
+
 int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_array4 *U0, const qk_array4 *Ustage, const qk_array4 *Uout, double dt,
-		   int64_t *ncells_bad, cudaStream_t s, bool *handled)
+		   int64_t *ncells_bad, cudaStream_t s, bool *handled, bool keepf)
 {
 	*handled = false;
+	if (L->fused)
+		L->fused->fo_valid = false;
 	// configurations the fused kernels are instantiated for; anything else runs the faithful path
 	const int ns = prm->nscalars, nms = prm->nmscalars;
 	const bool inst = (ns == 0 && nms == 0) || (ns == 1 && nms == 0) || (ns == 3 && nms == 2);
@@ -152,6 +172,10 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	QK_TRY(L->ensure_counters());
 	FusedState *F = L->fused;
 	const int nb = (int)L->valid.size();
+	if (keepf && F->fo[0].empty()) {
+		for (int d = 0; d < 3; ++d)
+			QK_TRY(L->alloc_fabs(F->fo[d], nv, 0, d));
+	}
 	// box table through the pinned ring
 	const int slot = F->ring;
 	F->ring = (F->ring + 1) % 8;
@@ -174,10 +198,24 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		B.rhs = A4(F->rhs[b]);
 		for (int d = 0; d < 3; ++d) {
 			B.hF[d] = A4(F->hF[d][b]);
+			if (keepf)
+				B.fo[d] = A4(F->fo[d][b]);
 			B.lo[d] = L->valid[b].lo[d];
 			B.hi[d] = L->valid[b].hi[d];
 			maxn[d] = std::max(maxn[d], B.hi[d] - B.lo[d] + 1);
 		}
+	}
+	if (L->comm && L->nranks > 1) {
+		// Every rank must run the same kernel family: a rank on the faithful path pairs different collectives than one on the fused path.
+		// The alignment of the local rows is negotiated once per level; a rank whose rows later stop qualifying fails loudly instead of hanging.
+		if (F->tma_agreed < 0) {
+			int64_t v = tma ? 0 : 1; // sum of "cannot" over ranks
+			QK_TRY(L->global_sum(&v, s));
+			F->tma_agreed = (v == 0) ? 1 : 0;
+		}
+		if (F->tma_agreed == 1 && !tma)
+			return QK_ERR_UNSUPPORTED;
+		tma = (F->tma_agreed == 1);
 	}
 	SweepBox *db = F->d_boxes + (size_t)slot * nb;
 	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(SweepBox) * nb, cudaMemcpyHostToDevice, s));
@@ -187,9 +225,13 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 
 	const bool dual = (prm->integrator_order == 2);
 	int rc;
-	if (order == 2 && !tma)
-		return 0; // the PLM kernels exist in the TMA-staged form only: the faithful path takes the stage (*handled stays false)
-	if (order == 2)
+	if ((order == 2 || keepf) && !tma)
+		return 0; // the PLM and the flux-keeping kernels exist in the TMA-staged form only: the faithful path takes the stage (*handled stays false)
+	if (keepf)
+		rc = (prm->arith == QK_ARITH_FAST)
+			 ? qk_sweep_stage_relaxed_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s)
+			 : qk_sweep_stage_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s);
+	else if (order == 2)
 		rc = (prm->arith == QK_ARITH_FAST) ? qk_sweep_stage_relaxed_plm(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s)
 						   : sweep_stage_dispatch_plm<0>(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s);
 	else if (prm->arith == QK_ARITH_FAST && tma) // the relaxed kernels exist in the TMA-staged form only
@@ -197,10 +239,12 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	else
 		rc = sweep_stage_dispatch<0>(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
 	QK_TRY(rc);
+	// redoFlag.sum() over all ranks (QuokkaSimulation.hpp:1146): in-place device all-reduce of the two counters, then the one D2H copy
+	if (L->comm && L->nranks > 1)
+		QK_TRY(qk_comm_allreduce_dev_u64(L->comm, L->d_counters, 2, 0, s));
 	QK_CUDA(cudaMemcpyAsync(L->h_counters, L->d_counters, 32, cudaMemcpyDeviceToHost, s));
 	QK_CUDA(cudaStreamSynchronize(s));
-	int64_t flagged = (int64_t)(L->h_counters[0] + L->h_counters[1]);
-	QK_TRY(L->global_sum(&flagged, s));
+	const int64_t flagged = (int64_t)(L->h_counters[0] + L->h_counters[1]);
 	if (flagged > 0) {
 		// redo the whole stage with the faithful path (FOFC lives there); it recomputes F(U0) itself in stage 2
 		L->scr.rk_valid = false;
@@ -211,6 +255,7 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		if (ncells_bad)
 			*ncells_bad = bad;
 	} else {
+		F->fo_valid = keepf;
 		if (ncells_bad)
 			*ncells_bad = 0;
 	}

@@ -19,6 +19,8 @@ struct SweepBox {
 	A4 chi3;       // chi_x, chi_y, chi_z (ng = 2)
 	A4 rhs;        // 6+NS RHS components + div v as the last component (valid cells)
 	A4 hF[3];      // per direction: 0.5*F(U0) (6+NS) + 0.5*faceVel(U0), nodal in that direction
+	A4 fo[3];      // KEEPF instantiations only: the stage's own face fluxes F (6+NS), nodal in that direction, TIGHT rows (what
+		       // incrementFluxRegisters reads through an alias FArrayBox, src/simulation.hpp:1345-1387)
 	int lo[3], hi[3];
 };
 
@@ -688,9 +690,11 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 			return r_;                                                                                                                   \
 	} while (0)
 
-template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3>
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
 static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], bool tma, cudaStream_t s)
 {
+	if (nb == 0)
+		return 0; // a rank without boxes (more ranks than boxes) launches nothing and still joins the stage's collectives
 	{
 		ProfScope p("fused_prim", s);
 		const int64_t cells = (int64_t)(maxn[0] + 2 * ng) * (maxn[1] + 2 * ng) * (maxn[2] + 2 * ng);
@@ -721,7 +725,7 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		constexpr int XSTAGE = (ARITH == 1) ? 1 : STAGE;
 		constexpr bool XDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL, ORDER>;
+			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL, ORDER, KEEPF>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES));
@@ -729,7 +733,7 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 			}
 			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
 			kern<<<grid, 128, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES, s>>>(c, d_tab);
-		} else if constexpr (ARITH == 0 && ORDER == 3) {
+		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			dim3 grid(tiles_x, (rows + 3) / 4, nb);
 			k_sweep_x<ARITH, NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
 		} else {
@@ -744,14 +748,14 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		constexpr int YSTAGE = (ARITH == 1) ? 1 : STAGE;
 		constexpr bool YDUAL = (ARITH == 1) ? false : DUAL;
 		if (tma) {
-			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, YSTAGE, YDUAL, false, ORDER>;
+			auto kern = k_march_t<ARITH, 1, NS, NMS, REINT, YSTAGE, YDUAL, false, ORDER, KEEPF>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
 			kern<<<grid, 128, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else if constexpr (ARITH == 0 && ORDER == 3) {
+		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			k_sweep_m<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();
@@ -761,14 +765,14 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		const int nseg = (maxn[2] + SEG - 1) / SEG;
 		dim3 grid((maxn[0] + 31) / 32, (maxn[1] + 3) / 4, nb * nseg);
 		if (tma) {
-			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true, ORDER>;
+			auto kern = k_march_t<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true, ORDER, KEEPF>;
 			static bool attr_set = false;
 			if (!attr_set) {
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
 			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
-		} else if constexpr (ARITH == 0 && ORDER == 3) {
+		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			k_sweep_m<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
 		QK_KERNEL_CHECK();
@@ -776,36 +780,39 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 	return 0;
 }
 
-template <int ARITH, int NS, int NMS, bool REINT, int ORDER = 3>
+template <int ARITH, int NS, int NMS, bool REINT, int ORDER = 3, bool KEEPF = false>
 static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma,
 			  cudaStream_t s)
 {
+	if (KEEPF && !tma)
+		return QK_ERR_UNSUPPORTED; // the flux-keeping kernels exist in the TMA-staged form only
 	if (stage == 1)
-		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s)
-			    : launch_stage<ARITH, NS, NMS, REINT, 1, false, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s);
-	return launch_stage<ARITH, NS, NMS, REINT, 2, true, ORDER>(ng, d_counters, c, t, nb, maxn, tma, s);
+		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s)
+			    : launch_stage<ARITH, NS, NMS, REINT, 1, false, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s);
+	return launch_stage<ARITH, NS, NMS, REINT, 2, true, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s);
 }
 
 
-// entry of one translation unit: all instantiated trait sets of one arithmetic mode
+// entry of one translation unit: all instantiated trait sets of one arithmetic mode (KEEPF = false: qk_sweep.cu / qk_sweep_relaxed.cu;
+// KEEPF = true, the same kernels also storing the stage's face fluxes for the flux registers: qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu)
 // PLM (reconstructionOrder_ = 2) is instantiated for the trait set of config C4's hydro (no scalars, reconstruct_eint = false), TMA form only
-template <int ARITH>
+template <int ARITH, bool KEEPF = false>
 static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3], int stage,
 				    bool dual, cudaStream_t s)
 {
-	return dispatch_stage<ARITH, 0, 0, false, 2>(ng, d_counters, c, db, nb, maxn, stage, dual, true, s);
+	return dispatch_stage<ARITH, 0, 0, false, 2, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, true, s);
 }
 
-template <int ARITH>
+template <int ARITH, bool KEEPF = false>
 static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3],
 				int stage, bool dual, bool tma, cudaStream_t s)
 {
 	if (ns == 0)
-		return reint ? dispatch_stage<ARITH, 0, 0, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-			     : dispatch_stage<ARITH, 0, 0, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		return reint ? dispatch_stage<ARITH, 0, 0, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 0, 0, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
 	if (ns == 1)
-		return reint ? dispatch_stage<ARITH, 1, 0, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-			     : dispatch_stage<ARITH, 1, 0, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
-	return reint ? dispatch_stage<ARITH, 3, 2, true>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-		     : dispatch_stage<ARITH, 3, 2, false>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		return reint ? dispatch_stage<ARITH, 1, 0, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 1, 0, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+	return reint ? dispatch_stage<ARITH, 3, 2, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
+		     : dispatch_stage<ARITH, 3, 2, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
 }

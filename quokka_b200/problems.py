@@ -166,7 +166,7 @@ class ShellProblem:
     def __init__(self, ncell, max_grid_size, initial=None):
         from .capi import QK_BC_INT_DIR
 
-        self.ncell = [int(ncell)] * 3
+        self.ncell = [int(ncell)] * 3 if np.isscalar(ncell) else [int(c) for c in ncell]
         self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in self.ncell))
         self.dx = [self.prob_hi / c for c in self.ncell]
         self.boxes = chop_domain(self.ncell, max_grid_size)
