@@ -25,10 +25,45 @@
 // R0 (relaxed arithmetic only): instead of the three 0.5*F(U0) face arrays, stage 1 keeps its complete right-hand side
 // R(U0) per cell (in the z-face scratch array) and stage 2 forms 0.5*R(U0) + 0.5*R(U1): algebraically the same update
 // (the RK2 flux average is linear), 120 B/cell less traffic in each stage, but not the reference's rounding order.
+//
+// Staging is by TENSOR-MAP TMA (cp.async.bulk.tensor.4d, qk_tma.cuh): one copy brings a whole [36 x (NV+1)] row tile of the primitives
+// (cells i0-2 .. i0+33: the x neighbours of the carbuncle term ride in the same tile), one copy each the transverse rows, the partial RHS,
+// U0 and the stage-1 data -- 7 copies per marching step instead of one 1-D bulk copy per component row (23-35), which removes most of the
+// uniform-datapath address arithmetic from the issue stream.  Descriptors: TM_COUNT CUtensorMaps per box, encoded on the host (qk_sweep.cu).
+enum SweepTmap {
+	TM_PRIM_M36 = 0, // prim   box {36, 1, 1, NV+1}
+	TM_PRIM_R32,	 // prim   box {32, 1, 1, 1}     one component row (transverse velocity rows of the marching sweeps)
+	TM_PRIM_X38,	 // prim   box {38, 1, 1, NV+1}  x sweep window
+	TM_PRIM_Y3,	 // prim   box {34, 3, 1, 1}     rows j-1 .. j+1 of one component (x sweep)
+	TM_PRIM_Z3,	 // prim   box {34, 1, 3, 1}     rows k-1 .. k+1
+	TM_RHS,		 // rhs    box {32, 1, 1, NV+1}
+	TM_HF0,		 // hF[0]  box {32, 1, 1, NV+1}
+	TM_HF1,
+	TM_HF2,
+	TM_R0,	  // hF[2]  box {32, 1, 1, NV}     R(U0) of the relaxed mode
+	TM_U0,	  // U0     box {32, 1, 1, NV}
+	TM_COUNT
+};
+constexpr int TMAP_BYTES = 128; // sizeof(CUtensorMap)
+// The descriptors travel as __grid_constant__ kernel PARAMETERS (the one place a TMA descriptor needs no proxy fence and cannot go stale in the
+// per-SM descriptor cache): a launch covers at most TMAP_MAXB boxes, each kernel family carries only the descriptors it uses.
+constexpr int TMAP_MAXB = 24;
+enum { MM_PRIM = 0, MM_ROW, MM_RHS, MM_STAGE2, MM_U0, MM_COUNT }; // marching sweeps: prim tile, one-component row, rhs, hF[DIR] | R(U0), U0
+enum { XM_PRIM = 0, XM_Y3, XM_Z3, XM_HF, XM_COUNT };		   // x sweep
+struct alignas(64) TmapBytes {
+	unsigned char b[TMAP_BYTES];
+};
+struct MarchMaps {
+	TmapBytes m[TMAP_MAXB][MM_COUNT];
+};
+struct XMaps {
+	TmapBytes m[TMAP_MAXB][XM_COUNT];
+};
+
 template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 	static constexpr int NR = 4;
-	static constexpr int PR = (NV + 1) * 32 + 36; // rows n*32 for n = 0..NV (n = NV: chi; n = 1 unused) + wide vx row
-	static constexpr int WIDE = (NV + 1) * 32;
+	static constexpr int XW = 36;					// cells i0-2 .. i0+33 of every component (+ chi)
+	static constexpr int PR = (((NV + 1) * XW + 15) / 16) * 16;	// one prim slot, padded to a 128-byte multiple
 	static constexpr int TR = 64;
 	static constexpr int AUX_HF = 0;
 	static constexpr int HF_ROWS = (STAGE == 2) ? (R0 ? (LAST ? NV : 0) : NV + 1) : 0;
@@ -36,12 +71,12 @@ template <int NV, int STAGE, bool LAST, bool R0> struct MarchSmem {
 	static constexpr int AUX_U0 = AUX_RHS + (NV + 1) * 32;
 	static constexpr int AUX = AUX_U0 + (LAST ? NV * 32 : 0);
 	static constexpr int WARP_DOUBLES = NR * PR + TR + AUX;
-	static constexpr int WARP_BYTES = WARP_DOUBLES * 8 + 64; // + mbarriers: [0..3] prim, [4] trans, [5] aux
+	static constexpr int WARP_BYTES = WARP_DOUBLES * 8 + 128; // + mbarriers: [0..3] prim, [4] trans, [5] aux (every TMA destination stays 128-byte aligned)
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
 template <int ARITH, int DIR, int NS, int NMS, bool REINT, int STAGE, bool DUAL, bool LAST, int ORDER = 3, bool KEEPF = false>
-__global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS : 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, int nseg, unsigned long long *__restrict__ counters)
+__global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS : 4) k_march_t(FastConst c, const SweepBox *__restrict__ boxes, const __grid_constant__ MarchMaps tmaps, int nseg, unsigned long long *__restrict__ counters)
 {
 	constexpr int NV = 6 + NS;
 	constexpr bool R0 = (ARITH == 1);
@@ -64,7 +99,6 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 	if (i0 <= B.hi[0] && t <= B.hi[TD] && s0 <= B.hi[DIR]) {
 		const int nact = min(32, B.hi[0] - i0 + 1);
 		const bool active = lane < nact;
-		const unsigned rowb = (unsigned)((nact + 1) & ~1) * 8u, wideb = rowb + 32u;
 		const int s1 = min(s0 + SEG, B.hi[DIR] + 1);
 		const int i = i0 + lane;
 		const A4 &q = B.prim;
@@ -72,10 +106,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 		const A4 &rh = B.rhs;
 		const A4 &u0 = B.U0;
 		const A4 &uo = B.Uo;
-		// offset of (i0, row) in an array, the transverse index fixed at t
-		auto off_row = [&](const A4 &a, int row) -> int64_t {
-			return (DIR == 1) ? a.off(i0, row, t) : a.off(i0, t, row);
-		};
+		const TmapBytes *const M = tmaps.m[box]; // this box's descriptors (parameter space)
 		if (lane == 0) {
 #pragma unroll
 			for (int b = 0; b < 6; ++b)
@@ -84,83 +115,65 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 		}
 		__syncwarp();
 
-		// running source pointers (warp-uniform): row r+3 of prim, the transverse rows of r+1, face r / cell r-1 of the aux arrays
-		const int64_t sN = (DIR == 1) ? q.js : q.ks;
-		const int64_t sT = (DIR == 1) ? q.ks : q.js; // y sweep: V = z; z sweep: W = y
-		const int64_t shN = (DIR == 1) ? h.js : h.ks, srN = (DIR == 1) ? rh.js : rh.ks, soN = (DIR == 1) ? uo.js : uo.ks,
-			      suN = (DIR == 1) ? u0.js : u0.ks;
-		const double *src_q = q.p + off_row(q, s0 - 3);
-		const double *src_t = q.p + off_row(q, s0 - 1) + ((DIR == 1) ? 3 : 2) * q.ns; // vz | vy
-		const double *src_h = h.p + off_row(h, s0 - 1);
-		const double *src_r = rh.p + off_row(rh, s0 - 2);
-		const double *src_u = u0.p + off_row(u0, s0 - 2);
-
-		auto issue_prim = [&](int slot) { // copies the row at src_q
-			double *dst = prim_s + slot * SM::PR;
-			uint64_t *bar = &bars[slot];
-			mbar_arrive_expect_tx(bar, (unsigned)NV * rowb + wideb);
-#pragma unroll
-			for (int n = 0; n <= NV; ++n) {
-				if (n == 1)
-					continue;
-				bulk_g2s(dst + n * 32, src_q + n * q.ns, rowb, bar);
-			}
-			bulk_g2s(dst + SM::WIDE, src_q - 2 + q.ns, wideb, bar);
+		// tile coordinates (warp-uniform): x of the tile, the fixed transverse index and the origin of the marching index in each array
+		const int64_t shN = (DIR == 1) ? h.js : h.ks, srN = (DIR == 1) ? rh.js : rh.ks, soN = (DIR == 1) ? uo.js : uo.ks;
+		const int qx = i0 - 2 - q.bx, qT = (DIR == 1) ? t - q.bz : t - q.by, qN0 = (DIR == 1) ? q.by : q.bz;
+		const int hx = i0 - h.bx, hT = (DIR == 1) ? t - h.bz : t - h.by, hN0 = (DIR == 1) ? h.by : h.bz;
+		const int rx = i0 - rh.bx, rT = (DIR == 1) ? t - rh.bz : t - rh.by, rN0 = (DIR == 1) ? rh.by : rh.bz;
+		const int ux = i0 - u0.bx, uT = (DIR == 1) ? t - u0.bz : t - u0.by, uN0 = (DIR == 1) ? u0.by : u0.bz;
+		int row_q = s0 - 3; // next prim row to stage
+		int row_t = s0 - 1; // next cell whose transverse rows are staged
+		// one tile copy: marching coordinate nn, transverse coordinate tt
+		auto tile = [&](double *dst, int which, int x, int nn, int tt, int comp, uint64_t *bar) {
+			tma_tile_g2s(dst, &M[which], x, (DIR == 1) ? nn : tt, (DIR == 1) ? tt : nn, comp, bar);
 		};
-		auto issue_trans = [&]() { // the two transverse rows at src_t
-			double *dst = trans_s;
+		auto issue_prim = [&](int slot) { // row row_q, all components, cells i0-2 .. i0+33
+			uint64_t *bar = &bars[slot];
+			mbar_arrive_expect_tx(bar, (unsigned)(NV + 1) * SM::XW * 8u);
+			tile(prim_s + slot * SM::PR, MM_PRIM, qx, row_q - qN0, qT, 0, bar);
+		};
+		auto issue_trans = [&]() { // the other transverse velocity component either side of cell row_t (y sweep: v_z at z -+ 1; z sweep: v_y at y -+ 1)
 			uint64_t *bar = &bars[4];
-			mbar_arrive_expect_tx(bar, 2u * rowb);
-			bulk_g2s(dst, src_t - sT, rowb, bar);
-			bulk_g2s(dst + 32, src_t + sT, rowb, bar);
+			mbar_arrive_expect_tx(bar, 2u * 256u);
+			tile(trans_s, MM_ROW, qx + 2, row_t - qN0, qT - 1, (DIR == 1) ? 3 : 2, bar);
+			tile(trans_s + 32, MM_ROW, qx + 2, row_t - qN0, qT + 1, (DIR == 1) ? 3 : 2, bar);
 		};
 		// what the end of step r reads: hF of face r (stage 2), rhs (+U0) of cell r-1
 		auto aux_bytes = [&](int r) -> unsigned {
 			unsigned b = 0;
 			if (r >= s0) {
 				if (STAGE == 2 && !R0)
-					b += (unsigned)(NV + 1) * rowb;
+					b += (unsigned)(NV + 1) * 256u;
 				if (r > s0)
-					b += (unsigned)(NV + 1) * rowb + (LAST ? (unsigned)NV * rowb : 0u) + ((STAGE == 2 && R0 && LAST) ? (unsigned)NV * rowb : 0u);
+					b += (unsigned)(NV + 1) * 256u + (LAST ? (unsigned)NV * 256u : 0u) + ((STAGE == 2 && R0 && LAST) ? (unsigned)NV * 256u : 0u);
 			}
 			return b;
 		};
-		auto issue_aux = [&](int r) { // src_h at face r, src_r / src_u at cell r-1
+		auto issue_aux = [&](int r) {
 			uint64_t *bar = &bars[5];
 			mbar_arrive_expect_tx(bar, aux_bytes(r));
-			if (STAGE == 2 && !R0) {
-#pragma unroll
-				for (int n = 0; n <= NV; ++n)
-					bulk_g2s(aux_s + SM::AUX_HF + n * 32, src_h + n * h.ns, rowb, bar);
-			}
+			if (STAGE == 2 && !R0)
+				tile(aux_s + SM::AUX_HF, MM_STAGE2, hx, r - hN0, hT, 0, bar); // 0.5 F(U0) of face r
 			if (r > s0) {
-				if (STAGE == 2 && R0 && LAST) { // R(U0) of cell r-1
-#pragma unroll
-					for (int n = 0; n < NV; ++n)
-						bulk_g2s(aux_s + SM::AUX_HF + n * 32, src_h - shN + n * h.ns, rowb, bar);
-				}
-#pragma unroll
-				for (int n = 0; n <= NV; ++n)
-					bulk_g2s(aux_s + SM::AUX_RHS + n * 32, src_r + n * rh.ns, rowb, bar);
-				if (LAST) {
-#pragma unroll
-					for (int n = 0; n < NV; ++n)
-						bulk_g2s(aux_s + SM::AUX_U0 + n * 32, src_u + n * u0.ns, rowb, bar);
-				}
+				if (STAGE == 2 && R0 && LAST)
+					tile(aux_s + SM::AUX_HF, MM_STAGE2, hx, r - 1 - hN0, hT, 0, bar); // R(U0) of cell r-1
+				tile(aux_s + SM::AUX_RHS, MM_RHS, rx, r - 1 - rN0, rT, 0, bar);
+				if (LAST)
+					tile(aux_s + SM::AUX_U0, MM_U0, ux, r - 1 - uN0, uT, 0, bar);
 			}
 		};
-		// component n (n = NV: chi) of this lane's cell in a prim slot
-		auto PV = [&](const double *sl, int n) -> double { return (n == 1) ? sl[SM::WIDE + lane + 2] : sl[n * 32 + lane]; };
+		// component n (n = NV: chi) of this lane's cell in a prim slot (cell i0 + lane sits at entry lane + 2 of a 36-wide row)
+		auto PV = [&](const double *sl, int n) -> double { return sl[n * SM::XW + lane + 2]; };
 
 		// prologue: rows s0-3 .. s0 into slots 0 .. 3, transverse rows of cell s0-1
 		for (int sl = 0; sl < SM::NR; ++sl) {
 			if (elect_one())
 				issue_prim(sl);
-			src_q += sN;
+			++row_q;
 		}
 		if (elect_one())
 			issue_trans();
-		src_t += sN;
+		++row_t;
 		// rows s0-3 .. s0 -> unlimited interface value at the low face of cell s0-1
 #pragma unroll
 		for (int b = 0; b < 4; ++b)
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 		__syncwarp();
 		if (elect_one())
 			issue_prim(0); // row s0+1 replaces row s0-3
-		src_q += sN;
+		++row_q;
 		unsigned aux_phase = 0;
 		int64_t o_h = h.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
 		int64_t o_r = rh.off(i, (DIR == 1) ? s0 - 1 : t, (DIR == 1) ? t : s0 - 1);
@@ -192,9 +205,6 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 			const bool have_aux = aux_bytes(r) != 0;
 			if (have_aux && elect_one())
 				issue_aux(r);
-			src_h += shN;
-			src_r += srN;
-			src_u += suN;
 			const double *s_p2 = prim_s + k4 * SM::PR;
 			const double *s_p1 = prim_s + ((k4 + 3) & 3) * SM::PR;
 			const double *s_0 = prim_s + ((k4 + 2) & 3) * SM::PR;
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 			double am[NV], ap[NV];
 			double vN0 = 0, mV = 0, mW = 0;
 			if (active) {
-				const double chi = s_0[NV * 32 + lane], omchi = 1. - chi;
+				const double chi = s_0[NV * SM::XW + lane + 2], omchi = 1. - chi;
 #pragma unroll
 				for (int n = 0; n < NV; ++n) {
 					const double qm1 = PV(s_m1, n), q0 = PV(s_0, n), qp1 = PV(s_p1, n), qp2 = PV(s_p2, n);
@@ -211,7 +221,10 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 						vN0 = q0;
 					if (ORDER == 3) {
 						const double ifh = ppm_iface(qm1, q0, qp1, qp2);
-						f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
+						if (ARITH == 1)
+							r_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
+						else
+							f_ppm_flat(qm1, q0, qp1, ifl[n], ifh, chi, omchi, am[n], ap[n]);
 						ifl[n] = ifh;
 					} else {
 						f_plm_flat(qm1, q0, qp1, chi, omchi, am[n], ap[n]);
@@ -221,9 +234,9 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 			mbar_wait(&bars[4], tpar);
 			if (active) { // transverse velocity-difference minima of cell r (hydro_system.hpp:1022-1033)
 				const double *tr = trans_s;
-				const double x0 = s_0[SM::WIDE + lane + 2], xm = s_0[SM::WIDE + lane + 1], xp = s_0[SM::WIDE + lane + 3];
+				const double x0 = s_0[SM::XW + lane + 2], xm = s_0[SM::XW + lane + 1], xp = s_0[SM::XW + lane + 3];
 				const double mx = dmin(xp - x0, x0 - xm); // along x
-				const double t0 = s_0[((DIR == 1) ? 3 : 2) * 32 + lane];
+				const double t0 = s_0[((DIR == 1) ? 3 : 2) * SM::XW + lane + 2];
 				const double mt = dmin(tr[32 + lane] - t0, t0 - tr[lane]); // along the other transverse axis
 				if (DIR == 1) { // V = z, W = x
 					mV = mt;
@@ -240,8 +253,8 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 				if (r + 1 <= s1)
 					issue_trans();
 			}
-			src_q += sN;
-			src_t += sN;
+			++row_q;
+			++row_t;
 			if (r >= s0) {
 				double G[NV + 1];
 				if (active) {
@@ -353,18 +366,19 @@ __global__ void __launch_bounds__(128, (ARITH == 1 && !LAST) ? QK_MARCH_Y_BLOCKS
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int XROWS = 8;
 template <int NV, int STAGE> struct XSmem {
-	static constexpr int PW = 38;			    // cells x0-4 .. x0+33 of every component (+ chi)
-	static constexpr int PRIM = (NV + 1) * PW;	    // 16-byte multiple for every NV
-	static constexpr int TW = 34;			    // cells x0-2 .. x0+31 of the transverse velocity rows
-	static constexpr int TRANS = 4 * TW;		    // vy(j-1), vy(j+1), vz(k-1), vz(k+1)
-	static constexpr int AUX = (STAGE == 2) ? (NV + 1) * 32 : 0; // 0.5 F(U0) at faces x0 .. x0+31 (stage 2 only; the relaxed mode never runs STAGE 2 here)
+	static constexpr int PW = 38;				     // cells x0-4 .. x0+33 of every component (+ chi)
+	static constexpr int PRIM = (((NV + 1) * PW + 15) / 16) * 16; // one [38 x (NV+1)] tile, padded to a 128-byte multiple
+	static constexpr int TW = 34;				     // cells x0-2 .. x0+31 of the transverse velocity rows
+	static constexpr int T3 = ((3 * TW + 15) / 16) * 16;	     // rows -1, 0, +1 of one component (one [34 x 3] tile)
+	static constexpr int TRANS = 2 * T3;			     // vy at j-1 .. j+1, vz at k-1 .. k+1
+	static constexpr int AUX = (STAGE == 2) ? (NV + 1) * 32 : 0;  // 0.5 F(U0) at faces x0 .. x0+31 (stage 2 only; the relaxed mode never runs STAGE 2 here)
 	static constexpr int STAGE_DOUBLES = PRIM + TRANS + AUX;
-	static constexpr int WARP_BYTES = 2 * STAGE_DOUBLES * 8 + 16; // two stages + two mbarriers
+	static constexpr int WARP_BYTES = 2 * STAGE_DOUBLES * 8 + 128; // two stages + two mbarriers
 	static constexpr int BLOCK_BYTES = 4 * WARP_BYTES;
 };
 
 template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
-__global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes)
+__global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *__restrict__ boxes, const __grid_constant__ XMaps tmaps)
 {
 	constexpr int NV = 6 + NS;
 	using SM = XSmem<NV, STAGE>;
@@ -385,36 +399,27 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 	const A4 &q = B.prim;
 	const A4 &h = B.hF[0];
 	const A4 &r = B.rhs;
+	const TmapBytes *const M = tmaps.m[blockIdx.z];
 	if (lane == 0) {
 		mbar_init(&bars[0], 1);
 		mbar_init(&bars[1], 1);
 		mbar_init_fence();
 	}
 	__syncwarp();
-	constexpr unsigned PB = SM::PW * 8, TB = SM::TW * 8, AB = 32 * 8;
 	// (j, k) of the row being staged / computed, advanced incrementally (one integer division per warp instead of two per row)
 	int jn = B.lo[1] + row0 % ny, kn = B.lo[2] + row0 / ny; // next row to stage
 	int j = jn, k = kn;					  // row being computed
-	auto issue = [&](int m) { // stage row row0+m = (jn, kn)
-		const int j = jn, k = kn;
+	const int qx = x0 - 4 - q.bx, hx = x0 - h.bx;
+	auto issue = [&](int m) { // stage row row0+m = (jn, kn): 3 tile copies (4 in stage 2)
 		double *dst = st0 + (m & 1) * SM::STAGE_DOUBLES;
 		uint64_t *bar = &bars[m & 1];
-		mbar_arrive_expect_tx(bar, (unsigned)(NV + 1) * PB + 4u * TB + ((STAGE == 2) ? (unsigned)(NV + 1) * AB : 0u));
-		const double *src = q.p + q.off(x0 - 4, j, k);
-#pragma unroll
-		for (int n = 0; n <= NV; ++n)
-			bulk_g2s(dst + n * SM::PW, src + n * q.ns, PB, bar);
-		const double *sy = src + 2 + 2 * q.ns, *sz = src + 2 + 3 * q.ns; // vy, vz rows starting at x0-2
-		bulk_g2s(dst + SM::PRIM, sy - q.js, TB, bar);
-		bulk_g2s(dst + SM::PRIM + SM::TW, sy + q.js, TB, bar);
-		bulk_g2s(dst + SM::PRIM + 2 * SM::TW, sz - q.ks, TB, bar);
-		bulk_g2s(dst + SM::PRIM + 3 * SM::TW, sz + q.ks, TB, bar);
-		if (STAGE == 2) {
-			const double *sh = h.p + h.off(x0, j, k);
-#pragma unroll
-			for (int n = 0; n <= NV; ++n)
-				bulk_g2s(dst + SM::PRIM + SM::TRANS + n * 32, sh + n * h.ns, AB, bar);
-		}
+		mbar_arrive_expect_tx(bar, (unsigned)((NV + 1) * SM::PW + 6 * SM::TW + ((STAGE == 2) ? (NV + 1) * 32 : 0)) * 8u);
+		const int jy = jn - q.by, kz = kn - q.bz;
+		tma_tile_g2s(dst, &M[XM_PRIM], qx, jy, kz, 0, bar);
+		tma_tile_g2s(dst + SM::PRIM, &M[XM_Y3], qx + 2, jy - 1, kz, 2, bar);	     // vy at j-1, j, j+1
+		tma_tile_g2s(dst + SM::PRIM + SM::T3, &M[XM_Z3], qx + 2, jy, kz - 1, 3, bar); // vz at k-1, k, k+1
+		if (STAGE == 2)
+			tma_tile_g2s(dst + SM::PRIM + SM::TRANS, &M[XM_HF], hx, jn - h.by, kn - h.bz, 0, bar);
 	};
 	if (elect_one())
 		issue(0);
@@ -444,15 +449,18 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 			if (n == 1)
 				q0v1 = q0;
 			if (ORDER == 3)
-				f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+				if (ARITH == 1)
+					r_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+				else
+					f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
 			else
 				f_plm_flat(qm1, q0, qp1, chi, omchi, am[n], ap[n]);
 		}
 		// transverse minima: V = y, W = z (cell x0-1+lane sits at index lane+1 of a transverse row)
 		const double *tr = sp + SM::PRIM;
 		const double vy0 = sp[2 * SM::PW + lane + 3], vz0 = sp[3 * SM::PW + lane + 3];
-		const double mV = dmin(tr[SM::TW + lane + 1] - vy0, vy0 - tr[lane + 1]);
-		const double mW = dmin(tr[3 * SM::TW + lane + 1] - vz0, vz0 - tr[2 * SM::TW + lane + 1]);
+		const double mV = dmin(tr[2 * SM::TW + lane + 1] - vy0, vy0 - tr[lane + 1]);				  // rows j+1, j-1
+		const double mW = dmin(tr[SM::T3 + 2 * SM::TW + lane + 1] - vz0, vz0 - tr[SM::T3 + lane + 1]); // rows k+1, k-1
 		double Ls[NV];
 #pragma unroll
 		for (int n = 0; n < NV; ++n)

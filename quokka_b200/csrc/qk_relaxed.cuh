@@ -21,6 +21,49 @@ __device__ __forceinline__ double r_rcp(double b)
 	return __fma_rn(y0, e, y0);
 }
 
+// 1/sqrt(x) to about 1 ulp for finite normal x > 0 (rsqrt seed + two coupled Newton steps; no slow path: x = 0, inf, subnormal or negative
+// give inf / NaN, caught downstream as a non-finite cell)
+__device__ __forceinline__ double r_rsqrt(double x)
+{
+	double y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+	const double hx = 0.5 * x;
+	double e = __fma_rn(-hx * y0, y0, 0.5); // 0.5 (1 - x y0^2)
+	y0 = __fma_rn(y0, e, y0);
+	e = __fma_rn(-hx * y0, y0, 0.5);
+	return __fma_rn(y0, e, y0);
+}
+// sqrt(x) = x * rsqrt(x) for x > 0; sqrt(0) = 0 is kept (a cold gas at rest has |v| = 0), NaN for x < 0 as sqrt
+__device__ __forceinline__ double r_sqrtx(double x)
+{
+	const double s = x * r_rsqrt(x);
+	return (x == 0.0) ? 0.0 : s;
+}
+
+// PPM limiting + FlattenShocks of one cell (ppm_limit / f_ppm_flat of the exact path) with the monotonized-central slope of the extremum
+// branch formed without the int -> double sign arithmetic: sign(a) min(...) where a b > 0, else 0 (same value except where a * b underflows)
+__device__ __forceinline__ void r_ppm_flat(double qm1, double q0, double qp1, double if_lo, double if_hi, double chi, double omchi, double &am, double &ap)
+{
+	// bounds = minmax(q0, qm1, qp1).  q0 can be left out: where it is the extremum of the three (a b <= 0) both clamped edges land on the same
+	// side of q0, the extremum branch is taken and its slope h is 0 -- the cell is reconstructed as q0 whatever the bounds were
+	const bool up = (qm1 < qp1);
+	const double lo = up ? qm1 : qp1, hi = up ? qp1 : qm1;
+	const double am0 = clampd(if_lo, lo, hi), ap0 = clampd(if_hi, lo, hi);
+	const double dq_minus = q0 - am0, dq_plus = ap0 - q0;
+	const double a = qp1 - q0, b = q0 - qm1;
+	const double m = dmin(0.25 * fabs(a + b), dmin(fabs(a), fabs(b))); // 0.5 * MC
+	const double h = (a * b > 0.0) ? copysign(m, a) : 0.0;		    // 0.5 * dq0
+	const bool ext = (dq_plus * dq_minus <= 0.0);
+	// edge offsets from q0: a_minus = q0 - em, a_plus = q0 + ep; FlattenShocks (hydro_system.hpp:688-691) chi a + (1 - chi) q0 = q0 -+ chi e
+	const double tm = 2.0 * dq_plus, tp = 2.0 * dq_minus;
+	double em = (fabs(dq_minus) >= fabs(tm)) ? tm : dq_minus;
+	double ep = (fabs(dq_plus) >= fabs(tp)) ? tp : dq_plus;
+	em = ext ? h : em;
+	ep = ext ? h : ep;
+	am = __fma_rn(-chi, em, q0);
+	ap = __fma_rn(chi, ep, q0);
+}
+
 // pressure the EOS returns for an input pressure P: identity inside [1e-200, 1e200], else the eos_reset floor
 // rho k_B T_min / (mu m_u)  (extern/Microphysics/interfaces/eos.H:97-139)
 __device__ __forceinline__ double r_p_of_p(const FastConst &c, double rho, double P) { return (P < 1.e-200 || P > 1.e200) ? rho * c.pfloor : P; }
@@ -74,7 +117,9 @@ __device__ __forceinline__ void r_hllc(const FastConst &c, const double *__restr
 {
 	constexpr int iN = 1 + DIR, iV = 1 + (DIR + 1) % 3, iW = 1 + (DIR + 2) % 3;
 	const double rho_L = L[0], rho_R = R[0];
-	const double yL = r_rcp(rho_L), yR = r_rcp(rho_R);
+	// one refined 1/sqrt(rho) per state gives both sqrt(rho) (Roe weights) and 1/rho
+	const double qL = r_rsqrt(rho_L), qR = r_rsqrt(rho_R);
+	const double yL = qL * qL, yR = qR * qR;
 	const double vsq_L = L[1] * L[1] + L[2] * L[2] + L[3] * L[3];
 	const double vsq_R = R[1] * R[1] + R[2] * R[2] + R[3] * R[3];
 	const double ke_L = 0.5 * rho_L * vsq_L, ke_R = 0.5 * rho_R * vsq_R;
@@ -92,13 +137,13 @@ __device__ __forceinline__ void r_hllc(const FastConst &c, const double *__restr
 	}
 	// one eos(rp) per state in closed form
 	const double p_L = r_p_of_p(c, rho_L, P_L), p_R = r_p_of_p(c, rho_R, P_R);
-	const double cs_L = sqrt(c.h.gamma * p_L * yL), cs_R = sqrt(c.h.gamma * p_R * yR);
+	const double cs_L = r_sqrtx(c.h.gamma * p_L * yL), cs_R = r_sqrtx(c.h.gamma * p_R * yR);
 	const double E_L = p_L * c.inv_gm1 + ke_L;
 	const double E_R = p_R * c.inv_gm1 + ke_R;
 	const double uL = L[iN], vL = L[iV], wL = L[iW];
 	const double uR = R[iN], vR = R[iV], wR = R[iW];
 
-	const double wl = sqrt(rho_L), wr = sqrt(rho_R);
+	const double wl = rho_L * qL, wr = rho_R * qR;
 	const double norm = r_rcp(wl + wr);
 	const double u_tilde = (wl * uL + wr * uR) * norm;
 	const double v_tilde = (wl * vL + wr * vR) * norm;
@@ -110,7 +155,7 @@ __device__ __forceinline__ void r_hllc(const FastConst &c, const double *__restr
 	const double C_tilde_rho = 0.5 * (Eint_L * yL + Eint_R * yR);
 	const double C_tilde_P = 0.5 * c.bk * (Eint_L * r_rcp(p_L) + Eint_R * r_rcp(p_R)) + c.inv_gm1;
 	const double cs_exp = H_tilde - 0.5 * vsq_tilde - C_tilde_rho;
-	const double cs_tilde = (cs_exp <= 0) ? 0.5 * (cs_L + cs_R) : sqrt(cs_exp * r_rcp(C_tilde_P));
+	const double cs_tilde = (cs_exp <= 0) ? 0.5 * (cs_L + cs_R) : r_sqrtx(cs_exp * r_rcp(C_tilde_P));
 	const double s_NL = 0.5 * c.h.G * dmax(dU, 0.);
 	const double S_L = dmin(uL - (cs_L + s_NL), u_tilde - (cs_tilde + s_NL));
 	const double S_R = dmax(uR + (cs_R + s_NL), u_tilde + (cs_tilde + s_NL));
@@ -119,7 +164,7 @@ __device__ __forceinline__ void r_hllc(const FastConst &c, const double *__restr
 	const double theta = (tp * tp) * (tp * tp);
 	const double mL = rho_L * (S_L - uL), mR = rho_R * (S_R - uR);
 	const double S_star = (theta * (P_R - P_L) + (mL * uL - mR * uR)) * r_rcp(mL - mR);
-	const double chi = dmin(1., sqrt(dmax(vsq_L, vsq_R)) * r_rcp(cs_max));
+	const double chi = dmin(1., r_sqrtx(dmax(vsq_L, vsq_R)) * r_rcp(cs_max));
 	const double phi = chi * (2. - chi);
 	const double P_LR = 0.5 * (P_L + P_R) + 0.5 * phi * (mL * (S_star - uL) + mR * (S_star - uR));
 

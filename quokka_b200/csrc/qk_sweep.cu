@@ -18,22 +18,60 @@
 // REDONE by the faithful path of qk_level.cu, which owns the first-order flux correction.
 #include "qk_sweep_kernels.cuh"
 
+#include <cuda.h> // CUtensorMap and its enums only: the encoder is resolved at run time (no link against libcuda)
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // qk_sweep_relaxed.cu: the same kernels instantiated with relaxed arithmetic (FMA contraction, closed-form EOS)
-int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3], int stage,
+int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3], int stage,
 			   bool dual, bool tma, cudaStream_t s);
 
-int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3], int stage, bool dual,
+int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3], int stage, bool dual,
 			       cudaStream_t s);
 // qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu: the TMA-staged kernels instantiated with KEEPF = true (they also store the stage's own face
 // fluxes into SweepBox::fo for incrementFluxRegisters); arith selects the translation unit, order 2 = the PLM instantiation
-int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3],
+int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3],
 			 int stage, bool dual, cudaStream_t s);
-int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb,
+int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb,
 				 const int maxn[3], int stage, bool dual, cudaStream_t s);
+
+// ---- tensor-map descriptors (TMA tiles of the marching / x sweeps, qk_march.cuh) ----------------------------------------------------------
+typedef CUresult (*qk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+				       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static qk_encode_tiled_fn encode_tiled()
+{
+	static qk_encode_tiled_fn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			fn = reinterpret_cast<qk_encode_tiled_fn>(p);
+	}
+	return fn;
+}
+static_assert(sizeof(CUtensorMap) == TMAP_BYTES, "descriptor size");
+
+// descriptor of a box {bx, by, bz, bc} of the FP64 array `a` viewed as a 4-D tensor (x, y, z, component); false when the array cannot be
+// described (odd pitches, unaligned base): the caller then runs the kernels without TMA staging
+static bool encode_tile(CUtensorMap *m, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc)
+{
+	qk_encode_tiled_fn enc = encode_tiled();
+	if (!enc || ((uintptr_t)a.p % 16) != 0 || (a.jstride % 2) != 0 || (a.kstride % 2) != 0 || (a.nstride % 2) != 0)
+		return false;
+	const cuuint64_t dims[4] = {(cuuint64_t)(a.end[0] - a.begin[0]), (cuuint64_t)(a.end[1] - a.begin[1]), (cuuint64_t)(a.end[2] - a.begin[2]),
+				    (cuuint64_t)a.ncomp};
+	const cuuint64_t strides[3] = {(cuuint64_t)a.jstride * 8, (cuuint64_t)a.kstride * 8, (cuuint64_t)a.nstride * 8};
+	const cuuint32_t box[4] = {bx, by, bz, bc};
+	const cuuint32_t es[4] = {1, 1, 1, 1};
+	if (bc > dims[3])
+		return false;
+	return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+		   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 struct FusedState {
 	int nv = 0; // 6 + nscalars the scratch was built for
@@ -42,6 +80,9 @@ struct FusedState {
 	bool fo_valid = false;	      // the last stage of this level ran fused with KEEPF and was not redone: fo[] are its fluxes
 	SweepBox *d_boxes = nullptr;
 	SweepBox *h_boxes = nullptr; // pinned staging, one table per in-flight stage (ring of 8)
+	CUtensorMap *h_maps = nullptr;			   // TM_COUNT descriptors per box of the stage being launched (host memory)
+	std::vector<CUtensorMap> static_maps;		   // descriptors of the level's own scratch (encoded once); empty: TMA staging unavailable
+	bool maps_ok = false;
 	int ring = 0;
 	cudaEvent_t ev[8];
 	bool ev_used[8];
@@ -56,6 +97,8 @@ void qk_fused_free(qk_level *L)
 	FusedState *F = L->fused;
 	if (F->d_boxes)
 		cudaFree(F->d_boxes);
+	if (F->h_maps)
+		free(F->h_maps);
 	if (F->h_boxes) {
 		cudaFreeHost(F->h_boxes);
 		for (int i = 0; i < 8; ++i)
@@ -135,6 +178,21 @@ static int fused_setup(qk_level *L, int nv)
 		return rc;
 	QK_CUDA(cudaMalloc(&F->d_boxes, sizeof(SweepBox) * nb * 8));
 	QK_CUDA(cudaMallocHost(&F->h_boxes, sizeof(SweepBox) * nb * 8));
+	F->h_maps = static_cast<CUtensorMap *>(aligned_alloc(64, sizeof(CUtensorMap) * TM_COUNT * std::max(nb, 1)));
+	if (!F->h_maps)
+		return QK_ERR_NOMEM;
+	// descriptors of the scratch arrays never change
+	F->static_maps.assign((size_t)TM_COUNT * nb, CUtensorMap{});
+	F->maps_ok = true;
+	for (int b = 0; b < nb && F->maps_ok; ++b) {
+		CUtensorMap *m = &F->static_maps[(size_t)TM_COUNT * b];
+		const unsigned nc = (unsigned)nv + 1;
+		F->maps_ok = encode_tile(&m[TM_PRIM_M36], F->prim[b], 36, 1, 1, nc) && encode_tile(&m[TM_PRIM_R32], F->prim[b], 32, 1, 1, 1) &&
+			     encode_tile(&m[TM_PRIM_X38], F->prim[b], 38, 1, 1, nc) && encode_tile(&m[TM_PRIM_Y3], F->prim[b], 34, 3, 1, 1) &&
+			     encode_tile(&m[TM_PRIM_Z3], F->prim[b], 34, 1, 3, 1) && encode_tile(&m[TM_RHS], F->rhs[b], 32, 1, 1, nc) &&
+			     encode_tile(&m[TM_HF0], F->hF[0][b], 32, 1, 1, nc) && encode_tile(&m[TM_HF1], F->hF[1][b], 32, 1, 1, nc) &&
+			     encode_tile(&m[TM_HF2], F->hF[2][b], 32, 1, 1, nc) && encode_tile(&m[TM_R0], F->hF[2][b], 32, 1, 1, (unsigned)nv);
+	}
 	for (int i = 0; i < 8; ++i) {
 		QK_CUDA(cudaEventCreateWithFlags(&F->ev[i], cudaEventDisableTiming));
 		F->ev_used[i] = false;
@@ -183,12 +241,14 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		QK_CUDA(cudaEventSynchronize(F->ev[slot]));
 	SweepBox *hb = F->h_boxes + (size_t)slot * nb;
 	int maxn[3] = {1, 1, 1};
-	bool tma = (getenv("QK_NO_TMA") == nullptr);
-	auto rows16 = [](const qk_array4 &a, int lo0) {
-		return ((uintptr_t)a.p % 16 == 0) && (a.jstride % 2 == 0) && (a.kstride % 2 == 0) && (a.nstride % 2 == 0) && ((lo0 - a.begin[0]) % 2 == 0);
-	};
+	bool tma = (getenv("QK_NO_TMA") == nullptr) && F->maps_ok;
+	CUtensorMap *hm = F->h_maps;
 	for (int b = 0; b < nb; ++b) {
-		tma = tma && rows16(U0[b], L->valid[b].lo[0]) && rows16(F->prim[b], L->valid[b].lo[0]);
+		// the tile descriptors: the level's own scratch (encoded once) + the caller's U0 (its arrays rotate from step to step)
+		if (tma) {
+			memcpy(hm + (size_t)TM_COUNT * b, &F->static_maps[(size_t)TM_COUNT * b], sizeof(CUtensorMap) * TM_COUNT);
+			tma = encode_tile(&hm[(size_t)TM_COUNT * b + TM_U0], U0[b], 32, 1, 1, (unsigned)nv);
+		}
 		SweepBox &B = hb[b];
 		B.U0 = A4(U0[b]);
 		B.Us = A4(Ustage[b]);
@@ -218,6 +278,7 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		tma = (F->tma_agreed == 1);
 	}
 	SweepBox *db = F->d_boxes + (size_t)slot * nb;
+	const unsigned char *dm = reinterpret_cast<const unsigned char *>(hm); // HOST table: the launchers copy what a kernel uses into its parameters
 	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(SweepBox) * nb, cudaMemcpyHostToDevice, s));
 	QK_CUDA(cudaEventRecord(F->ev[slot], s));
 	F->ev_used[slot] = true;
@@ -229,15 +290,15 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		return 0; // the PLM and the flux-keeping kernels exist in the TMA-staged form only: the faithful path takes the stage (*handled stays false)
 	if (keepf)
 		rc = (prm->arith == QK_ARITH_FAST)
-			 ? qk_sweep_stage_relaxed_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s)
-			 : qk_sweep_stage_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s);
+			 ? qk_sweep_stage_relaxed_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, s)
+			 : qk_sweep_stage_keepf(ns, prm->reconstruct_eint != 0, order, L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, s);
 	else if (order == 2)
-		rc = (prm->arith == QK_ARITH_FAST) ? qk_sweep_stage_relaxed_plm(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s)
-						   : sweep_stage_dispatch_plm<0>(L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, s);
+		rc = (prm->arith == QK_ARITH_FAST) ? qk_sweep_stage_relaxed_plm(L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, s)
+						   : sweep_stage_dispatch_plm<0>(L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, s);
 	else if (prm->arith == QK_ARITH_FAST && tma) // the relaxed kernels exist in the TMA-staged form only
-		rc = qk_sweep_stage_relaxed(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		rc = qk_sweep_stage_relaxed(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, tma, s);
 	else
-		rc = sweep_stage_dispatch<0>(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		rc = sweep_stage_dispatch<0>(ns, prm->reconstruct_eint != 0, L->nghost, L->d_counters, c, db, dm, nb, maxn, stage, dual, tma, s);
 	QK_TRY(rc);
 	// redoFlag.sum() over all ranks (QuokkaSimulation.hpp:1146): in-place device all-reduce of the two counters, then the one D2H copy
 	if (L->comm && L->nranks > 1)

@@ -4,10 +4,10 @@
 // (src/QuokkaSimulation.hpp:1195-1198,1280-1283) straight from those arrays, so refined levels no longer need the one-kernel-per-operator path.
 #include "qk_sweep_kernels.cuh"
 
-int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, int nb, const int maxn[3],
+int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3],
 			 int stage, bool dual, cudaStream_t s)
 {
 	if (order == 2)
-		return sweep_stage_dispatch_plm<0, true>(ng, d_counters, c, static_cast<const SweepBox *>(boxes), nb, maxn, stage, dual, s);
-	return sweep_stage_dispatch<0, true>(ns, reint, ng, d_counters, c, static_cast<const SweepBox *>(boxes), nb, maxn, stage, dual, true, s);
+		return sweep_stage_dispatch_plm<0, true>(ng, d_counters, c, static_cast<const SweepBox *>(boxes), static_cast<const unsigned char *>(tmaps), nb, maxn, stage, dual, s);
+	return sweep_stage_dispatch<0, true>(ns, reint, ng, d_counters, c, static_cast<const SweepBox *>(boxes), static_cast<const unsigned char *>(tmaps), nb, maxn, stage, dual, true, s);
 }

@@ -690,8 +690,22 @@ __global__ void __launch_bounds__(128) k_sweep_m(FastConst c, const SweepBox *__
 			return r_;                                                                                                                   \
 	} while (0)
 
+// descriptors of one launch of a marching sweep along dir (1 | 2) from the host table [box][TM_COUNT]
+static void fill_march_maps(MarchMaps &mm, const unsigned char *h_maps, int b0, int nbc, int dir, bool r0)
+{
+	for (int b = 0; b < nbc; ++b) {
+		const unsigned char *src = h_maps + (size_t)(b0 + b) * TM_COUNT * TMAP_BYTES;
+		memcpy(mm.m[b][MM_PRIM].b, src + TM_PRIM_M36 * TMAP_BYTES, TMAP_BYTES);
+		memcpy(mm.m[b][MM_ROW].b, src + TM_PRIM_R32 * TMAP_BYTES, TMAP_BYTES);
+		memcpy(mm.m[b][MM_RHS].b, src + TM_RHS * TMAP_BYTES, TMAP_BYTES);
+		memcpy(mm.m[b][MM_STAGE2].b, src + (r0 ? TM_R0 : (TM_HF0 + dir)) * TMAP_BYTES, TMAP_BYTES);
+		memcpy(mm.m[b][MM_U0].b, src + TM_U0 * TMAP_BYTES, TMAP_BYTES);
+	}
+}
+
 template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
-static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, int nb, const int maxn[3], bool tma, cudaStream_t s)
+static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, const unsigned char *h_maps, int nb, const int maxn[3],
+			bool tma, cudaStream_t s)
 {
 	if (nb == 0)
 		return 0; // a rank without boxes (more ranks than boxes) launches nothing and still joins the stage's collectives
@@ -731,8 +745,21 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nb);
-			kern<<<grid, 128, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES, s>>>(c, d_tab);
+			for (int b0 = 0; b0 < nb; b0 += TMAP_MAXB) { // descriptors are kernel parameters: at most TMAP_MAXB boxes per launch
+				const int nbc = std::min(TMAP_MAXB, nb - b0);
+				XMaps xm;
+				for (int b = 0; b < nbc; ++b) {
+					const unsigned char *src = h_maps + (size_t)(b0 + b) * TM_COUNT * TMAP_BYTES;
+					memcpy(xm.m[b][XM_PRIM].b, src + TM_PRIM_X38 * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_Y3].b, src + TM_PRIM_Y3 * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_Z3].b, src + TM_PRIM_Z3 * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_HF].b, src + TM_HF0 * TMAP_BYTES, TMAP_BYTES);
+				}
+				dim3 grid(tiles_x, (rows + 4 * XROWS - 1) / (4 * XROWS), nbc);
+				kern<<<grid, 128, XSmem<6 + NS, XSTAGE>::BLOCK_BYTES, s>>>(c, d_tab + b0, xm);
+				if (b0 + TMAP_MAXB < nb)
+					QK_KERNEL_CHECK();
+			}
 		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			dim3 grid(tiles_x, (rows + 3) / 4, nb);
 			k_sweep_x<ARITH, NS, NMS, REINT, STAGE, DUAL><<<grid, 128, 0, s>>>(c, d_tab, tiles_x, rows);
@@ -754,7 +781,15 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+			for (int b0 = 0; b0 < nb; b0 += TMAP_MAXB) {
+				const int nbc = std::min(TMAP_MAXB, nb - b0);
+				MarchMaps mm;
+				fill_march_maps(mm, h_maps, b0, nbc, 1, YSTAGE == 2 && ARITH == 1);
+				grid.z = nbc * nseg;
+				kern<<<grid, 128, MarchSmem<6 + NS, YSTAGE, false, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab + b0, mm, nseg, d_counters);
+				if (b0 + TMAP_MAXB < nb)
+					QK_KERNEL_CHECK();
+			}
 		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			k_sweep_m<ARITH, 1, NS, NMS, REINT, STAGE, DUAL, false><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
@@ -771,7 +806,15 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES));
 				attr_set = true;
 			}
-			kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab, nseg, d_counters);
+			for (int b0 = 0; b0 < nb; b0 += TMAP_MAXB) {
+				const int nbc = std::min(TMAP_MAXB, nb - b0);
+				MarchMaps mm;
+				fill_march_maps(mm, h_maps, b0, nbc, 2, ARITH == 1);
+				grid.z = nbc * nseg;
+				kern<<<grid, 128, MarchSmem<6 + NS, STAGE, true, ARITH == 1>::BLOCK_BYTES, s>>>(c, d_tab + b0, mm, nseg, d_counters);
+				if (b0 + TMAP_MAXB < nb)
+					QK_KERNEL_CHECK();
+			}
 		} else if constexpr (ARITH == 0 && ORDER == 3 && !KEEPF) {
 			k_sweep_m<ARITH, 2, NS, NMS, REINT, STAGE, DUAL, true><<<grid, 128, 0, s>>>(c, d_tab, nseg, d_counters);
 		}
@@ -781,15 +824,15 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 }
 
 template <int ARITH, int NS, int NMS, bool REINT, int ORDER = 3, bool KEEPF = false>
-static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, int nb, const int maxn[3], int stage, bool dual, bool tma,
-			  cudaStream_t s)
+static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, const unsigned char *m, int nb, const int maxn[3], int stage,
+			  bool dual, bool tma, cudaStream_t s)
 {
 	if (KEEPF && !tma)
 		return QK_ERR_UNSUPPORTED; // the flux-keeping kernels exist in the TMA-staged form only
 	if (stage == 1)
-		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s)
-			    : launch_stage<ARITH, NS, NMS, REINT, 1, false, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s);
-	return launch_stage<ARITH, NS, NMS, REINT, 2, true, ORDER, KEEPF>(ng, d_counters, c, t, nb, maxn, tma, s);
+		return dual ? launch_stage<ARITH, NS, NMS, REINT, 1, true, ORDER, KEEPF>(ng, d_counters, c, t, m, nb, maxn, tma, s)
+			    : launch_stage<ARITH, NS, NMS, REINT, 1, false, ORDER, KEEPF>(ng, d_counters, c, t, m, nb, maxn, tma, s);
+	return launch_stage<ARITH, NS, NMS, REINT, 2, true, ORDER, KEEPF>(ng, d_counters, c, t, m, nb, maxn, tma, s);
 }
 
 
@@ -797,22 +840,22 @@ static int dispatch_stage(int ng, unsigned long long *d_counters, const FastCons
 // KEEPF = true, the same kernels also storing the stage's face fluxes for the flux registers: qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu)
 // PLM (reconstructionOrder_ = 2) is instantiated for the trait set of config C4's hydro (no scalars, reconstruct_eint = false), TMA form only
 template <int ARITH, bool KEEPF = false>
-static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3], int stage,
-				    bool dual, cudaStream_t s)
+static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, const unsigned char *dm, int nb, const int maxn[3],
+				    int stage, bool dual, cudaStream_t s)
 {
-	return dispatch_stage<ARITH, 0, 0, false, 2, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, true, s);
+	return dispatch_stage<ARITH, 0, 0, false, 2, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, true, s);
 }
 
 template <int ARITH, bool KEEPF = false>
-static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, int nb, const int maxn[3],
-				int stage, bool dual, bool tma, cudaStream_t s)
+static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, const unsigned char *dm, int nb,
+				const int maxn[3], int stage, bool dual, bool tma, cudaStream_t s)
 {
 	if (ns == 0)
-		return reint ? dispatch_stage<ARITH, 0, 0, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-			     : dispatch_stage<ARITH, 0, 0, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		return reint ? dispatch_stage<ARITH, 0, 0, true, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 0, 0, false, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s);
 	if (ns == 1)
-		return reint ? dispatch_stage<ARITH, 1, 0, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-			     : dispatch_stage<ARITH, 1, 0, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
-	return reint ? dispatch_stage<ARITH, 3, 2, true, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s)
-		     : dispatch_stage<ARITH, 3, 2, false, 3, KEEPF>(ng, d_counters, c, db, nb, maxn, stage, dual, tma, s);
+		return reint ? dispatch_stage<ARITH, 1, 0, true, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s)
+			     : dispatch_stage<ARITH, 1, 0, false, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s);
+	return reint ? dispatch_stage<ARITH, 3, 2, true, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s)
+		     : dispatch_stage<ARITH, 3, 2, false, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s);
 }

@@ -52,3 +52,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 		     "r"(smem_u32(bar))
 		     : "memory");
 }
+
+// ---- tensor-map TMA (cp.async.bulk.tensor, SASS UTMALDG): one copy moves a [x-tile, rows, components] box of a 4-D array (x, y, z, component)
+// described by a CUtensorMap the host encoded (cuTensorMapEncodeTiled); elements outside the array are zero-filled and still counted in the
+// transaction bytes, so ragged tiles need no special cases.  dst must be 128-byte aligned.
+__device__ __forceinline__ void tma_tile_g2s(void *dst, const void *tmap, int x, int y, int z, int n, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(smem_u32(dst)),
+		     "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(n), "r"(smem_u32(bar))
+		     : "memory");
+}
+// the descriptors live in global memory and are rewritten by the host between launches: acquire them before the first use in a warp
+__device__ __forceinline__ void tmap_acquire(const void *tmap)
+{
+	asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+}
