@@ -5,6 +5,8 @@
 // flags a cell (redoFlag), so the rare first-order-flux-correction case keeps the reference's
 // exact semantics (src/QuokkaSimulation.hpp:1146-1184, 1233-1271).
 #include "qk_level.h"
+
+#include <cuda.h> // CUtensorMap and its enums only: the encoder is resolved at run time (no link against libcuda)
 #include "qk_kernels.cuh"
 
 #include <algorithm>
@@ -812,6 +814,43 @@ static qk_box face_of(qk_box b, int d)
 }
 
 // pad_x: round the x pitch up to an even number of doubles so that every row starts 16-byte aligned (TMA bulk copies)
+// ---- tensor-map descriptors (TMA tiles of the hydro and radiation sweeps, qk_march.cuh / qk_rad_kernels.cuh) ----------------------------------------------------------
+typedef CUresult (*qk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+				       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static qk_encode_tiled_fn encode_tiled()
+{
+	static qk_encode_tiled_fn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+			fn = reinterpret_cast<qk_encode_tiled_fn>(p);
+	}
+	return fn;
+}
+
+// descriptor of a box {bx, by, bz, bc} of the FP64 array `a` viewed as a 4-D tensor (x, y, z, component); false when the array cannot be
+// described (odd pitches, unaligned base): the caller then runs the kernels without TMA staging
+bool qk_encode_tile(void *map128, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc)
+{
+	CUtensorMap *m = static_cast<CUtensorMap *>(map128);
+	qk_encode_tiled_fn enc = encode_tiled();
+	if (!enc || ((uintptr_t)a.p % 16) != 0 || (a.jstride % 2) != 0 || (a.kstride % 2) != 0 || (a.nstride % 2) != 0)
+		return false;
+	const cuuint64_t dims[4] = {(cuuint64_t)(a.end[0] - a.begin[0]), (cuuint64_t)(a.end[1] - a.begin[1]), (cuuint64_t)(a.end[2] - a.begin[2]),
+				    (cuuint64_t)a.ncomp};
+	const cuuint64_t strides[3] = {(cuuint64_t)a.jstride * 8, (cuuint64_t)a.kstride * 8, (cuuint64_t)a.nstride * 8};
+	const cuuint32_t box[4] = {bx, by, bz, bc};
+	const cuuint32_t es[4] = {1, 1, 1, 1};
+	if (bc > dims[3])
+		return false;
+	return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+		   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+
 int qk_level::alloc_fabs(std::vector<qk_array4> &out, int ncomp, int grow, int face_dir, bool pad_x)
 {
 	const int nb = (int)valid.size();

@@ -152,5 +152,8 @@ int qk_comm_send(qk_comm *c, const void *buf, size_t bytes, int peer, cudaStream
 int qk_comm_recv(qk_comm *c, void *buf, size_t bytes, int peer, cudaStream_t s);
 int qk_comm_allreduce_sum_i64(qk_comm *c, int64_t *v, cudaStream_t s);
 int qk_comm_allreduce_max_f64(qk_comm *c, double *v, cudaStream_t s);
+// CUtensorMap (128 bytes at map128) of a box {bx, by, bz, bc} of the FP64 array `a` viewed as a 4-D tensor (x, y, z, component); false when the
+// array cannot be described (odd pitches, unaligned base, no driver entry point): the caller then runs its kernels without TMA staging
+bool qk_encode_tile(void *map128, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc);
 int qk_comm_allreduce_dev_u64(qk_comm *c, unsigned long long *d_vals, int count, int is_max, cudaStream_t s);
 }

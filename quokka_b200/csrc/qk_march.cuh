@@ -44,15 +44,10 @@ enum SweepTmap {
 	TM_U0,	  // U0     box {32, 1, 1, NV}
 	TM_COUNT
 };
-constexpr int TMAP_BYTES = 128; // sizeof(CUtensorMap)
 // The descriptors travel as __grid_constant__ kernel PARAMETERS (the one place a TMA descriptor needs no proxy fence and cannot go stale in the
-// per-SM descriptor cache): a launch covers at most TMAP_MAXB boxes, each kernel family carries only the descriptors it uses.
-constexpr int TMAP_MAXB = 24;
+// per-SM descriptor cache): a launch covers at most TMAP_MAXB boxes (qk_tma.cuh), each kernel family carries only the descriptors it uses.
 enum { MM_PRIM = 0, MM_ROW, MM_RHS, MM_STAGE2, MM_U0, MM_COUNT }; // marching sweeps: prim tile, one-component row, rhs, hF[DIR] | R(U0), U0
 enum { XM_PRIM = 0, XM_Y3, XM_Z3, XM_HF, XM_COUNT };		   // x sweep
-struct alignas(64) TmapBytes {
-	unsigned char b[TMAP_BYTES];
-};
 struct MarchMaps {
 	TmapBytes m[TMAP_MAXB][MM_COUNT];
 };

@@ -537,8 +537,8 @@ extern "C" int qk_rad_add_fluxes_rk2(const qk_rad_params *prm, int nboxes, const
 }
 
 // qk_rad_relaxed.cu: the TMA-staged sweeps instantiated with relaxed arithmetic (compiled with FMA contraction)
-int qk_rad_stage_relaxed(int order, const void *rad_const, const void *boxes, int nb, const int maxn[3], int stage, bool keep, bool fix, int g, double dtdx,
-			 double dtdy, double dtdz, cudaStream_t s);
+int qk_rad_stage_relaxed(int order, const void *rad_const, const void *boxes, const void *maps, int nb, const int maxn[3], int stage, bool keep, bool fix, int g,
+			 double dtdx, double dtdy, double dtdz, cudaStream_t s);
 
 // ---- fused stage ------------------------------------------------------------------------------------------------
 struct RadState {
@@ -550,6 +550,7 @@ struct RadState {
 	cudaEvent_t ev[8];
 	bool ev_used[8];
 	bool s0_valid = false;
+	std::vector<RadMaps> maps; // tensor-map descriptors of the stage being launched, one entry per chunk of TMAP_MAXB boxes
 };
 
 void qk_rad_free(qk_level *L)
@@ -737,17 +738,18 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	QK_CUDA(cudaEventRecord(R->ev[slot], s));
 	R->ev_used[slot] = true;
 	const RadConst c = make_rad_const(prm);
-	// The TMA-staged sweeps (qk_rad_kernels.cuh) bulk-copy rows of the caller's state and of the level's scratch: every row must start on a
-	// 16-byte boundary (even pitches, even ghost offset) and the x sweep reads four ghost cells.  Anything else takes the first-generation
+	// The TMA-staged sweeps (qk_rad_kernels.cuh) copy tiles of the caller's state and of the level's scratch through tensor maps: pitches must be
+	// even (16-byte strides), the base 16-byte aligned, and the x sweep reads four ghost cells.  Anything else takes the first-generation
 	// direction-split kernels below (global loads; exact arithmetic only).
 	bool tma = !tile_form && (getenv("QK_RAD_V1") == nullptr) && (L->nghost >= 4);
-	auto rows16 = [](const qk_array4 &a, int lo0) {
-		return ((uintptr_t)a.p % 16 == 0) && (a.jstride % 2 == 0) && (a.kstride % 2 == 0) && (a.nstride % 2 == 0) && ((lo0 - a.begin[0]) % 2 == 0);
-	};
-	for (int b = 0; b < nb && tma; ++b) {
+	R->maps.resize((size_t)(nb + TMAP_MAXB - 1) / TMAP_MAXB);
+	for (int b = 0; b < nb && tma; ++b) { // the tiles need the ghost cells to exist and every array to be describable (even pitches, aligned base)
 		const int lo0 = L->valid[b].lo[0];
-		tma = rows16(U0[b], lo0) && rows16(Ustage[b], lo0) && rows16(R->acc[b], lo0) && rows16(R->S0[b], lo0) && (lo0 - 4 >= Ustage[b].begin[0]) &&
-		      (L->valid[b].lo[1] - 3 >= Ustage[b].begin[1]) && (L->valid[b].lo[2] - 3 >= Ustage[b].begin[2]);
+		TmapBytes *m = R->maps[b / TMAP_MAXB].m[b % TMAP_MAXB];
+		tma = (lo0 - 4 >= Ustage[b].begin[0]) && (L->valid[b].lo[1] - 3 >= Ustage[b].begin[1]) && (L->valid[b].lo[2] - 3 >= Ustage[b].begin[2]) &&
+		      qk_encode_tile(m[RM_US].b, Ustage[b], 32, 1, 1, 4) && qk_encode_tile(m[RM_USX].b, Ustage[b], 38, 1, 1, 4) &&
+		      qk_encode_tile(m[RM_U0].b, U0[b], 32, 1, 1, 4) && qk_encode_tile(m[RM_ACC].b, R->acc[b], 32, 1, 1, 4) &&
+		      qk_encode_tile(m[RM_S0].b, R->S0[b], 32, 1, 1, 4);
 	}
 	const bool relaxed = (prm->arith == QK_ARITH_FAST) && tma; // the relaxed arithmetic exists in the TMA-staged form only
 	if (!tma) {
@@ -764,8 +766,8 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 		ProfScope p("rad_stage", s);
 		const bool fix = (ng == 1);
 		for (int g = 0; g < ng && rc == 0; ++g)
-			rc = relaxed ? qk_rad_stage_relaxed(prm->reconstruction_order, &c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s)
-				     : dispatch_rad_tma<0>(prm->reconstruction_order, c, db2, nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
+			rc = relaxed ? qk_rad_stage_relaxed(prm->reconstruction_order, &c, db2, R->maps.data(), nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s)
+				     : dispatch_rad_tma<0>(prm->reconstruction_order, c, db2, R->maps.data(), nb, maxn, stage, keep, fix, g, dtdx, dtdy, dtdz, s);
 		if (rc == 0 && !fix) {
 			const int64_t cells = (int64_t)maxn[0] * maxn[1] * maxn[2];
 			dim3 grid((unsigned)std::min<int64_t>((cells + 255) / 256, 4096), nb);

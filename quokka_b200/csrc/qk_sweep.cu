@@ -18,7 +18,7 @@
 // REDONE by the faithful path of qk_level.cu, which owns the first-order flux correction.
 #include "qk_sweep_kernels.cuh"
 
-#include <cuda.h> // CUtensorMap and its enums only: the encoder is resolved at run time (no link against libcuda)
+#include <cuda.h> // CUtensorMap (the encoder lives in qk_level.cu: qk_encode_tile)
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -37,41 +37,8 @@ int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long lo
 int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb,
 				 const int maxn[3], int stage, bool dual, cudaStream_t s);
 
-// ---- tensor-map descriptors (TMA tiles of the marching / x sweeps, qk_march.cuh) ----------------------------------------------------------
-typedef CUresult (*qk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
-				       const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static qk_encode_tiled_fn encode_tiled()
-{
-	static qk_encode_tiled_fn fn = nullptr;
-	static bool tried = false;
-	if (!tried) {
-		tried = true;
-		void *p = nullptr;
-		cudaDriverEntryPointQueryResult qres;
-		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-			fn = reinterpret_cast<qk_encode_tiled_fn>(p);
-	}
-	return fn;
-}
 static_assert(sizeof(CUtensorMap) == TMAP_BYTES, "descriptor size");
-
-// descriptor of a box {bx, by, bz, bc} of the FP64 array `a` viewed as a 4-D tensor (x, y, z, component); false when the array cannot be
-// described (odd pitches, unaligned base): the caller then runs the kernels without TMA staging
-static bool encode_tile(CUtensorMap *m, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc)
-{
-	qk_encode_tiled_fn enc = encode_tiled();
-	if (!enc || ((uintptr_t)a.p % 16) != 0 || (a.jstride % 2) != 0 || (a.kstride % 2) != 0 || (a.nstride % 2) != 0)
-		return false;
-	const cuuint64_t dims[4] = {(cuuint64_t)(a.end[0] - a.begin[0]), (cuuint64_t)(a.end[1] - a.begin[1]), (cuuint64_t)(a.end[2] - a.begin[2]),
-				    (cuuint64_t)a.ncomp};
-	const cuuint64_t strides[3] = {(cuuint64_t)a.jstride * 8, (cuuint64_t)a.kstride * 8, (cuuint64_t)a.nstride * 8};
-	const cuuint32_t box[4] = {bx, by, bz, bc};
-	const cuuint32_t es[4] = {1, 1, 1, 1};
-	if (bc > dims[3])
-		return false;
-	return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, a.p, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-		   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
+static bool encode_tile(CUtensorMap *m, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc) { return qk_encode_tile(m, a, bx, by, bz, bc); }
 
 struct FusedState {
 	int nv = 0; // 6 + nscalars the scratch was built for

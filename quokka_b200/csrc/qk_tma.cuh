@@ -62,7 +62,13 @@ __device__ __forceinline__ void tma_tile_g2s(void *dst, const void *tmap, int x,
 		     "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(n), "r"(smem_u32(bar))
 		     : "memory");
 }
-// the descriptors live in global memory and are rewritten by the host between launches: acquire them before the first use in a warp
+constexpr int TMAP_BYTES = 128; // sizeof(CUtensorMap)
+constexpr int TMAP_MAXB = 24;	// boxes per launch of a kernel that carries its descriptors as __grid_constant__ parameters
+struct alignas(64) TmapBytes {
+	unsigned char b[TMAP_BYTES];
+};
+// for descriptors that live in global memory and are rewritten between launches: acquire them before the first use in a warp (unused: the
+// sweep kernels take their descriptors as parameters, where no fence is needed -- measured: the fence cost the x sweep 27 %)
 __device__ __forceinline__ void tmap_acquire(const void *tmap)
 {
 	asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
