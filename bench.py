@@ -453,21 +453,23 @@ def main_ours(args):
                               "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}))
         sim.close()
         return 0
-    # end to end through the C ABI from host buffers: upload, one step, download -- every step
+    # end to end through the C ABI from host buffers: every step uploads the state (pinned host memory, the VALID cells: ghost cells are the
+    # step's own business), advances it and downloads the result; per box the copy runs on its own stream and overlaps the (un)packing
+    # kernel of the previous box (qk_sim_set_state_valid / qk_sim_get_state_valid)
     e2e_steps = max(1, min(args.steps, 5))
-    sim.download()
+    sim.download_valid()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sim.upload()
+        sim.upload_valid()
         dt = sim.computeTimestep()
         r = sim.advanceSingleTimestepAtLevel(dt)
         assert r >= 0
-        sim.download()
+        sim.download_valid()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_val = ncells_total * e2e_steps / e2e_s / 1e6
-    hb = sim.h2d_bytes()
+    hb = sim.valid_bytes()
     sim.close()
     del sim
     torch.cuda.empty_cache()
@@ -541,7 +543,7 @@ def main_ours(args):
                 "config": make_config(world, ncell), "arith": ARITH_TEXT[args.arith],
                 "clocks": clk, "gpu_launches": int(launches),
                 "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": hb, "d2h_bytes_per_step": hb, "steps": e2e_steps,
-                        "note": "host-buffer plugin call: pinned state upload + step + state download per step"},
+                        "note": "host-buffer plugin call: pinned upload of the valid cells + step + download per step (PCIe-bound)"},
                 "roofline": roof, "sweeps": sweep_fracs(prof, ncell_local, args.steps),
                 "kernel_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
         if other:
@@ -869,7 +871,7 @@ def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
         fp64_per_cell, opmix = 740, "profiles/r01_ncu_opmix_exact.txt"
     else:  # keeps R(U0) per cell instead
         DESIGN = {"sweep_x": 56 + 56, "sweep_y": 56 + 112, "sweep_z": 56 + 56 + 48 + 48 + 48}
-        fp64_per_cell, opmix = 480, "profiles/r01_ncu_opmix_relaxed.txt"
+        fp64_per_cell, opmix = 431, "profiles/r02_ncu_opmix_relaxed_2.txt (y sweep: 226.07 M FP64-pipe warp instructions over 524 288 rows of 32 cells)"
     # measured DRAM traffic per launch (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum, stage-1/stage-2 launches averaged) from the
     # committed capture profiles/ncu_traffic.json -- reported only while the kernel sources are the ones that were profiled
     TRAFFIC, traffic_note = {}, "profiles/ncu_traffic.json missing"

@@ -480,6 +480,12 @@ int qk_sim_state_desc(qk_sim *sim, int which, int local_box, qk_array4 *out);
 /* host <-> device copy of state_new of one local box (whole FAB incl. ghosts); stream-ordered, see qk_sim_sync */
 int qk_sim_set_state(qk_sim *sim, int local_box, const double *host);
 int qk_sim_get_state(qk_sim *sim, int local_box, double *host);
+/* the same for the VALID cells only: host = contiguous (ncomp, nz, ny, nx) array of the box's valid cells (what a host-resident caller
+ * owns; the step fills the ghost cells itself, src/simulation.hpp:1704-1785).  Copies run on their own stream and overlap the (un)packing
+ * kernel of the previous box; qk_sim_sync waits for both.  qk_sim_box_valid_doubles = ncomp * number of valid cells. */
+int64_t qk_sim_box_valid_doubles(const qk_sim *sim, int local_box);
+int qk_sim_set_state_valid(qk_sim *sim, int local_box, const double *host_valid);
+int qk_sim_get_state_valid(qk_sim *sim, int local_box, double *host_valid);
 int qk_sim_sync(qk_sim *sim);
 void qk_sim_reset_clock(qk_sim *sim, double t, double dt_prev);
 int qk_sim_compute_timestep(qk_sim *sim, double stop_time, double *dt_out);

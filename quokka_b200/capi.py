@@ -306,6 +306,9 @@ SYMBOLS = {
     "qk_sim_box_doubles": (C.c_int64, [_VP, C.c_int]),
     "qk_sim_state_desc": (C.c_int, [_VP, C.c_int, C.c_int, _A4P]),
     "qk_sim_set_state": (C.c_int, [_VP, C.c_int, _VP]),
+    "qk_sim_box_valid_doubles": (C.c_int64, [_VP, C.c_int]),
+    "qk_sim_set_state_valid": (C.c_int, [_VP, C.c_int, _VP]),
+    "qk_sim_get_state_valid": (C.c_int, [_VP, C.c_int, _VP]),
     "qk_sim_get_state": (C.c_int, [_VP, C.c_int, _VP]),
     "qk_sim_sync": (C.c_int, [_VP]),
     "qk_sim_reset_clock": (None, [_VP, C.c_double, C.c_double]),

@@ -297,11 +297,11 @@ template <int ORDER> __global__ void __launch_bounds__(128) k_rad_x(RadConst c, 
 	const RadBox2 &B = boxes[blockIdx.z];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
-	const int row = blockIdx.y * 4 + warp;
+	const int row = blockIdx.x * 4 + warp; // rows in grid.x: a 512 x 512 cross-section has more row groups than grid.y allows
 	if (row >= ny * nz)
 		return; // whole warp
 	const int j = B.lo[1] + row % ny, k = B.lo[2] + row / ny;
-	const int x0 = B.lo[0] + blockIdx.x * 30;
+	const int x0 = B.lo[0] + blockIdx.y * 30;
 	if (x0 > B.hi[0])
 		return;
 	const int i = x0 - 1 + lane;
@@ -642,7 +642,7 @@ static int launch_rad_split(const RadConst &c, const RadBox2 *tab, int nb, const
 			    double dtdz, cudaStream_t s)
 {
 	{
-		dim3 grid((maxn[0] + 29) / 30, (maxn[1] * maxn[2] + 3) / 4, nb);
+		dim3 grid((maxn[1] * maxn[2] + 3) / 4, (maxn[0] + 29) / 30, nb);
 		k_rad_x<ORDER><<<grid, 128, 0, s>>>(c, tab, g, dtdx);
 		QK_KERNEL_CHECK();
 	}

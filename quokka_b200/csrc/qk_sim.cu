@@ -44,6 +44,12 @@ struct qk_sim {
 	int64_t rad_failures = 0;    // nf_coupling + nf_dust + nf_outer over the run (:1692-1699)
 	int last_nsub = 0;
 	int64_t rad_cell_updates = 0; // radiationCellUpdates_
+	// host <-> device transfer of the VALID cells only (qk_sim_set_state_valid / qk_sim_get_state_valid): contiguous staging per box, copies on
+	// their own stream, (un)packing kernels on the simulation's stream, one event per box
+	double *stage = nullptr;
+	std::vector<size_t> stage_off;
+	cudaStream_t copy_stream = nullptr;
+	std::vector<cudaEvent_t> box_ev;
 };
 int qk_hydro_max_signal_both(const qk_hydro_params *prm, int nboxes, const qk_box *valid, const qk_array4 *cons, double out[2], cudaStream_t s);
 
@@ -134,6 +140,14 @@ extern "C" void qk_sim_destroy(qk_sim *s)
 	for (int i = 0; i < 4; ++i)
 		if (s->pool[i])
 			cudaFree(s->pool[i]);
+	if (s->copy_stream) {
+		cudaStreamSynchronize(s->copy_stream);
+		cudaStreamDestroy(s->copy_stream);
+	}
+	for (cudaEvent_t e : s->box_ev)
+		cudaEventDestroy(e);
+	if (s->stage)
+		cudaFree(s->stage);
 	if (s->ev0)
 		cudaEventDestroy(s->ev0);
 	if (s->ev1)
@@ -207,11 +221,99 @@ extern "C" int qk_sim_get_state(qk_sim *s, int b, double *host)
 	QK_CUDA(cudaMemcpyAsync(host, s->snew[b].p, (size_t)qk_sim_box_doubles(s, b) * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
 	return 0;
 }
+// ---- valid cells only: what a host-resident caller actually owns (ghost cells are filled by the step itself) ----
+__global__ void __launch_bounds__(256) k_stage_copy(A4 a, Box3 bx, int ncomp, double *__restrict__ stage, int to_state)
+{
+	const int nx = bx.hi[0] - bx.lo[0] + 1, ny = bx.hi[1] - bx.lo[1] + 1, nz = bx.hi[2] - bx.lo[2] + 1;
+	const int64_t total = (int64_t)nx * ny * nz * ncomp;
+	for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (int64_t)gridDim.x * 256) {
+		const int64_t row = t / nx;
+		const int i = (int)(t - row * nx);
+		const int64_t pl = row / ny;
+		const int j = (int)(row - pl * ny);
+		const int n = (int)(pl / nz), k = (int)(pl - (int64_t)n * nz);
+		double *p = a.p + a.off(bx.lo[0] + i, bx.lo[1] + j, bx.lo[2] + k) + (int64_t)n * a.ns;
+		if (to_state)
+			*p = stage[t];
+		else
+			stage[t] = *p;
+	}
+}
+
+static int stage_setup(qk_sim *s)
+{
+	if (s->stage)
+		return 0;
+	size_t tot = 0;
+	s->stage_off.resize(s->nb);
+	for (int b = 0; b < s->nb; ++b) {
+		s->stage_off[b] = tot;
+		tot += (size_t)Box3(s->lev->valid[b]).ncells() * s->lev->ncomp;
+	}
+	if (cudaMalloc(&s->stage, std::max<size_t>(tot, 1) * sizeof(double)) != cudaSuccess)
+		return QK_ERR_NOMEM;
+	QK_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+	s->box_ev.resize(s->nb);
+	for (int b = 0; b < s->nb; ++b)
+		QK_CUDA(cudaEventCreateWithFlags(&s->box_ev[b], cudaEventDisableTiming));
+	return 0;
+}
+
+extern "C" int64_t qk_sim_box_valid_doubles(const qk_sim *s, int b)
+{
+	if (!s || b < 0 || b >= s->nb)
+		return 0;
+	return Box3(s->lev->valid[b]).ncells() * s->lev->ncomp;
+}
+
+// state_new of local box b from / to a contiguous host array (ncomp, nz, ny, nx) of its VALID cells (pinned for asynchronous copies).  The copy
+// runs on a separate stream and the (un)packing kernel on the simulation's, so the copy of box b+1 overlaps the kernel of box b.  Ghost cells
+// are not transferred: the step fills them (fillBoundaryConditions) before anything reads them.
+extern "C" int qk_sim_set_state_valid(qk_sim *s, int b, const double *host)
+{
+	if (!s || b < 0 || b >= s->nb || !host)
+		return QK_ERR_BAD_ARG;
+	int rc = stage_setup(s);
+	if (rc)
+		return rc;
+	s->sig_valid = false;
+	const int64_t n = qk_sim_box_valid_doubles(s, b);
+	double *st = s->stage + s->stage_off[b];
+	if (b == 0) { // the staging buffer may still be read by the kernels of an earlier download: order the copy stream behind them
+		QK_CUDA(cudaEventRecord(s->ev0, s->stream));
+		QK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev0, 0));
+	}
+	QK_CUDA(cudaMemcpyAsync(st, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->copy_stream));
+	QK_CUDA(cudaEventRecord(s->box_ev[b], s->copy_stream));
+	QK_CUDA(cudaStreamWaitEvent(s->stream, s->box_ev[b], 0));
+	k_stage_copy<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s->stream>>>(A4(s->snew[b]), Box3(s->lev->valid[b]), s->lev->ncomp, st, 1);
+	QK_KERNEL_CHECK();
+	return 0;
+}
+extern "C" int qk_sim_get_state_valid(qk_sim *s, int b, double *host)
+{
+	if (!s || b < 0 || b >= s->nb || !host)
+		return QK_ERR_BAD_ARG;
+	int rc = stage_setup(s);
+	if (rc)
+		return rc;
+	const int64_t n = qk_sim_box_valid_doubles(s, b);
+	double *st = s->stage + s->stage_off[b];
+	k_stage_copy<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s->stream>>>(A4(s->snew[b]), Box3(s->lev->valid[b]), s->lev->ncomp, st, 0);
+	QK_KERNEL_CHECK();
+	QK_CUDA(cudaEventRecord(s->box_ev[b], s->stream));
+	QK_CUDA(cudaStreamWaitEvent(s->copy_stream, s->box_ev[b], 0));
+	QK_CUDA(cudaMemcpyAsync(host, st, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+	return 0;
+}
+
 extern "C" int qk_sim_sync(qk_sim *s)
 {
 	if (!s)
 		return QK_ERR_BAD_ARG;
 	QK_CUDA(cudaStreamSynchronize(s->stream));
+	if (s->copy_stream)
+		QK_CUDA(cudaStreamSynchronize(s->copy_stream));
 	return 0;
 }
 extern "C" void qk_sim_reset_clock(qk_sim *s, double t, double dt_prev)

@@ -149,6 +149,8 @@ template <int ARITH, int NS, bool REINT> __global__ void __launch_bounds__(256) 
 // each axis) are evaluated from 7-point pressure and 5-point velocity lines held in registers, so the chi_x/chi_y/chi_z arrays
 // are never written or re-read (k_fchi + k_fchimin: 0.48 ms per stage at 256^3).  With the closed-form EOS a chi evaluation is
 // ~25 instructions; the exact mode, whose rho c_s^2 costs a sound-speed evaluation per cell, keeps the two-kernel form.
+// (Round 2 tried a shared-memory tile form -- each directional chi evaluated once per cell, 3.8 evaluations per output instead of 9 -- and
+// measured it SLOWER: 0.48 vs 0.42 ms per launch at 256^3; the index decode and the block barrier cost more than the saved evaluations.)
 template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi9(FastConst c, const SweepBox *__restrict__ boxes)
 {
 	const SweepBox &B = boxes[blockIdx.y];

@@ -91,6 +91,30 @@ class HydroSimulation:
     def h2d_bytes(self):
         return sum(int(t.numel()) * 8 for t in self._host_buffers())
 
+    # -- state transfer, valid cells only (what a host-resident caller owns; the step fills the ghost cells) --
+    def _host_valid_buffers(self):
+        if getattr(self, "_pinned_valid", None) is None:
+            import torch
+
+            self._pinned_valid = []
+            for bx in self.local_boxes:
+                nz, ny, nx = bx.shape()
+                self._pinned_valid.append(torch.empty((self.problem.ncomp, nz, ny, nx), dtype=torch.float64).pin_memory())
+        return self._pinned_valid
+
+    def upload_valid(self):
+        for b, t in enumerate(self._host_valid_buffers()):
+            check(self.lib.qk_sim_set_state_valid(self.handle, b, t.data_ptr()), "qk_sim_set_state_valid")
+
+    def download_valid(self):
+        for b, t in enumerate(self._host_valid_buffers()):
+            check(self.lib.qk_sim_get_state_valid(self.handle, b, t.data_ptr()), "qk_sim_get_state_valid")
+        check(self.lib.qk_sim_sync(self.handle), "qk_sim_sync")
+        return [t.numpy() for t in self._pinned_valid]
+
+    def valid_bytes(self):
+        return sum(int(t.numel()) * 8 for t in self._host_valid_buffers())
+
     def state_valid(self):
         """state_new_cc_ on the valid cells of the local boxes -> dict box_id -> (ncomp, nz, ny, nx)"""
         ng = self.problem.nghost
