@@ -97,7 +97,7 @@ typedef struct qk_hydro_params {
 	double small_dens;	      /* eos_init small_dens = 1e-100 (QuokkaSimulation.hpp:166) */
 	double density_floor;	      /* densityFloor_ (simulation.hpp:172) */
 	double temp_floor;	      /* tempFloor_ (simulation.hpp:173) */
-	double K_visc;		      /* artificialViscosityK_ (QuokkaSimulation.hpp:120); only 0 is supported by the fused path */
+	double K_visc;		      /* artificialViscosityK_ (QuokkaSimulation.hpp:120); != 0 takes the one-kernel-per-operator path */
 	double small_x;		      /* network_rp::small_x, mass-scalar floor (hydro_system.hpp:730) */
 	int32_t reconstruct_eint;     /* HydroSystem_Traits::reconstruct_eint */
 	int32_t nscalars;	      /* Physics_Traits::numPassiveScalars (includes mass scalars) */
@@ -205,7 +205,11 @@ typedef struct qk_rad_params {
 	int32_t integrator_order;     /* 1 forward Euler | 2 RK2 (IMEX PD-ARS transport part, IMEX_a32 = 0.5, :52) */
 	int32_t arith;		      /* QK_ARITH_EXACT (0, the default of a zero-initialised struct): bit-identical to the oracle; QK_ARITH_FAST: relaxed
 				       * transport sweeps.  qk_rad_subcycle overrides it with hydro->arith. */
-	int32_t reserved_;
+	int32_t use_wavespeed_correction; /* radiation.use_wavespeed_correction (src/QuokkaSimulation.hpp:133, radiation_system.hpp:1018-1022,1100-1109): on faces
+				       * with even i+j+k the diffusive term of the ENERGY flux is scaled by min(1, 1/tau_cell), tau_cell = the harmonic mean of
+				       * dl rho kappa_F of the two cells (ComputeCellOpticalDepth :803-871).  Constant flux-mean opacity only. */
+	double kappa_F;		      /* ComputeFluxMeanOpacity (constant); read only with use_wavespeed_correction */
+	double cell_dx[3];	      /* cell sizes for qk_rad_compute_fluxes with use_wavespeed_correction (the stage-level entries take the level's) */
 } qk_rad_params;
 
 /* RadSystem::ConservedToPrimitive(cons, primVar, ghostRange)  radiation_system.hpp:589-614.  prim has 4*ngroups components

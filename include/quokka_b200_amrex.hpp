@@ -370,13 +370,19 @@ template <typename problem_t> class RadSystemB200
 	// RadSystem::ComputeFluxes<DIR>(x1Flux, x1FluxDiffusive, left, right, x1FluxRange, consVar, dx, use_wavespeed_correction)  :985-1139
 	template <FluxDir DIR>
 	static void ComputeFluxes(array_t &x1Flux_in, array_t &x1FluxDiffusive_in, arrayconst_t &x1LeftState_in, arrayconst_t &x1RightState_in,
-				  amrex::Box const &indexRange, arrayconst_t &consVar_in, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> /*dx*/,
+				  amrex::Box const &indexRange, arrayconst_t &consVar_in, amrex::GpuArray<amrex::Real, AMREX_SPACEDIM> dx,
 				  bool const use_wavespeed_correction)
 	{
+		qk_rad_params prm = make_rad_params<problem_t>();
 		if (use_wavespeed_correction) {
-			amrex::Abort("libquokka_b200: the optical-depth wavespeed correction is not provided (radiation.use_wavespeed_correction = 0)");
+			// ComputeCellOpticalDepth (:803-871) with a CONSTANT flux-mean opacity, one photon group (what the library provides): the
+			// problem's ComputeFluxMeanOpacity is sampled once; a density- or temperature-dependent opacity keeps the stock kernel
+			prm.use_wavespeed_correction = 1;
+			prm.kappa_F = RadSystem<problem_t>::ComputeFluxMeanOpacity(1.0, 1.0);
+			for (int d = 0; d < AMREX_SPACEDIM; ++d) {
+				prm.cell_dx[d] = dx[d];
+			}
 		}
-		const qk_rad_params prm = make_rad_params<problem_t>();
 		const qk_array4 f = view(x1Flux_in);
 		const qk_array4 fd = view(x1FluxDiffusive_in);
 		const qk_array4 l = view(x1LeftState_in);

@@ -230,6 +230,10 @@ template <typename problem_t> void QuokkaSimulation<problem_t>::subcycleRadiatio
 		qk_rad_params rp = b2::make_rad_params<problem_t>();
 		rp.reconstruction_order = radiationReconstructionOrder_;
 		rp.integrator_order = 2;
+		if (use_wavespeed_correction_) { // radiation.use_wavespeed_correction (src/QuokkaSimulation.hpp:133,1960): constant flux-mean opacity
+			rp.use_wavespeed_correction = 1;
+			rp.kappa_F = RadSystem<problem_t>::ComputeFluxMeanOpacity(1.0, 1.0);
+		}
 		const qk_rad_source_params sp = b2::make_rad_source_params<problem_t>();
 		amrex::MultiFab U_tmp(grids[lev], dmap[lev], Physics_Indices<problem_t>::nvarTotal_cc, nghost_cc_);
 		// operatorSplitSourceTerms (:1860-1885) evaluates RadSystem::SetRadEnergySource box by box before every solve, at time_subcycle +

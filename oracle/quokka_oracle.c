@@ -818,7 +818,9 @@ static void rad_pressure(int dir, double erad, const double Fv[3], const double 
 	*S = (0.1 < sq) ? sq : 0.1; /* std::max(0.1, sqrt(Tnormal)) */
 }
 
-/* RadSystem::ComputeFluxes<DIR>  :985-1139, use_wavespeed_correction = false (epsilon = 1).  fdiff may be NULL. */
+/* RadSystem::ComputeFluxes<DIR>  :985-1139; with prm->use_wavespeed_correction the energy component's diffusive term is scaled by
+ * epsilon = min(1, 1 / tau_cell) on faces with even i+j+k (:1018-1022,1100-1109; ComputeCellOpticalDepth :803-871 for one group and a constant
+ * flux-mean opacity; the gas temperature the reference evaluates there does not enter a constant opacity).  fdiff may be NULL. */
 void orc_rad_compute_fluxes(const qk_rad_params *prm, int dir, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left,
 			    const qk_array4 *right, const qk_array4 *cons, const qk_box *facebx)
 {
@@ -867,8 +869,17 @@ void orc_rad_compute_fluxes(const qk_rad_params *prm, int dir, const qk_array4 *
 					const double U_L[4] = {erad_L, FL[0], FL[1], FL[2]};
 					const double U_R[4] = {erad_R, FR[0], FR[1], FR[2]};
 					const double a = S_R / (S_R - S_L), b = S_L / (S_R - S_L), d = S_R * S_L / (S_R - S_L);
+					double eps0 = 1.0;
+					if (prm->use_wavespeed_correction && ((i + j + k) % 2 == 0)) { /* no correction for odd zones :1105 */
+						const double dl = prm->cell_dx[dir];
+						const double tau_L = dl * A4(cons, i - e0, j - e1, k - e2, 0) * prm->kappa_F;
+						const double tau_R = dl * A4(cons, i, j, k, 0) * prm->kappa_F;
+						const double tau = (tau_L * tau_R * 2.) / (tau_L + tau_R); /* harmonic mean :864 */
+						const double inv = 1.0 / tau;
+						eps0 = (inv < 1.0) ? inv : 1.0; /* std::min(1.0, 1.0 / tau_cell) */
+					}
 					for (int n = 0; n < 4; ++n) {
-						const double eps = 1.0;
+						const double eps = (n == 0) ? eps0 : 1.0;
 						A4(flux, i, j, k, 4 * g + n) = a * F_L[n] - b * F_R[n] + (eps * d) * (U_R[n] - U_L[n]);
 						if (fdiff)
 							A4(fdiff, i, j, k, 4 * g + n) = a * F_L[n] - b * F_R[n] + d * (U_R[n] - U_L[n]);
@@ -1984,9 +1995,12 @@ static void rad_stage1_level(orc_level *L, const qk_rad_params *prm, double dt, 
 	const int nb = L->nb, ng = L->d.nghost, nc = L->d.ncomp;
 	const double *dx = L->d.dx;
 	orc_fill_boundary(L, Uold, 0, nc); /* :1798 */
+	qk_rad_params pl = *prm; /* ComputeCellOpticalDepth uses the level's cell sizes */
+	for (int d = 0; d < 3; ++d)
+		pl.cell_dx[d] = dx[d];
 	for (int b = 0; b < nb; ++b) {
 		qk_array4 f[3];
-		rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, f);
+		rad_fluxes_of_box(&pl, &Uold[b], L->boxes[b], ng, f);
 		orc_rad_predict_step(prm, &Uold[b], &Unew[b], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
 		for (int d = 0; d < 3; ++d)
 			free_a4(&f[d]);
@@ -2000,10 +2014,13 @@ static void rad_stage2_level(orc_level *L, const qk_rad_params *prm, double dt, 
 	orc_fill_boundary(L, Unew, 0, nc); /* :1831 */
 	/* stateInter and stateNew alias in the reference (:1840-1841): every box's fluxes are computed from the intermediate
 	 * state before that box is overwritten, and ghost cells of other boxes are not touched by the update */
+	qk_rad_params pl = *prm;
+	for (int d = 0; d < 3; ++d)
+		pl.cell_dx[d] = dx[d];
 	for (int b = 0; b < nb; ++b) {
 		qk_array4 fo[3], f[3];
-		rad_fluxes_of_box(prm, &Uold[b], L->boxes[b], ng, fo);
-		rad_fluxes_of_box(prm, &Unew[b], L->boxes[b], ng, f);
+		rad_fluxes_of_box(&pl, &Uold[b], L->boxes[b], ng, fo);
+		rad_fluxes_of_box(&pl, &Unew[b], L->boxes[b], ng, f);
 		orc_rad_add_fluxes_rk2(prm, &Unew[b], &Uold[b], &Unew[b], &fo[0], &fo[1], &fo[2], &f[0], &f[1], &f[2], dt, dx, &L->boxes[b]);
 		for (int d = 0; d < 3; ++d) {
 			free_a4(&fo[d]);

@@ -464,6 +464,28 @@ void rad_fluxes(const qk_box *valid, const qk_array4 *flux, const qk_array4 *fdi
 	copy_out(f, flux);
 	copy_out(fd, fdiff);
 }
+// the same with the optical-depth wavespeed correction (radiation.use_wavespeed_correction, :1018-1022,1100-1109): needs the gas state of
+// consVar (ComputeCellOpticalDepth :803-871), the cell sizes and a problem type with opacities (R2 .. R7)
+template <typename P, FluxDir DIR>
+void rad_fluxes_wsc(const qk_box *valid, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left, const qk_array4 *right, const qk_array4 *cons,
+		    int ngcons, const double *dx3)
+{
+	set_eos<P>();
+	const int nh = RadSystem<P>::nvarHyperbolic_;
+	auto c = make_mf(valid, -1, RadSystem<P>::nvar_, ngcons);
+	auto l = make_mf(valid, static_cast<int>(DIR), nh, 1);
+	auto r = make_mf(valid, static_cast<int>(DIR), nh, 1);
+	auto f = make_mf(valid, static_cast<int>(DIR), nh, 0);
+	auto fd = make_mf(valid, static_cast<int>(DIR), nh, 0);
+	copy_in(c, cons);
+	copy_in(l, left);
+	copy_in(r, right);
+	amrex::GpuArray<amrex::Real, 3> dx{dx3[0], dx3[1], dx3[2]};
+	RadSystem<P>::template ComputeFluxes<DIR>(f.array(0), fd.array(0), l.const_array(0), r.const_array(0),
+						  amrex::surroundingNodes(to_box(valid), static_cast<int>(DIR)), c.const_array(0), dx, true);
+	copy_out(f, flux);
+	copy_out(fd, fdiff);
+}
 template <typename P>
 void rad_update(int op, const qk_box *valid, const qk_array4 *unew, const qk_array4 *u0, const qk_array4 *u1, const qk_array4 *const *fold,
 		const qk_array4 *const *fnew, double dt, const double *dx3)
@@ -686,6 +708,13 @@ int ref_rad_compute_fluxes(int problem, int dir, const qk_box *valid, const qk_a
 {
 	ensure_init();
 	DISPATCH_R(problem, DISPATCH_D(dir, (rad_fluxes<P, D>(valid, flux, fdiff, left, right, cons, ngcons))));
+	return 0;
+}
+int ref_rad_compute_fluxes_wsc(int problem, int dir, const qk_box *valid, const qk_array4 *flux, const qk_array4 *fdiff, const qk_array4 *left,
+			       const qk_array4 *right, const qk_array4 *cons, int ngcons, const double *dx3)
+{
+	ensure_init();
+	DISPATCH_RS(problem, DISPATCH_D(dir, (rad_fluxes_wsc<P, D>(valid, flux, fdiff, left, right, cons, ngcons, dx3))));
 	return 0;
 }
 int ref_rad_update(int problem, int op, const qk_box *valid, const qk_array4 *unew, const qk_array4 *u0, const qk_array4 *u1, const qk_array4 *fxo,

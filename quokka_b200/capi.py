@@ -97,12 +97,17 @@ class qk_rad_params(C.Structure):
         ("reconstruction_order", C.c_int32),
         ("integrator_order", C.c_int32),
         ("arith", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("use_wavespeed_correction", C.c_int32),
+        ("kappa_F", C.c_double),
+        ("cell_dx", C.c_double * 3),
     ]
 
 
-def rad_params(c_light=1.0, c_hat=1.0, Erad_floor=0.0, ngroups=1, nstart=6, recon_order=3, integrator_order=2, arith=QK_ARITH_EXACT) -> qk_rad_params:
+def rad_params(c_light=1.0, c_hat=1.0, Erad_floor=0.0, ngroups=1, nstart=6, recon_order=3, integrator_order=2, arith=QK_ARITH_EXACT,
+               wavespeed_correction=0, kappa_F=0.0, cell_dx=(1.0, 1.0, 1.0)) -> qk_rad_params:
     p = qk_rad_params()
+    p.use_wavespeed_correction, p.kappa_F = int(wavespeed_correction), kappa_F
+    p.cell_dx[:] = list(cell_dx)
     p.c_light, p.c_hat, p.Erad_floor = c_light, c_hat, Erad_floor
     p.ngroups, p.nstart, p.reconstruction_order, p.integrator_order = ngroups, nstart, recon_order, integrator_order
     p.arith = arith

@@ -114,7 +114,7 @@ extern "C" const char *qk_error_string(int code)
 	case QK_ERR_BAD_ARG:
 		return "bad argument";
 	case QK_ERR_UNSUPPORTED:
-		return "unsupported configuration (isothermal EOS, K_visc != 0, > QK_MAX_SCALARS scalars, MHD)";
+		return "unsupported configuration (isothermal EOS, > QK_MAX_SCALARS scalars, MHD)";
 	case QK_ERR_NOMEM:
 		return "out of device memory";
 	case QK_ERR_NOT_CONVERGED:
@@ -129,7 +129,7 @@ static int check_params(const qk_hydro_params *p)
 {
 	if (!p)
 		return QK_ERR_BAD_ARG;
-	if (p->gamma == 1.0 || p->K_visc != 0.0 || p->nscalars > QK_MAX_SCALARS || p->nscalars < 0 || p->nmscalars > p->nscalars)
+	if (p->gamma == 1.0 || p->nscalars > QK_MAX_SCALARS || p->nscalars < 0 || p->nmscalars > p->nscalars)
 		return QK_ERR_UNSUPPORTED;
 	return qk_require_device();
 }

@@ -64,12 +64,19 @@ template <int DIR> __global__ void __launch_bounds__(TPB) k_rad_flux_op(RadConst
 			R[n] = right(i, j, k, 4 * g + n);
 		}
 		const double *cR = cons.p + cons.off(i, j, k) + (c.nstart + 4 * g) * cons.ns;
-		rad_face_flux<DIR>(c, L, R, cR - sc, cR, cons.ns, F);
+		const int64_t roff = (int64_t)(c.nstart + 4 * g) * cons.ns;
+		rad_face_flux<DIR>(c, L, R, cR - sc, cR, cons.ns, F, i + j + k, roff);
+		double Fd0 = F[0];
+		if (have_fdiff && c.wsc && ((i + j + k) % 2) == 0) { // the "diffusive" flux is the expression with epsilon = 1 (:1130-1131)
+			double Fd[4];
+			rad_face_flux<DIR>(c, L, R, cR - sc, cR, cons.ns, Fd);
+			Fd0 = Fd[0];
+		}
 #pragma unroll
 		for (int n = 0; n < 4; ++n) {
 			flux(i, j, k, 4 * g + n) = F[n];
 			if (have_fdiff)
-				fdiff(i, j, k, 4 * g + n) = F[n]; // epsilon = 1: the "diffusive" flux is the same expression (:1130-1131)
+				fdiff(i, j, k, 4 * g + n) = (n == 0) ? Fd0 : F[n];
 		}
 	}
 }
@@ -175,7 +182,7 @@ template <int ORDER, int DIR> __device__ __forceinline__ void rad_face_of_cell(c
 	const A4 &u = B.Us;
 	const int64_t su = (DIR == 0) ? 1 : (DIR == 1) ? u.js : u.ks;
 	const double *cR = u.p + u.off(i, j, k) + (c.nstart + 4 * g) * u.ns;
-	rad_face_flux<DIR>(c, L, R, cR - su, cR, u.ns, F);
+	rad_face_flux<DIR>(c, L, R, cR - su, cR, u.ns, F, i + j + k, (int64_t)(c.nstart + 4 * g) * u.ns);
 }
 
 __device__ __forceinline__ int rs_idx(int d, int n, int lz, int ly, int lx) { return (((d * 4 + n) * RSZ + lz) * RSY + ly) * RSX + lx; }
@@ -320,7 +327,7 @@ template <int ORDER> __global__ void __launch_bounds__(128) k_rad_x(RadConst c, 
 	if (face_ok) {
 		const A4 &u = B.Us;
 		const double *cR = u.p + u.off(i, j, k) + (c.nstart + 4 * g) * u.ns;
-		rad_face_flux<0>(c, Ls, am, cR - 1, cR, u.ns, F);
+		rad_face_flux<0>(c, Ls, am, cR - 1, cR, u.ns, F, i + j + k, (int64_t)(c.nstart + 4 * g) * u.ns);
 	}
 	const bool upd = (lane >= 1) && (lane <= 30) && (i <= B.hi[0]);
 	const A4 &a = B.acc;
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(128, 4) k_rad_m(RadConst c, const RadBox2 *__r
 			rad_cell_parabola<ORDER>(w[n][0], w[n][1], w[n][2], w[n][3], w[n][4], am[n], ap[n]);
 		if (s >= s0) {
 			double F[4];
-			rad_face_flux<DIR>(c, apL, am, cu - suN, cu, u.ns, F);
+			rad_face_flux<DIR>(c, apL, am, cu - suN, cu, u.ns, F, i + t + s, (int64_t)(c.nstart + 4 * g) * u.ns);
 			if (s > s0) { // cell s-1: both faces known
 				const int64_t oac = oa - saN;
 				double cons[4];
@@ -488,6 +495,8 @@ extern "C" int qk_rad_compute_fluxes(const qk_rad_params *prm, int dir, int nbox
 	QK_TRY(check_rad(prm));
 	if (dir < 0 || dir > 2)
 		return QK_ERR_BAD_ARG;
+	if (prm->use_wavespeed_correction && prm->ngroups != 1)
+		return QK_ERR_UNSUPPORTED; // the multigroup optical depth is not built
 	const RadConst c = make_rad_const(prm);
 	ProfScope prof_("rad_compute_fluxes", S(stream));
 	for (int b = 0; b < nboxes; ++b) {
@@ -737,7 +746,13 @@ extern "C" int qk_rad_advance_stage(qk_level *L, const qk_rad_params *prm, int s
 	QK_CUDA(cudaMemcpyAsync(db, hb, sizeof(RadBox) * nb, cudaMemcpyHostToDevice, s));
 	QK_CUDA(cudaEventRecord(R->ev[slot], s));
 	R->ev_used[slot] = true;
-	const RadConst c = make_rad_const(prm);
+	RadConst c = make_rad_const(prm);
+	for (int d = 0; d < 3; ++d)
+		c.dl[d] = L->dx[d]; // ComputeCellOpticalDepth of the stage uses the level's cell sizes
+	if (tile_form && prm->use_wavespeed_correction)
+		return QK_ERR_UNSUPPORTED;
+	if (prm->use_wavespeed_correction && ng != 1)
+		return QK_ERR_UNSUPPORTED; // the multigroup optical depth (DefineOpacityExponentsAndLowerValues) is not built
 	// The TMA-staged sweeps (qk_rad_kernels.cuh) copy tiles of the caller's state and of the level's scratch through tensor maps: pitches must be
 	// even (16-byte strides), the base 16-byte aligned, and the x sweep reads four ghost cells.  Anything else takes the first-generation
 	// direction-split kernels below (global loads; exact arithmetic only).

@@ -18,7 +18,8 @@
 // REDONE by the faithful path of qk_level.cu, which owns the first-order flux correction.
 #include "qk_sweep_kernels.cuh"
 
-#include <cuda.h> // CUtensorMap (the encoder lives in qk_level.cu: qk_encode_tile)
+#include <cuda.h>
+#include <stdio.h> // CUtensorMap (the encoder lives in qk_level.cu: qk_encode_tile)
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -185,8 +186,19 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	const bool inst = (ns == 0 && nms == 0) || (ns == 1 && nms == 0) || (ns == 3 && nms == 2);
 	const int order = prm->reconstruction_order;
 	// PPM for every instantiated trait set; PLM (minmod) for the scalar-free, reconstruct_eint = false set (config C4's hydro)
-	if (!(order == 3 || (order == 2 && ns == 0 && !prm->reconstruct_eint)) || !inst || !prm->use_dual_energy || L->nghost < 4)
+	const bool can = (order == 3 || (order == 2 && ns == 0 && !prm->reconstruct_eint)) && inst && prm->use_dual_energy && L->nghost >= 4 && prm->K_visc == 0.0;
+	if (!can) {
+		// say so once: the one-kernel-per-operator path is 3-4x slower and a maintainer flipping a run-time switch should know
+		static bool warned = false;
+		if (!warned && getenv("QK_QUIET") == nullptr) {
+			warned = true;
+			fprintf(stderr,
+				"[quokka_b200] this configuration takes the one-kernel-per-operator path (fused sweeps exist for PPM, for PLM without scalars and "
+				"reconstruct_eint, with dual energy, 4 ghost cells and K_visc = 0): reconstruction_order = %d, nscalars = %d, K_visc = %g\n",
+				order, ns, prm->K_visc);
+		}
 		return 0;
+	}
 	if (L->fused && L->fused->tainted)
 		return 0;
 	FastConst c;

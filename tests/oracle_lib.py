@@ -123,6 +123,8 @@ def ref() -> C.CDLL:
     lib.ref_rad_params.argtypes = [C.c_int, _RPRM]
     lib.ref_rad_cons_to_prim.argtypes = [C.c_int, _BXP, _A4P, _A4P, C.c_int]
     lib.ref_rad_compute_fluxes.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int]
+    if hasattr(lib, "ref_rad_compute_fluxes_wsc"):
+        lib.ref_rad_compute_fluxes_wsc.argtypes = [C.c_int, C.c_int, _BXP, _A4P, _A4P, _A4P, _A4P, _A4P, C.c_int, C.POINTER(C.c_double)]
     lib.ref_rad_update.argtypes = [C.c_int, C.c_int, _BXP] + [_A4P] * 9 + [C.c_double, _D3]
     lib.ref_interp_cons_lin_minmax.argtypes = [_A4P, _A4P, C.c_int, _BXP, _BXP, _BXP, C.POINTER(C.c_int), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.ref_pre_post_interp_state.argtypes = [C.c_int, _BXP, _A4P]

@@ -160,6 +160,29 @@ def test_compute_fluxes(lib, problem, solver, d, kind):
     assert np.isfinite(Fo.a).all()
 
 
+@pytest.mark.parametrize("problem", [0, 2])
+@pytest.mark.parametrize("d", [0, 1, 2])
+def test_compute_fluxes_with_artificial_viscosity(lib, problem, d):
+    """artificialViscosityK_ = 0.1 (hydro_system.hpp:1052-1076): operator entry and the one-kernel flux function, bit-exact vs the oracle
+    (which tests/test_oracle_vs_ref.py pins to the reference with the same K_visc)"""
+    prm, cons, po, chis, L, R, _, _ = oracle_states(problem, d, "shocked", order=3, flatten=True)
+    prm.K_visc = 0.1
+    nv = po.ncomp
+    fb0 = ol.face_box(VALID, d, 0)
+    Fo, Vo = ol.HostFab(fb0, nv), ol.HostFab(fb0, 1)
+    ol.oracle().orc_compute_fluxes(one(prm), QK_HLLC, d, one(Fo.desc()), one(Vo.desc()), one(L.desc()), one(R.desc()), one(po.desc()), one(fb0))
+    dp, dl, dr = dev(po), dev(L), dev(R)
+    dF, dV = dev(ol.HostFab(fb0, nv)), dev(ol.HostFab(fb0, 1))
+    check(lib.qk_hydro_compute_fluxes(one(prm), QK_HLLC, d, 1, one(VALID), one(dF.desc()), one(dV.desc()), one(dl.desc()), one(dr.desc()),
+                                      one(dp.desc()), None))
+    exact(dF.numpy(), Fo.a, "flux with artificial viscosity")
+    exact(dV.numpy(), Vo.a, "facevel")
+    prm.K_visc = 0.0
+    F0 = ol.HostFab(fb0, nv)
+    ol.oracle().orc_compute_fluxes(one(prm), QK_HLLC, d, one(F0.desc()), one(Vo.desc()), one(L.desc()), one(R.desc()), one(po.desc()), one(fb0))
+    assert (F0.a[0] != Fo.a[0]).any()
+
+
 @pytest.mark.parametrize("problem", [0, 1, 2])
 @pytest.mark.parametrize("order", [1, 2, 3])
 @pytest.mark.parametrize("d", [0, 1, 2])
@@ -304,6 +327,6 @@ def test_eos_reset_edge(lib):
 
 def test_unsupported_params(lib):
     prm = params(0)
-    prm.K_visc = 0.1
+    prm.gamma = 1.0  # isothermal EOS: not built
     dc = dev(ol.HostFab(VALID.grown(NG), 6))
     assert lib.qk_hydro_conserved_to_primitive(one(prm), 1, one(VALID), one(dc.desc()), one(dc.desc()), NG, None) == capi.QK_ERR_UNSUPPORTED

@@ -341,6 +341,64 @@ def test_relaxed_rad_beam_properties(lib, case):
     assert nbad <= 0.15 * ntot
 
 
+WSC = dict(c_light=10.0, c_hat=5.0, Erad_floor=0.0, wavespeed_correction=1, kappa_F=2.0)
+
+
+@pytest.mark.parametrize("d", [0, 1, 2])
+def test_rad_compute_fluxes_with_wavespeed_correction(lib, d):
+    """use_wavespeed_correction through the operator entry: flux and diffusive flux bit-exact vs the oracle (pinned to the reference's
+    ComputeFluxes<DIR>(..., dx, true) by tests/test_oracle_rad_vs_ref.py)"""
+    prm = rad_params(recon_order=3, cell_dx=DX3, **WSC)
+    cons = make_cons(prm, "smooth")
+    cons.a[0] = np.random.default_rng(5).uniform(0.5, 50.0, cons.a[0].shape)
+    q = oracle_prim(prm, cons)
+    l, r = oracle_recon(prm, q, 3, d)
+    fb = ol.face_box(VALID, d)
+    fo, fdo = ol.HostFab(fb, 4), ol.HostFab(fb, 4)
+    ol.oracle().orc_rad_compute_fluxes(one(prm), d, one(fo.desc()), one(fdo.desc()), one(l.desc()), one(r.desc()), one(cons.desc()), one(fb))
+    dc, dl, dr = dev(cons), dev(l), dev(r)
+    df, dfd = dev(ol.HostFab(fb, 4)), dev(ol.HostFab(fb, 4))
+    check(lib.qk_rad_compute_fluxes(one(prm), d, 1, one(VALID), one(df.desc()), one(dfd.desc()), one(dl.desc()), one(dr.desc()), one(dc.desc()), None))
+    exact(df.numpy(), fo.a, "flux")
+    exact(dfd.numpy(), fdo.a, "diffusive flux")
+    assert (fo.a[0] != fdo.a[0]).any()
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("v1", [False, True])
+def test_fused_rad_stage_pair_with_wavespeed_correction(lib, order, v1, monkeypatch):
+    """the correction inside the fused stage (TMA-staged and first-generation sweeps): three substeps bit-exact vs the oracle's level driver;
+    the relaxed sweeps within RELAXED_TOL"""
+    if v1:
+        monkeypatch.setenv("QK_RAD_V1", "1")
+    prm = rad_params(recon_order=order, **WSC)
+    p = RadProblem((32, 16, 16), 16, (1, 0, 1), prm)
+    st = p.states("smooth")
+    rng = np.random.default_rng(9)
+    for a in st:
+        a[0] = rng.uniform(0.5, 50.0, a[0].shape)  # tau = dx rho kappa_F straddles 1
+    dt = 0.3 * min(p.dx) / prm.c_hat
+    got = gpu_rad_steps(lib, p, st, dt, 3)
+    want = oracle_rad_steps(p, st, dt, 3)
+    p.prm = rad_params(recon_order=order, **{**WSC, "wavespeed_correction": 0})
+    plain = oracle_rad_steps(p, st, dt, 3)
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        exact(got[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], want[b][prm.nstart:, ng:-ng, ng:-ng, ng:-ng], f"box {b}")
+    assert any((w[prm.nstart] != q[prm.nstart]).any() for w, q in zip(want, plain)), "the correction did nothing"
+    if not v1:
+        p.prm = rad_params(recon_order=order, arith=capi.QK_ARITH_FAST, **WSC)
+        rel = gpu_rad_steps(lib, p, st, dt, 3)
+        worst = 0.0
+        for n in range(prm.nstart, p.ncomp):
+            scale = max(np.abs(w[n, ng:-ng, ng:-ng, ng:-ng]).max() for w in want)
+            if n != prm.nstart:
+                scale = max(scale, prm.c_light * max(np.abs(w[prm.nstart, ng:-ng, ng:-ng, ng:-ng]).max() for w in want))
+            worst = max(worst, max(np.abs(g[n, ng:-ng, ng:-ng, ng:-ng] - w[n, ng:-ng, ng:-ng, ng:-ng]).max() for g, w in zip(rel, want)) / scale)
+        print(f"relaxed sweeps with the wavespeed correction, order {order}: worst L-inf / scale = {worst:.3e}")
+        assert worst < RELAXED_TOL
+
+
 def test_rad_stage_argument_checks(lib):
     prm = rad_params()
     p = RadProblem((16, 16, 16), 16, (1, 1, 1), prm)

@@ -174,3 +174,31 @@ def test_lower_order_reconstruction_through_the_stage_entry(lib, order, arith):
             assert (np.abs(got - ref).reshape(p.ncomp, -1).max(axis=1) / scale < 2e-14).all()
             assert not np.array_equal(got, ref)
     o.orc_level_destroy(L)
+
+
+def test_artificial_viscosity_takes_the_operator_path(lib):
+    """artificialViscosityK_ != 0: the production entry declines the fused sweeps (one stderr notice) and the one-kernel-per-operator path
+    reproduces the oracle's level driver bit for bit"""
+    p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic")
+    prm = p.params()
+    prm.K_visc = 0.1
+    st = p.states(seed=21, kind="shocked")
+    dt = 1.0e-4
+    lib.qk_prof_enable(1)
+    f1, f2, fb1, fb2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    counts = prof(lib)
+    lib.qk_prof_enable(0)
+    assert counts.get("sweep_x", 0) == 0 and counts.get("flux_function", 0) > 0
+    L, keep = oracle_level(p, st)
+    o = ol.oracle()
+    ok = o.orc_advance_hydro_level(L, C.byref(prm), dt, 1.0e9, None, None)
+    assert ok == 1
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        ref = oracle_state(p, L, 0, b)
+        exact(f2[b][:, ng:-ng, ng:-ng, ng:-ng], ref[:, ng:-ng, ng:-ng, ng:-ng], f"oracle box {b}")
+    o.orc_level_destroy(L)
+    # and it is not a no-op
+    prm0 = p.params()
+    g1, g2, _, _ = run_pair(lib, p, prm0, st, dt, lib.qk_hydro_advance_stage)
+    assert any((a[:, ng:-ng, ng:-ng, ng:-ng] != b[:, ng:-ng, ng:-ng, ng:-ng]).any() for a, b in zip(f2, g2))

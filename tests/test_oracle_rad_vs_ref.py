@@ -86,6 +86,39 @@ def test_rad_compute_fluxes(problem, order, d, kind):
         assert bad.any()
 
 
+@pytest.mark.parametrize("problem", [2, 3])
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("d", [0, 1, 2])
+def test_rad_compute_fluxes_with_wavespeed_correction(problem, order, d):
+    """radiation.use_wavespeed_correction = true (radiation_system.hpp:1018-1022,1100-1109 + ComputeCellOpticalDepth :803-871): the energy
+    flux's diffusive term is scaled by min(1, 1 / tau_cell) on faces with even i + j + k.  Problem types with opacities (the source-term
+    harness types R2 = RadhydroShell cgs, kappa_F = 20; R3 dimensionless, kappa_F = 2); gas densities chosen so that tau straddles 1."""
+    from quokka_b200.capi import qk_hydro_params, qk_rad_source_params
+
+    hp, prm, sp = qk_hydro_params(), qk_rad_params(), qk_rad_source_params()
+    assert ol.ref().ref_rad_source_params(problem, C.byref(hp), C.byref(prm), C.byref(sp)) == 0
+    prm.use_wavespeed_correction = 1
+    prm.kappa_F = sp.kappa_F
+    prm.cell_dx[:] = list(DX)
+    cons = make_cons(prm, "smooth")
+    rng = np.random.default_rng(5)
+    cons.a[0] = rng.uniform(0.05, 5.0, cons.a[0].shape) * (20.0 / sp.kappa_F)  # tau = dl rho kappa_F in (0.07, 13)
+    cons.a[4] = 10.0 * cons.a[0]  # a positive internal energy for the reference's (unused) gas temperature
+    q = prim_of(prm, cons)
+    l, r = recon(prm, q, order, d)
+    fb = ol.face_box(VALID, d)
+    fo, fdo, fr, fdr = (ol.HostFab(fb, 4 * prm.ngroups) for _ in range(4))
+    ol.oracle().orc_rad_compute_fluxes(C.byref(prm), d, C.byref(fo.desc()), C.byref(fdo.desc()), C.byref(l.desc()), C.byref(r.desc()),
+                                       C.byref(cons.desc()), C.byref(fb))
+    ol.ref().ref_rad_compute_fluxes_wsc(problem, d, C.byref(VALID), C.byref(fr.desc()), C.byref(fdr.desc()), C.byref(l.desc()), C.byref(r.desc()),
+                                        C.byref(cons.desc()), NG, DX)
+    exact(fo.a, fr.a)
+    exact(fdo.a, fdr.a)
+    changed = (fo.a[0] != fdo.a[0])
+    assert changed.any() and not changed.all(), "the correction must act on some (even, optically thick) faces only"
+    exact(fo.a[1:], fdo.a[1:])  # only the energy component carries epsilon
+
+
 def fluxes_of(prm, cons, order):
     q = prim_of(prm, cons)
     out = []

@@ -148,6 +148,33 @@ def test_compute_fluxes(problem, solver, d, kind):
 
 
 @pytest.mark.parametrize("problem", [0, 2])
+@pytest.mark.parametrize("d", [0, 1, 2])
+def test_compute_fluxes_with_artificial_viscosity(problem, d):
+    """artificialViscosityK_ != 0 (Colella & Woodward 1984 eq. 4.2, hydro_system.hpp:1052-1076): K max(-div v, 0) (U_L - U_R) is added to
+    the density, energy and scalar fluxes -- the momentum components are overwritten by the unmodified Riemann flux afterwards (:1078-1081)"""
+    prm, cons, po, chis, L, R = full_states(problem, d, "shocked", order=3)
+    prm.K_visc = 0.1
+    nv = po.ncomp
+    g1 = VALID.grown(1)
+    ol.oracle().orc_flatten_shocks(d, C.byref(po.desc()), C.byref(chis[0].desc()), C.byref(chis[1].desc()), C.byref(chis[2].desc()),
+                                   C.byref(L.desc()), C.byref(R.desc()), C.byref(g1), nv)
+    fb0 = ol.face_box(VALID, d, 0)
+    Fo, Vo = ol.HostFab(fb0, nv), ol.HostFab(fb0, 1)
+    Fr, Vr = ol.HostFab(fb0, nv), ol.HostFab(fb0, 1)
+    F0 = ol.HostFab(fb0, nv)
+    ol.oracle().orc_compute_fluxes(C.byref(prm), QK_HLLC, d, C.byref(Fo.desc()), C.byref(Vo.desc()), C.byref(L.desc()), C.byref(R.desc()),
+                                   C.byref(po.desc()), C.byref(fb0))
+    ol.ref().ref_compute_fluxes(problem, QK_HLLC, d, C.byref(VALID), C.byref(Fr.desc()), C.byref(Vr.desc()), C.byref(L.desc()), C.byref(R.desc()),
+                                C.byref(po.desc()), NG, 0.1)
+    exact(Fo.a, Fr.a)
+    exact(Vo.a, Vr.a)
+    ol.ref().ref_compute_fluxes(problem, QK_HLLC, d, C.byref(VALID), C.byref(F0.desc()), C.byref(Vr.desc()), C.byref(L.desc()), C.byref(R.desc()),
+                                C.byref(po.desc()), NG, 0.0)
+    assert (Fr.a[0] != F0.a[0]).any(), "the viscosity term did nothing on shocked data"
+    exact(Fr.a[1:4], F0.a[1:4])  # momentum fluxes carry no artificial viscosity
+
+
+@pytest.mark.parametrize("problem", [0, 2])
 def test_update_ops(problem):
     prm = params(problem)
     cons = make_cons(problem, "shocked")
