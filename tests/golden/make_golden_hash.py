@@ -24,8 +24,14 @@ def digest(state):
 
 
 def main():
+    # `--full` adds the benchmarked size itself, Sedov 256^3 in 128^3 boxes x 100 steps (configs[1]; 36 minutes of the reference on 8 cores)
+    cases = [(32, 16, 100), (64, 32, 100), (128, 64, 100)] + ([(256, 128, 100)] if "--full" in sys.argv else [])
     out = {}
-    for ncell, box, nsteps in [(32, 16, 100), (64, 32, 100), (128, 64, 100)]:
+    path = os.path.join(HERE, "sedov_hashes.json")
+    if os.path.exists(path):  # keep entries this invocation does not regenerate
+        with open(path) as f:
+            out = json.load(f)
+    for ncell, box, nsteps in cases:
         state, time, dts, retries = run_reference(ncell, box, nsteps, threads=os.cpu_count() or 8)
         out[f"sedov{ncell}_b{box}_s{nsteps}"] = {"ncell": ncell, "box": box, "nsteps": nsteps, "time": repr(float(time)), "retries": retries,
                                                    "sha256": digest(state), "sums": [repr(float(state[c].sum())) for c in range(6)],
