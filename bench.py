@@ -868,7 +868,7 @@ def roofline(prof, ncell_local, steps, ms_total, arith="relaxed"):
     ALG = 96
     if arith == "exact":  # keeps 0.5*F(U0) on the faces between the RK stages
         DESIGN = {"flux_function": 48 + 24 + 56, "sweep_x": 56 + 56 + 56, "sweep_y": 56 + 56 + 112, "sweep_z": 56 + 56 + 56 + 48 + 48}
-        fp64_per_cell, opmix = 740, "profiles/r01_ncu_opmix_exact.txt"
+        fp64_per_cell, opmix = 784, "profiles/r02_ncu_opmix_exact_2.txt (y sweep: 410.9 M FP64-pipe warp instructions over 524 288 rows of 32 cells)"
     else:  # keeps R(U0) per cell instead
         DESIGN = {"sweep_x": 56 + 56, "sweep_y": 56 + 112, "sweep_z": 56 + 56 + 48 + 48 + 48}
         fp64_per_cell, opmix = 431, "profiles/r02_ncu_opmix_relaxed_2.txt (y sweep: 226.07 M FP64-pipe warp instructions over 524 288 rows of 32 cells)"
