@@ -42,6 +42,11 @@ enum SweepTmap {
 	TM_HF2,
 	TM_R0,	  // hF[2]  box {32, 1, 1, NV}     R(U0) of the relaxed mode
 	TM_U0,	  // U0     box {32, 1, 1, NV}
+	// the concatenated x sweep (k_sweep_xc): its windows start at an arbitrary cell and a tensor-map copy of FP64 must start at an EVEN x
+	// coordinate (16 bytes; an odd one raises "illegal instruction" on sm_100a -- scripts/diag/tma_coord_test.cu), so they are one pair wider
+	TM_PRIM_X40, // prim   box {40, 1, 1, NV+1}
+	TM_PRIM_Y3W, // prim   box {36, 3, 1, 1}
+	TM_PRIM_Z3W, // prim   box {36, 1, 3, 1}
 	TM_COUNT
 };
 // The descriptors travel as __grid_constant__ kernel PARAMETERS (the one place a TMA descriptor needs no proxy fence and cannot go stale in the
@@ -514,5 +519,225 @@ __global__ void __launch_bounds__(128) k_sweep_xt(FastConst c, const SweepBox *_
 			j = B.lo[1];
 			++k;
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// x sweep over the CONCATENATED rows of a box (round 2; replaces k_sweep_xt wherever every box is at least 30 cells wide).
+// k_sweep_xt cuts every row into 30-cell tiles of its own, so a 128-cell row costs five warp passes of which the last one
+// updates 8 cells (17 % of the lanes of the sweep idle; 43 % for the 32-cell boxes of an AMR level).  Here the rows of a box
+// are laid end to end as SLOTS -- row r contributes the nx + 2 cells lo-1 .. hi+1 (the two end cells carry a parabola only) --
+// and tile t owns slots 30 t .. 30 t + 29 of that sequence, whatever row they fall in: lane l of the warp holds slot
+// 30 t - 1 + l, lanes 1 .. 30 are the owned ones (parabola, face flux against lane l-1, update against lane l+1 exactly as in
+// k_sweep_xt), lanes 0 and 31 the halo.  A tile that runs over the end of a row continues with the first slots of the next
+// row: its lanes then read from two staged windows, A (the row the tile starts in; double-buffered across tiles) and B (the
+// next row, cells lo-4 .. lo+35; one buffer, requested as soon as the previous tile has read its own).  The first slot of a
+// row is never a face and the last never an update, so no shuffle crosses a row boundary with a value that is used.
+// 130 slots per 128-cell row -> 4.33 warp passes instead of 5.  Stage 2 of the exact mode reads 0.5 F(U0) with plain
+// loads after the Riemann solve (a staged copy would have to live in the single B buffer until then).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int XC_TILES = 8; // consecutive tiles per warp
+constexpr int XC_WARPS = 3; // warps per CTA: 3 windows per warp -> 36 KB per CTA at NV = 6, six CTAs (18 warps) per SM
+template <int NV> struct XCSmem {
+	static constexpr int PW = 40;				     // cells c0-3-sh .. c0+36-sh of every component (+ chi), c0 = the cell of lane 0, sh = 0 | 1 so that the window starts at an even x
+	static constexpr int PRIM = (((NV + 1) * PW + 15) / 16) * 16; // one [40 x (NV+1)] tile, padded to a 128-byte multiple
+	static constexpr int TW = 36;				     // cells c0-1-sh .. c0+34-sh of the transverse velocity rows
+	static constexpr int T3 = ((3 * TW + 15) / 16) * 16;	     // rows -1, 0, +1 of one component (one [36 x 3] tile)
+	static constexpr int BUF = PRIM + 2 * T3;		     // one window: primitives, vy at j-1 .. j+1, vz at k-1 .. k+1
+	static constexpr int WARP_BYTES = 3 * BUF * 8 + 128;	     // windows A (two) and B + three mbarriers
+	static constexpr int BLOCK_BYTES = XC_WARPS * WARP_BYTES;
+};
+
+template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
+__global__ void __launch_bounds__(32 * XC_WARPS) k_sweep_xc(FastConst c, const SweepBox *__restrict__ boxes, const __grid_constant__ XMaps tmaps)
+{
+	constexpr int NV = 6 + NS;
+	using SM = XCSmem<NV>;
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+	double *const st0 = reinterpret_cast<double *>(smem_raw + (size_t)warp * SM::WARP_BYTES);
+	uint64_t *const bars = reinterpret_cast<uint64_t *>(st0 + 3 * SM::BUF); // [0], [1]: windows A; [2]: window B
+	const SweepBox &B = boxes[blockIdx.z];
+	const int nx = B.hi[0] - B.lo[0] + 1, ny = B.hi[1] - B.lo[1] + 1, nz = B.hi[2] - B.lo[2] + 1;
+	const int nslot = nx + 2, nrows = ny * nz;
+	const int ntiles = (nrows * nslot + 29) / 30; // the host checked that the slot count fits an int and nx >= 30
+	const int t0 = (blockIdx.x * XC_WARPS + warp) * XC_TILES;
+	if (t0 >= ntiles)
+		return; // whole warp
+	const int nt = min(XC_TILES, ntiles - t0);
+	const A4 &q = B.prim;
+	const A4 &h = B.hF[0];
+	const A4 &r = B.rhs;
+	const TmapBytes *const M = tmaps.m[blockIdx.z];
+	if (lane == 0) {
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		mbar_init(&bars[2], 1);
+		mbar_init_fence();
+	}
+	__syncwarp();
+	// one window: the 40 cells from array column qx (EVEN) of row (j, k) of every primitive + chi, and the transverse velocity rows around them
+	auto issue_win = [&](double *dst, uint64_t *bar, int qx, int j, int k) {
+		mbar_arrive_expect_tx(bar, (unsigned)((NV + 1) * SM::PW + 6 * SM::TW) * 8u);
+		const int jy = j - q.by, kz = k - q.bz;
+		tma_tile_g2s(dst, &M[XM_PRIM], qx, jy, kz, 0, bar);
+		tma_tile_g2s(dst + SM::PRIM, &M[XM_Y3], qx + 2, jy - 1, kz, 2, bar);	     // vy at j-1, j, j+1
+		tma_tile_g2s(dst + SM::PRIM + SM::T3, &M[XM_Z3], qx + 2, jy, kz - 1, 3, bar); // vz at k-1, k, k+1
+	};
+	// the tile being computed (warp-uniform): slot of lane 0 within its row (pos0, -1 for the first tile of a box), that row (rowA -> jA, kA),
+	// how many lanes stay in it (nA) and whether the remaining lanes continue in the next row (two -> jB, kB)
+	int pos0, rowA, jA, kA;
+	{
+		const int g0 = 30 * t0 - 1;
+		rowA = (g0 < 0) ? 0 : (int)((unsigned)g0 / (unsigned)nslot);
+		pos0 = g0 - rowA * nslot;
+		const int kq = (int)((unsigned)rowA / (unsigned)ny);
+		jA = B.lo[1] + (rowA - kq * ny);
+		kA = B.lo[2] + kq;
+	}
+	auto next_row = [&](int j, int k, int &jn, int &kn) {
+		jn = j + 1;
+		kn = k;
+		if (jn > B.hi[1]) {
+			jn = B.lo[1];
+			++kn;
+		}
+	};
+	int nA = min(32, nslot - pos0);
+	bool two = (nA < 32) && (rowA + 1 < nrows);
+	int jB, kB;
+	next_row(jA, kA, jB, kB);
+	double *const winB = st0 + 2 * SM::BUF;
+	// array column of cell lo - 4 (the first cell window B needs; 0 for the level's own scratch, whose ghost width is 4): even, or the host
+	// would not have chosen this kernel.  Window A wants to start at column qx0 + pos0: it starts one column earlier when that is odd.
+	const int qx0 = B.lo[0] - 4 - q.bx;
+	if (elect_one()) {
+		issue_win(st0, &bars[0], qx0 + (pos0 & ~1), jA, kA);
+		if (two)
+			issue_win(winB, &bars[2], qx0, jB, kB);
+	}
+	unsigned bpar = 0;
+	for (int m = 0; m < nt; ++m) {
+		__syncwarp();
+		// the next tile: 30 slots further on, at most one row further (nslot >= 32)
+		const bool more = (m + 1 < nt);
+		int pos0n = pos0 + 30, rowAn = rowA, jAn = jA, kAn = kA;
+		if (pos0n >= nslot) {
+			pos0n -= nslot;
+			++rowAn;
+			jAn = jB;
+			kAn = kB;
+		}
+		const int nAn = min(32, nslot - pos0n);
+		const bool twon = (nAn < 32) && (rowAn + 1 < nrows);
+		int jBn, kBn;
+		next_row(jAn, kAn, jBn, kBn);
+		if (more && elect_one())
+			issue_win(st0 + ((m + 1) & 1) * SM::BUF, &bars[(m + 1) & 1], qx0 + (pos0n & ~1), jAn, kAn);
+		// this lane's slot
+		const bool inB = (lane >= nA) && two;
+		const int lq = inB ? lane - nA : lane + (pos0 & 1); // position within its window: the own cell sits at index lq + 3 of a prim row
+		const int pos = inB ? lane - nA : pos0 + lane;	    // slot within its row: cell lo - 1 + pos
+		const bool valid = (lane < nA) || inB;	  // lanes past the last slot of the box compute on whatever window A holds and store nothing
+		const int i = B.lo[0] - 1 + pos;
+		const int j = inB ? jB : jA, k = inB ? kB : kA;
+		const double *sp = inB ? winB : st0 + (m & 1) * SM::BUF;
+		mbar_wait(&bars[m & 1], (unsigned)(m >> 1) & 1u);
+		if (two) {
+			mbar_wait(&bars[2], bpar);
+			bpar ^= 1u;
+		}
+		// PPM + flattening of the own cell (it sits at index lq + 3 of a prim row)
+		const double chi = sp[NV * SM::PW + lq + 3], omchi = 1. - chi;
+		double am[NV], ap[NV], q0v1 = 0;
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double *p = sp + n * SM::PW + lq + 3;
+			const double qm2 = p[-2], qm1 = p[-1], q0 = p[0], qp1 = p[1], qp2 = p[2];
+			if (n == 1)
+				q0v1 = q0;
+			if (ORDER == 3)
+				if (ARITH == 1)
+					r_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+				else
+					f_ppm_flat(qm1, q0, qp1, ppm_iface(qm2, qm1, q0, qp1), ppm_iface(qm1, q0, qp1, qp2), chi, omchi, am[n], ap[n]);
+			else
+				f_plm_flat(qm1, q0, qp1, chi, omchi, am[n], ap[n]);
+		}
+		// transverse minima: V = y, W = z (the own cell sits at index lq + 1 of a transverse row)
+		const double *tr = sp + SM::PRIM;
+		const double vy0 = sp[2 * SM::PW + lq + 3], vz0 = sp[3 * SM::PW + lq + 3];
+		const double mV = dmin(tr[2 * SM::TW + lq + 1] - vy0, vy0 - tr[lq + 1]);			  // rows j+1, j-1
+		const double mW = dmin(tr[SM::T3 + 2 * SM::TW + lq + 1] - vz0, vz0 - tr[SM::T3 + lq + 1]); // rows k+1, k-1
+		__syncwarp(); // window B has been read by every lane: the next tile's may land in it
+		if (more && twon && elect_one())
+			issue_win(winB, &bars[2], qx0, jBn, kBn);
+		double Ls[NV];
+#pragma unroll
+		for (int n = 0; n < NV; ++n)
+			Ls[n] = shfl_up1(ap[n]);
+		const double mVl = shfl_up1(mV), mWl = shfl_up1(mW);
+		const double du = q0v1 - shfl_up1(q0v1);
+		double dw = dmin(mVl, mV);
+		dw = dmin(dmin(mWl, mW), dw);
+		// a face needs the cell on its low side in the same row (pos >= 1 puts it in lane - 1), an update the face on its high side (lane + 1)
+		const bool face_ok = valid && (lane >= 1) && (pos >= 1);
+		const bool upd = valid && (lane >= 1) && (lane <= 30) && (pos >= 1) && (pos <= nx);
+		const bool own_face = face_ok && (lane <= 30); // lane 31's face is lane 1's of the next tile
+		double G[NV + 1];
+		if (face_ok) {
+			double F[NV], vf;
+			hllc_face<ARITH, 0, NS, NMS, REINT>(c, Ls, am, du, dw, F, vf);
+			if (KEEPF && own_face) { // the stage's own flux of face i, for the flux registers
+				const A4 &fk = B.fo[0];
+				const int64_t of = fk.off(i, j, k);
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					fk.p[of + n * fk.ns] = F[n];
+			}
+			if (STAGE == 1) {
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					G[n] = F[n];
+				G[NV] = vf;
+				if (DUAL && own_face) { // flux_rk2 = 0 + 0.5 F (QuokkaSimulation.hpp:1106-1107)
+					const int64_t oh = h.off(i, j, k);
+#pragma unroll
+					for (int n = 0; n <= NV; ++n)
+						h.p[oh + n * h.ns] = 0.0 + 0.5 * G[n];
+				}
+			} else {
+				const int64_t oh = h.off(i, j, k); // 0.5 F(U0) of face i
+#pragma unroll
+				for (int n = 0; n < NV; ++n)
+					G[n] = h.p[oh + n * h.ns] + 0.5 * F[n];
+				G[NV] = h.p[oh + NV * h.ns] + 0.5 * vf;
+			}
+		} else {
+#pragma unroll
+			for (int n = 0; n <= NV; ++n)
+				G[n] = 0.0;
+		}
+		const int64_t orr = upd ? r.off(i, j, k) : 0;
+#pragma unroll
+		for (int n = 0; n < NV; ++n) {
+			const double Gn = shfl_dn1(G[n]);
+			if (upd)
+				r.p[orr + n * r.ns] = c.inv_dx[0] * (G[n] - Gn);
+		}
+		const double Vn = shfl_dn1(G[NV]);
+		if (upd) {
+			const double dv = div_dx<ARITH>(c, 0, Vn - G[NV]);
+			r.p[orr + NV * r.ns] = dv;
+		}
+		pos0 = pos0n;
+		rowA = rowAn;
+		jA = jAn;
+		kA = kAn;
+		nA = nAn;
+		two = twon;
+		jB = jBn;
+		kB = kBn;
 	}
 }

@@ -26,17 +26,17 @@
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 // qk_sweep_relaxed.cu: the same kernels instantiated with relaxed arithmetic (FMA contraction, closed-form EOS)
-int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3], int stage,
+int qk_sweep_stage_relaxed(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[5], int stage,
 			   bool dual, bool tma, cudaStream_t s);
 
-int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3], int stage, bool dual,
+int qk_sweep_stage_relaxed_plm(int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[5], int stage, bool dual,
 			       cudaStream_t s);
 // qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu: the TMA-staged kernels instantiated with KEEPF = true (they also store the stage's own face
 // fluxes into SweepBox::fo for incrementFluxRegisters); arith selects the translation unit, order 2 = the PLM instantiation
-int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3],
+int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[5],
 			 int stage, bool dual, cudaStream_t s);
 int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb,
-				 const int maxn[3], int stage, bool dual, cudaStream_t s);
+				 const int maxn[5], int stage, bool dual, cudaStream_t s);
 
 static_assert(sizeof(CUtensorMap) == TMAP_BYTES, "descriptor size");
 static bool encode_tile(CUtensorMap *m, const qk_array4 &a, unsigned bx, unsigned by, unsigned bz, unsigned bc) { return qk_encode_tile(m, a, bx, by, bz, bc); }
@@ -159,7 +159,9 @@ static int fused_setup(qk_level *L, int nv)
 			     encode_tile(&m[TM_PRIM_X38], F->prim[b], 38, 1, 1, nc) && encode_tile(&m[TM_PRIM_Y3], F->prim[b], 34, 3, 1, 1) &&
 			     encode_tile(&m[TM_PRIM_Z3], F->prim[b], 34, 1, 3, 1) && encode_tile(&m[TM_RHS], F->rhs[b], 32, 1, 1, nc) &&
 			     encode_tile(&m[TM_HF0], F->hF[0][b], 32, 1, 1, nc) && encode_tile(&m[TM_HF1], F->hF[1][b], 32, 1, 1, nc) &&
-			     encode_tile(&m[TM_HF2], F->hF[2][b], 32, 1, 1, nc) && encode_tile(&m[TM_R0], F->hF[2][b], 32, 1, 1, (unsigned)nv);
+			     encode_tile(&m[TM_HF2], F->hF[2][b], 32, 1, 1, nc) && encode_tile(&m[TM_R0], F->hF[2][b], 32, 1, 1, (unsigned)nv) &&
+			     encode_tile(&m[TM_PRIM_X40], F->prim[b], 40, 1, 1, nc) && encode_tile(&m[TM_PRIM_Y3W], F->prim[b], 36, 3, 1, 1) &&
+			     encode_tile(&m[TM_PRIM_Z3W], F->prim[b], 36, 1, 3, 1);
 	}
 	for (int i = 0; i < 8; ++i) {
 		QK_CUDA(cudaEventCreateWithFlags(&F->ev[i], cudaEventDisableTiming));
@@ -219,7 +221,8 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	if (F->ev_used[slot])
 		QK_CUDA(cudaEventSynchronize(F->ev[slot]));
 	SweepBox *hb = F->h_boxes + (size_t)slot * nb;
-	int maxn[3] = {1, 1, 1};
+	int maxn[5] = {1, 1, 1, 1 << 30, 0}; // largest extents; smallest nx; largest slot count of the concatenated x sweep (launch_stage)
+	int64_t max_slots = 0;
 	bool tma = (getenv("QK_NO_TMA") == nullptr) && F->maps_ok;
 	CUtensorMap *hm = F->h_maps;
 	for (int b = 0; b < nb; ++b) {
@@ -243,7 +246,10 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 			B.hi[d] = L->valid[b].hi[d];
 			maxn[d] = std::max(maxn[d], B.hi[d] - B.lo[d] + 1);
 		}
+		maxn[3] = std::min(maxn[3], B.hi[0] - B.lo[0] + 1);
+		max_slots = std::max<int64_t>(max_slots, (int64_t)(B.hi[1] - B.lo[1] + 1) * (B.hi[2] - B.lo[2] + 1) * (B.hi[0] - B.lo[0] + 3));
 	}
+	maxn[4] = (max_slots < (int64_t(1) << 31) - 64 && (L->nghost & 1) == 0) ? (int)max_slots : 0; // (its windows start at even array columns)
 	if (L->comm && L->nranks > 1) {
 		// Every rank must run the same kernel family: a rank on the faithful path pairs different collectives than one on the fused path.
 		// The alignment of the local rows is negotiated once per level; a rank whose rows later stop qualifying fails loudly instead of hanging.

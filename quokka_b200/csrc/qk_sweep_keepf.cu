@@ -4,7 +4,7 @@
 // (src/QuokkaSimulation.hpp:1195-1198,1280-1283) straight from those arrays, so refined levels no longer need the one-kernel-per-operator path.
 #include "qk_sweep_kernels.cuh"
 
-int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[3],
+int qk_sweep_stage_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb, const int maxn[5],
 			 int stage, bool dual, cudaStream_t s)
 {
 	if (order == 2)

@@ -705,8 +705,9 @@ static void fill_march_maps(MarchMaps &mm, const unsigned char *h_maps, int b0, 
 	}
 }
 
+// maxn: [0..2] the largest box extents of the launch, [3] the smallest nx, [4] the largest nrows * (nx + 2) (0: does not fit an int)
 template <int ARITH, int NS, int NMS, bool REINT, int STAGE, bool DUAL, int ORDER = 3, bool KEEPF = false>
-static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, const unsigned char *h_maps, int nb, const int maxn[3],
+static int launch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *d_tab, const unsigned char *h_maps, int nb, const int maxn[5],
 			bool tma, cudaStream_t s)
 {
 	if (nb == 0)
@@ -740,7 +741,34 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 		// and are the same kernels in both stages
 		constexpr int XSTAGE = (ARITH == 1) ? 1 : STAGE;
 		constexpr bool XDUAL = (ARITH == 1) ? false : DUAL;
-		if (tma) {
+		// every box at least 30 cells wide: the rows of a box are laid end to end and cut into 30-slot tiles (k_sweep_xc, qk_march.cuh);
+		// QK_XCAT=0 keeps the per-row tiles of k_sweep_xt.  maxn[3] carries the smallest nx of the launch, maxn[4] the largest slot count.
+		const char *xe = getenv("QK_XCAT");
+		const bool xcat_env = !(xe != nullptr && xe[0] == '0');
+		if (tma && xcat_env && maxn[3] >= 30 && maxn[4] > 0) {
+			auto kern = k_sweep_xc<ARITH, NS, NMS, REINT, XSTAGE, XDUAL, ORDER, KEEPF>;
+			static bool attr_set = false;
+			if (!attr_set) {
+				QK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, XCSmem<6 + NS>::BLOCK_BYTES));
+				attr_set = true;
+			}
+			const int tiles = (maxn[4] + 29) / 30;
+			for (int b0 = 0; b0 < nb; b0 += TMAP_MAXB) {
+				const int nbc = std::min(TMAP_MAXB, nb - b0);
+				XMaps xm;
+				for (int b = 0; b < nbc; ++b) {
+					const unsigned char *src = h_maps + (size_t)(b0 + b) * TM_COUNT * TMAP_BYTES;
+					memcpy(xm.m[b][XM_PRIM].b, src + TM_PRIM_X40 * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_Y3].b, src + TM_PRIM_Y3W * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_Z3].b, src + TM_PRIM_Z3W * TMAP_BYTES, TMAP_BYTES);
+					memcpy(xm.m[b][XM_HF].b, src + TM_HF0 * TMAP_BYTES, TMAP_BYTES);
+				}
+				dim3 grid((tiles + XC_WARPS * XC_TILES - 1) / (XC_WARPS * XC_TILES), 1, nbc);
+				kern<<<grid, 32 * XC_WARPS, XCSmem<6 + NS>::BLOCK_BYTES, s>>>(c, d_tab + b0, xm);
+				if (b0 + TMAP_MAXB < nb)
+					QK_KERNEL_CHECK();
+			}
+		} else if (tma) {
 			auto kern = k_sweep_xt<ARITH, NS, NMS, REINT, XSTAGE, XDUAL, ORDER, KEEPF>;
 			static bool attr_set = false;
 			if (!attr_set) {
@@ -826,7 +854,7 @@ static int launch_stage(int ng, unsigned long long *d_counters, const FastConst 
 }
 
 template <int ARITH, int NS, int NMS, bool REINT, int ORDER = 3, bool KEEPF = false>
-static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, const unsigned char *m, int nb, const int maxn[3], int stage,
+static int dispatch_stage(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *t, const unsigned char *m, int nb, const int maxn[5], int stage,
 			  bool dual, bool tma, cudaStream_t s)
 {
 	if (KEEPF && !tma)
@@ -842,7 +870,7 @@ static int dispatch_stage(int ng, unsigned long long *d_counters, const FastCons
 // KEEPF = true, the same kernels also storing the stage's face fluxes for the flux registers: qk_sweep_keepf.cu / qk_sweep_relaxed_keepf.cu)
 // PLM (reconstructionOrder_ = 2) is instantiated for the trait set of config C4's hydro (no scalars, reconstruct_eint = false), TMA form only
 template <int ARITH, bool KEEPF = false>
-static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, const unsigned char *dm, int nb, const int maxn[3],
+static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, const unsigned char *dm, int nb, const int maxn[5],
 				    int stage, bool dual, cudaStream_t s)
 {
 	return dispatch_stage<ARITH, 0, 0, false, 2, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, true, s);
@@ -850,7 +878,7 @@ static int sweep_stage_dispatch_plm(int ng, unsigned long long *d_counters, cons
 
 template <int ARITH, bool KEEPF = false>
 static int sweep_stage_dispatch(int ns, bool reint, int ng, unsigned long long *d_counters, const FastConst &c, const SweepBox *db, const unsigned char *dm, int nb,
-				const int maxn[3], int stage, bool dual, bool tma, cudaStream_t s)
+				const int maxn[5], int stage, bool dual, bool tma, cudaStream_t s)
 {
 	if (ns == 0)
 		return reint ? dispatch_stage<ARITH, 0, 0, true, 3, KEEPF>(ng, d_counters, c, db, dm, nb, maxn, stage, dual, tma, s)

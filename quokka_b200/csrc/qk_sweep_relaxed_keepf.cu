@@ -3,7 +3,7 @@
 #include "qk_sweep_kernels.cuh"
 
 int qk_sweep_stage_relaxed_keepf(int ns, bool reint, int order, int ng, unsigned long long *d_counters, const FastConst &c, const void *boxes, const void *tmaps, int nb,
-				 const int maxn[3], int stage, bool dual, cudaStream_t s)
+				 const int maxn[5], int stage, bool dual, cudaStream_t s)
 {
 	if (order == 2)
 		return sweep_stage_dispatch_plm<1, true>(ng, d_counters, c, static_cast<const SweepBox *>(boxes), static_cast<const unsigned char *>(tmaps), nb, maxn, stage, dual, s);

@@ -202,3 +202,42 @@ def test_artificial_viscosity_takes_the_operator_path(lib):
     prm0 = p.params()
     g1, g2, _, _ = run_pair(lib, p, prm0, st, dt, lib.qk_hydro_advance_stage)
     assert any((a[:, ng:-ng, ng:-ng, ng:-ng] != b[:, ng:-ng, ng:-ng, ng:-ng]).any() for a, b in zip(f2, g2))
+
+
+XCAT_CASES = {
+    # name: (ncell, cuts, periodic, bc, nscalars, nmscalars, reint)
+    "row128": ((128, 12, 10), ((), (), ()), (0, 0, 0), "reflect", 0, 0, 0),       # 130 slots per row: tiles run over row ends every 4.33 tiles
+    "amr32": ((64, 32, 32), ((32,), (16,), ()), (1, 1, 1), "periodic", 0, 0, 0),  # 34 slots per row: almost every tile covers two rows
+    "ragged": ((72, 37, 45), ((34,), (), (20,)), (0, 0, 0), "reflect", 1, 0, 1),  # nx = 34 and 38 (even: TMA-staged), a scalar, reconstruct_eint
+    "nx30": ((30, 9, 7), ((), (), ()), (0, 0, 0), "outflow", 0, 0, 0),            # the narrowest box the concatenated kernel takes
+}
+
+
+@pytest.mark.parametrize("case", sorted(XCAT_CASES))
+@pytest.mark.parametrize("arith", ["exact", "relaxed"])
+def test_concatenated_x_sweep_equals_per_row_tiles(lib, case, arith, monkeypatch):
+    """k_sweep_xc (rows of a box laid end to end, 30-slot tiles that may cover the end of one row and the start of the next; the x sweep
+    every box >= 30 cells wide takes) against k_sweep_xt (QK_XCAT=0: 30-cell tiles per row): the same arithmetic per cell, so the new
+    state is BIT-IDENTICAL after both stages in either arithmetic mode."""
+    ncell, cuts, periodic, bc, ns, nms, reint = XCAT_CASES[case]
+    p = RaggedProblem(ncell, cuts, periodic, bc, nscalars=ns)
+    prm = p.params(nmscalars=nms, reconstruct_eint=reint, arith=capi.QK_ARITH_FAST if arith == "relaxed" else capi.QK_ARITH_EXACT)
+    st = p.states(seed=31, kind="shocked")
+    dt = 1.0e-4
+    monkeypatch.delenv("QK_XCAT", raising=False)
+    lib.qk_prof_enable(1)
+    a1, a2, ab1, ab2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    counts = prof(lib)
+    lib.qk_prof_enable(0)
+    assert counts.get("sweep_x", 0) == 2 and counts.get("flux_function", 0) == 0, counts
+    monkeypatch.setenv("QK_XCAT", "0")
+    b1, b2, bb1, bb2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
+    assert (ab1, ab2, bb1, bb2) == (0, 0, 0, 0)
+    ng = p.nghost
+    for b in range(len(p.boxes)):
+        exact(a1[b][:, ng:-ng, ng:-ng, ng:-ng], b1[b][:, ng:-ng, ng:-ng, ng:-ng], f"stage 1 box {b}")
+        exact(a2[b][:, ng:-ng, ng:-ng, ng:-ng], b2[b][:, ng:-ng, ng:-ng, ng:-ng], f"stage 2 box {b}")
+    if arith == "exact":  # and the reference's bits
+        g1, g2, _, _ = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage_faithful)
+        for b in range(len(p.boxes)):
+            exact(a2[b][:, ng:-ng, ng:-ng, ng:-ng], g2[b][:, ng:-ng, ng:-ng, ng:-ng], f"faithful box {b}")
