@@ -107,6 +107,8 @@ typedef struct qk_hydro_params {
 	int32_t integrator_order;     /* integratorOrder_: 1|2 */
 	int32_t abort_on_fofc_failure; /* abortOnFofcFailure_ */
 	int32_t arith;		      /* QK_ARITH_* */
+	double cs_isothermal;	      /* EOS_Traits::cs_isothermal (src/hydro/EOS.hpp:34), read only when gamma == 1: the isothermal EOS
+				       * (HydroSystem::is_eos_isothermal(), hydro_system.hpp:133) runs on the one-kernel-per-operator path */
 } qk_hydro_params;
 
 /* ---- library / device --------------------------------------------------------------------- */

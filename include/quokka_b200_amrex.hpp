@@ -14,6 +14,7 @@
 #pragma once
 
 #include <array>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -142,6 +143,13 @@ template <typename problem_t> inline auto make_params() -> qk_hydro_params
 	p.integrator_order = 2;
 	p.abort_on_fofc_failure = 1;
 	p.arith = QK_ARITH_EXACT;
+	// src/hydro/EOS.hpp:34; problem traits that are not isothermal need not define it (the reference reads it only inside
+	// `if constexpr (is_eos_isothermal())`, hydro_system.hpp:132-133)
+	if constexpr (quokka::EOS_Traits<problem_t>::gamma == 1.0) {
+		p.cs_isothermal = quokka::EOS_Traits<problem_t>::cs_isothermal;
+	} else {
+		p.cs_isothermal = NAN;
+	}
 	return p;
 }
 

@@ -186,6 +186,8 @@ static double cons_pressure(const qk_hydro_params *prm, const qk_array4 *c, int 
 	const double vx = px / rho, vy = py / rho, vz = pz / rho;
 	const double ke = 0.5 * rho * (vx * vx + vy * vy + vz * vz);
 	const double thermal = E - ke;
+	if (prm->gamma == 1.0) /* is_eos_isothermal(), hydro_system.hpp:365-366 */
+		return rho * prm->cs_isothermal * prm->cs_isothermal;
 	return eos_pressure(prm, rho, thermal);
 }
 /* HydroSystem::ComputeSoundSpeed(cons,i,j,k)  hydro_system.hpp:374-394 */
@@ -242,6 +244,8 @@ void orc_flattening_coefficients(const qk_hydro_params *prm, int dir, const qk_a
 						const double r = A4(q, ii, jj, kk, 0);
 						v = eos_pressure(prm, r, r * v);
 					}
+					if (prm->gamma == 1.0) /* :579-586 */
+						v = A4(q, ii, jj, kk, 0) * (prm->cs_isothermal * prm->cs_isothermal);
 					P[s + 2] = v;
 				}
 				const double Pplus2 = P[4], Pplus1 = P[3], Pc = P[2], Pminus1 = P[1], Pminus2 = P[0];
@@ -249,8 +253,13 @@ void orc_flattening_coefficients(const qk_hydro_params *prm, int dir, const qk_a
 				const double beta = (beta_denom != 0) ? (fabs(Pplus1 - Pminus1) / beta_denom) : 0;
 				const double chi_min = dmax(0., dmin(1., (beta_max - beta) / (beta_max - beta_min)));
 				const double rho = A4(q, i, j, k, 0);
-				const double cs = eos_sound_speed(prm, rho, Pc);
-				const double K_S = (cs * cs) * rho; /* std::pow(cs,2)*rho */
+				double K_S;
+				if (prm->gamma == 1.0) { /* :604-606 */
+					K_S = rho * prm->cs_isothermal * prm->cs_isothermal;
+				} else {
+					const double cs = eos_sound_speed(prm, rho, Pc);
+					K_S = (cs * cs) * rho; /* std::pow(cs,2)*rho */
+				}
 				const double Z = fabs(Pplus1 - Pminus1) / K_S;
 				const int vn = 1 + dir;
 				double chi = 1.0;
@@ -475,8 +484,12 @@ void orc_compute_fluxes(const qk_hydro_params *prm, int solver, int dir, const q
 				const double vz_L = A4(L, i, j, k, 3), vz_R = A4(R, i, j, k, 3);
 				const double ke_L = 0.5 * rho_L * (vx_L * vx_L + vy_L * vy_L + vz_L * vz_L);
 				const double ke_R = 0.5 * rho_R * (vx_R * vx_R + vy_R * vy_R + vz_R * vz_R);
-				double Eint_L, Eint_R, P_L, P_R;
-				if (prm->reconstruct_eint) {
+				double Eint_L = NAN, Eint_R = NAN, P_L, P_R;
+				const int iso = (prm->gamma == 1.0);
+				if (iso) { /* :910-915: E and Eint stay NAN, their fluxes are set to zero below */
+					P_L = rho_L * (prm->cs_isothermal * prm->cs_isothermal);
+					P_R = rho_R * (prm->cs_isothermal * prm->cs_isothermal);
+				} else if (prm->reconstruct_eint) {
 					const double eint_L = A4(L, i, j, k, 4), eint_R = A4(R, i, j, k, 4);
 					P_L = eos_pressure(prm, rho_L, eint_L * rho_L);
 					P_R = eos_pressure(prm, rho_R, eint_R * rho_R);
@@ -488,10 +501,10 @@ void orc_compute_fluxes(const qk_hydro_params *prm, int solver, int dir, const q
 					Eint_L = A4(L, i, j, k, 5);
 					Eint_R = A4(R, i, j, k, 5);
 				}
-				const double cs_L = eos_sound_speed(prm, rho_L, P_L);
-				const double E_L = eos_eint_from_pres(prm, rho_L, P_L) + ke_L;
-				const double cs_R = eos_sound_speed(prm, rho_R, P_R);
-				const double E_R = eos_eint_from_pres(prm, rho_R, P_R) + ke_R;
+				const double cs_L = iso ? prm->cs_isothermal : eos_sound_speed(prm, rho_L, P_L);
+				const double E_L = iso ? NAN : eos_eint_from_pres(prm, rho_L, P_L) + ke_L;
+				const double cs_R = iso ? prm->cs_isothermal : eos_sound_speed(prm, rho_R, P_R);
+				const double E_R = iso ? NAN : eos_eint_from_pres(prm, rho_R, P_R) + ke_R;
 				hstate sL, sR;
 				sL.rho = rho_L;
 				sL.u = A4(L, i, j, k, velN);
@@ -547,6 +560,10 @@ void orc_compute_fluxes(const qk_hydro_params *prm, int solver, int dir, const q
 				F[velN] = Fc[1];
 				F[velV] = Fc[2];
 				F[velW] = Fc[3];
+				if (iso) { /* :1083-1087 */
+					F[EN] = 0;
+					F[EI] = 0;
+				}
 				const double v_norm = (F[0] >= 0.) ? (F[0] / rho_R) : (F[0] / rho_L);
 				A4(facevel, i, j, k, 0) = v_norm;
 				if (F[0] >= 0.) {
@@ -747,7 +764,7 @@ double orc_max_signal_speed(const qk_hydro_params *prm, int which, const qk_arra
 		for (int j = bx->lo[1]; j <= bx->hi[1]; ++j)
 			for (int i = bx->lo[0]; i <= bx->hi[0]; ++i) {
 				const double rho = A4(c, i, j, k, RHO), px = A4(c, i, j, k, MX), py = A4(c, i, j, k, MY), pz = A4(c, i, j, k, MZ);
-				const double cs = cons_sound_speed(prm, c, i, j, k);
+				const double cs = (prm->gamma == 1.0) ? prm->cs_isothermal : cons_sound_speed(prm, c, i, j, k); /* :214-218, 242-246 */
 				double sig;
 				if (which == 0) {
 					const double vx = px / rho, vy = py / rho, vz = pz / rho;

@@ -82,6 +82,7 @@ class qk_hydro_params(C.Structure):
         ("integrator_order", C.c_int32),
         ("abort_on_fofc_failure", C.c_int32),
         ("arith", C.c_int32),
+        ("cs_isothermal", C.c_double),
     ]
 
 
@@ -148,7 +149,8 @@ M_U = 1.6605390666e-24  # :55
 
 
 def hydro_params(gamma=1.4, reconstruct_eint=0, nscalars=0, nmscalars=0, recon_order=3, arith=QK_ARITH_EXACT,
-                 density_floor=0.0, temp_floor=0.0, mean_molecular_weight=M_U, boltzmann_constant=K_B) -> qk_hydro_params:
+                 density_floor=0.0, temp_floor=0.0, mean_molecular_weight=M_U, boltzmann_constant=K_B,
+                 cs_isothermal=float("nan")) -> qk_hydro_params:
     """Defaults = the reference's defaults (simulation.hpp:172-173, QuokkaSimulation.hpp:107-131,165-166)."""
     p = qk_hydro_params()
     p.gamma = gamma
@@ -168,6 +170,7 @@ def hydro_params(gamma=1.4, reconstruct_eint=0, nscalars=0, nmscalars=0, recon_o
     p.integrator_order = 2
     p.abort_on_fofc_failure = 1
     p.arith = arith
+    p.cs_isothermal = cs_isothermal  # EOS_Traits default NAN (src/hydro/EOS.hpp:34); read only when gamma == 1
     return p
 
 

@@ -480,8 +480,6 @@ extern "C" int qk_tag_pressure_gradient(const qk_hydro_params *prm, int nboxes, 
 {
 	if (!prm)
 		return QK_ERR_BAD_ARG;
-	if (prm->gamma == 1.0)
-		return QK_ERR_UNSUPPORTED;
 	return tag_common(0, make_hydro_const(prm), nboxes, valid, cons, 0, tags, 0.0, eta_threshold, P_min, ntagged, stream);
 }
 

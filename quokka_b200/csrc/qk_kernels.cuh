@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(TPB) k_cons_to_prim(HydroConst c, Iter it, A4 
 		prim.p[op + 4 * prim.ns] = Eint_cons / rho;
 		prim.p[op + 5 * prim.ns] = Eaux / rho;
 	} else {
-		prim.p[op + 4 * prim.ns] = eos_pressure(c, rho, Eint_cons);
+		prim.p[op + 4 * prim.ns] = c.iso ? rho * c.cs_iso * c.cs_iso : eos_pressure(c, rho, Eint_cons); // ComputePressure, :365-366
 		prim.p[op + 5 * prim.ns] = Eaux;
 	}
 	for (int n = 0; n < c.ns; ++n)
@@ -77,11 +77,18 @@ __global__ void __launch_bounds__(TPB) k_flat_coefs(HydroConst c, int dir, Iter 
 			const double r = q.p[o + m * s];
 			v = eos_pressure(c, r, r * v);
 		}
+		if (c.iso) // hydro_system.hpp:579-586
+			v = q.p[o + m * s] * (c.cs_iso * c.cs_iso);
 		P[m + 2] = v;
 	}
 	const double rho = q.p[o];
-	const double cs = eos_sound_speed(c, rho, P[2]);
-	const double KS = (cs * cs) * rho;
+	double KS;
+	if (c.iso) { // :604-606
+		KS = rho * c.cs_iso * c.cs_iso;
+	} else {
+		const double cs = eos_sound_speed(c, rho, P[2]);
+		KS = (cs * cs) * rho;
+	}
 	const double vm1 = q.p[o - s + (1 + dir) * q.ns], vp1 = q.p[o + s + (1 + dir) * q.ns];
 	chi(i, j, k, 0) = flatten_chi(P[0], P[1], P[3], P[4], KS, vm1, vp1);
 }
@@ -323,7 +330,7 @@ __device__ __forceinline__ void enforce_limits_cell(const HydroConst &c, double 
 				U[6 + n] /= sp_sum;
 		}
 	}
-	if (rho_new > 2.2250738585072014e-308) {
+	if ((rho_new > 2.2250738585072014e-308) && !c.iso) { // hydro_system.hpp:746
 		const double vx1 = U[1] / rho_new, vx2 = U[2] / rho_new, vx3 = U[3] / rho_new;
 		const double Ekin = 0.5 * rho_new * (vx1 * vx1 + vx2 * vx2 + vx3 * vx3);
 		const double Etot = U[4];
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(TPB) k_max_signal(HydroConst c, int which, Ite
 	if (it.get((int64_t)blockIdx.x * TPB + threadIdx.x, i, j, k)) {
 		const double rho = u(i, j, k, 0), px = u(i, j, k, 1), py = u(i, j, k, 2), pz = u(i, j, k, 3), E = u(i, j, k, 4);
 		const double P = cons_pressure(c, rho, px, py, pz, E);
-		const double cs = eos_sound_speed(c, rho, P);
+		const double cs = c.iso ? c.cs_iso : eos_sound_speed(c, rho, P); // hydro_system.hpp:214-218, 242-246
 		if (which == 0) {
 			const double vx = px / rho, vy = py / rho, vz = pz / rho;
 			sig = fabs(cs + sqrt(vx * vx + vy * vy + vz * vz));
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(TPB) k_max_signal2(HydroConst c, Iter it, A4 u
 		const int64_t o = u.off(i, j, k);
 		const double rho = u.p[o], px = u.p[o + u.ns], py = u.p[o + 2 * u.ns], pz = u.p[o + 3 * u.ns], E = u.p[o + 4 * u.ns];
 		const double P = cons_pressure(c, rho, px, py, pz, E);
-		const double cs = eos_sound_speed(c, rho, P);
+		const double cs = c.iso ? c.cs_iso : eos_sound_speed(c, rho, P);
 		const double vx = px / rho, vy = py / rho, vz = pz / rho;
 		s0 = dmax(s0, fabs(cs + sqrt(vx * vx + vy * vy + vz * vz)));
 		const double kinetic_energy = (px * px + py * py + pz * pz) / (2.0 * rho);

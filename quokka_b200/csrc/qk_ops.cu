@@ -129,7 +129,7 @@ static int check_params(const qk_hydro_params *p)
 {
 	if (!p)
 		return QK_ERR_BAD_ARG;
-	if (p->gamma == 1.0 || p->nscalars > QK_MAX_SCALARS || p->nscalars < 0 || p->nmscalars > p->nscalars)
+	if (p->nscalars > QK_MAX_SCALARS || p->nscalars < 0 || p->nmscalars > p->nscalars)
 		return QK_ERR_UNSUPPORTED;
 	return qk_require_device();
 }

@@ -27,6 +27,10 @@
 struct HydroConst {
 	double gamma, gm1, mu, mumn, boltz, mintemp, mindens, dfloor, tfloor, small_x, G, K_visc;
 	int reconstruct_eint, ns, nms, nv;
+	// isothermal EOS (gamma == 1: HydroSystem::is_eos_isothermal(), hydro_system.hpp:132-133): P = rho cs_iso^2, c_s = cs_iso, no energy fluxes.
+	// Only the one-kernel-per-operator path runs it (qk_sweep.cu sends gamma == 1 there).
+	double cs_iso;
+	int iso;
 };
 
 inline HydroConst make_hydro_const(const qk_hydro_params *p)
@@ -48,6 +52,8 @@ inline HydroConst make_hydro_const(const qk_hydro_params *p)
 	c.ns = p->nscalars;
 	c.nms = p->nmscalars;
 	c.nv = 6 + p->nscalars;
+	c.iso = (p->gamma == 1.0) ? 1 : 0;
+	c.cs_iso = p->cs_isothermal;
 	return c;
 }
 
@@ -139,6 +145,8 @@ __device__ __forceinline__ EosRP eos_rp_all(const HydroConst &c, double rho, dou
 // HydroSystem::ComputePressure(cons,i,j,k)  src/hydro/hydro_system.hpp:349-372
 __device__ __forceinline__ double cons_pressure(const HydroConst &c, double rho, double px, double py, double pz, double E)
 {
+	if (c.iso)
+		return rho * c.cs_iso * c.cs_iso; // hydro_system.hpp:365-366
 	const double vx = px / rho, vy = py / rho, vz = pz / rho;
 	const double ke = 0.5 * rho * (vx * vx + vy * vy + vz * vz);
 	return eos_pressure(c, rho, E - ke);
@@ -224,7 +232,11 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 	const double ke_L = 0.5 * rho_L * (L[1] * L[1] + L[2] * L[2] + L[3] * L[3]);
 	const double ke_R = 0.5 * rho_R * (R[1] * R[1] + R[2] * R[2] + R[3] * R[3]);
 	double P_L, P_R, Eint_L, Eint_R;
-	if (c.reconstruct_eint) {
+	if (c.iso) { // hydro_system.hpp:910-915: E and Eint stay NAN in the reference; their fluxes are set to zero at the end
+		P_L = rho_L * (c.cs_iso * c.cs_iso);
+		P_R = rho_R * (c.cs_iso * c.cs_iso);
+		Eint_L = Eint_R = __longlong_as_double(0x7ff8000000000000LL);
+	} else if (c.reconstruct_eint) {
 		P_L = eos_pressure(c, rho_L, L[4] * rho_L);
 		P_R = eos_pressure(c, rho_R, R[4] * rho_R);
 		Eint_L = rho_L * L[5];
@@ -235,8 +247,14 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		Eint_L = L[5];
 		Eint_R = R[5];
 	}
-	const EosRP eL = eos_rp_all(c, rho_L, P_L);
-	const EosRP eR = eos_rp_all(c, rho_R, P_R);
+	EosRP eL, eR;
+	if (c.iso) {
+		eL.cs = eR.cs = c.cs_iso;
+		eL.Eint = eR.Eint = eL.dedp = eR.dedp = eL.drdp = eR.drdp = Eint_L;
+	} else {
+		eL = eos_rp_all(c, rho_L, P_L);
+		eR = eos_rp_all(c, rho_R, P_R);
+	}
 	const double cs_L = eL.cs, cs_R = eR.cs;
 	const double E_L = eL.Eint + ke_L;
 	const double E_R = eR.Eint + ke_R;
@@ -294,7 +312,7 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		const double C_tilde_P = 0.5 * (eiL * eL.drdp + eiR * eR.drdp + rho_L * eL.dedp + rho_R * eR.dedp);
 		const double cs_exp = H_tilde - 0.5 * vsq_tilde - C_tilde_rho;
 		double cs_tilde;
-		if (cs_exp <= 0) {
+		if (c.iso || cs_exp <= 0) { // gamma == 1: HLLC.hpp:76-88 (G_L = G_R = 1 = c.G)
 			cs_tilde = 0.5 * (cs_L + cs_R);
 		} else {
 			cs_tilde = sqrt(cs_exp / C_tilde_P);
@@ -381,6 +399,10 @@ __device__ __forceinline__ void face_flux(const HydroConst &c, int dir, const do
 		F[5] = F[5] + viscosity * (Eint_L - Eint_R);
 		for (int n = 0; n < c.ns; ++n)
 			F[6 + n] = F[6 + n] + viscosity * (L[6 + n] - R[6 + n]);
+	}
+	if (c.iso) { // hydro_system.hpp:1083-1087
+		F[4] = 0;
+		F[5] = 0;
 	}
 	// face-centred normal velocity (hydro_system.hpp:1089-1091)
 	vface = (F[0] >= 0.) ? (F[0] / rho_R) : (F[0] / rho_L);

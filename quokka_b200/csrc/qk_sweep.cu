@@ -188,7 +188,8 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 	const bool inst = (ns == 0 && nms == 0) || (ns == 1 && nms == 0) || (ns == 3 && nms == 2);
 	const int order = prm->reconstruction_order;
 	// PPM for every instantiated trait set; PLM (minmod) for the scalar-free, reconstruct_eint = false set (config C4's hydro)
-	const bool can = (order == 3 || (order == 2 && ns == 0 && !prm->reconstruct_eint)) && inst && prm->use_dual_energy && L->nghost >= 4 && prm->K_visc == 0.0;
+	const bool can = (order == 3 || (order == 2 && ns == 0 && !prm->reconstruct_eint)) && inst && prm->use_dual_energy && L->nghost >= 4 && prm->K_visc == 0.0 &&
+			 prm->gamma != 1.0; // the isothermal EOS (is_eos_isothermal(), hydro_system.hpp:133) is built on the operator path only
 	if (!can) {
 		// say so once: the one-kernel-per-operator path is 3-4x slower and a maintainer flipping a run-time switch should know
 		static bool warned = false;
@@ -196,8 +197,8 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 			warned = true;
 			fprintf(stderr,
 				"[quokka_b200] this configuration takes the one-kernel-per-operator path (fused sweeps exist for PPM, for PLM without scalars and "
-				"reconstruct_eint, with dual energy, 4 ghost cells and K_visc = 0): reconstruction_order = %d, nscalars = %d, K_visc = %g\n",
-				order, ns, prm->K_visc);
+				"reconstruct_eint, with dual energy, 4 ghost cells, K_visc = 0 and gamma != 1): reconstruction_order = %d, nscalars = %d, K_visc = %g, gamma = %g\n",
+				order, ns, prm->K_visc, prm->gamma);
 		}
 		return 0;
 	}

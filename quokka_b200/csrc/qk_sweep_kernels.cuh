@@ -73,16 +73,29 @@ template <int ARITH, int NS, bool REINT> __global__ void __launch_bounds__(256) 
 		const int j = B.lo[1] - 2 + (int)(jk - (jk / ny) * ny);
 		const int64_t o = q.off(i, j, k);
 		const int64_t st[3] = {1, q.js, q.ks};
-		const double rho = q.p[o];
 		double Pc[3][5];
 		double vm1[3], vp1[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			vm1[d] = q.p[o - st[d] + (1 + d) * q.ns];
+			vp1[d] = q.p[o + st[d] + (1 + d) * q.ns];
+		}
+		// chi is exactly 1 along every direction in which the flow does not converge (v(+1) >= v(-1), hydro_system.hpp:619-622): a cell that
+		// converges along none of them needs neither its pressures nor its sound speed.  Same bits; gas at rest, expansion waves and the
+		// interior of a blast take this exit.
+		if (!((vp1[0] < vm1[0]) || (vp1[1] < vm1[1]) || (vp1[2] < vm1[2]))) {
+			const int64_t oc1 = B.chi3.off(i, j, k);
+#pragma unroll
+			for (int d = 0; d < 3; ++d)
+				B.chi3.p[oc1 + d * B.chi3.ns] = 1.0;
+			continue;
+		}
+		const double rho = q.p[o];
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
 #pragma unroll
 			for (int m = -2; m <= 2; ++m)
 				Pc[d][m + 2] = q.p[o + m * st[d] + 4 * q.ns];
-			vm1[d] = q.p[o - st[d] + (1 + d) * q.ns];
-			vp1[d] = q.p[o + st[d] + (1 + d) * q.ns];
 		}
 		if (ARITH != 0) { // relaxed arithmetic (qk_relaxed.cuh): rho c_s^2 = gamma p in closed form
 			if (REINT) {
@@ -170,6 +183,17 @@ template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi9(Fas
 		for (int d = 0; d < 3; ++d) {
 			double P[7], v[5], r3[3];
 #pragma unroll
+			for (int m = -2; m <= 2; ++m)
+				v[m + 2] = q.p[o + m * st[d] + (1 + d) * q.ns];
+			// chi is exactly 1 wherever the flow does not converge along d (v(+1) >= v(-1), hydro_system.hpp:619-622): none of the three
+			// cells converging -> this direction contributes min(chi, 1) and its pressures are never read.  Gas at rest, expansion waves
+			// and the interior of a blast take this exit; the value is the same bit for bit.
+			if (!((v[2] < v[0]) || (v[3] < v[1]) || (v[4] < v[2]))) {
+				chi = first ? 1.0 : dmin(chi, 1.0);
+				first = false;
+				continue;
+			}
+#pragma unroll
 			for (int m = -3; m <= 3; ++m) {
 				double pv = q.p[o + m * st[d] + 4 * q.ns];
 				if (REINT) { // pressures from the specific internal energies (hydro_system.hpp:577-586)
@@ -178,9 +202,6 @@ template <int NS, bool REINT> __global__ void __launch_bounds__(256) k_fchi9(Fas
 				}
 				P[m + 3] = pv;
 			}
-#pragma unroll
-			for (int m = -2; m <= 2; ++m)
-				v[m + 2] = q.p[o + m * st[d] + (1 + d) * q.ns];
 #pragma unroll
 			for (int m = -1; m <= 1; ++m)
 				r3[m + 1] = q.p[o + m * st[d]];

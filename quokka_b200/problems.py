@@ -94,6 +94,49 @@ class SedovProblem:
         return a
 
 
+class IsothermalWaveProblem:
+    """An isothermal-EOS problem (EOS_Traits::gamma = 1 with cs_isothermal, src/hydro/EOS.hpp:32-37; the EOS of the reference's
+    BinaryOrbitCIC / StarCluster / RadForce problems): colliding density enhancements in a periodic box, strong enough to shock.
+    Pressure is rho cs^2, there are no energy fluxes (hydro_system.hpp:1083-1087); the energy components only see the dual-energy sync."""
+
+    gamma = 1.0
+    cs_isothermal = 1.3
+    cfl = 0.3
+    stop_time = 1.0
+    ncomp = 6
+    nghost = 4
+
+    def __init__(self, ncell, max_grid_size):
+        self.ncell = [int(c) for c in (ncell if hasattr(ncell, "__len__") else (ncell,) * 3)]
+        self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in self.ncell))
+        self.dx = [1.0 / c for c in self.ncell]
+        self.boxes = chop_domain(self.ncell, max_grid_size)
+        self.periodic = (1, 1, 1)
+        self.bc_lo = [0] * (3 * self.ncomp)  # QK_BC_INT_DIR: interior / periodic
+        self.bc_hi = list(self.bc_lo)
+
+    def params(self, **kw):
+        return hydro_params(gamma=self.gamma, reconstruct_eint=0, cs_isothermal=self.cs_isothermal, **kw)
+
+    def initial_state(self, box: qk_box, ng=None) -> np.ndarray:
+        ng = self.nghost if ng is None else ng
+        g = box.grown(ng)
+        nz, ny, nx = g.shape()
+        a = np.zeros((self.ncomp, nz, ny, nx))
+        z, y, x = np.meshgrid(*[(np.arange(box.lo[d], box.hi[d] + 1) + 0.5) * self.dx[d] for d in (2, 1, 0)], indexing="ij")
+        rho = 1.0 + 0.8 * np.sin(2 * np.pi * x) * np.cos(2 * np.pi * y) + 0.5 * np.exp(-((x - 0.5) ** 2 + (y - 0.4) ** 2 + (z - 0.6) ** 2) / 0.01)
+        vx = 2.0 * np.sin(2 * np.pi * (y + z))
+        vy = -1.5 * np.cos(2 * np.pi * x)
+        vz = 1.0 * np.sin(4 * np.pi * x) * np.sin(2 * np.pi * y)
+        v = a[:, ng:nz - ng, ng:ny - ng, ng:nx - ng]
+        v[0] = rho
+        v[1], v[2], v[3] = rho * vx, rho * vy, rho * vz
+        eint = rho * self.cs_isothermal ** 2  # any positive value: the isothermal EOS never reads it
+        v[4] = eint + 0.5 * rho * (vx * vx + vy * vy + vz * vz)
+        v[5] = eint
+        return a
+
+
 class SodProblem:
     """HydroShocktube (src/problems/HydroShocktube/test_hydro_shocktube.cpp:28-91, tests/shocktube.in), config C1 of
     BASELINE.json, on a uniform level.  The reference builds it with AMREX_SPACEDIM = 1; here the tube is 4 cells thick and

@@ -39,7 +39,7 @@ class GenericProblem:
     stop_time = 1.0
     nghost = 4
 
-    def __init__(self, ncell, max_grid, periodic, bc_kind, nscalars=0, gamma=1.4):
+    def __init__(self, ncell, max_grid, periodic, bc_kind, nscalars=0, gamma=1.4, cs_isothermal=float("nan")):
         self.ncell = list(ncell)
         self.domain = qk_box.make((0, 0, 0), tuple(c - 1 for c in ncell))
         self.dx = [1.0 / c for c in ncell]
@@ -48,6 +48,7 @@ class GenericProblem:
         self.ncomp = 6 + nscalars
         self.nscalars = nscalars
         self.gamma = gamma
+        self.cs_isothermal = cs_isothermal  # read only when gamma == 1 (EOS_Traits::cs_isothermal, src/hydro/EOS.hpp:34)
         lo = []
         for n in range(self.ncomp):
             for d in range(3):
@@ -61,11 +62,11 @@ class GenericProblem:
         self.bc_hi = list(lo)
 
     def params(self, **kw):
-        return capi.hydro_params(gamma=self.gamma, nscalars=self.nscalars, **kw)
+        return capi.hydro_params(gamma=self.gamma, nscalars=self.nscalars, cs_isothermal=self.cs_isothermal, **kw)
 
     def states(self, seed=1, kind="shocked"):
         rho, v, P, rng = ol.random_cons(self.domain, self.nscalars, seed, kind)
-        U = ol.cons_from_prim(rho, v, P, self.gamma, rng, self.nscalars)
+        U = ol.cons_from_prim(rho, v, P, self.gamma if self.gamma != 1.0 else 1.4, rng, self.nscalars)  # isothermal: energies are never read
         out = []
         ng = self.nghost
         for bx in self.boxes:
@@ -151,9 +152,14 @@ def run_stage_pair(lib, p, prm, st, dt, entry):
 
 
 @pytest.mark.parametrize("which", ["production", "faithful"])
-@pytest.mark.parametrize("case", ["reflect_multi", "periodic_scalars", "mass_scalars", "single_box", "eint"])
+@pytest.mark.parametrize("case", ["reflect_multi", "periodic_scalars", "mass_scalars", "single_box", "eint", "isothermal", "isothermal_plm"])
 def test_advance_two_stages(lib, which, case):
-    if case == "reflect_multi":
+    if case.startswith("isothermal"):
+        # gamma = 1 (HydroSystem::is_eos_isothermal(), hydro_system.hpp:133): P = rho cs_iso^2, c_s = cs_iso, no energy fluxes; both entries
+        # run the one-kernel-per-operator path (qk_sweep.cu sends gamma == 1 there)
+        p = GenericProblem((32, 16, 32), 16, (1, 0, 1), "reflect", nscalars=1, gamma=1.0, cs_isothermal=1.3)
+        prm = p.params(recon_order=3 if case == "isothermal" else 2)
+    elif case == "reflect_multi":
         p = GenericProblem((32, 32, 32), 16, (0, 0, 0), "reflect")
         prm = p.params()
     elif case == "periodic_scalars":
@@ -185,15 +191,19 @@ def test_advance_two_stages(lib, which, case):
     o.orc_level_destroy(L)
 
 
+@pytest.mark.parametrize("eos", ["gamma_law", "isothermal"])
 @pytest.mark.parametrize("which", ["production", "faithful"])
-def test_fofc_fallback(lib, which):
+def test_fofc_fallback(lib, which, eos):
     """a violent state + large dt makes PredictStep flag cells: first-order flux correction must reproduce the
     reference's replaceFluxes/redo sequence (QuokkaSimulation.hpp:1146-1184) bit for bit"""
-    p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic")
+    if eos == "isothermal":
+        p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic", gamma=1.0, cs_isothermal=1.3)
+    else:
+        p = GenericProblem((32, 32, 32), 16, (1, 1, 1), "periodic")
     prm = p.params()
     prm.abort_on_fofc_failure = 0
     st = p.states(seed=9, kind="shocked")
-    dt = 4.0e-3
+    dt = 4.0e-3 if eos == "gamma_law" else 1.0e-2  # isothermal: 13 cells flagged in stage 1, 34 in stage 2
     L, keep = oracle_level(p, st)
     o = ol.oracle()
     bo1, bo2 = C.c_int64(), C.c_int64()
@@ -210,9 +220,12 @@ def test_fofc_fallback(lib, which):
 
 
 def run_gpu_sedov(ncell, box, nsteps):
+    return run_gpu_problem(SedovProblem(ncell, box), nsteps)
+
+
+def run_gpu_problem(prob, nsteps):
     from quokka_b200.simulation import HydroSimulation
 
-    prob = SedovProblem(ncell, box)
     sim = HydroSimulation(prob)
     sim.setInitialConditions()
     dts = []
@@ -225,6 +238,20 @@ def run_gpu_sedov(ncell, box, nsteps):
     t, retries, upd = sim.time, sim.retries, sim.cellUpdates
     sim.close()
     return out, t, retries, upd, dts
+
+
+def test_isothermal_run_vs_oracle():
+    """The isothermal EOS (gamma = 1, cs_isothermal; HydroSystem::is_eos_isothermal(), hydro_system.hpp:133) through the library's own time loop:
+    32^3 periodic box in eight boxes, 15 steps of shocking flow -- state, time (i.e. every dt, from c_s = cs_isothermal) and retry count
+    bit-identical to the oracle's level driver, whose isothermal operators are pinned to the reference's templates."""
+    from quokka_b200.problems import IsothermalWaveProblem
+    from test_oracle_golden import run_oracle_problem
+
+    ref, t_ref, r_ref = run_oracle_problem(IsothermalWaveProblem(32, 16), 15)
+    got, t, r, upd, dts = run_gpu_problem(IsothermalWaveProblem(32, 16), 15)
+    assert t == t_ref and r == r_ref and upd == 32 ** 3 * 15
+    exact(got, ref, "isothermal 32^3")
+    assert np.isfinite(got).all() and np.abs(got[0] - 1.0).max() > 0.1
 
 
 @pytest.mark.parametrize("name", ["sedov16_b16_s5", "sedov32_b16_s10", "sedov32_b32_s30"])
