@@ -11,6 +11,7 @@
 //   problem 2: scalars      gamma=5/3, mu=m_u, reconstruct_eint=true,  3 passive scalars of which 2 mass scalars
 //   problem 3: isothermal   gamma=1, cs_isothermal=1.3, reconstruct_eint=false, 1 passive scalar   (the is_eos_isothermal() branches,
 //                           src/hydro/hydro_system.hpp:133; BinaryOrbitCIC / StarCluster / RadForce use this EOS)
+//   problem 4: isothermal   gamma=1, cs_isothermal=0.7, reconstruct_eint=true, 3 passive scalars of which 2 mass scalars
 #include <cstdint>
 #include <cstring>
 
@@ -39,6 +40,8 @@ struct P1 {
 struct P2 {
 };
 struct P3 {
+};
+struct P4 {
 };
 
 template <> struct quokka::EOS_Traits<P0> {
@@ -98,6 +101,21 @@ template <> struct HydroSystem_Traits<P3> {
 template <> struct Physics_Traits<P3> {
 	static constexpr bool is_hydro_enabled = true;
 	static constexpr int numMassScalars = 0;
+	static constexpr int numPassiveScalars = numMassScalars + 1;
+	static constexpr bool is_radiation_enabled = false;
+	static constexpr bool is_mhd_enabled = false;
+	static constexpr int nGroups = 1;
+};
+
+template <> struct quokka::EOS_Traits<P4> {
+	static constexpr double gamma = 1.0;
+	static constexpr double cs_isothermal = 0.7;
+	static constexpr double mean_molecular_weight = C::m_u;
+	static constexpr double boltzmann_constant = C::k_B;
+};
+template <> struct Physics_Traits<P4> {
+	static constexpr bool is_hydro_enabled = true;
+	static constexpr int numMassScalars = 2;
 	static constexpr int numPassiveScalars = numMassScalars + 1;
 	static constexpr bool is_radiation_enabled = false;
 	static constexpr bool is_mhd_enabled = false;
@@ -628,6 +646,10 @@ void rad_source_terms(const qk_box *valid, const qk_array4 *cons, const qk_array
 	} break;                                                                                                                                     \
 	case 3: {                                                                                                                                    \
 		using P = P3;                                                                                                                        \
+		CALL;                                                                                                                                \
+	} break;                                                                                                                                     \
+	case 4: {                                                                                                                                    \
+		using P = P4;                                                                                                                        \
 		CALL;                                                                                                                                \
 	} break;                                                                                                                                     \
 	default:                                                                                                                                     \

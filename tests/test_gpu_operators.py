@@ -14,10 +14,10 @@ from quokka_b200.capi import QK_HLLC, QK_LLF, QK_MC, QK_MINMOD, check, hydro_par
 
 pytestmark = pytest.mark.gpu
 
-PROBLEMS = {0: (1.4, 0, 0, 0), 1: (1.4, 1, 0, 0), 2: (5.0 / 3.0, 1, 3, 2), 3: (1.0, 0, 1, 0)}
+PROBLEMS = {0: (1.4, 0, 0, 0), 1: (1.4, 1, 0, 0), 2: (5.0 / 3.0, 1, 3, 2), 3: (1.0, 0, 1, 0), 4: (1.0, 1, 3, 2)}
 # problem 3: the isothermal EOS (gamma = 1, cs_isothermal = 1.3: HydroSystem::is_eos_isothermal(), hydro_system.hpp:133); the oracle's
 # isothermal branches are pinned to the reference's templates by tests/test_oracle_vs_ref.py (harness problem 3)
-CS_ISO = {3: 1.3}
+CS_ISO = {3: 1.3, 4: 0.7}
 VALID = qk_box.make((3, -2, 5), (38, 17, 24))  # 36 x 20 x 20: not a multiple of the block size, non-zero origin
 NG = 4
 
@@ -69,7 +69,7 @@ def oracle_prim(problem, kind):
     return prm, cons, po
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("kind", ["smooth", "shocked"])
 def test_cons_to_prim(lib, problem, kind):
     prm, cons, po = oracle_prim(problem, kind)
@@ -78,7 +78,7 @@ def test_cons_to_prim(lib, problem, kind):
     exact(dp.numpy(), po.a, "prim")
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_flattening_coefficients(lib, problem, d):
     prm, cons, po = oracle_prim(problem, "shocked")
@@ -127,7 +127,7 @@ def oracle_states(problem, d, kind, order=3, flatten=True):
     return prm, cons, po, chis, L, R, L0, R0
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_flatten_shocks(lib, problem, d):
     prm, cons, po, chis, L, R, L0, R0 = oracle_states(problem, d, "shocked")
@@ -144,7 +144,7 @@ def test_flatten_shocks(lib, problem, d):
     exact(dr.numpy(), R.a, "right")
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("solver", [QK_HLLC, QK_LLF])
 @pytest.mark.parametrize("d", [0, 1, 2])
 @pytest.mark.parametrize("kind", ["smooth", "shocked"])
@@ -163,7 +163,7 @@ def test_compute_fluxes(lib, problem, solver, d, kind):
     assert np.isfinite(Fo.a).all()
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_compute_fluxes_with_artificial_viscosity(lib, problem, d):
     """artificialViscosityK_ = 0.1 (hydro_system.hpp:1052-1076): operator entry and the one-kernel flux function, bit-exact vs the oracle
@@ -186,7 +186,7 @@ def test_compute_fluxes_with_artificial_viscosity(lib, problem, d):
     assert (F0.a[0] != Fo.a[0]).any()
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("order", [1, 2, 3])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_flux_function_fused(lib, problem, order, d):
@@ -206,7 +206,7 @@ def test_flux_function_fused(lib, problem, order, d):
     exact(dV.numpy(), Vo.a, "facevel")
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_fo_flux_function_fused(lib, problem, d):
     """hydroFOFluxFunction<DIR> (donor cell + LLF)."""
@@ -222,7 +222,7 @@ def test_fo_flux_function_fused(lib, problem, d):
     exact(dV.numpy(), Vo.a, "facevel")
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 def test_update_ops(lib, problem):
     prm = params(problem)
     cons = make_cons(problem, "shocked")

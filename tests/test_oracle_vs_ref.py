@@ -16,9 +16,9 @@ from quokka_b200.capi import QK_HLLC, QK_LLF, QK_MC, QK_MINMOD, hydro_params, qk
 pytestmark = pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref/libquokka_ref.so not built")
 
 # harness problem id -> (gamma, reconstruct_eint, nscalars, nmscalars)   (oracle/ref_build/ref_harness.cpp)
-PROBLEMS = {0: (1.4, 0, 0, 0), 1: (1.4, 1, 0, 0), 2: (5.0 / 3.0, 1, 3, 2), 3: (1.0, 0, 1, 0)}
+PROBLEMS = {0: (1.4, 0, 0, 0), 1: (1.4, 1, 0, 0), 2: (5.0 / 3.0, 1, 3, 2), 3: (1.0, 0, 1, 0), 4: (1.0, 1, 3, 2)}
 # problem 3: the isothermal EOS (gamma = 1, EOS_Traits::cs_isothermal = 1.3; every is_eos_isothermal() branch of hydro_system.hpp / HLLC.hpp)
-CS_ISO = {3: 1.3}
+CS_ISO = {3: 1.3, 4: 0.7}
 VALID = qk_box.make((3, -2, 5), (14, 7, 12))
 NG = 4
 
@@ -57,14 +57,14 @@ def both_prim(problem, kind):
     return prm, cons, po, pr
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("kind", ["smooth", "shocked"])
 def test_cons_to_prim(problem, kind):
     _, _, po, pr = both_prim(problem, kind)
     exact(po.a, pr.a)
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_flattening_coefficients(problem, d):
     prm, cons, po, _ = both_prim(problem, "shocked")
@@ -127,7 +127,7 @@ def test_flatten_shocks(problem, d):
     exact(R.a, Rr.a)
 
 
-@pytest.mark.parametrize("problem", [0, 1, 2, 3])
+@pytest.mark.parametrize("problem", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("solver", [QK_HLLC, QK_LLF])
 @pytest.mark.parametrize("d", [0, 1, 2])
 @pytest.mark.parametrize("kind", ["smooth", "shocked"])
@@ -152,7 +152,7 @@ def test_compute_fluxes(problem, solver, d, kind):
         assert (Fo.a[4] == 0).all() and (Fo.a[5] == 0).all() and (Fo.a[0] != 0).any()
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 @pytest.mark.parametrize("d", [0, 1, 2])
 def test_compute_fluxes_with_artificial_viscosity(problem, d):
     """artificialViscosityK_ != 0 (Colella & Woodward 1984 eq. 4.2, hydro_system.hpp:1052-1076): K max(-div v, 0) (U_L - U_R) is added to
@@ -179,7 +179,7 @@ def test_compute_fluxes_with_artificial_viscosity(problem, d):
     exact(Fr.a[1:4], F0.a[1:4])  # momentum fluxes carry no artificial viscosity
 
 
-@pytest.mark.parametrize("problem", [0, 2, 3])
+@pytest.mark.parametrize("problem", [0, 2, 3, 4])
 def test_update_ops(problem):
     prm = params(problem)
     cons = make_cons(problem, "shocked")
