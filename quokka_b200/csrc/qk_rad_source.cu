@@ -283,6 +283,10 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 		if (hydro->arith == QK_ARITH_FAST) { // relaxed arithmetic (qk_rad_source.cuh): closed-form EOS, reciprocal products
 			if (minb == 6)
 				k_rad_source<qk_rsrc::DivPlain, 6, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+			else if (minb == 5)
+				k_rad_source<qk_rsrc::DivPlain, 5, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+			else if (minb == 4)
+				k_rad_source<qk_rsrc::DivPlain, 4, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
 			else
 				k_rad_source<qk_rsrc::DivPlain, 8, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
 		} else if (plain_div) {
