@@ -287,6 +287,10 @@ extern "C" int qk_rad_add_source_terms(const qk_hydro_params *hydro, const qk_ra
 				k_rad_source<qk_rsrc::DivPlain, 5, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
 			else if (minb == 4)
 				k_rad_source<qk_rsrc::DivPlain, 4, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+			else if (minb == 10)
+				k_rad_source<qk_rsrc::DivPlain, 10, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
+			else if (minb == 12)
+				k_rad_source<qk_rsrc::DivPlain, 12, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
 			else
 				k_rad_source<qk_rsrc::DivPlain, 8, true><<<grid, SRC_TPB, 0, s>>>(k, tab, prm->nstart, dcount);
 		} else if (plain_div) {

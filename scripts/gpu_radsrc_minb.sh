@@ -1,7 +1,7 @@
 #!/bin/bash
 # relaxed source-term solve: resident CTAs per SM the kernel is compiled for (register cap 64 / 80 / 96 / 128) inside config C4's coarse step
 OUT=gpurun_out/${1:-r02_minb}; mkdir -p $OUT
-for m in 8 6 5 4; do
+for m in ${MINBS:-8 6 5 4}; do
 QK_RADSRC_MINB=$m timeout 300 python bench.py --workload radhydro --arith relaxed --steps 2 --warmup 1 --no-extras --no-subrecords > $OUT/radhydro_minb$m.json 2> $OUT/radhydro_minb$m.err
 python -c "
 import json
