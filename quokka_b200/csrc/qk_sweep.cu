@@ -223,7 +223,7 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 		QK_CUDA(cudaEventSynchronize(F->ev[slot]));
 	SweepBox *hb = F->h_boxes + (size_t)slot * nb;
 	int maxn[5] = {1, 1, 1, 1 << 30, 0}; // largest extents; smallest nx; largest slot count of the concatenated x sweep (launch_stage)
-	int64_t max_slots = 0;
+	int64_t max_slots = 0, total_slots = 0;
 	bool tma = (getenv("QK_NO_TMA") == nullptr) && F->maps_ok;
 	CUtensorMap *hm = F->h_maps;
 	for (int b = 0; b < nb; ++b) {
@@ -248,9 +248,21 @@ int qk_fused_stage(qk_level *L, const qk_hydro_params *prm, int stage, const qk_
 			maxn[d] = std::max(maxn[d], B.hi[d] - B.lo[d] + 1);
 		}
 		maxn[3] = std::min(maxn[3], B.hi[0] - B.lo[0] + 1);
-		max_slots = std::max<int64_t>(max_slots, (int64_t)(B.hi[1] - B.lo[1] + 1) * (B.hi[2] - B.lo[2] + 1) * (B.hi[0] - B.lo[0] + 3));
+		const int64_t slots = (int64_t)(B.hi[1] - B.lo[1] + 1) * (B.hi[2] - B.lo[2] + 1) * (B.hi[0] - B.lo[0] + 3);
+		max_slots = std::max<int64_t>(max_slots, slots);
+		total_slots += slots;
 	}
 	maxn[4] = (max_slots < (int64_t(1) << 31) - 64 && (L->nghost & 1) == 0) ? (int)max_slots : 0; // (its windows start at even array columns)
+	{
+		// The concatenated x sweep pays off where the launch fills the GPU several times over (256^3 per GPU: 570 k tiles, x sweep 7 % faster).
+		// On the small levels of an AMR hierarchy (a few 10 k tiles: the Sod tube of config C1, a 64^3 Sedov) its tiles, most of which wait for
+		// two staged windows, are latency-bound and the per-row tiles are up to 1.5x faster (measured inside the reference's driver,
+		// profiles/r02_ref_cuda_amr_final.json vs r02_ref_cuda_amr_xcat0.json): below QK_XCAT_MIN_TILES (default 65536) tiles the level keeps them.
+		const char *e = getenv("QK_XCAT_MIN_TILES"); // read per call: the parity tests switch it
+		const long long min_tiles = e ? atoll(e) : 65536ll;
+		if (total_slots / 30 < min_tiles)
+			maxn[4] = 0;
+	}
 	if (L->comm && L->nranks > 1) {
 		// Every rank must run the same kernel family: a rank on the faithful path pairs different collectives than one on the fused path.
 		// The alignment of the local rows is negotiated once per level; a rank whose rows later stop qualifying fails loudly instead of hanging.

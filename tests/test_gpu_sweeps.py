@@ -225,6 +225,7 @@ def test_concatenated_x_sweep_equals_per_row_tiles(lib, case, arith, monkeypatch
     st = p.states(seed=31, kind="shocked")
     dt = 1.0e-4
     monkeypatch.delenv("QK_XCAT", raising=False)
+    monkeypatch.setenv("QK_XCAT_MIN_TILES", "0")  # levels this small keep the per-row tiles by default (qk_sweep.cu): force the concatenated sweep
     lib.qk_prof_enable(1)
     a1, a2, ab1, ab2 = run_pair(lib, p, prm, st, dt, lib.qk_hydro_advance_stage)
     counts = prof(lib)
